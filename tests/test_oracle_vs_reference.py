@@ -1,0 +1,88 @@
+"""CPU: pins oracle/path_oracle.py + oracle/dvgo_ops.py against tests/golden/ref_tiny.pt, which
+oracle/make_golden.py produced by running the reference's own Python under shims."""
+import torch
+import torch.nn.functional as F
+
+from oracle import dvgo_ops
+
+RTOL = 1e-4  # BASELINE.json north_star: rgb/alpha and gradients within 1e-4 relative in fp32
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+def _call(orc, cfg, g, t=None, rot_params=None, **kw):
+    return orc.forward(t, rot_params, rays_o=g["rays_o"], rays_d=g["rays_d"], viewdirs=g["viewdirs"], near=cfg.near,
+                       far=cfg.far, stepsize=cfg.stepsize, bg=cfg.bg, **kw)
+
+
+def test_render_outputs_match_reference(golden_tiny, oracle_tiny):
+    orc, cfg = oracle_tiny
+    g = golden_tiny
+    with torch.no_grad():
+        out = _call(orc, cfg, g, t=g["render"]["t"], render_weights=True)
+    ref = g["render"]["out"]
+    for k in ["t_hat_pcd", "rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "alphainv_last_direct",
+              "weights"]:
+        assert _rel(out[k], ref[k]) < RTOL, k
+    agg = g["render"]["agg"]
+    assert torch.equal(orc.trace["ray_id"], agg["ray_id"])
+    assert torch.equal(orc.trace["step_id"], agg["step_id"])
+    assert torch.equal(orc.trace["pts"], agg["ray_pts"])
+    assert _rel(orc.trace["alpha"], agg["alpha"]) < RTOL
+    assert _rel(orc.trace["rgb"], agg["rgbs"]) < RTOL
+    assert _rel(orc.trace["alpha_direct"], agg["alpha_direct"]) < RTOL
+    assert _rel(orc.trace["weights"], g["render"]["last_weights"]) < RTOL
+
+
+def test_repose_outputs_match_reference(golden_tiny, oracle_tiny):
+    orc, cfg = oracle_tiny
+    g = golden_tiny
+    with torch.no_grad():
+        out = _call(orc, cfg, g, rot_params=g["repose"]["rot_params"], render_weights=True)
+    ref = g["repose"]["out"]
+    for k in ["t_hat_pcd", "rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "weights"]:
+        assert _rel(out[k], ref[k]) < RTOL, k
+
+
+def test_train_gradients_match_reference(golden_tiny):
+    from conftest import oracle_from_golden
+    g = golden_tiny
+    orc, cfg = oracle_from_golden(g)
+    for v in orc.s.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    out = _call(orc, cfg, g, t=g["train"]["t"])
+    loss = F.mse_loss(out["rgb_marched"], g["train"]["target"]) * 200.0
+    loss.backward()
+    assert abs(loss.item() - g["train"]["loss"].item()) < 1e-4 * g["train"]["loss"].item()
+    for k, ref in g["train"]["grads"].items():
+        assert orc.s[k].grad is not None, k
+        assert _rel(orc.s[k].grad, ref) < RTOL, k
+
+
+def test_adam_restatement_matches_reference_optimizer(golden_tiny):
+    a = golden_tiny["adam"]
+    for i, masked in enumerate([False, True]):
+        p = a["before"][i].clone()
+        gr = a["grads"][i]
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        for step in range(1, a["steps"] + 1):
+            fn = dvgo_ops.masked_adam_upd if masked else dvgo_ops.adam_upd
+            fn(p, gr, m, v, step, 0.9, 0.99, a["lrs"][i], 1e-8)
+        assert torch.equal(p, a["after"][i])
+        assert torch.equal(m, a["exp_avg"][i])
+        assert torch.equal(v, a["exp_avg_sq"][i])
+
+
+def test_empty_ray_batch_falls_back_to_background(oracle_tiny, golden_tiny):
+    orc, cfg = oracle_tiny
+    g = golden_tiny
+    ro = g["rays_o"][:7]
+    rd = -g["rays_d"][:7]            # looking away from the cloud: no sample in the bbox survives
+    with torch.no_grad():
+        out = orc.forward(g["render"]["t"], rays_o=ro, rays_d=rd, viewdirs=-g["viewdirs"][:7], near=cfg.near,
+                          far=cfg.far, stepsize=cfg.stepsize, bg=cfg.bg)
+    assert out["alphainv_last"] is None
+    assert torch.equal(out["rgb_marched"], torch.ones(7, 3) * cfg.bg)
