@@ -1,0 +1,536 @@
+// K2 — multi-level uniform grid over the warped cloud, ray-sample candidate generation and the
+// exact 8-nearest-neighbour query.  Replaces lib/temporalpoints.py:373-399,434-444 (sample_ray
+// + the KeOps brute-force Kmin_argKmin + the radius rule) and
+// lib/cuda/render_utils_kernel.cu:12-236.
+//
+// Data layout (one opaque blob in HBM):
+//   header (GridHeader, 256 B)  — written on the device from the device-side bbox, so building
+//                                 the grid needs no host synchronisation
+//   cell_start int[cap+1]       — dense table; cells are ordered  top-cell-major, Morton inside a
+//                                 top cell, so that EVERY level-l cell (2^l fine cells per axis)
+//                                 is one contiguous range [cell_start[k], cell_start[k + 8^l])
+//   top_dilated int[top_cap]    — number of points in the 3x3x3 top-level neighbourhood
+//   sorted float4[N]            — points in cell order, .w = original index (bit pattern)
+//   key/rank int[N], scan temp
+// Top-level cells have edge 1.01*sqrt(query_radius) (0.101 for the reference's rule "8th squared
+// distance <= 0.01"), so the 27 top cells around a sample contain every point that can matter.
+//
+// Query = ascend levels: scan the 3x3x3 neighbourhood at level l with a register top-8 of
+// 64-bit keys (d2 bits << 32 | index, i.e. lexicographic (d2, index)); the result is exact as soon
+// as the 8th distance is inside the neighbourhood's guaranteed radius; otherwise jump to the
+// level whose cell edge covers the 8th distance found so far.
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+struct GridHeader {
+  float origin[3];
+  float cell;       // finest cell edge
+  float inv_cell;
+  float top_cell;   // cell * 2^L
+  int L;
+  int top_dim[3];
+  int n_top;
+  int n_cells;      // n_top << 3L
+  float r2;         // query_radius (compared with squared distances)
+  float bmin[3];    // padded bbox used by the sampler (cloud bbox -/+ bbox_pad)
+  float bmax[3];
+  int n_points;
+  int overflow;
+  int cell_capacity;
+  int top_capacity;
+  long long off_cell_start, off_top, off_sorted, off_key, off_rank, off_scan;
+  long long scan_bytes;
+  int pad_[16];
+};
+static_assert(sizeof(GridHeader) <= 256, "header must fit 256 bytes");
+
+struct GridLayout {
+  size_t off_cell_start, off_top, off_sorted, off_key, off_rank, off_scan, scan_bytes, total;
+  int top_capacity;
+};
+
+static size_t scan_temp_bytes(int n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int*)nullptr, (int*)nullptr, n);
+  return bytes;
+}
+
+static GridLayout grid_layout(int N, int cap) {
+  GridLayout g;
+  g.top_capacity = cap / 8 > 4096 ? cap / 8 : 4096;
+  size_t o = 256;
+  g.off_cell_start = o; o = apn_align(o + sizeof(int) * ((size_t)cap + 1));
+  g.off_top = o;        o = apn_align(o + sizeof(int) * (size_t)g.top_capacity);
+  g.off_sorted = o;     o = apn_align(o + sizeof(float4) * (size_t)N);
+  g.off_key = o;        o = apn_align(o + sizeof(int) * (size_t)N);
+  g.off_rank = o;       o = apn_align(o + sizeof(int) * (size_t)N);
+  g.off_scan = o;
+  g.scan_bytes = scan_temp_bytes(cap + 1);
+  o = apn_align(o + g.scan_bytes);
+  g.total = o;
+  return g;
+}
+
+struct GridView {
+  const GridHeader* h;
+  const int* cell_start;
+  const int* top;
+  const float4* sorted;
+};
+__device__ __forceinline__ GridView grid_view(const void* blob) {
+  GridView v;
+  v.h = (const GridHeader*)blob;
+  const char* b = (const char*)blob;
+  v.cell_start = (const int*)(b + v.h->off_cell_start);
+  v.top = (const int*)(b + v.h->off_top);
+  v.sorted = (const float4*)(b + v.h->off_sorted);
+  return v;
+}
+
+// spread the low 10 bits of v so that there are two zero bits between consecutive bits
+__device__ __forceinline__ unsigned int part1by2(unsigned int v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+// key of the fine cell (ix,iy,iz); L = number of Morton levels inside a top cell
+__device__ __forceinline__ int cell_key(int ix, int iy, int iz, int L, int tx, int ty) {
+  const int m = (1 << L) - 1;
+  const int top = ((iz >> L) * ty + (iy >> L)) * tx + (ix >> L);
+  const unsigned int low = part1by2(ix & m) | (part1by2(iy & m) << 1) | (part1by2(iz & m) << 2);
+  return (top << (3 * L)) | (int)low;
+}
+
+// ---------------------------------------------------------------------------------------
+// build
+// ---------------------------------------------------------------------------------------
+__global__ void grid_header_kernel(void* blob, const float* __restrict__ bbox, int N, float r2, float pad, float cell_hint,
+                                   int cap, GridLayout lay) {
+  GridHeader* h = (GridHeader*)blob;
+  const float rq = sqrtf(r2);
+  const float top = rq * 1.01f;
+  int L = (int)rintf(log2f(top / fmaxf(cell_hint, 1e-9f)));
+  L = max(0, min(L, 6));
+  float ext[3];
+  int td[3];
+  for (int c = 0; c < 3; ++c) {
+    h->bmin[c] = __fsub_rn(bbox[c], pad);       // torch: min(xyz) - query_radius
+    h->bmax[c] = __fadd_rn(bbox[3 + c], pad);
+    ext[c] = bbox[3 + c] - bbox[c];
+  }
+  float cell = top / (float)(1 << L);
+  bool bad = !(ext[0] >= 0.f && ext[1] >= 0.f && ext[2] >= 0.f) || !isfinite(ext[0] + ext[1] + ext[2]);
+  long long n_top = 0;
+  if (!bad) {
+    for (int c = 0; c < 3; ++c) td[c] = (int)((ext[c] + 2.f * pad) / top) + 2;  // covers bmax+pad+top/2 for any cell <= top
+    n_top = (long long)td[0] * td[1] * td[2];
+    if (n_top > lay.top_capacity || n_top > cap) bad = true;
+  }
+  if (bad) {
+    td[0] = td[1] = td[2] = 0;
+    n_top = 0;
+    L = 0;
+  } else {
+    while (L > 0 && (n_top << (3 * L)) > (long long)cap) --L;
+    cell = top / (float)(1 << L);
+  }
+  for (int c = 0; c < 3; ++c) {
+    h->origin[c] = bbox[c] - pad - 0.5f * cell;
+    h->top_dim[c] = td[c];
+  }
+  h->cell = cell;
+  h->inv_cell = 1.0f / cell;
+  h->top_cell = top;
+  h->L = L;
+  h->n_top = (int)n_top;
+  h->n_cells = (int)(n_top << (3 * L));
+  h->r2 = r2;
+  h->n_points = N;
+  h->overflow = bad ? 1 : 0;
+  h->cell_capacity = cap;
+  h->top_capacity = lay.top_capacity;
+  h->off_cell_start = lay.off_cell_start;
+  h->off_top = lay.off_top;
+  h->off_sorted = lay.off_sorted;
+  h->off_key = lay.off_key;
+  h->off_rank = lay.off_rank;
+  h->off_scan = lay.off_scan;
+  h->scan_bytes = lay.scan_bytes;
+}
+
+__device__ __forceinline__ void point_cell(const GridHeader* h, float x, float y, float z, int& ix, int& iy, int& iz) {
+  const int dx = h->top_dim[0] << h->L, dy = h->top_dim[1] << h->L, dz = h->top_dim[2] << h->L;
+  ix = min(max((int)floorf((x - h->origin[0]) * h->inv_cell), 0), dx - 1);
+  iy = min(max((int)floorf((y - h->origin[1]) * h->inv_cell), 0), dy - 1);
+  iz = min(max((int)floorf((z - h->origin[2]) * h->inv_cell), 0), dz - 1);
+}
+
+__global__ void grid_count_kernel(void* blob, const float* __restrict__ xyz, int N) {
+  const GridHeader* h = (const GridHeader*)blob;
+  if (h->overflow) return;
+  int* cnt = (int*)((char*)blob + h->off_cell_start);
+  int* key = (int*)((char*)blob + h->off_key);
+  int* rank = (int*)((char*)blob + h->off_rank);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    int ix, iy, iz;
+    point_cell(h, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], ix, iy, iz);
+    const int k = cell_key(ix, iy, iz, h->L, h->top_dim[0], h->top_dim[1]);
+    key[i] = k;
+    rank[i] = atomicAdd(cnt + k, 1);
+  }
+}
+
+__global__ void grid_scatter_kernel(void* blob, const float* __restrict__ xyz, int N) {
+  const GridHeader* h = (const GridHeader*)blob;
+  if (h->overflow) return;
+  const int* start = (const int*)((char*)blob + h->off_cell_start);
+  const int* key = (const int*)((char*)blob + h->off_key);
+  const int* rank = (const int*)((char*)blob + h->off_rank);
+  float4* sorted = (float4*)((char*)blob + h->off_sorted);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    sorted[start[key[i]] + rank[i]] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
+  }
+}
+
+__global__ void grid_top_kernel(void* blob) {
+  const GridHeader* h = (const GridHeader*)blob;
+  if (h->overflow) return;
+  const int* start = (const int*)((char*)blob + h->off_cell_start);
+  int* top = (int*)((char*)blob + h->off_top);
+  const int tx = h->top_dim[0], ty = h->top_dim[1], tz = h->top_dim[2], sh = 3 * h->L;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < h->n_top; t += gridDim.x * blockDim.x) {
+    const int x = t % tx, y = (t / tx) % ty, z = t / (tx * ty);
+    int s = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int nx = x + dx, ny = y + dy, nz = z + dz;
+          if (nx < 0 || ny < 0 || nz < 0 || nx >= tx || ny >= ty || nz >= tz) continue;
+          const int q = (nz * ty + ny) * tx + nx;
+          s += start[(q + 1) << sh] - start[q << sh];
+        }
+    top[t] = s;
+  }
+}
+
+extern "C" size_t apn_grid_workspace_bytes(int N, int cell_capacity) {
+  if (N <= 0 || cell_capacity <= 0) return 0;
+  return grid_layout(N, cell_capacity).total;
+}
+
+extern "C" int apn_grid_build(const float* xyz, const float* bbox, int N, float query_radius, float bbox_pad,
+                              float cell_hint, int cell_capacity, void* grid, size_t grid_bytes, apn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  APN_CHECK_ARG(xyz && bbox && grid, "null pointer");
+  APN_CHECK_ARG(N > 0 && cell_capacity >= 64 && query_radius > 0.f && cell_hint > 0.f, "bad sizes");
+  const GridLayout lay = grid_layout(N, cell_capacity);
+  APN_CHECK_ARG(grid_bytes >= lay.total, "grid workspace too small");
+  char* b = (char*)grid;
+  grid_header_kernel<<<1, 1, 0, stream>>>(grid, bbox, N, query_radius, bbox_pad, cell_hint, cell_capacity, lay);
+  APN_LAUNCH_CHECK();
+  APN_CUDA(cudaMemsetAsync(b + lay.off_cell_start, 0, sizeof(int) * ((size_t)cell_capacity + 1), stream));
+  const int blocks = min(apn_div_up(N, 256), APN_SM_COUNT * 8);
+  grid_count_kernel<<<blocks, 256, 0, stream>>>(grid, xyz, N);
+  APN_LAUNCH_CHECK();
+  size_t tb = lay.scan_bytes;
+  int* cs = (int*)(b + lay.off_cell_start);
+  APN_CUDA(cub::DeviceScan::ExclusiveSum(b + lay.off_scan, tb, cs, cs, cell_capacity + 1, stream));
+  apn_count_launch(2);
+  grid_scatter_kernel<<<blocks, 256, 0, stream>>>(grid, xyz, N);
+  APN_LAUNCH_CHECK();
+  grid_top_kernel<<<APN_SM_COUNT, 256, 0, stream>>>(grid);
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int apn_grid_describe(const void* grid, float* host_out64, apn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  APN_CHECK_ARG(grid && host_out64, "null pointer");
+  APN_CUDA(cudaMemcpyAsync(host_out64, grid, 256, cudaMemcpyDeviceToHost, stream));
+  APN_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// scan helper
+// ---------------------------------------------------------------------------------------
+__global__ void scan_tail_kernel(const int* __restrict__ in, int* __restrict__ out, int n) {
+  out[n] = (n > 0) ? out[n - 1] + in[n - 1] : 0;
+}
+extern "C" size_t apn_scan_workspace_bytes(int n) { return apn_align(scan_temp_bytes(n > 0 ? n : 1)); }
+extern "C" int apn_exclusive_scan_i32(const int32_t* in, int32_t* out, int n, void* ws, size_t ws_bytes,
+                                      apn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  APN_CHECK_ARG(in && out && in != out, "need distinct in/out");
+  APN_CHECK_ARG(n >= 0, "n < 0");
+  if (n > 0) {
+    size_t tb = scan_temp_bytes(n);
+    APN_CHECK_ARG(ws && ws_bytes >= tb, "scan workspace too small");
+    APN_CUDA(cub::DeviceScan::ExclusiveSum(ws, tb, in, out, n, stream));
+    apn_count_launch(2);
+  }
+  scan_tail_kernel<<<1, 1, 0, stream>>>(in, out, n);
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// candidates
+// ---------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void ray_candidates_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int R, float near,
+                                      float far, float stepdist, const void* __restrict__ blob, int* __restrict__ cand_count,
+                                      const int* __restrict__ cand_base, int* __restrict__ cand_ray,
+                                      int* __restrict__ cand_step) {
+  const GridView g = grid_view(blob);
+  const GridHeader* h = g.h;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int count = 0;
+  if (!h->overflow) {
+    const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
+    const RaySetup s = ray_setup(rays_o, rays_d, r, bmin, bmax, near, far, stepdist);
+    const int base = FILL ? cand_base[r] : 0;
+    const int L = h->L, tx = h->top_dim[0], ty = h->top_dim[1];
+    for (int step = 0; step < s.n_steps; ++step) {
+      float px, py, pz;
+      ray_point(s, step, stepdist, px, py, pz);
+      const bool out = (bmin[0] > px) | (bmin[1] > py) | (bmin[2] > pz) | (bmax[0] < px) | (bmax[1] < py) | (bmax[2] < pz);
+      if (out) continue;
+      int ix, iy, iz;
+      point_cell(h, px, py, pz, ix, iy, iz);
+      const int t = ((iz >> L) * ty + (iy >> L)) * tx + (ix >> L);
+      if (g.top[t] < APN_K) continue;
+      if (FILL) {
+        cand_ray[base + count] = r;
+        cand_step[base + count] = step;
+      }
+      ++count;
+    }
+  }
+  if (!FILL) cand_count[r] = count;
+}
+
+extern "C" int apn_ray_candidates(const float* rays_o, const float* rays_d, int R, float near, float far, float stepdist,
+                                  const void* grid, int fill, int32_t* cand_count, const int32_t* cand_base,
+                                  int32_t* cand_ray, int32_t* cand_step, apn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  APN_CHECK_ARG(rays_o && rays_d && grid, "null pointer");
+  APN_CHECK_ARG(stepdist > 0.f, "stepdist must be positive");
+  if (R <= 0) return 0;
+  const int blocks = apn_div_up(R, 128);
+  if (fill) {
+    APN_CHECK_ARG(cand_base && cand_ray && cand_step, "fill pass needs cand_base/cand_ray/cand_step");
+    ray_candidates_kernel<true><<<blocks, 128, 0, stream>>>(rays_o, rays_d, R, near, far, stepdist, grid, nullptr, cand_base,
+                                                             cand_ray, cand_step);
+  } else {
+    APN_CHECK_ARG(cand_count, "count pass needs cand_count");
+    ray_candidates_kernel<false><<<blocks, 128, 0, stream>>>(rays_o, rays_d, R, near, far, stepdist, grid, cand_count,
+                                                              nullptr, nullptr, nullptr);
+  }
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// k-NN
+// ---------------------------------------------------------------------------------------
+#define KEY_INF 0x7f800000ffffffffull  // (+inf, max index)
+
+template <int K>
+__device__ __forceinline__ void topk_insert(unsigned long long (&b)[K], unsigned long long key) {
+  if (key < b[K - 1]) {
+    b[K - 1] = key;
+#pragma unroll
+    for (int i = K - 1; i > 0; --i) {
+      const unsigned long long lo = b[i - 1], hi = b[i];
+      const bool sw = hi < lo;
+      b[i - 1] = sw ? hi : lo;
+      b[i] = sw ? lo : hi;
+    }
+  }
+}
+
+__device__ __forceinline__ void scan_range(const float4* __restrict__ sorted, int s, int e, float qx, float qy, float qz,
+                                           unsigned long long (&best)[APN_K]) {
+  for (int i = s; i < e; ++i) {
+    const float4 P = __ldg(sorted + i);
+    const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
+    topk_insert<APN_K>(best, key);
+  }
+}
+
+// Exact K-NN of q.  If bounded, returns false as soon as it is certain that the K-th squared
+// distance exceeds r2.  Unbounded queries fall back to a full scan when the top level cannot
+// certify the result (never happens for queries inside a dense cloud).
+__device__ bool knn_search(const GridView& g, float qx, float qy, float qz, bool bounded,
+                           unsigned long long (&best)[APN_K]) {
+  const GridHeader* h = g.h;
+  const int L = h->L, tx = h->top_dim[0], ty = h->top_dim[1], tz = h->top_dim[2];
+  const float lx0 = qx - h->origin[0], ly0 = qy - h->origin[1], lz0 = qz - h->origin[2];
+  int ix, iy, iz;
+  point_cell(h, qx, qy, qz, ix, iy, iz);
+  int l = 0;
+  while (true) {
+#pragma unroll
+    for (int k = 0; k < APN_K; ++k) best[k] = KEY_INF;
+    const int cx = ix >> l, cy = iy >> l, cz = iz >> l;
+    const int dxm = tx << (L - l), dym = ty << (L - l), dzm = tz << (L - l);
+    const int span = 1 << (3 * l);
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int nz = cz + dz;
+      if (nz < 0 || nz >= dzm) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int ny = cy + dy;
+        if (ny < 0 || ny >= dym) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int nx = cx + dx;
+          if (nx < 0 || nx >= dxm) continue;
+          const int key = cell_key(nx << l, ny << l, nz << l, L, tx, ty);
+          const int s = __ldg(g.cell_start + key), e = __ldg(g.cell_start + key + span);
+          scan_range(g.sorted, s, e, qx, qy, qz, best);
+        }
+      }
+    }
+    const float d8 = __uint_as_float((unsigned int)(best[APN_K - 1] >> 32));
+    const float sl = h->cell * (float)(1 << l);
+    const float mx = fminf(lx0 - cx * sl, (cx + 1) * sl - lx0);
+    const float my = fminf(ly0 - cy * sl, (cy + 1) * sl - ly0);
+    const float mz = fminf(lz0 - cz * sl, (cz + 1) * sl - lz0);
+    const float gr = (sl + fminf(mx, fminf(my, mz))) * 0.999f;
+    if (gr > 0.f && d8 <= gr * gr) return !bounded || d8 <= h->r2;
+    if (bounded && gr > 0.f && gr * gr > h->r2 && d8 > h->r2) return false;  // every unseen point is farther than rq
+    if (l == L) {
+      if (bounded) return false;
+#pragma unroll
+      for (int k = 0; k < APN_K; ++k) best[k] = KEY_INF;
+      scan_range(g.sorted, 0, h->n_points, qx, qy, qz, best);
+      return true;
+    }
+    // next level: cell edge must cover the K-th distance found so far (if any)
+    int nl = l + 1;
+    if (d8 < INFINITY) {
+      const float need = sqrtf(d8) * 1.002f;
+      while (nl < L && h->cell * (float)(1 << nl) < need) ++nl;
+    }
+    l = nl;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
+           const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand,
+           int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep) {
+  const GridView g = grid_view(blob);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand) return;
+  const GridHeader* h = g.h;
+  const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
+  const RaySetup s = ray_setup(rays_o, rays_d, cand_ray[i], bmin, bmax, near, far, stepdist);
+  float px, py, pz;
+  ray_point(s, cand_step[i], stepdist, px, py, pz);
+  unsigned long long best[APN_K];
+  const bool ok = knn_search(g, px, py, pz, true, best);
+  keep[i] = ok ? 1 : 0;
+  if (ok) {
+    int4 a, b;
+    a.x = (int)(unsigned int)best[0]; a.y = (int)(unsigned int)best[1]; a.z = (int)(unsigned int)best[2]; a.w = (int)(unsigned int)best[3];
+    b.x = (int)(unsigned int)best[4]; b.y = (int)(unsigned int)best[5]; b.z = (int)(unsigned int)best[6]; b.w = (int)(unsigned int)best[7];
+    reinterpret_cast<int4*>(nn_idx)[2 * (size_t)i] = a;
+    reinterpret_cast<int4*>(nn_idx)[2 * (size_t)i + 1] = b;
+    if (nn_d2) {
+#pragma unroll
+      for (int k = 0; k < APN_K; ++k) nn_d2[(size_t)i * APN_K + k] = __uint_as_float((unsigned int)(best[k] >> 32));
+    }
+  }
+}
+
+extern "C" int apn_knn(const float* rays_o, const float* rays_d, float near, float far, float stepdist, const void* grid,
+                       const int32_t* cand_ray, const int32_t* cand_step, int n_cand, int32_t* nn_idx, float* nn_d2,
+                       int32_t* keep, apn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_cand <= 0) return 0;
+  APN_CHECK_ARG(rays_o && rays_d && grid && cand_ray && cand_step && nn_idx && keep, "null pointer");
+  knn_kernel<<<apn_div_up(n_cand, 128), 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand,
+                                                         nn_idx, nn_d2, keep);
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void compact_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far,
+                               float stepdist, const void* __restrict__ blob, const int* __restrict__ cand_ray,
+                               const int* __restrict__ cand_step, const int* __restrict__ cand_base,
+                               const int* __restrict__ keep, const int* __restrict__ kept_pos,
+                               const int* __restrict__ nn_idx_cand, int n_cand, int R, float* __restrict__ pts,
+                               int* __restrict__ ray_id, int* __restrict__ step_id, int* __restrict__ nn_idx,
+                               int* __restrict__ ray_start) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= R) ray_start[i] = kept_pos[(i < R) ? cand_base[i] : n_cand];
+  if (i >= n_cand || !keep[i]) return;
+  const GridHeader* h = (const GridHeader*)blob;
+  const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
+  const int r = cand_ray[i], st = cand_step[i];
+  const RaySetup s = ray_setup(rays_o, rays_d, r, bmin, bmax, near, far, stepdist);
+  float px, py, pz;
+  ray_point(s, st, stepdist, px, py, pz);
+  const size_t o = kept_pos[i];
+  pts[3 * o] = px; pts[3 * o + 1] = py; pts[3 * o + 2] = pz;
+  ray_id[o] = r;
+  step_id[o] = st;
+  reinterpret_cast<int4*>(nn_idx)[2 * o] = reinterpret_cast<const int4*>(nn_idx_cand)[2 * (size_t)i];
+  reinterpret_cast<int4*>(nn_idx)[2 * o + 1] = reinterpret_cast<const int4*>(nn_idx_cand)[2 * (size_t)i + 1];
+}
+
+extern "C" int apn_compact_samples(const float* rays_o, const float* rays_d, float near, float far, float stepdist,
+                                   const void* grid, const int32_t* cand_ray, const int32_t* cand_step,
+                                   const int32_t* cand_base, const int32_t* keep, const int32_t* kept_pos,
+                                   const int32_t* nn_idx_cand, int n_cand, int R, float* pts, int32_t* ray_id,
+                                   int32_t* step_id, int32_t* nn_idx, int32_t* ray_start, apn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  APN_CHECK_ARG(rays_o && rays_d && grid && cand_base && kept_pos && ray_start, "null pointer");
+  APN_CHECK_ARG(n_cand == 0 || (cand_ray && cand_step && keep && nn_idx_cand), "null candidate arrays");
+  const int n = (n_cand > R + 1) ? n_cand : R + 1;
+  compact_kernel<<<apn_div_up(n, 256), 256, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, cand_base,
+                                                        keep, kept_pos, nn_idx_cand, n_cand, R, pts, ray_id, step_id, nn_idx,
+                                                        ray_start);
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(128)
+knn_points_kernel(const float* __restrict__ query, int n_query, const void* __restrict__ blob, int k,
+                  int* __restrict__ nn_idx, float* __restrict__ nn_d2) {
+  const GridView g = grid_view(blob);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_query) return;
+  unsigned long long best[APN_K];
+  if (g.h->overflow) {
+#pragma unroll
+    for (int j = 0; j < APN_K; ++j) best[j] = KEY_INF;
+  } else {
+    knn_search(g, query[3 * i], query[3 * i + 1], query[3 * i + 2], false, best);
+  }
+#pragma unroll
+  for (int j = 0; j < APN_K; ++j) {
+    if (j < k) {
+      nn_idx[(size_t)i * k + j] = (int)(unsigned int)best[j];
+      if (nn_d2) nn_d2[(size_t)i * k + j] = __uint_as_float((unsigned int)(best[j] >> 32));
+    }
+  }
+}
+
+extern "C" int apn_knn_points(const float* query, int n_query, const void* grid, int k, int32_t* nn_idx, float* nn_d2,
+                              apn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  APN_CHECK_ARG(k >= 1 && k <= APN_K, "1 <= k <= 8");
+  if (n_query <= 0) return 0;
+  APN_CHECK_ARG(query && grid && nn_idx, "null pointer");
+  knn_points_kernel<<<apn_div_up(n_query, 128), 128, 0, stream>>>(query, n_query, grid, k, nn_idx, nn_d2);
+  APN_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,269 @@
+/*
+ * apn.h — C ABI of libapn_sm100.so: the B200 (sm_100a) point-cloud render path of
+ * Articulated-Point-NeRF.
+ *
+ * Every entry point takes raw device pointers, sizes and a cudaStream_t (passed as void*);
+ * nothing allocates, nothing synchronises the host unless stated.  All floating point data
+ * is fp32, all indices int32 unless stated.  Return value: 0 on success, negative on error;
+ * apn_last_error() returns the message of the last failing call on this thread.
+ *
+ * Each group cites the reference interface it replaces (paths relative to the reference
+ * repository root).
+ */
+#ifndef APN_H_
+#define APN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APN_K 8            /* neighbours per sample (lib/temporalpoints.py:42) */
+#define APN_C 128          /* feature channels / MLP width (configs/nerf/default.py:60) */
+#define APN_POS_FREQS 10   /* posbase_pe  (lib/tineuvox.py:96) */
+#define APN_VIEW_FREQS 4   /* viewbase_pe (lib/tineuvox.py:96) */
+#define APN_PE_POS 63      /* 3 + 3*2*10 */
+#define APN_PE_VIEW 27     /* 3 + 3*2*4  */
+
+typedef void* apn_stream_t; /* cudaStream_t */
+
+int apn_version(void);
+const char* apn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long apn_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  Linear blend skinning.
+ * Replaces lib/temporalpoints.py:401-414 (get_weights: softmax(raw/max(eps,theta)) + merge),
+ * lib/pointwarper.py:241-266 (blend of bone 4x4s, point transform, + global_t),
+ * lib/temporalpoints.py:569 (torch.inverse of the blended frame; only [:3,:3] is consumed,
+ * lib/temporalpoints.py:478) and lib/temporalpoints.py:424 (min/max of the warped cloud).
+ *   raw_w (N,J)  theta_weight (1)  merge_rules (J) int32 or NULL (= identity)
+ *   bone_T (J,4,4) row-major  xyz (N,3)  global_t (3)
+ *   xyz_out (N,3)  ginv_out (N,9) = inverse(G[:3,:3])  w_out (N,J) merged weights or NULL
+ *   bbox (6) = min xyz, max xyz of xyz_out (initialised by the call)
+ * ------------------------------------------------------------------------------------- */
+int apn_lbs_fwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
+                const float* bone_T, const float* xyz, const float* global_t, int N, int J,
+                float* xyz_out, float* ginv_out, float* w_out, float* bbox, apn_stream_t stream);
+
+size_t apn_lbs_bwd_workspace_bytes(int N, int J);
+/* d_raw (N,J), d_theta (1), d_bone_T (J,4,4; last row 0), d_global_t (3) are overwritten.
+ * d_w (N,J) is the extra gradient arriving on the merged weights (regularisers) or NULL. */
+int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
+                const float* bone_T, const float* xyz, int N, int J, const float* ginv,
+                const float* d_xyz, const float* d_ginv, const float* d_w,
+                float* d_raw, float* d_theta, float* d_bone_T, float* d_global_t,
+                void* workspace, size_t workspace_bytes, apn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  Uniform multi-level grid over the warped cloud + exact 8-NN of ray samples.
+ * Replaces lib/temporalpoints.py:373-399 (sample_ray -> render_utils_cuda.sample_pts_on_rays,
+ * lib/cuda/render_utils_kernel.cu:12-236), lib/temporalpoints.py:434-437 (KeOps
+ * Kmin_argKmin(K=8) brute force) and lib/temporalpoints.py:440-444 (radius rule).
+ * Neighbour contract: d2 = (dx*dx + dy*dy) + dz*dz in fp32 without FMA, the 8 smallest
+ * ascending by (d2, point index); a sample is kept iff it lies inside the padded bbox and
+ * its 8th d2 <= query_radius (the reference compares the SQUARED distance with 0.01).
+ * ------------------------------------------------------------------------------------- */
+size_t apn_grid_workspace_bytes(int N, int cell_capacity);
+/* Builds the grid in `grid` (opaque blob of apn_grid_workspace_bytes). bbox (6) comes from
+ * apn_lbs_fwd.  cell_hint ~ 1.5x mean point spacing; bbox_pad = query_radius (0.01). */
+int apn_grid_build(const float* xyz, const float* bbox, int N, float query_radius, float bbox_pad,
+                   float cell_hint, int cell_capacity, void* grid, size_t grid_bytes, apn_stream_t stream);
+/* copies the 64-float/int descriptor of the grid to host memory (synchronises the stream) */
+int apn_grid_describe(const void* grid, float* host_out64, apn_stream_t stream);
+
+/* exclusive scan of n int32 -> out[0..n] (out[n] = total); ws >= apn_scan_workspace_bytes(n) */
+size_t apn_scan_workspace_bytes(int n);
+int apn_exclusive_scan_i32(const int32_t* in, int32_t* out, int n, void* ws, size_t ws_bytes, apn_stream_t stream);
+
+/* pass 1: number of candidate samples per ray (inside the padded bbox and with >= 8 points
+ * in the coarse neighbourhood); pass 2 (fill=1) writes (ray, step) of every candidate at
+ * cand_base[ray]+k. */
+int apn_ray_candidates(const float* rays_o, const float* rays_d, int R, float near, float far, float stepdist,
+                       const void* grid, int fill, int32_t* cand_count, const int32_t* cand_base,
+                       int32_t* cand_ray, int32_t* cand_step, apn_stream_t stream);
+/* exact 8-NN of every candidate; keep[i] = 1 iff the sample survives the radius rule.
+ * nn_idx (n_cand,8) original point indices ascending by (d2, index); nn_d2 (n_cand,8) or NULL. */
+int apn_knn(const float* rays_o, const float* rays_d, float near, float far, float stepdist, const void* grid,
+            const int32_t* cand_ray, const int32_t* cand_step, int n_cand,
+            int32_t* nn_idx, float* nn_d2, int32_t* keep, apn_stream_t stream);
+/* order-preserving compaction of the kept candidates (kept_pos = exclusive scan of keep).
+ * ray_start (R+1): first kept sample of each ray. */
+int apn_compact_samples(const float* rays_o, const float* rays_d, float near, float far, float stepdist,
+                        const void* grid, const int32_t* cand_ray, const int32_t* cand_step, const int32_t* cand_base,
+                        const int32_t* keep, const int32_t* kept_pos, const int32_t* nn_idx_cand, int n_cand, int R,
+                        float* pts, int32_t* ray_id, int32_t* step_id, int32_t* nn_idx, int32_t* ray_start,
+                        apn_stream_t stream);
+/* brute-force-free k-NN of arbitrary query points against the grid (init self-k-NN,
+ * lib/temporalpoints.py:104-111; chamfer K=1, :747-751). max_d2 <= 0: unbounded. */
+int apn_knn_points(const float* query, int n_query, const void* grid, int k, int32_t* nn_idx, float* nn_d2,
+                   apn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  Aggregation: gather + positional encoding + feature MLP + inverse-distance reduce + heads.
+ * Replaces lib/temporalpoints.py:446-515 (aggregate_pts after the k-NN), lib/tineuvox.py:65-88
+ * (RGBNet), :158 (densitynet), :396-400/646-670 (activate_density / Raw2Alpha ->
+ * lib/cuda/render_utils_kernel.cu:358-428), :872-878 (poc_fre).
+ * ------------------------------------------------------------------------------------- */
+typedef struct apn_mlp_weights {
+  /* feat_net: Linear(d_in,128)+LeakyReLU, 2x[Linear(128,128)+LeakyReLU], Linear(128,128)+LeakyReLU
+   * (lib/temporalpoints.py:123-130). torch Linear layout: W (out,in) row-major. */
+  const float* w[4];
+  const float* b[4];
+  const float* density_w;   /* (1,128) */
+  const float* density_b;   /* (1)     */
+  const float* rgb_feat_w;  /* (128,128) rgbnet.feature_linears */
+  const float* rgb_feat_b;  /* (128) */
+  const float* rgb_v0_w;    /* (64,155)  rgbnet.views_linears.0 */
+  const float* rgb_v0_b;    /* (64) */
+  const float* rgb_v2_w;    /* (3,64)    rgbnet.views_linears.2 */
+  const float* rgb_v2_b;    /* (3) */
+} apn_mlp_weights;
+
+typedef struct apn_agg_inputs {
+  int M;                       /* kept samples */
+  int N;                       /* points */
+  int d_in;                    /* 191, or 255 with a 64-wide pose embedding */
+  const float* pts;            /* (M,3) sample positions */
+  const int32_t* nn_idx;       /* (M,8) */
+  const int32_t* ray_id;       /* (M) */
+  const float* xyz;            /* (N,3) warped cloud */
+  const float* ginv;           /* (N,9) */
+  const float* feat;           /* (N,128) canonical_feat */
+  const float* pose_emb;       /* (d_in-191) or NULL */
+  const float* viewdirs;       /* (R,3) */
+  /* direct branch (lib/temporalpoints.py:459-470) */
+  const float* canonical_alpha; /* (N) */
+  const float* canonical_rgbs;  /* (N,3) */
+  const float* direct_eps;      /* (N) */
+  float mean_min_distance;
+  float eps;                   /* 1e-6 */
+  float act_shift;
+  float interval;              /* stepsize * voxel_size_ratio */
+} apn_agg_inputs;
+
+typedef struct apn_agg_outputs {
+  float* alpha;         /* (M) */
+  float* rgb;           /* (M,3) after sigmoid */
+  float* alpha_direct;  /* (M) */
+  float* rgb_direct;    /* (M,3) */
+  float* idw;           /* (M,8) normalised inverse-distance weights (also used by render_weights) */
+  /* saved for backward (may be NULL in inference): */
+  float* x0;            /* (8M, ld0) MLP input rows, ld0 = round_up(d_in, 4) */
+  float* act[4];        /* (8M,128) post-activation of each feat_net layer */
+  float* h;             /* (M,128) reduced feature */
+  float* exp_d;         /* (M) exp(density+shift) */
+  float* fv;            /* (M,160) [rgb feature 128 | view PE 27 | pad] */
+  float* v0;            /* (M,64) hidden of views_linears */
+} apn_agg_outputs;
+
+size_t apn_aggregate_scratch_bytes(int M, int d_in);
+/* fp32 CUDA-core path (parity mode; also the training path). If out->x0 etc. are NULL the
+ * activations live in `scratch` only. */
+int apn_aggregate_fwd(const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* out,
+                      void* scratch, size_t scratch_bytes, apn_stream_t stream);
+
+typedef struct apn_agg_grads {
+  /* incoming */
+  const float* d_alpha;  /* (M) */
+  const float* d_rgb;    /* (M,3) */
+  /* outgoing; all ACCUMULATED into (caller zeroes) */
+  float* d_xyz;          /* (N,3) */
+  float* d_ginv;         /* (N,9) */
+  float* d_feat;         /* (N,128) */
+  float* d_w[4];
+  float* d_b[4];
+  float* d_density_w;
+  float* d_density_b;
+  float* d_rgb_feat_w;
+  float* d_rgb_feat_b;
+  float* d_rgb_v0_w;
+  float* d_rgb_v0_b;
+  float* d_rgb_v2_w;
+  float* d_rgb_v2_b;
+} apn_agg_grads;
+
+size_t apn_aggregate_bwd_scratch_bytes(int M, int d_in);
+int apn_aggregate_bwd(const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* saved,
+                      const apn_agg_grads* g, void* scratch, size_t scratch_bytes, apn_stream_t stream);
+
+/* tcgen05 (5th-gen tensor core) fused inference path: same contract as apn_aggregate_fwd for
+ * alpha / rgb / alpha_direct / rgb_direct / idw; nothing is saved for backward.
+ * precision: 0 = bf16 operands (1 pass), 1 = bf16x3 split operands (fp32-class, parity mode). */
+size_t apn_aggregate_tc_weights_bytes(int d_in);
+int apn_aggregate_tc_pack_weights(const apn_mlp_weights* w, int d_in, void* packed, apn_stream_t stream);
+int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_weights,
+                         const apn_agg_outputs* out, int precision, apn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4  Ray compositing.
+ * Replaces lib/temporalpoints.py:611-677: alpha > thres mask, Alphas2Weights
+ * (lib/tineuvox.py:627-643 -> lib/cuda/render_utils_kernel.cu:431-561, early stop at T<1e-3),
+ * weight > thres mask, torch_scatter.segment_coo sums for rgb / depth, + alphainv_last*bg.
+ *   ray_start (R+1) offsets into the ray-major sample list
+ *   T_save (M) and n_used (R) are written when non-NULL (needed by the backward)
+ * ------------------------------------------------------------------------------------- */
+int apn_composite_fwd(const float* alpha, const float* rgb, const int32_t* step_id, const float* extra, int n_extra,
+                      const int32_t* ray_start, int R, float thres, float bg,
+                      float* rgb_marched, float* alphainv_last, float* depth, float* extra_marched,
+                      float* T_save, int32_t* n_used, apn_stream_t stream);
+int apn_composite_bwd(const float* alpha, const float* rgb, const int32_t* step_id, const int32_t* ray_start, int R,
+                      float thres, float bg, const float* T_save, const int32_t* n_used, const float* alphainv_last,
+                      const float* d_rgb_marched, const float* d_alphainv_last, const float* d_depth,
+                      float* d_alpha, float* d_rgb, apn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4b  Adam.  Replaces adam_upd_cuda.{adam_upd, masked_adam_upd, adam_upd_with_perlr}
+ * (lib/cuda/adam_upd.cpp:79-86, lib/cuda/adam_upd_kernel.cu:9-132) called by
+ * lib/masked_adam.py:39-72.  Multi-tensor: one launch for a list of tensors.
+ *   mode 0 = plain, 1 = skip where grad==0, 2 = per-element lr (perlr != NULL)
+ * ------------------------------------------------------------------------------------- */
+typedef struct apn_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  const float* perlr;   /* mode 2 only */
+  long long numel;
+  float step_size;      /* lr*sqrt(1-b2^t)/(1-b1^t), computed in float as adam_upd_kernel.cu:72 */
+  int mode;
+} apn_adam_tensor;
+float apn_adam_step_size(int step, float beta1, float beta2, float lr);
+/* `tensors` is a HOST array of n_tensors descriptors (copied into kernel parameters in chunks). */
+int apn_adam_multi(const apn_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
+                   apn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Reference-compatible single ops (the pybind surface of lib/cuda/render_utils.cpp:144-155).
+ * int64 ids as in the reference.  sample_pts_on_rays is two-phase because the total is
+ * data dependent (the reference does N_steps.sum().item(), render_utils_kernel.cu:206).
+ * ------------------------------------------------------------------------------------- */
+int apn_infer_t_minmax(const float* rays_o, const float* rays_d, const float* xyz_min, const float* xyz_max,
+                       float near, float far, int R, float* t_min, float* t_max, apn_stream_t stream);
+int apn_infer_n_samples(const float* t_min, const float* t_max, float stepdist, int R, int64_t* n_samples,
+                        apn_stream_t stream);
+int apn_infer_ray_start_dir(const float* rays_o, const float* rays_d, const float* t_min, int R,
+                            float* rays_start, float* rays_dir, apn_stream_t stream);
+/* n_cumsum (R) inclusive cumsum of n_samples; total = n_cumsum[R-1] known to the caller */
+int apn_sample_pts_on_rays_fill(const float* rays_start, const float* rays_dir, const float* xyz_min,
+                                const float* xyz_max, const int64_t* n_cumsum, int R, long long total, float stepdist,
+                                float* pts, uint8_t* mask_outbbox, int64_t* ray_id, int64_t* step_id,
+                                apn_stream_t stream);
+int apn_raw2alpha(const float* density, float shift, float interval, long long n, float* exp_d, float* alpha,
+                  apn_stream_t stream);
+int apn_raw2alpha_backward(const float* exp_d, const float* grad_back, float interval, long long n, float* grad,
+                           apn_stream_t stream);
+/* weight/T/alphainv_last/i_start/i_end must be pre-filled 0/1/1/0/0 as render_utils_kernel.cu:478-482 */
+int apn_alpha2weight(const float* alpha, const int64_t* ray_id, long long n_pts, int n_rays, float* weight, float* T,
+                     float* alphainv_last, int64_t* i_start, int64_t* i_end, apn_stream_t stream);
+int apn_alpha2weight_backward(const float* alpha, const float* weight, const float* T, const float* alphainv_last,
+                              const int64_t* i_start, const int64_t* i_end, int n_rays, const float* grad_weights,
+                              const float* grad_last, float* grad, apn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APN_H_ */
