@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(LBS_TILE)
 lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_weight, float eps,
                const int* __restrict__ rules, const float* __restrict__ bone_T, const float* __restrict__ xyz,
                const float* __restrict__ global_t, int N, int J, float* __restrict__ xyz_out,
-               float* __restrict__ ginv_out, float* __restrict__ w_out, float* __restrict__ bbox) {
+               float* __restrict__ ginv_out, float* __restrict__ w_out, float* __restrict__ g_out,
+               float* __restrict__ bbox) {
   extern __shared__ float smem[];
   const int JP = J | 1;
   float* sT = smem;                    // J*12
@@ -84,7 +85,7 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
     sT[i] = bone_T[j * 16 + c];        // rows 0..2 of the 4x4
   }
   for (int j = threadIdx.x; j < J; j += blockDim.x) sR[j] = rules ? rules[j] : j;
-  const float theta = fmaxf(eps, theta_weight[0]);
+  const float theta = theta_weight ? fmaxf(eps, theta_weight[0]) : 1.f;
   const float gx = global_t ? global_t[0] : 0.f, gy = global_t ? global_t[1] : 0.f, gz = global_t ? global_t[2] : 0.f;
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mxv[3] = {-INFINITY, -INFINITY, -INFINITY};
   const int n_tiles = (N + LBS_TILE - 1) / LBS_TILE;
@@ -97,7 +98,7 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
     const int p = threadIdx.x;
     if (p < n_valid) {
       float* row = sW + p * JP;
-      softmax_row(row, J, theta);
+      if (theta_weight) softmax_row(row, J, theta);   // NULL: the caller passes final weights
       if (rules) {
         for (int j = 0; j < J; ++j) {
           const int t = sR[j];
@@ -131,6 +132,13 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
       inverse3x3(A, inv);
 #pragma unroll
       for (int c = 0; c < 9; ++c) ginv_out[9 * n + c] = inv[c];
+      if (g_out) {
+        float4* go = reinterpret_cast<float4*>(g_out + 16 * n);
+        go[0] = make_float4(G[0], G[1], G[2], G[3]);
+        go[1] = make_float4(G[4], G[5], G[6], G[7]);
+        go[2] = make_float4(G[8], G[9], G[10], G[11]);
+        go[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+      }
     }
     if (w_out) {
       __syncthreads();
@@ -155,8 +163,8 @@ __global__ void __launch_bounds__(LBS_TILE)
 lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_weight, float eps,
                const int* __restrict__ rules, const float* __restrict__ bone_T, const float* __restrict__ xyz, int N,
                int J, const float* __restrict__ ginv, const float* __restrict__ d_xyz,
-               const float* __restrict__ d_ginv, const float* __restrict__ d_w, float* __restrict__ d_raw,
-               float* __restrict__ partial) {
+               const float* __restrict__ d_ginv, const float* __restrict__ d_w, const float* __restrict__ d_g,
+               float* __restrict__ d_raw, float* __restrict__ partial) {
   extern __shared__ float smem[];
   const int JP = J | 1;
   const int n_out = J * 12;
@@ -174,8 +182,7 @@ lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
     sAcc[i] = 0.f;
   }
   for (int j = threadIdx.x; j < J; j += blockDim.x) sR[j] = rules ? rules[j] : j;
-  const float theta_raw = theta_weight[0];
-  const float theta = fmaxf(eps, theta_raw);
+  const float theta = theta_weight ? fmaxf(eps, theta_weight[0]) : 1.f;
   float acc_theta = 0.f, acc_g[3] = {0.f, 0.f, 0.f};
   const int n_tiles = (N + LBS_TILE - 1) / LBS_TILE;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -190,7 +197,7 @@ lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
     if (p < n_valid) {
       float* row = sW + p * JP;
       float* mrow = sM + p * JP;
-      softmax_row(row, J, theta);
+      if (theta_weight) softmax_row(row, J, theta);
       for (int j = 0; j < J; ++j) mrow[j] = row[j];
       if (rules) {
         for (int j = 0; j < J; ++j) {
@@ -225,6 +232,10 @@ lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
       dg[0] = dA[0] + gx * x; dg[1] = dA[1] + gx * y; dg[2] = dA[2] + gx * z; dg[3] = gx;
       dg[4] = dA[3] + gy * x; dg[5] = dA[4] + gy * y; dg[6] = dA[5] + gy * z; dg[7] = gy;
       dg[8] = dA[6] + gz * x; dg[9] = dA[7] + gz * y; dg[10] = dA[8] + gz * z; dg[11] = gz;
+      if (d_g) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) dg[c] += d_g[16 * n + c];
+      }
       // dm_j, then dw_j = dm_{rules[j]}, softmax backward
       float* dwrow = sDW + p * JP;
       for (int j = 0; j < J; ++j) {
@@ -234,16 +245,20 @@ lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
         for (int c = 0; c < 12; ++c) s = fmaf(dg[c], T[c], s);
         dwrow[j] = s;  // dm_j
       }
-      float dot = 0.f;
-      for (int j = 0; j < J; ++j) dot = fmaf(row[j], dwrow[sR[j]], dot);
-      float th = 0.f;
-      for (int j = 0; j < J; ++j) {
-        const float dz = row[j] * (dwrow[sR[j]] - dot);
-        const float rawv = __ldg(raw_w + n * J + j);
-        th = fmaf(-dz, rawv, th);
-        row[j] = dz / theta;  // d_raw
+      if (theta_weight) {
+        float dot = 0.f;
+        for (int j = 0; j < J; ++j) dot = fmaf(row[j], dwrow[sR[j]], dot);
+        float th = 0.f;
+        for (int j = 0; j < J; ++j) {
+          const float dz = row[j] * (dwrow[sR[j]] - dot);
+          const float rawv = __ldg(raw_w + n * J + j);
+          th = fmaf(-dz, rawv, th);
+          row[j] = dz / theta;  // d_raw
+        }
+        acc_theta += th / (theta * theta);
+      } else {
+        for (int j = 0; j < J; ++j) row[j] = dwrow[sR[j]];
       }
-      acc_theta += th / (theta * theta);
     } else {
 #pragma unroll
       for (int c = 0; c < 12; ++c) dg[c] = 0.f;
@@ -288,7 +303,7 @@ __global__ void lbs_bwd_reduce_kernel(const float* __restrict__ partial, int n_b
     d_bone_T[j * 16 + c] = s;
     if (c < 4) d_bone_T[j * 16 + 12 + c] = 0.f;
   } else if (o == n_out) {
-    d_theta[0] = (theta_weight[0] > eps) ? s : 0.f;   // torch.max(eps, theta): gradient to the larger
+    if (d_theta) d_theta[0] = (theta_weight && theta_weight[0] > eps) ? s : 0.f;   // torch.max(eps, theta): gradient to the larger
   } else if (d_global_t) {
     d_global_t[o - n_out - 1] = s;
   }
@@ -302,17 +317,17 @@ static int lbs_grid(int N) {
 
 extern "C" int apn_lbs_fwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
                            const float* bone_T, const float* xyz, const float* global_t, int N, int J, float* xyz_out,
-                           float* ginv_out, float* w_out, float* bbox, apn_stream_t stream_) {
+                           float* ginv_out, float* w_out, float* g_out, float* bbox, apn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   APN_CHECK_ARG(N > 0 && J > 0 && J <= LBS_MAX_J, "need N > 0 and 0 < J <= 128");
-  APN_CHECK_ARG(raw_w && theta_weight && bone_T && xyz && xyz_out && ginv_out && bbox, "null pointer");
+  APN_CHECK_ARG(raw_w && bone_T && xyz && xyz_out && ginv_out && bbox, "null pointer");
   const int JP = J | 1;
   const size_t smem = sizeof(float) * (J * 12 + J + (size_t)LBS_TILE * JP);
   APN_CUDA(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   lbs_init_bbox_kernel<<<1, 32, 0, stream>>>(bbox);
   APN_LAUNCH_CHECK();
   lbs_fwd_kernel<<<lbs_grid(N), LBS_TILE, smem, stream>>>(raw_w, theta_weight, eps, merge_rules, bone_T, xyz, global_t, N,
-                                                         J, xyz_out, ginv_out, w_out, bbox);
+                                                         J, xyz_out, ginv_out, w_out, g_out, bbox);
   APN_LAUNCH_CHECK();
   return 0;
 }
@@ -329,11 +344,13 @@ extern "C" size_t apn_lbs_bwd_workspace_bytes(int N, int J) {
 
 extern "C" int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
                            const float* bone_T, const float* xyz, int N, int J, const float* ginv, const float* d_xyz,
-                           const float* d_ginv, const float* d_w, float* d_raw, float* d_theta, float* d_bone_T,
+                           const float* d_ginv, const float* d_w, const float* d_g, float* d_raw, float* d_theta,
+                           float* d_bone_T,
                            float* d_global_t, void* workspace, size_t workspace_bytes, apn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   APN_CHECK_ARG(N > 0 && J > 0 && J <= LBS_MAX_J, "need N > 0 and 0 < J <= 128");
-  APN_CHECK_ARG(raw_w && theta_weight && bone_T && xyz && ginv && d_raw && d_theta && d_bone_T && workspace, "null pointer");
+  APN_CHECK_ARG(raw_w && bone_T && xyz && ginv && d_raw && d_bone_T && workspace, "null pointer");
+  APN_CHECK_ARG(!theta_weight || d_theta, "d_theta is required when theta_weight is given");
   APN_CHECK_ARG(workspace_bytes >= apn_lbs_bwd_workspace_bytes(N, J), "workspace too small");
   const int JP = J | 1;
   const size_t smem = sizeof(float) * (J * 12 + J + 3 * (size_t)LBS_TILE * JP + LBS_TILE * 13 + J * 12);
@@ -341,7 +358,7 @@ extern "C" int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float 
   APN_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = lbs_bwd_grid(N);
   lbs_bwd_kernel<<<grid, LBS_TILE, smem, stream>>>(raw_w, theta_weight, eps, merge_rules, bone_T, xyz, N, J, ginv, d_xyz,
-                                                  d_ginv, d_w, d_raw, (float*)workspace);
+                                                  d_ginv, d_w, d_g, d_raw, (float*)workspace);
   APN_LAUNCH_CHECK();
   const int n = J * 12 + 4;
   lbs_bwd_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const float*)workspace, grid, J, theta_weight, eps, d_theta,

@@ -1,0 +1,61 @@
+"""MaskedAdam with the reference's interface (lib/masked_adam.py:17-72), served by the multi-tensor
+kernel in csrc/adam.cu: one launch updates every parameter tensor of every group instead of one
+launch per tensor.
+
+Update rule (lib/cuda/adam_upd_kernel.cu:9-58,72): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+p -= lr sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps); `skip_zero_grad` groups skip elements with g == 0.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class MaskedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.99), eps=1e-8):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        defaults = dict(lr=lr, betas=betas, eps=eps, skip_zero_grad=False)
+        self.per_lr = None
+        super().__init__(params, defaults)
+
+    def set_pervoxel_lr(self, count):
+        assert self.param_groups[0]['params'][0].shape == count.shape
+        self.per_lr = (count.float() / count.max()).contiguous()
+
+    @torch.no_grad()
+    def step(self):
+        batches = {}
+        for group in self.param_groups:
+            lr = group['lr']
+            beta1, beta2 = group['betas']
+            eps = group['eps']
+            skip_zero_grad = group.get('skip_zero_grad', False)
+            for param in group['params']:
+                if param.grad is None:
+                    continue
+                state = self.state[param]
+                if len(state) == 0:
+                    state['step'] = 0
+                    state['exp_avg'] = torch.zeros_like(param, memory_format=torch.preserve_format)
+                    state['exp_avg_sq'] = torch.zeros_like(param, memory_format=torch.preserve_format)
+                state['step'] += 1
+                grad = param.grad if param.grad.is_contiguous() else param.grad.contiguous()
+                if self.per_lr is not None and param.shape == self.per_lr.shape:
+                    mode, perlr = 2, self.per_lr
+                elif skip_zero_grad:
+                    mode, perlr = 1, None
+                else:
+                    mode, perlr = 0, None
+                ss = ops.adam_step_size(state['step'], beta1, beta2, lr)
+                batches.setdefault((beta1, beta2, eps), []).append(
+                    (param.data, grad, state['exp_avg'], state['exp_avg_sq'], perlr, ss, mode))
+        for (beta1, beta2, eps), entries in batches.items():
+            ops.adam_multi(entries, beta1, beta2, eps)

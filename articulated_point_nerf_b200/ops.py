@@ -1,0 +1,428 @@
+"""Torch-facing operators over libapn_sm100.so: tensors in, tensors out, autograd where the
+reference differentiates.  Every function launches hand-written sm_100a kernels through the C ABI
+(include/apn.h); nothing here computes on the CPU or falls back to PyTorch ops.
+
+Stage names follow the reference's profiler ranges (lib/temporalpoints.py:421-653):
+forward_warp -> sample_ray / knn / knn-post -> feat_net / densitynet / rgbnet -> pre-mask /
+Alphas2Weights / post-mask / segment_coo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import AggGrads, AggInputs, AggOutputs, AdamTensor, MlpWeights, check, ptr, stream
+
+K_NEIGHBOURS = 8
+FEAT_DIM = 128
+PE_POS = 63
+PE_VIEW = 27
+FV_LD = 160
+V0_DIM = 64
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _empty(shape, device, dtype=torch.float32):
+    return torch.empty(shape, device=device, dtype=dtype)
+
+
+# --------------------------------------------------------------------------------------
+# K1: linear blend skinning
+# --------------------------------------------------------------------------------------
+class _LBS(torch.autograd.Function):
+    """get_weights + blend + transform + frame inverse + bbox (lib/temporalpoints.py:401-414,424,569;
+    lib/pointwarper.py:241-266).  theta_weight=None: `raw_w` already holds the final weights."""
+
+    @staticmethod
+    def forward(ctx, raw_w, theta_weight, bone_T, global_t, xyz, rules, eps, want_frames):
+        lib = _lib.load()
+        raw_w, bone_T, xyz = _f32(raw_w), _f32(bone_T), _f32(xyz)
+        theta_weight = None if theta_weight is None else _f32(theta_weight)
+        global_t = None if global_t is None else _f32(global_t)
+        N, J = raw_w.shape
+        dev = raw_w.device
+        xyz_out = _empty((N, 3), dev)
+        ginv = _empty((N, 9), dev)
+        w_out = _empty((N, J), dev)
+        g_out = _empty((N, 4, 4), dev) if want_frames else None
+        bbox = _empty((6,), dev)
+        check(lib.apn_lbs_fwd(ptr(raw_w), ptr(theta_weight), float(eps), ptr(rules), ptr(bone_T), ptr(xyz), ptr(global_t),
+                              N, J, ptr(xyz_out), ptr(ginv), ptr(w_out), ptr(g_out), ptr(bbox), stream()), "apn_lbs_fwd")
+        ctx.save_for_backward(raw_w, theta_weight, bone_T, xyz, ginv, rules)
+        ctx.eps = float(eps)
+        ctx.has_gt = global_t is not None
+        ctx.want_frames = want_frames
+        ctx.mark_non_differentiable(bbox)
+        return xyz_out, ginv, w_out, bbox, (g_out if want_frames else torch.zeros(0, device=dev))
+
+    @staticmethod
+    def backward(ctx, d_xyz, d_ginv, d_w, _d_bbox, d_g):
+        lib = _lib.load()
+        raw_w, theta_weight, bone_T, xyz, ginv, rules = ctx.saved_tensors
+        N, J = raw_w.shape
+        dev = raw_w.device
+        d_xyz = None if d_xyz is None else _f32(d_xyz)
+        d_ginv = None if d_ginv is None else _f32(d_ginv)
+        d_w = None if d_w is None else _f32(d_w)
+        d_g = _f32(d_g) if (ctx.want_frames and d_g is not None) else None
+        d_raw = _empty((N, J), dev)
+        d_theta = _empty((1,), dev) if theta_weight is not None else None
+        d_bone = _empty((J, 4, 4), dev)
+        d_gt = _empty((3,), dev)
+        ws_bytes = lib.apn_lbs_bwd_workspace_bytes(N, J)
+        ws = _empty((ws_bytes,), dev, torch.uint8)
+        check(lib.apn_lbs_bwd(ptr(raw_w), ptr(theta_weight), ctx.eps, ptr(rules), ptr(bone_T), ptr(xyz), N, J, ptr(ginv),
+                              ptr(d_xyz), ptr(d_ginv), ptr(d_w), ptr(d_g), ptr(d_raw), ptr(d_theta), ptr(d_bone), ptr(d_gt),
+                              ptr(ws), ws_bytes, stream()), "apn_lbs_bwd")
+        return (d_raw, None if d_theta is None else d_theta.reshape(theta_weight.shape), d_bone,
+                (d_gt if ctx.has_gt else None), None, None, None, None)
+
+
+def lbs(raw_w, theta_weight, bone_T, global_t, xyz, rules: Optional[torch.Tensor] = None, eps: float = 1e-6,
+        want_frames: bool = False):
+    """-> warped xyz (N,3), inverse frames (N,9), merged skinning weights (N,J), bbox (6) [min, max],
+    blended frames (N,4,4) if want_frames."""
+    if rules is not None:
+        rules = rules.to(torch.int32).contiguous()
+    xyz_out, ginv, w, bbox, g = _LBS.apply(raw_w, theta_weight, bone_T, global_t, xyz, rules, eps, want_frames)
+    return (xyz_out, ginv, w, bbox, g) if want_frames else (xyz_out, ginv, w, bbox)
+
+
+# --------------------------------------------------------------------------------------
+# K2: grid + ray samples + exact 8-NN
+# --------------------------------------------------------------------------------------
+class Grid:
+    """Opaque multi-level uniform grid over a warped cloud (csrc/grid_knn.cu)."""
+
+    def __init__(self, xyz: torch.Tensor, bbox: torch.Tensor, query_radius: float, bbox_pad: float, cell_hint: float,
+                 cell_capacity: Optional[int] = None):
+        lib = _lib.load()
+        self.xyz = _f32(xyz.detach())
+        self.N = self.xyz.shape[0]
+        if cell_capacity is None:
+            cell_capacity = int(min(max(8 * self.N, 1 << 18), 1 << 25))
+        self.cell_capacity = cell_capacity
+        self.bytes = lib.apn_grid_workspace_bytes(self.N, cell_capacity)
+        self.blob = _empty((self.bytes,), self.xyz.device, torch.uint8)
+        check(lib.apn_grid_build(ptr(self.xyz), ptr(_f32(bbox)), self.N, float(query_radius), float(bbox_pad),
+                                 float(cell_hint), cell_capacity, ptr(self.blob), self.bytes, stream()), "apn_grid_build")
+
+    def describe(self) -> dict:
+        """Synchronising debug helper: header fields of the grid."""
+        lib = _lib.load()
+        host = (C.c_float * 64)()
+        check(lib.apn_grid_describe(ptr(self.blob), C.cast(host, C.c_void_p), stream()), "apn_grid_describe")
+        raw = bytes(host)
+        import struct
+        f = struct.unpack_from("<6f", raw, 0)
+        i = struct.unpack_from("<6i", raw, 24)
+        r2 = struct.unpack_from("<f", raw, 48)[0]
+        bm = struct.unpack_from("<6f", raw, 52)
+        n_points, overflow = struct.unpack_from("<2i", raw, 76)
+        return dict(origin=f[0:3], cell=f[3], inv_cell=f[4], top_cell=f[5], L=i[0], top_dim=i[1:4], n_top=i[4],
+                    n_cells=i[5], r2=r2, bmin=bm[0:3], bmax=bm[3:6], n_points=n_points, overflow=overflow)
+
+    def knn(self, query: torch.Tensor, k: int = K_NEIGHBOURS):
+        """Exact k-NN (k <= 8) of arbitrary points: indices (n,k) int32 ascending by (d2, index), d2 (n,k)."""
+        lib = _lib.load()
+        q = _f32(query.detach())
+        n = q.shape[0]
+        idx = _empty((n, k), q.device, torch.int32)
+        d2 = _empty((n, k), q.device)
+        check(lib.apn_knn_points(ptr(q), n, ptr(self.blob), k, ptr(idx), ptr(d2), stream()), "apn_knn_points")
+        return idx, d2
+
+
+def exclusive_scan(x: torch.Tensor) -> torch.Tensor:
+    """int32 (n) -> int32 (n+1), out[n] = total."""
+    lib = _lib.load()
+    n = x.numel()
+    out = _empty((n + 1,), x.device, torch.int32)
+    ws_bytes = lib.apn_scan_workspace_bytes(n)
+    ws = _empty((max(ws_bytes, 1),), x.device, torch.uint8)
+    check(lib.apn_exclusive_scan_i32(ptr(x), ptr(out), n, ptr(ws), ws_bytes, stream()), "apn_exclusive_scan_i32")
+    return out
+
+
+@dataclass
+class Samples:
+    """Kept ray samples, ray-major and near-to-far (what lib/temporalpoints.py:427-447 leaves)."""
+    pts: torch.Tensor        # (M,3)
+    ray_id: torch.Tensor     # (M) int32
+    step_id: torch.Tensor    # (M) int32
+    nn_idx: torch.Tensor     # (M,8) int32
+    ray_start: torch.Tensor  # (R+1) int32
+    n_rays: int
+    n_candidates: int
+
+    @property
+    def M(self) -> int:
+        return self.pts.shape[0]
+
+
+def sample_and_knn(grid: Grid, rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far: float, stepdist: float,
+                   return_d2: bool = False):
+    """sample_ray + Kmin_argKmin + radius rule, fused (lib/temporalpoints.py:421-447)."""
+    lib = _lib.load()
+    rays_o, rays_d = _f32(rays_o), _f32(rays_d)
+    R = rays_o.shape[0]
+    dev = rays_o.device
+    st = stream()
+    count = _empty((R,), dev, torch.int32)
+    check(lib.apn_ray_candidates(ptr(rays_o), ptr(rays_d), R, near, far, stepdist, ptr(grid.blob), 0, ptr(count), None,
+                                 None, None, st), "apn_ray_candidates(count)")
+    base = exclusive_scan(count)
+    n_cand = int(base[R].item())
+    cand_ray = _empty((n_cand,), dev, torch.int32)
+    cand_step = _empty((n_cand,), dev, torch.int32)
+    nn_c = _empty((n_cand, K_NEIGHBOURS), dev, torch.int32)
+    keep = _empty((n_cand,), dev, torch.int32)
+    d2_c = _empty((n_cand, K_NEIGHBOURS), dev) if return_d2 else None
+    if n_cand > 0:
+        check(lib.apn_ray_candidates(ptr(rays_o), ptr(rays_d), R, near, far, stepdist, ptr(grid.blob), 1, None, ptr(base),
+                                     ptr(cand_ray), ptr(cand_step), st), "apn_ray_candidates(fill)")
+        check(lib.apn_knn(ptr(rays_o), ptr(rays_d), near, far, stepdist, ptr(grid.blob), ptr(cand_ray), ptr(cand_step),
+                          n_cand, ptr(nn_c), ptr(d2_c), ptr(keep), st), "apn_knn")
+    kept_pos = exclusive_scan(keep)
+    M = int(kept_pos[n_cand].item())
+    pts = _empty((M, 3), dev)
+    ray_id = _empty((M,), dev, torch.int32)
+    step_id = _empty((M,), dev, torch.int32)
+    nn_idx = _empty((M, K_NEIGHBOURS), dev, torch.int32)
+    ray_start = _empty((R + 1,), dev, torch.int32)
+    check(lib.apn_compact_samples(ptr(rays_o), ptr(rays_d), near, far, stepdist, ptr(grid.blob), ptr(cand_ray),
+                                  ptr(cand_step), ptr(base), ptr(keep), ptr(kept_pos), ptr(nn_c), n_cand, R, ptr(pts),
+                                  ptr(ray_id), ptr(step_id), ptr(nn_idx), ptr(ray_start), st), "apn_compact_samples")
+    smp = Samples(pts, ray_id, step_id, nn_idx, ray_start, R, n_cand)
+    if return_d2:
+        return smp, dict(cand_ray=cand_ray, cand_step=cand_step, keep=keep, d2=d2_c, nn=nn_c)
+    return smp
+
+
+# --------------------------------------------------------------------------------------
+# K3: aggregation (exact fp32 path, differentiable)
+# --------------------------------------------------------------------------------------
+MLP_KEYS = ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3", "density_w", "density_b", "rgb_feat_w", "rgb_feat_b",
+            "rgb_v0_w", "rgb_v0_b", "rgb_v2_w", "rgb_v2_b")
+
+
+def _mlp_struct(ws: Sequence[torch.Tensor]) -> MlpWeights:
+    s = MlpWeights()
+    for l in range(4):
+        s.w[l] = ptr(ws[2 * l])
+        s.b[l] = ptr(ws[2 * l + 1])
+    (s.density_w, s.density_b, s.rgb_feat_w, s.rgb_feat_b, s.rgb_v0_w, s.rgb_v0_b, s.rgb_v2_w,
+     s.rgb_v2_b) = [ptr(t) for t in ws[8:16]]
+    return s
+
+
+@dataclass
+class AggConst:
+    """Non-tensor / non-differentiable inputs of the aggregation."""
+    pts: torch.Tensor
+    nn_idx: torch.Tensor
+    ray_id: torch.Tensor
+    viewdirs: torch.Tensor
+    canonical_alpha: torch.Tensor
+    canonical_rgbs: torch.Tensor
+    direct_eps: torch.Tensor
+    mean_min_distance: float
+    eps: float
+    act_shift: float
+    interval: float
+    direct: bool = True
+
+
+def _agg_inputs(c: AggConst, xyz, ginv, feat, pose_emb, M, d_in) -> AggInputs:
+    a = AggInputs()
+    a.M, a.N, a.d_in = M, xyz.shape[0], d_in
+    a.pts, a.nn_idx, a.ray_id = ptr(c.pts), ptr(c.nn_idx), ptr(c.ray_id)
+    a.xyz, a.ginv, a.feat, a.pose_emb = ptr(xyz), ptr(ginv), ptr(feat), ptr(pose_emb)
+    a.viewdirs = ptr(c.viewdirs)
+    a.canonical_alpha, a.canonical_rgbs, a.direct_eps = ptr(c.canonical_alpha), ptr(c.canonical_rgbs), ptr(c.direct_eps)
+    a.mean_min_distance, a.eps, a.act_shift, a.interval = c.mean_min_distance, c.eps, c.act_shift, c.interval
+    return a
+
+
+class _Aggregate(torch.autograd.Function):
+    """lib/temporalpoints.py:446-515 after the k-NN.  Differentiable w.r.t. the warped cloud, the inverse
+    frames, canonical_feat, the pose embedding and all MLP weights.  The direct branch
+    (lib/temporalpoints.py:459-470) is returned without a graph: no loss in run.py reads it."""
+
+    @staticmethod
+    def forward(ctx, c: AggConst, xyz, ginv, feat, pose_emb, *ws):
+        lib = _lib.load()
+        xyz, ginv, feat = _f32(xyz), _f32(ginv), _f32(feat)
+        pose_emb = None if pose_emb is None else _f32(pose_emb).reshape(-1)
+        ws = [_f32(w) for w in ws]
+        M = c.pts.shape[0]
+        dev = xyz.device
+        d_in = PE_POS + FEAT_DIM + (0 if pose_emb is None else pose_emb.numel())
+        ld0 = (d_in + 3) // 4 * 4
+        rows = M * K_NEIGHBOURS
+        alpha, rgb = _empty((M,), dev), _empty((M, 3), dev)
+        alpha_d = _empty((M,), dev) if c.direct else None
+        rgb_d = _empty((M, 3), dev) if c.direct else None
+        idw = _empty((M, K_NEIGHBOURS), dev)
+        need_grad = any(ctx.needs_input_grad)
+        out = AggOutputs()
+        out.alpha, out.rgb, out.alpha_direct, out.rgb_direct, out.idw = ptr(alpha), ptr(rgb), ptr(alpha_d), ptr(rgb_d), ptr(idw)
+        a = _agg_inputs(c, xyz, ginv, feat, pose_emb, M, d_in)
+        w = _mlp_struct(ws)
+        saved = None
+        scratch, scratch_bytes = None, 0
+        if M > 0:
+            if need_grad:
+                saved = dict(x0=_empty((rows, ld0), dev), act=[_empty((rows, FEAT_DIM), dev) for _ in range(4)],
+                             h=_empty((M, FEAT_DIM), dev), exp_d=_empty((M,), dev), fv=_empty((M, FV_LD), dev),
+                             v0=_empty((M, V0_DIM), dev))
+                out.x0 = ptr(saved["x0"])
+                for l in range(4):
+                    out.act[l] = ptr(saved["act"][l])
+                out.h, out.exp_d, out.fv, out.v0 = ptr(saved["h"]), ptr(saved["exp_d"]), ptr(saved["fv"]), ptr(saved["v0"])
+            else:
+                scratch_bytes = lib.apn_aggregate_scratch_bytes(M, d_in)
+                scratch = _empty((scratch_bytes,), dev, torch.uint8)
+            check(lib.apn_aggregate_fwd(C.byref(a), C.byref(w), C.byref(out), ptr(scratch), scratch_bytes, stream()),
+                  "apn_aggregate_fwd")
+        ctx.c, ctx.saved, ctx.d_in = c, saved, d_in
+        ctx.tensors = (xyz, ginv, feat, pose_emb, ws, alpha, rgb, idw)
+        ctx.mark_non_differentiable(idw)
+        if c.direct:
+            ctx.mark_non_differentiable(alpha_d, rgb_d)
+        return alpha, rgb, alpha_d, rgb_d, idw
+
+    @staticmethod
+    def backward(ctx, d_alpha, d_rgb, *_):
+        lib = _lib.load()
+        c = ctx.c
+        xyz, ginv, feat, pose_emb, ws, alpha, rgb, idw = ctx.tensors
+        M = c.pts.shape[0]
+        dev = xyz.device
+        need = ctx.needs_input_grad      # (c, xyz, ginv, feat, pose_emb, *ws)
+        d_xyz = torch.zeros_like(xyz) if need[1] else None
+        d_ginv = torch.zeros_like(ginv) if need[2] else None
+        d_feat = torch.zeros_like(feat) if need[3] else None
+        d_pose = torch.zeros_like(pose_emb) if (pose_emb is not None and need[4]) else None
+        d_ws = [torch.zeros_like(w) for w in ws]
+        if M > 0:
+            d_alpha = torch.zeros_like(alpha) if d_alpha is None else _f32(d_alpha)
+            d_rgb = torch.zeros_like(rgb) if d_rgb is None else _f32(d_rgb)
+            sv = ctx.saved
+            out = AggOutputs()
+            out.alpha, out.rgb, out.idw = ptr(alpha), ptr(rgb), ptr(idw)
+            out.x0 = ptr(sv["x0"])
+            for l in range(4):
+                out.act[l] = ptr(sv["act"][l])
+            out.h, out.exp_d, out.fv, out.v0 = ptr(sv["h"]), ptr(sv["exp_d"]), ptr(sv["fv"]), ptr(sv["v0"])
+            g = AggGrads()
+            g.d_alpha, g.d_rgb = ptr(d_alpha), ptr(d_rgb)
+            g.d_xyz, g.d_ginv, g.d_feat, g.d_pose_emb = ptr(d_xyz), ptr(d_ginv), ptr(d_feat), ptr(d_pose)
+            for l in range(4):
+                g.d_w[l] = ptr(d_ws[2 * l])
+                g.d_b[l] = ptr(d_ws[2 * l + 1])
+            (g.d_density_w, g.d_density_b, g.d_rgb_feat_w, g.d_rgb_feat_b, g.d_rgb_v0_w, g.d_rgb_v0_b, g.d_rgb_v2_w,
+             g.d_rgb_v2_b) = [ptr(t) for t in d_ws[8:16]]
+            a = _agg_inputs(c, xyz, ginv, feat, pose_emb, M, ctx.d_in)
+            w = _mlp_struct(ws)
+            sb = lib.apn_aggregate_bwd_scratch_bytes(M, ctx.d_in)
+            scratch = _empty((sb,), dev, torch.uint8)
+            check(lib.apn_aggregate_bwd(C.byref(a), C.byref(w), C.byref(out), C.byref(g), ptr(scratch), sb, stream()),
+                  "apn_aggregate_bwd")
+        ctx.saved = None
+        if d_pose is not None and pose_emb is not None:
+            d_pose = d_pose.reshape(pose_emb.shape)
+        return (None, d_xyz, d_ginv, d_feat, d_pose, *[dw if need[5 + i] else None for i, dw in enumerate(d_ws)])
+
+
+def aggregate(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch.Tensor]):
+    """-> alpha (M), rgb (M,3), alpha_direct (M)|None, rgb_direct (M,3)|None, idw (M,8)."""
+    assert len(weights) == 16, "expected feat_net (4x w,b), densitynet, rgbnet (3x w,b)"
+    return _Aggregate.apply(c, xyz, ginv, feat, pose_emb, *weights)
+
+
+# --------------------------------------------------------------------------------------
+# K4: compositing
+# --------------------------------------------------------------------------------------
+class _Composite(torch.autograd.Function):
+    """pre-mask + Alphas2Weights + post-mask + segment_coo (lib/temporalpoints.py:611-677)."""
+
+    @staticmethod
+    def forward(ctx, alpha, rgb, step_id, extra, ray_start, n_rays, thres, bg, want_depth):
+        lib = _lib.load()
+        alpha, rgb = _f32(alpha), _f32(rgb)
+        dev = alpha.device
+        M, R = alpha.shape[0], int(n_rays)
+        rgb_m = _empty((R, 3), dev)
+        last = _empty((R,), dev)
+        depth = _empty((R,), dev) if want_depth else None
+        n_extra = 0 if extra is None else extra.shape[1]
+        extra = None if extra is None else _f32(extra)
+        extra_m = _empty((R, n_extra), dev) if n_extra else None
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        T_save = _empty((M,), dev) if need_grad else None
+        n_used = _empty((R,), dev, torch.int32) if need_grad else None
+        check(lib.apn_composite_fwd(ptr(alpha), ptr(rgb), ptr(step_id) if want_depth else None, ptr(extra), n_extra,
+                                    ptr(ray_start), R, float(thres), float(bg), ptr(rgb_m), ptr(last), ptr(depth),
+                                    ptr(extra_m), ptr(T_save), ptr(n_used), stream()), "apn_composite_fwd")
+        ctx.save_for_backward(alpha, rgb, step_id, ray_start, T_save, n_used, last)
+        ctx.meta = (R, float(thres), float(bg), want_depth)
+        outs = [rgb_m, last, depth if want_depth else torch.zeros(0, device=dev),
+                extra_m if n_extra else torch.zeros(0, device=dev)]
+        ctx.mark_non_differentiable(outs[3])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_rgb_m, d_last, d_depth, _d_extra):
+        lib = _lib.load()
+        alpha, rgb, step_id, ray_start, T_save, n_used, last = ctx.saved_tensors
+        R, thres, bg, want_depth = ctx.meta
+        d_alpha = torch.empty_like(alpha)
+        d_rgb = torch.empty_like(rgb)
+        d_rgb_m = None if d_rgb_m is None else _f32(d_rgb_m)
+        d_last = None if d_last is None else _f32(d_last)
+        d_depth = _f32(d_depth) if (want_depth and d_depth is not None) else None
+        check(lib.apn_composite_bwd(ptr(alpha), ptr(rgb), ptr(step_id) if want_depth else None, ptr(ray_start), R, thres, bg,
+                                    ptr(T_save), ptr(n_used), ptr(last), ptr(d_rgb_m), ptr(d_last), ptr(d_depth),
+                                    ptr(d_alpha), ptr(d_rgb), stream()), "apn_composite_bwd")
+        return d_alpha, d_rgb, None, None, None, None, None, None, None
+
+
+def composite(alpha, rgb, step_id, ray_start, n_rays: int, thres: float, bg: float, extra=None, want_depth=True):
+    """-> rgb_marched (R,3), alphainv_last (R), depth (R)|None, extra_marched (R,n_extra)|None."""
+    rgb_m, last, depth, extra_m = _Composite.apply(alpha, rgb, step_id, extra, ray_start, n_rays, thres, bg, want_depth)
+    return rgb_m, last, (depth if want_depth else None), (extra_m if extra is not None else None)
+
+
+# --------------------------------------------------------------------------------------
+# K4b: Adam
+# --------------------------------------------------------------------------------------
+def adam_step_size(step: int, beta1: float, beta2: float, lr: float) -> float:
+    return float(_lib.load().apn_adam_step_size(int(step), beta1, beta2, lr))
+
+
+def adam_multi(entries, beta1: float, beta2: float, eps: float) -> None:
+    """entries: list of (param, grad, exp_avg, exp_avg_sq, perlr|None, step_size, mode)."""
+    if not entries:
+        return
+    lib = _lib.load()
+    arr = (AdamTensor * len(entries))()
+    for i, (p, g, m, v, pl, ss, mode) in enumerate(entries):
+        for t in (p, g, m, v):
+            if t.dtype != torch.float32:
+                raise _lib.ApnError("Adam tensors must be fp32")
+        arr[i].param, arr[i].grad, arr[i].exp_avg, arr[i].exp_avg_sq = ptr(p), ptr(g), ptr(m), ptr(v)
+        arr[i].perlr = ptr(pl)
+        arr[i].numel = p.numel()
+        arr[i].step_size = ss
+        arr[i].mode = mode
+    check(lib.apn_adam_multi(C.cast(arr, C.c_void_p), len(entries), beta1, beta2, eps, stream()), "apn_adam_multi")

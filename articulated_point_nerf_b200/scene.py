@@ -319,3 +319,34 @@ def make_scene(cfg: SceneConfig | str) -> Scene:
     lo, hi = frustum_bbox(HW, Ks, poses, cfg.near, cfg.far, inverse_y=cfg.inverse_y)
     voxel_size = float(((hi - lo).prod() / cfg.num_voxels) ** (1 / 3))
     return Scene(cfg, joints, bones, pcd, h, feat, rgbs, alpha, skeleton_pcd, lo, hi, voxel_size, HW, Ks, poses)
+
+
+# --------------------------------------------------------------------------------------
+# model construction on top of a scene (tests, bench.py, smoke())
+# --------------------------------------------------------------------------------------
+def build_model(scene: Scene, seed: int = 0, density_bias: float = 7.0, theta_std: float = 0.2,
+                density_gain: float = 300.0, rgb_gain: float = 8.0, device=None):
+    """TemporalPoints on random-init weights of the reference's architecture, with the output heads rescaled so
+    that kept-sample alpha spreads over (0,1) and early ray termination triggers."""
+    from .heads import TiNeuVoxHeads, poc_fre
+    from .temporalpoints import TemporalPoints
+    torch.manual_seed(seed)
+    cfg = scene.cfg
+    heads = TiNeuVoxHeads(scene.xyz_min.numpy(), scene.xyz_max.numpy(), num_voxels=cfg.num_voxels,
+                          num_voxels_base=cfg.num_voxels, alpha_init=1e-3, net_width=128, no_view_dir=False)
+    model = TemporalPoints(
+        canonical_pcd=scene.canonical_pcd.clone(), canonical_alpha=scene.canonical_alpha.clone(),
+        canonical_feat=scene.canonical_feat.clone(), canonical_rgbs=scene.canonical_rgbs.clone(),
+        skeleton_pcd=scene.skeleton_pcd.clone(), joints=scene.joints.clone(), bones=scene.bones,
+        xyz_min=scene.xyz_min.numpy(), xyz_max=scene.xyz_max.numpy(), tineuvox=heads, stepsize=cfg.stepsize,
+        voxel_size=scene.voxel_size, fast_color_thres=cfg.fast_color_thres, pose_embedding_dim=cfg.pose_embedding_dim)
+    with torch.no_grad():
+        model.densitynet.bias.fill_(density_bias)
+        model.densitynet.weight.mul_(density_gain)
+        model.rgbnet.views_linears[2].weight.mul_(rgb_gain)
+        t_embed = poc_fre(torch.tensor([0.37]), model.time_poc)
+        out = model.forward_warp.transform_net(t_embed.unsqueeze(0))
+        model.forward_warp.transform_net.net[-1].weight.mul_(theta_std / float(out.std()))
+    if device is not None:
+        model = model.to(device)
+    return model

@@ -43,18 +43,22 @@ unsigned long long apn_launch_count(void);
  *   raw_w (N,J)  theta_weight (1)  merge_rules (J) int32 or NULL (= identity)
  *   bone_T (J,4,4) row-major  xyz (N,3)  global_t (3)
  *   xyz_out (N,3)  ginv_out (N,9) = inverse(G[:3,:3])  w_out (N,J) merged weights or NULL
+ *   g_out (N,4,4) blended frames (what PointWarper.forward(get_frames=True) returns) or NULL
+ *   theta_weight == NULL: raw_w already holds the final (soft-maxed, merged) weights, as passed
+ *   to PointWarper.forward (lib/pointwarper.py:213)
  *   bbox (6) = min xyz, max xyz of xyz_out (initialised by the call)
  * ------------------------------------------------------------------------------------- */
 int apn_lbs_fwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
                 const float* bone_T, const float* xyz, const float* global_t, int N, int J,
-                float* xyz_out, float* ginv_out, float* w_out, float* bbox, apn_stream_t stream);
+                float* xyz_out, float* ginv_out, float* w_out, float* g_out, float* bbox, apn_stream_t stream);
 
 size_t apn_lbs_bwd_workspace_bytes(int N, int J);
 /* d_raw (N,J), d_theta (1), d_bone_T (J,4,4; last row 0), d_global_t (3) are overwritten.
- * d_w (N,J) is the extra gradient arriving on the merged weights (regularisers) or NULL. */
+ * d_w (N,J) is the extra gradient arriving on the merged weights (regularisers) or NULL;
+ * d_g (N,4,4) the gradient arriving on g_out or NULL. */
 int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
                 const float* bone_T, const float* xyz, int N, int J, const float* ginv,
-                const float* d_xyz, const float* d_ginv, const float* d_w,
+                const float* d_xyz, const float* d_ginv, const float* d_w, const float* d_g,
                 float* d_raw, float* d_theta, float* d_bone_T, float* d_global_t,
                 void* workspace, size_t workspace_bytes, apn_stream_t stream);
 
@@ -174,6 +178,7 @@ typedef struct apn_agg_grads {
   float* d_xyz;          /* (N,3) */
   float* d_ginv;         /* (N,9) */
   float* d_feat;         /* (N,128) */
+  float* d_pose_emb;     /* (d_in-191) or NULL */
   float* d_w[4];
   float* d_b[4];
   float* d_density_w;

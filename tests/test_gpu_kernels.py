@@ -1,0 +1,366 @@
+"""GPU parity of each kernel group against the CPU oracle (oracle/), through the C ABI (ctypes).
+
+Bars (BASELINE.json north_star): neighbour / sample indices and every integer output bit-exact;
+fp32 outputs and gradients within RTOL = 1e-4 of the oracle, relative to the tensor's scale.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import RTOL, model_from_golden, oracle_for_scene, oracle_from_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from articulated_point_nerf_b200 import ops
+    return ops
+
+
+# ----------------------------------------------------------------------------------------
+# K1 linear blend skinning
+# ----------------------------------------------------------------------------------------
+def _lbs_case(N, J, seed, merge=False):
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.rand(N, J, generator=g) * 2
+    theta = torch.tensor([0.1])
+    T = torch.eye(4).repeat(J, 1, 1)
+    A = torch.linalg.qr(torch.randn(J, 3, 3, generator=g))[0]
+    T[:, :3, :3] = A * torch.sign(torch.linalg.det(A))[:, None, None]
+    T[:, :3, 3] = torch.randn(J, 3, generator=g) * 0.1
+    xyz = torch.randn(N, 3, generator=g) * 0.3
+    gt = torch.randn(3, generator=g) * 0.05
+    rules = torch.arange(J)
+    if merge:
+        rules[J // 2] = 1
+        rules[J - 1] = 0
+    return raw, theta, T, xyz, gt, rules
+
+
+def _lbs_oracle(raw, theta, T, xyz, gt, rules, eps=1e-6):
+    from oracle.path_oracle import get_weights
+    w = get_weights(raw, theta, eps, rules)
+    G = (T * w[:, :, None, None]).sum(1)
+    xh = torch.cat([xyz, torch.ones(len(xyz), 1)], -1)
+    out = torch.bmm(G, xh.unsqueeze(-1)).squeeze(-1)[:, :3] + gt
+    ginv = torch.inverse(G)[:, :3, :3]
+    return out, ginv, w, G
+
+
+@pytest.mark.parametrize("N,J,merge", [(1, 2, False), (127, 21, False), (4099, 29, True), (20000, 65, False)])
+def test_lbs_forward_backward(N, J, merge):
+    ops = _ops()
+    raw, theta, T, xyz, gt, rules = _lbs_case(N, J, N + J, merge)
+    leaves = [t.clone().requires_grad_(True) for t in (raw, theta, T, gt)]
+    o_xyz, o_ginv, o_w, _ = _lbs_oracle(leaves[0], leaves[1], leaves[2], xyz, leaves[3], rules)
+    gen = torch.Generator().manual_seed(1)
+    c1, c2, c3 = torch.randn(N, 3, generator=gen), torch.randn(N, 3, 3, generator=gen), torch.randn(N, J, generator=gen)
+    (o_xyz * c1).sum().add((o_ginv * c2).sum()).add((o_w * c3).sum()).backward()
+
+    d = "cuda"
+    cl = [t.detach().clone().to(d).requires_grad_(True) for t in (raw, theta, T, gt)]
+    k_xyz, k_ginv, k_w, bbox = ops.lbs(cl[0], cl[1], cl[2], cl[3], xyz.to(d), rules=rules.to(d) if merge else None)
+    assert rel_err(k_xyz, o_xyz) < 1e-5
+    assert rel_err(k_ginv.view(N, 3, 3), o_ginv) < 1e-5
+    assert rel_err(k_w, o_w) < 1e-5
+    assert torch.equal(bbox.cpu(), torch.cat([k_xyz.min(0)[0], k_xyz.max(0)[0]]).cpu())
+    (k_xyz * c1.to(d)).sum().add((k_ginv.view(N, 3, 3) * c2.to(d)).sum()).add((k_w * c3.to(d)).sum()).backward()
+    for a, b, name in zip(cl, leaves, ["raw_w", "theta", "bone_T", "global_t"]):
+        ref = b.grad if name != "bone_T" else b.grad * torch.tensor([1., 1., 1., 0.])[None, :, None]
+        got = a.grad if name != "bone_T" else a.grad
+        assert rel_err(got, ref) < RTOL, name
+
+
+def test_lbs_preblended_weights_and_frames():
+    """theta_weight=None: the PointWarper.forward contract (final weights in, frames out)."""
+    ops = _ops()
+    raw, theta, T, xyz, gt, rules = _lbs_case(513, 24, 5)
+    o_xyz, o_ginv, o_w, o_G = _lbs_oracle(raw, theta, T, xyz, gt, rules)
+    d = "cuda"
+    k_xyz, k_ginv, k_w, bbox, k_G = ops.lbs(o_w.to(d), None, T.to(d), gt.to(d), xyz.to(d), want_frames=True)
+    assert rel_err(k_xyz, o_xyz) < 1e-5
+    o_G = o_G.clone()
+    assert rel_err(k_G, o_G) < 1e-5
+    assert torch.equal(k_w.cpu(), o_w)
+
+
+# ----------------------------------------------------------------------------------------
+# K2 grid + sampling + exact 8-NN
+# ----------------------------------------------------------------------------------------
+def _cloud_and_rays(config="tiny", view=0):
+    from articulated_point_nerf_b200.scene import make_scene
+    scene = make_scene(config)
+    ro, rd, vd = [x.reshape(-1, 3).contiguous() for x in scene.rays(view)]
+    return scene, ro, rd, vd
+
+
+@pytest.mark.parametrize("config", ["tiny", "small"])
+def test_sample_and_knn_bit_exact(config):
+    """pts / ray_id / step_id / neighbour indices identical to the oracle's brute force (ties -> lower index)."""
+    ops = _ops()
+    from oracle.path_oracle import OraclePath
+    scene, ro, rd, vd = _cloud_and_rays(config)
+    cfg = scene.cfg
+    g = torch.Generator().manual_seed(3)
+    xyz = scene.canonical_pcd + torch.randn(scene.canonical_pcd.shape, generator=g) * 0.002
+    orc = OraclePath.__new__(OraclePath)
+    orc.K, orc.voxel_size = 8, scene.voxel_size
+    ref = orc.sample_and_knn(xyz, ro, rd, cfg.near, cfg.far, cfg.stepsize, 0.01)
+    d = "cuda"
+    xyz_d = xyz.to(d)
+    bbox = torch.cat([xyz_d.min(0)[0], xyz_d.max(0)[0]])
+    grid = ops.Grid(xyz_d, bbox, 0.01, 0.01, 1.5 * scene.lattice_h)
+    desc = grid.describe()
+    assert desc["overflow"] == 0 and desc["n_points"] == len(xyz)
+    smp, dbg = ops.sample_and_knn(grid, ro.to(d), rd.to(d), cfg.near, cfg.far, cfg.stepsize * scene.voxel_size, return_d2=True)
+    assert smp.M == len(ref["pts"])
+    assert torch.equal(smp.pts.cpu(), ref["pts"])
+    assert torch.equal(smp.ray_id.cpu().long(), ref["ray_id"])
+    assert torch.equal(smp.step_id.cpu().long(), ref["step_id"])
+    assert torch.equal(smp.nn_idx.cpu().long(), ref["s_i"])
+    # d2 of kept candidates are the oracle's bits
+    keep = dbg["keep"].bool()
+    assert torch.equal(dbg["d2"][keep].cpu(), ref["d2_all"][ref["keep"]])
+    # ray_start is the CSR of ray_id
+    rs = smp.ray_start.cpu().long()
+    counts = torch.bincount(ref["ray_id"], minlength=len(ro))
+    assert torch.equal(rs[1:] - rs[:-1], counts)
+
+
+def test_knn_points_matches_bruteforce_with_lattice_ties():
+    """Self k-NN of the canonical lattice cloud (exact ties everywhere): lowest index wins."""
+    ops = _ops()
+    from oracle.path_oracle import knn_bruteforce
+    scene, *_ = _cloud_and_rays("small")
+    pcd = scene.canonical_pcd
+    ref_d, ref_i = knn_bruteforce(pcd, pcd, 8)
+    d = "cuda"
+    p = pcd.to(d)
+    grid = ops.Grid(p, torch.cat([p.min(0)[0], p.max(0)[0]]), 0.01, 0.01, scene.lattice_h)
+    idx, d2 = grid.knn(p, 8)
+    assert torch.equal(idx.cpu().long(), ref_i)
+    assert torch.equal(d2.cpu(), ref_d)
+    # far-away queries still get the exact answer (falls back to wider levels / full scan)
+    q = torch.tensor([[3.0, 3.0, 3.0], [-2.0, 0.1, 0.4], [0.0, 0.0, 0.9]])
+    rd_, ri_ = knn_bruteforce(q, pcd, 8)
+    i2, d22 = grid.knn(q.to(d), 8)
+    assert torch.equal(i2.cpu().long(), ri_)
+    assert torch.equal(d22.cpu(), rd_)
+
+
+def test_rays_missing_the_cloud_give_no_samples():
+    ops = _ops()
+    scene, ro, rd, vd = _cloud_and_rays("tiny")
+    d = "cuda"
+    p = scene.canonical_pcd.to(d)
+    grid = ops.Grid(p, torch.cat([p.min(0)[0], p.max(0)[0]]), 0.01, 0.01, 1.5 * scene.lattice_h)
+    smp = ops.sample_and_knn(grid, ro[:7].to(d), (-rd[:7]).contiguous().to(d), scene.cfg.near, scene.cfg.far,
+                             scene.cfg.stepsize * scene.voxel_size)
+    assert smp.M == 0 and smp.ray_start.cpu().tolist() == [0] * 8
+
+
+# ----------------------------------------------------------------------------------------
+# K3 aggregation (exact path)
+# ----------------------------------------------------------------------------------------
+def _agg_setup(golden_tiny, need_grad):
+    ops = _ops()
+    g = golden_tiny
+    orc, cfg = oracle_from_golden(g)
+    if need_grad:
+        for v in orc.s.values():
+            if v.is_floating_point():
+                v.requires_grad_(True)
+    with torch.set_grad_enabled(need_grad):
+        wp = orc.warp(g["render"]["t"])
+        Ginv = torch.inverse(wp["G"])
+        smp = orc.sample_and_knn(wp["xyz"], g["rays_o"], g["rays_d"], cfg.near, cfg.far, cfg.stepsize, 0.01)
+        xyz = wp["xyz"].detach().requires_grad_(need_grad)
+        gi = Ginv.detach().requires_grad_(need_grad)
+        o = orc.aggregate(xyz, gi, smp, g["viewdirs"], cfg.stepsize)
+    model, scene = model_from_golden(g)
+    d = "cuda"
+    c = ops.AggConst(pts=smp["pts"].to(d), nn_idx=smp["s_i"].to(d).int().contiguous(), ray_id=smp["ray_id"].to(d).int(),
+                     viewdirs=g["viewdirs"].to(d), canonical_alpha=model.canonical_alpha.detach(),
+                     canonical_rgbs=model.canonical_rgbs.detach(), direct_eps=model.direct_eps.detach(),
+                     mean_min_distance=float(g["mean_min_distance"]), eps=1e-6, act_shift=g["act_shift"],
+                     interval=cfg.stepsize * g["voxel_size_ratio"], direct=True)
+    return ops, orc, o, xyz, gi, smp, model, c
+
+
+def test_aggregate_forward(golden_tiny):
+    ops, orc, o, xyz, gi, smp, model, c = _agg_setup(golden_tiny, False)
+    rgb, alpha, rgb_d, alpha_d, _ = o
+    with torch.no_grad():
+        k_alpha, k_rgb, k_ad, k_rd, k_idw = ops.aggregate(c, xyz.cuda(), gi[:, :3, :3].reshape(-1, 9).contiguous().cuda(),
+                                                          model.canonical_feat, None, model._mlp_weights())
+    assert rel_err(k_idw, orc.trace["idw"]) < 1e-5
+    assert rel_err(k_alpha, alpha) < RTOL
+    assert rel_err(k_rgb, rgb) < RTOL
+    assert rel_err(k_ad, alpha_d) < RTOL
+    assert rel_err(k_rd, rgb_d) < RTOL
+
+
+def test_aggregate_backward(golden_tiny):
+    ops, orc, o, xyz, gi, smp, model, c = _agg_setup(golden_tiny, True)
+    rgb, alpha, _, _, _ = o
+    gen = torch.Generator().manual_seed(2)
+    ca, cr = torch.randn(alpha.shape, generator=gen), torch.randn(rgb.shape, generator=gen)
+    ((alpha * ca).sum() + (rgb * cr).sum()).backward()
+    kx = xyz.detach().cuda().requires_grad_(True)
+    kg = gi.detach()[:, :3, :3].reshape(-1, 9).contiguous().cuda().requires_grad_(True)
+    model.zero_grad()
+    k_alpha, k_rgb, *_ = ops.aggregate(c, kx, kg, model.canonical_feat, None, model._mlp_weights())
+    ((k_alpha * ca.cuda()).sum() + (k_rgb * cr.cuda()).sum()).backward()
+    assert rel_err(kx.grad, xyz.grad) < RTOL
+    assert rel_err(kg.grad.view(-1, 3, 3), gi.grad[:, :3, :3]) < RTOL
+    named = dict(model.named_parameters())
+    for k in ["canonical_feat", "feat_net.0.weight", "feat_net.0.bias", "feat_net.2.0.weight", "feat_net.3.0.bias",
+              "feat_net.4.weight", "feat_net.4.bias", "densitynet.weight", "densitynet.bias",
+              "rgbnet.feature_linears.weight", "rgbnet.feature_linears.bias", "rgbnet.views_linears.0.weight",
+              "rgbnet.views_linears.0.bias", "rgbnet.views_linears.2.weight", "rgbnet.views_linears.2.bias"]:
+        assert named[k].grad is not None, k
+        assert rel_err(named[k].grad, orc.s[k].grad) < RTOL, k
+
+
+# ----------------------------------------------------------------------------------------
+# K4 compositing
+# ----------------------------------------------------------------------------------------
+def _ragged_rays(R, seed, max_len=40):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(0, max_len, (R,), generator=g)
+    lens[::7] = 0                       # empty rays
+    ray_id = torch.repeat_interleave(torch.arange(R), lens)
+    M = int(lens.sum())
+    alpha = torch.rand(M, generator=g) ** 3
+    alpha[torch.rand(M, generator=g) < 0.15] = 5e-5          # below the 1e-4 pre-mask
+    alpha[torch.rand(M, generator=g) < 0.05] = 0.97          # triggers early stop quickly
+    rgb = torch.rand(M, 3, generator=g)
+    first = torch.cumsum(lens, 0) - lens
+    step_id = torch.arange(M) - first[ray_id] + 3
+    ray_start = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(lens, 0)])
+    return alpha, rgb, ray_id, step_id, ray_start
+
+
+@pytest.mark.parametrize("R,seed", [(1, 0), (257, 1), (5000, 2)])
+def test_composite_forward_backward(R, seed):
+    ops = _ops()
+    from oracle.path_oracle import OraclePath
+    alpha, rgb, ray_id, step_id, ray_start = _ragged_rays(R, seed)
+    orc = OraclePath.__new__(OraclePath)
+    orc.thres = 1e-4
+    a = alpha.clone().requires_grad_(True)
+    c = rgb.clone().requires_grad_(True)
+    extra = torch.rand(len(alpha), 3, generator=torch.Generator().manual_seed(9))
+    rgb_m, last, depth, ex, _, _ = orc.composite(a, c, ray_id, step_id.float(), R, 1.0, extra)
+    gen = torch.Generator().manual_seed(4)
+    w1, w2, w3 = torch.randn(R, 3, generator=gen), torch.randn(R, generator=gen), torch.randn(R, generator=gen)
+    ((rgb_m * w1).sum() + (last * w2).sum() + (depth * w3).sum()).backward()
+    d = "cuda"
+    ka = alpha.to(d).requires_grad_(True)
+    kc = rgb.to(d).requires_grad_(True)
+    k_rgb, k_last, k_depth, k_ex = ops.composite(ka, kc, step_id.int().to(d), ray_start.int().to(d), R, 1e-4, 1.0,
+                                                 extra=extra.to(d), want_depth=True)
+    assert torch.equal(k_last.cpu(), last.detach())          # same fp32 product chain, same early stop
+    assert rel_err(k_rgb, rgb_m) < 1e-6
+    assert rel_err(k_depth, depth) < 1e-6
+    assert rel_err(k_ex, ex + last.detach()[:, None] * 1.0) < 1e-6
+    ((k_rgb * w1.to(d)).sum() + (k_last * w2.to(d)).sum() + (k_depth * w3.to(d)).sum()).backward()
+    assert rel_err(ka.grad, a.grad) < RTOL
+    assert rel_err(kc.grad, c.grad) < RTOL
+
+
+# ----------------------------------------------------------------------------------------
+# K4b Adam + reference-compatible single ops
+# ----------------------------------------------------------------------------------------
+def test_adam_bit_exact_all_modes():
+    from articulated_point_nerf_b200 import MaskedAdam
+    from oracle import dvgo_ops
+    gen = torch.Generator().manual_seed(0)
+    shapes = [(1,), (3, 5), (1031,), (128, 191), (4096 * 3 + 7,)]
+    ps = [torch.randn(s, generator=gen) for s in shapes]
+    gs = [torch.randn(s, generator=gen) * 0.1 for s in shapes]
+    for g_ in gs:
+        g_[torch.rand(g_.shape, generator=gen) < 0.4] = 0
+    params = [torch.nn.Parameter(p.clone().cuda()) for p in ps]
+    opt = MaskedAdam([{"params": params[:3], "lr": 1e-3, "skip_zero_grad": False},
+                      {"params": params[3:], "lr": 5e-4, "skip_zero_grad": True}])
+    ref_p = [p.clone() for p in ps]
+    ref_m = [torch.zeros_like(p) for p in ps]
+    ref_v = [torch.zeros_like(p) for p in ps]
+    for step in range(1, 4):
+        for p, g_ in zip(params, gs):
+            p.grad = (g_ * step).cuda()
+        opt.step()
+        for i in range(len(ps)):
+            fn = dvgo_ops.adam_upd if i < 3 else dvgo_ops.masked_adam_upd
+            fn(ref_p[i], gs[i] * step, ref_m[i], ref_v[i], step, 0.9, 0.99, 1e-3 if i < 3 else 5e-4, 1e-8)
+    for i, p in enumerate(params):
+        assert torch.equal(p.detach().cpu(), ref_p[i]), i
+        assert torch.equal(opt.state[p]["exp_avg"].cpu(), ref_m[i]), i
+        assert torch.equal(opt.state[p]["exp_avg_sq"].cpu(), ref_v[i]), i
+
+
+def test_adam_matches_reference_optimizer_golden(golden_tiny):
+    from articulated_point_nerf_b200 import MaskedAdam
+    a = golden_tiny["adam"]
+    p0 = torch.nn.Parameter(a["before"][0].clone().cuda())
+    p1 = torch.nn.Parameter(a["before"][1].clone().cuda())
+    opt = MaskedAdam([{"params": [p0], "lr": a["lrs"][0], "skip_zero_grad": False},
+                      {"params": [p1], "lr": a["lrs"][1], "skip_zero_grad": True}])
+    p0.grad, p1.grad = a["grads"][0].cuda(), a["grads"][1].cuda()
+    for _ in range(a["steps"]):
+        opt.step()
+    assert torch.equal(p0.detach().cpu(), a["after"][0])
+    assert torch.equal(p1.detach().cpu(), a["after"][1])
+
+
+def test_adam_perlr_mode():
+    from articulated_point_nerf_b200 import adam_upd_cuda
+    from oracle import dvgo_ops
+    gen = torch.Generator().manual_seed(5)
+    p, g_, pl = torch.randn(777, generator=gen), torch.randn(777, generator=gen), torch.rand(777, generator=gen)
+    m, v = torch.zeros(777), torch.zeros(777)
+    kp, km, kv = p.clone().cuda(), m.clone().cuda(), v.clone().cuda()
+    for step in (1, 2):
+        dvgo_ops.adam_upd_with_perlr(p, g_, m, v, pl, step, 0.9, 0.99, 1e-2, 1e-8)
+        adam_upd_cuda.adam_upd_with_perlr(kp, g_.cuda(), km, kv, pl.cuda(), step, 0.9, 0.99, 1e-2, 1e-8)
+    assert torch.equal(kp.cpu(), p) and torch.equal(km.cpu(), m) and torch.equal(kv.cpu(), v)
+
+
+def test_reference_compatible_render_utils(golden_tiny):
+    """render_utils_cuda.{sample_pts_on_rays, raw2alpha(+bwd), alpha2weight(+bwd)} vs the restated reference kernels."""
+    from articulated_point_nerf_b200 import render_utils_cuda as ru, Raw2Alpha, Alphas2Weights
+    from oracle import dvgo_ops
+    g = golden_tiny
+    d = "cuda"
+    lo = g["canonical_pcd"].min(0)[0] - 0.01
+    hi = g["canonical_pcd"].max(0)[0] + 0.01
+    stepdist = 0.5 * g["voxel_size"]
+    ref = dvgo_ops.sample_pts_on_rays(g["rays_o"], g["rays_d"], lo, hi, 2.0, 6.0, stepdist)
+    got = ru.sample_pts_on_rays(g["rays_o"].to(d), g["rays_d"].to(d), lo.to(d), hi.to(d), 2.0, 6.0, stepdist)
+    for a, b in zip(got, ref):
+        assert torch.equal(a.cpu(), b)
+    dens = torch.randn(5000, generator=torch.Generator().manual_seed(0)) * 4
+    e_r, a_r = dvgo_ops.raw2alpha(dens, -6.9, 0.5)
+    e_k, a_k = ru.raw2alpha(dens.to(d), -6.9, 0.5)
+    assert rel_err(e_k, e_r) < 1e-6 and rel_err(a_k, a_r) < 1e-6
+    gb = torch.randn(5000, generator=torch.Generator().manual_seed(1))
+    assert rel_err(ru.raw2alpha_backward(e_k, gb.to(d), 0.5), dvgo_ops.raw2alpha_backward(e_r, gb, 0.5)) < 1e-5
+    alpha, rgb, ray_id, step_id, ray_start = _ragged_rays(300, 7)
+    w_r, T_r, l_r, s_r, en_r = dvgo_ops.alpha2weight(alpha, ray_id, 300)
+    w_k, T_k, l_k, s_k, en_k = ru.alpha2weight(alpha.to(d), ray_id.to(d), 300)
+    assert torch.equal(w_k.cpu(), w_r) and torch.equal(T_k.cpu(), T_r) and torch.equal(l_k.cpu(), l_r)
+    assert torch.equal(s_k.cpu(), s_r) and torch.equal(en_k.cpu(), en_r)
+    gw, gl = torch.randn(len(alpha)), torch.randn(300)
+    g_r = dvgo_ops.alpha2weight_backward(alpha, w_r, T_r, l_r, s_r, en_r, 300, gw, gl)
+    g_k = ru.alpha2weight_backward(alpha.to(d), w_k, T_k, l_k, s_k, en_k, 300, gw.to(d), gl.to(d))
+    assert rel_err(g_k, g_r) < 1e-5
+    # autograd wrappers (lib/tineuvox.py:627-670)
+    x = dens.to(d).requires_grad_(True)
+    al = Raw2Alpha.apply(x, -6.9, 0.5)
+    w, last = Alphas2Weights.apply(al[:len(alpha)], ray_id.to(d), 300)
+    (w.sum() + last.sum()).backward()
+    assert torch.isfinite(x.grad).all()
+    # CPU tensors are rejected, like CHECK_INPUT
+    with pytest.raises(RuntimeError):
+        ru.raw2alpha(dens, -6.9, 0.5)
