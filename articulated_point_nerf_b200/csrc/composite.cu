@@ -116,7 +116,7 @@ extern "C" int apn_composite_fwd(const float* alpha, const float* rgb, const int
   if (R <= 0) return 0;
   APN_CHECK_ARG(ray_start && rgb_marched && alphainv_last, "null pointer");
   APN_CHECK_ARG(n_extra >= 0 && n_extra <= COMP_MAX_EXTRA, "0 <= n_extra <= 4");
-  APN_CHECK_ARG(n_extra == 0 || (extra && extra_marched), "extra channels need in/out buffers");
+  APN_CHECK_ARG(n_extra == 0 || extra_marched, "extra channels need an output buffer");   // `extra` is NULL when M == 0
   composite_fwd_kernel<<<apn_div_up(R, 128), 128, 0, stream>>>(alpha, rgb, step_id, extra, n_extra, ray_start, R, thres, bg,
                                                               rgb_marched, alphainv_last, depth, extra_marched, T_save, n_used);
   APN_LAUNCH_CHECK();
@@ -129,7 +129,7 @@ extern "C" int apn_composite_bwd(const float* alpha, const float* rgb, const int
                                  const float* d_depth, float* d_alpha, float* d_rgb, apn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (R <= 0) return 0;
-  APN_CHECK_ARG(ray_start && T_save && n_used && alphainv_last && d_alpha && d_rgb, "null pointer");
+  APN_CHECK_ARG(ray_start && n_used && alphainv_last, "null pointer");   // per-sample arrays are NULL when M == 0
   composite_bwd_kernel<<<apn_div_up(R, 128), 128, 0, stream>>>(alpha, rgb, step_id, ray_start, R, thres, bg, T_save, n_used,
                                                               alphainv_last, d_rgb_marched, d_alphainv_last, d_depth, d_alpha,
                                                               d_rgb);

@@ -265,8 +265,8 @@ extern "C" size_t apn_scan_workspace_bytes(int n) { return apn_align(scan_temp_b
 extern "C" int apn_exclusive_scan_i32(const int32_t* in, int32_t* out, int n, void* ws, size_t ws_bytes,
                                       apn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  APN_CHECK_ARG(in && out && in != out, "need distinct in/out");
   APN_CHECK_ARG(n >= 0, "n < 0");
+  APN_CHECK_ARG(out && (n == 0 || (in && in != out)), "need distinct in/out");
   if (n > 0) {
     size_t tb = scan_temp_bytes(n);
     APN_CHECK_ARG(ws && ws_bytes >= tb, "scan workspace too small");

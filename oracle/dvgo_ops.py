@@ -31,6 +31,13 @@ def _f(x) -> torch.Tensor:
     return torch.tensor(float(np.float32(x)), dtype=F32)
 
 
+def _sqrt_rn(x: torch.Tensor) -> torch.Tensor:
+    """Correctly rounded fp32 square root (what CUDA's sqrtf / __fsqrt_rn return).  torch's vectorised CPU
+    sqrt is off by one ulp in near-halfway cases (observed: sqrt(1.0474659f) -> 0x1.060154p+0 instead of
+    0x1.060156p+0), numpy's is IEEE."""
+    return torch.from_numpy(np.sqrt(x.detach().contiguous().numpy()))
+
+
 # ----------------------------------------------------------------------------------
 # ray sampling
 # ----------------------------------------------------------------------------------
@@ -59,7 +66,7 @@ def infer_n_samples(t_min, t_max, stepdist):
 def infer_ray_start_dir(rays_o, rays_d, t_min):
     """render_utils_kernel.cu:52-73."""
     d0, d1, d2 = rays_d[:, 0], rays_d[:, 1], rays_d[:, 2]
-    rnorm = torch.sqrt((d0 * d0 + d1 * d1) + d2 * d2)
+    rnorm = _sqrt_rn((d0 * d0 + d1 * d1) + d2 * d2)
     start = rays_o + rays_d * t_min[:, None]
     direc = rays_d / rnorm[:, None]
     return start, direc
@@ -195,7 +202,7 @@ def _adam_core(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, eps, ma
     m = _f(b1) * exp_avg + _f(omb1) * grad
     v = _f(b2) * exp_avg_sq + (_f(omb2) * grad) * grad
     num = _f(ss) * m if perlr is None else (_f(ss) * perlr) * m
-    p = param - num / (torch.sqrt(v) + _f(eps))
+    p = param - num / (_sqrt_rn(v) + _f(eps))
     if mask is None:
         exp_avg.copy_(m), exp_avg_sq.copy_(v), param.copy_(p)
     else:

@@ -190,12 +190,43 @@ class OraclePath:
         self.time_poc = torch.tensor([2.0 ** i for i in range(timebase_pe)])
         J = state['joints'].shape[0]
         self.parent_indices, self.parent_joint_ex = build_tree(bones, J)
+        self.nn_i = self.nn_distance = None
         if mean_min_distance is None:
-            _, nn_i = knn_bruteforce(self.pcd, self.pcd, neighbours)
-            nd = torch.sqrt(((self.pcd[:, None] - self.pcd[nn_i]) ** 2).sum(-1) + eps)
-            mean_min_distance = nd[:, 1].mean()
+            self.neighbourhood()
+            mean_min_distance = self.nn_distance[:, 1].mean()
         self.mean_min_distance = torch.as_tensor(mean_min_distance, dtype=F32)
         self.trace: Dict[str, torch.Tensor] = {}
+
+    def neighbourhood(self):
+        """lib/temporalpoints.py:104-111: static 8-NN of the canonical cloud (self included)."""
+        if self.nn_i is None:
+            _, self.nn_i = knn_bruteforce(self.pcd, self.pcd, self.K)
+            self.nn_distance = torch.sqrt(((self.pcd[:, None] - self.pcd[self.nn_i]) ** 2).sum(-1) + self.eps)
+        return self.nn_i, self.nn_distance
+
+    # -- regulariser losses (lib/temporalpoints.py:714-733,797-800) -----------------------------
+    def arap_loss(self, warped_pcd):
+        nn_i, nn_d = self.neighbourhood()
+        d = torch.sqrt((warped_pcd[:, None, :] - warped_pcd[nn_i, :]).pow(2).sum(-1) + self.eps)
+        return (nn_d - d).abs().sum()
+
+    def weight_tv_loss(self, weights):
+        nn_i, _ = self.neighbourhood()
+        return torch.abs(weights[:, None, :] - weights[nn_i, :]).mean()
+
+    def sparsity_loss(self, weights):
+        return -(weights * torch.log(weights + self.eps) + (1 - weights) * torch.log(1 - weights + self.eps)).mean()
+
+    @staticmethod
+    def transformation_reg_loss(global_t, thetas):
+        return (global_t.abs().sum() + thetas.abs().sum()) / len(thetas)
+
+    def joint_chamfer_loss(self, skeleton_pcd):
+        """lib/temporalpoints.py:731-733,738-763 (get_raw=True, second direction): every joint to its nearest
+        skeleton point."""
+        joints = self.s['joints']
+        _, i2 = knn_bruteforce(joints.detach(), skeleton_pcd, 1)
+        return ((joints[:, None, :] - skeleton_pcd[i2, :]) ** 2).sum(-1).sum()
 
     # -- sub-networks ---------------------------------------------------------------
     def transform_net(self, x):

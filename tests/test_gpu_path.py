@@ -50,20 +50,56 @@ def test_repose_matches_reference_golden(golden_tiny):
         assert rel_err(out[k], ref[k]) < RTOL, k
 
 
+# Gradients that pass through the positional encoding of the canonical-frame offset inherit its 2^9 frequency
+# (lib/tineuvox.py:872-878 with posbase_pe=10) and the LeakyReLU kinks of feat_net layer 0: a 1-ulp change of the
+# warped cloud moves them by > 1e-4 in the reference's OWN arithmetic (tests/test_cpu_host.py::
+# test_reference_gradients_are_ill_conditioned_in_the_warped_cloud measures it on the CPU oracle).  They are
+# therefore checked at 1e-4 against the oracle evaluated on the kernel's warped cloud (same bits in, straight-
+# through graph), and only loosely against the golden file, whose cloud differs in the last bits.
+PE_AMPLIFIED = ("weights", "joints", "theta_weight", "canonical_feat", "feat_net.0.weight", "feat_net.0.bias",
+                "forward_warp.")
+GOLDEN_LOOSE = 5e-2
+
+
 def test_train_step_gradients_match_reference_golden(golden_tiny):
+    from conftest import oracle_from_golden
     g = golden_tiny
     model, scene = model_from_golden(g)
     rk = _rk(scene, g)
     model.zero_grad(set_to_none=True)
-    res = model(g["train"]["t"].cuda(), False, rk, render_pcd_direct=False, poses=scene.poses.cuda(), Ks=scene.Ks.cuda())
+    warped = model.warp(g["train"]["t"].cuda())
+    res = model(g["train"]["t"].cuda(), False, rk, render_pcd_direct=False, poses=scene.poses.cuda(), Ks=scene.Ks.cuda(),
+                warped=warped)
     loss = F.mse_loss(res["rgb_marched"], g["train"]["target"].cuda()) * 200.0
     loss.backward()
     assert abs(loss.item() - g["train"]["loss"].item()) < RTOL * g["train"]["loss"].item()
     assert rel_err(res["rgb_marched"], g["train"]["rgb_marched"]) < RTOL
     named = dict(model.named_parameters())
+    # (1) against the reference's golden gradients
     for k, ref in g["train"]["grads"].items():
         assert named[k].grad is not None, k
-        assert rel_err(named[k].grad, ref) < RTOL, k
+        tol = GOLDEN_LOOSE if k.startswith(PE_AMPLIFIED) else RTOL
+        assert rel_err(named[k].grad, ref) < tol, k
+    # (2) every gradient at 1e-4 against the oracle run on the kernel's own warped cloud: the oracle's warp keeps
+    # its autograd graph, its VALUES are replaced by the kernel's (straight-through)
+    orc, cfg = oracle_from_golden(g)
+    for k in g["train"]["grads"]:
+        orc.s[k].requires_grad_(True)
+    wp = orc.warp(g["train"]["t"])
+    Ginv = torch.inverse(wp["G"])
+    xyz_k = warped["xyz"].detach().cpu()
+    ginv_k = warped["ginv"].detach().cpu().view(-1, 3, 3)
+    assert rel_err(xyz_k, wp["xyz"]) < 1e-6 and rel_err(ginv_k, Ginv[:, :3, :3]) < 2e-6
+    xyz = wp["xyz"] + (xyz_k - wp["xyz"]).detach()
+    pad = torch.zeros_like(Ginv)
+    pad[:, :3, :3] = ginv_k - Ginv[:, :3, :3].detach()
+    Ginv = Ginv + pad
+    smp = orc.sample_and_knn(xyz, g["rays_o"], g["rays_d"], cfg.near, cfg.far, cfg.stepsize, 0.01)
+    rgb, alpha, *_ = orc.aggregate(xyz, Ginv, smp, g["viewdirs"], cfg.stepsize)
+    rgb_m, *_ = orc.composite(alpha, rgb, smp["ray_id"], smp["step_id"], len(g["rays_o"]), cfg.bg)
+    (F.mse_loss(rgb_m, g["train"]["target"]) * 200.0).backward()
+    for k in g["train"]["grads"]:
+        assert rel_err(named[k].grad, orc.s[k].grad) < RTOL, k
 
 
 def test_regulariser_losses_match_reference_golden(golden_tiny):

@@ -86,3 +86,20 @@ def test_empty_ray_batch_falls_back_to_background(oracle_tiny, golden_tiny):
                           far=cfg.far, stepsize=cfg.stepsize, bg=cfg.bg)
     assert out["alphainv_last"] is None
     assert torch.equal(out["rgb_marched"], torch.ones(7, 3) * cfg.bg)
+
+
+def test_regulariser_losses_match_reference(golden_tiny, oracle_tiny):
+    from articulated_point_nerf_b200.scene import make_scene
+    orc, cfg = oracle_tiny
+    g = golden_tiny
+    scene = make_scene(g["config"])
+    with torch.no_grad():
+        out = _call(orc, cfg, g, t=g["train"]["t"])
+        got = {"arap": orc.arap_loss(out["t_hat_pcd"]), "weight_tv": orc.weight_tv_loss(orc.trace["weights"]),
+               "sparsity": orc.sparsity_loss(orc.trace["weights"]),
+               "transformation_reg": orc.transformation_reg_loss(out["global_t"], out["thetas"]),
+               "joint_chamfer": orc.joint_chamfer_loss(scene.skeleton_pcd)}
+    assert torch.equal(orc.nn_i, g["nn_i"])
+    for k, v in got.items():
+        ref = float(g["losses"][k])
+        assert abs(float(v) - ref) <= 1e-4 * max(abs(ref), 1e-3), (k, float(v), ref)
