@@ -136,3 +136,49 @@ def stream() -> int:
 
 def launch_count() -> int:
     return int(load().apn_launch_count())
+
+
+class _StageTimer:
+    """Optional CUDA-event brackets around the C-ABI call groups (bench.py's per-stage breakdown and the
+    roofline of the dominant kernel group).  Disabled by default: zero overhead on the product path."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []          # (name, start_event, end_event)
+
+    def reset(self, enabled: bool):
+        self.enabled = enabled
+        self.records = []
+
+    def totals(self):
+        """name -> (calls, total ms); synchronises."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.records:
+            n, ms = out.get(name, (0, 0.0))
+            out[name] = (n + 1, ms + a.elapsed_time(b))
+        return out
+
+
+STAGES = _StageTimer()
+
+
+class stage:
+    """with stage("aggregate_fwd"): ...   (names follow the reference's profiler ranges where one exists)"""
+    __slots__ = ("name", "a")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if STAGES.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if STAGES.enabled:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            STAGES.records.append((self.name, self.a, b))
+        return False

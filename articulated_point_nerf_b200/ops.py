@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import AggGrads, AggInputs, AggOutputs, AdamTensor, MlpWeights, check, ptr, stream
+from ._lib import AggGrads, AggInputs, AggOutputs, AdamTensor, MlpWeights, check, ptr, stage, stream
 
 K_NEIGHBOURS = 8
 FEAT_DIM = 128
@@ -55,8 +55,9 @@ class _LBS(torch.autograd.Function):
         w_out = _empty((N, J), dev)
         g_out = _empty((N, 4, 4), dev) if want_frames else None
         bbox = _empty((6,), dev)
-        check(lib.apn_lbs_fwd(ptr(raw_w), ptr(theta_weight), float(eps), ptr(rules), ptr(bone_T), ptr(xyz), ptr(global_t),
-                              N, J, ptr(xyz_out), ptr(ginv), ptr(w_out), ptr(g_out), ptr(bbox), stream()), "apn_lbs_fwd")
+        with stage("forward_warp"):
+            check(lib.apn_lbs_fwd(ptr(raw_w), ptr(theta_weight), float(eps), ptr(rules), ptr(bone_T), ptr(xyz), ptr(global_t),
+                                  N, J, ptr(xyz_out), ptr(ginv), ptr(w_out), ptr(g_out), ptr(bbox), stream()), "apn_lbs_fwd")
         ctx.save_for_backward(raw_w, theta_weight, bone_T, xyz, ginv, rules)
         ctx.eps = float(eps)
         ctx.has_gt = global_t is not None
@@ -80,9 +81,10 @@ class _LBS(torch.autograd.Function):
         d_gt = _empty((3,), dev)
         ws_bytes = lib.apn_lbs_bwd_workspace_bytes(N, J)
         ws = _empty((ws_bytes,), dev, torch.uint8)
-        check(lib.apn_lbs_bwd(ptr(raw_w), ptr(theta_weight), ctx.eps, ptr(rules), ptr(bone_T), ptr(xyz), N, J, ptr(ginv),
-                              ptr(d_xyz), ptr(d_ginv), ptr(d_w), ptr(d_g), ptr(d_raw), ptr(d_theta), ptr(d_bone), ptr(d_gt),
-                              ptr(ws), ws_bytes, stream()), "apn_lbs_bwd")
+        with stage("forward_warp_bwd"):
+            check(lib.apn_lbs_bwd(ptr(raw_w), ptr(theta_weight), ctx.eps, ptr(rules), ptr(bone_T), ptr(xyz), N, J, ptr(ginv),
+                                  ptr(d_xyz), ptr(d_ginv), ptr(d_w), ptr(d_g), ptr(d_raw), ptr(d_theta), ptr(d_bone), ptr(d_gt),
+                                  ptr(ws), ws_bytes, stream()), "apn_lbs_bwd")
         return (d_raw, None if d_theta is None else d_theta.reshape(theta_weight.shape), d_bone,
                 (d_gt if ctx.has_gt else None), None, None, None, None)
 
@@ -113,8 +115,9 @@ class Grid:
         self.cell_capacity = cell_capacity
         self.bytes = lib.apn_grid_workspace_bytes(self.N, cell_capacity)
         self.blob = _empty((self.bytes,), self.xyz.device, torch.uint8)
-        check(lib.apn_grid_build(ptr(self.xyz), ptr(_f32(bbox)), self.N, float(query_radius), float(bbox_pad),
-                                 float(cell_hint), cell_capacity, ptr(self.blob), self.bytes, stream()), "apn_grid_build")
+        with stage("grid_build"):
+            check(lib.apn_grid_build(ptr(self.xyz), ptr(_f32(bbox)), self.N, float(query_radius), float(bbox_pad),
+                                     float(cell_hint), cell_capacity, ptr(self.blob), self.bytes, stream()), "apn_grid_build")
 
     def describe(self) -> dict:
         """Synchronising debug helper: header fields of the grid."""
@@ -172,6 +175,11 @@ class Samples:
 def sample_and_knn(grid: Grid, rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far: float, stepdist: float,
                    return_d2: bool = False):
     """sample_ray + Kmin_argKmin + radius rule, fused (lib/temporalpoints.py:421-447)."""
+    with stage("sample_ray+knn"):
+        return _sample_and_knn(grid, rays_o, rays_d, near, far, stepdist, return_d2)
+
+
+def _sample_and_knn(grid, rays_o, rays_d, near, far, stepdist, return_d2):
     lib = _lib.load()
     rays_o, rays_d = _f32(rays_o), _f32(rays_d)
     R = rays_o.shape[0]
@@ -292,8 +300,9 @@ class _Aggregate(torch.autograd.Function):
             else:
                 scratch_bytes = lib.apn_aggregate_scratch_bytes(M, d_in)
                 scratch = _empty((scratch_bytes,), dev, torch.uint8)
-            check(lib.apn_aggregate_fwd(C.byref(a), C.byref(w), C.byref(out), ptr(scratch), scratch_bytes, stream()),
-                  "apn_aggregate_fwd")
+            with stage("feat_net"):
+                check(lib.apn_aggregate_fwd(C.byref(a), C.byref(w), C.byref(out), ptr(scratch), scratch_bytes, stream()),
+                      "apn_aggregate_fwd")
         ctx.c, ctx.saved, ctx.d_in = c, saved, d_in
         ctx.tensors = (xyz, ginv, feat, pose_emb, ws, alpha, rgb, idw)
         ctx.mark_non_differentiable(idw)
@@ -336,8 +345,9 @@ class _Aggregate(torch.autograd.Function):
             w = _mlp_struct(ws)
             sb = lib.apn_aggregate_bwd_scratch_bytes(M, ctx.d_in)
             scratch = _empty((sb,), dev, torch.uint8)
-            check(lib.apn_aggregate_bwd(C.byref(a), C.byref(w), C.byref(out), C.byref(g), ptr(scratch), sb, stream()),
-                  "apn_aggregate_bwd")
+            with stage("feat_net_bwd"):
+                check(lib.apn_aggregate_bwd(C.byref(a), C.byref(w), C.byref(out), C.byref(g), ptr(scratch), sb, stream()),
+                      "apn_aggregate_bwd")
         ctx.saved = None
         if d_pose is not None and pose_emb is not None:
             d_pose = d_pose.reshape(pose_emb.shape)
@@ -371,9 +381,10 @@ class _Composite(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         T_save = _empty((M,), dev) if need_grad else None
         n_used = _empty((R,), dev, torch.int32) if need_grad else None
-        check(lib.apn_composite_fwd(ptr(alpha), ptr(rgb), ptr(step_id) if want_depth else None, ptr(extra), n_extra,
-                                    ptr(ray_start), R, float(thres), float(bg), ptr(rgb_m), ptr(last), ptr(depth),
-                                    ptr(extra_m), ptr(T_save), ptr(n_used), stream()), "apn_composite_fwd")
+        with stage("Alphas2Weights"):
+            check(lib.apn_composite_fwd(ptr(alpha), ptr(rgb), ptr(step_id) if want_depth else None, ptr(extra), n_extra,
+                                        ptr(ray_start), R, float(thres), float(bg), ptr(rgb_m), ptr(last), ptr(depth),
+                                        ptr(extra_m), ptr(T_save), ptr(n_used), stream()), "apn_composite_fwd")
         ctx.save_for_backward(alpha, rgb, step_id, ray_start, T_save, n_used, last)
         ctx.meta = (R, float(thres), float(bg), want_depth)
         outs = [rgb_m, last, depth if want_depth else torch.zeros(0, device=dev),
@@ -391,9 +402,10 @@ class _Composite(torch.autograd.Function):
         d_rgb_m = None if d_rgb_m is None else _f32(d_rgb_m)
         d_last = None if d_last is None else _f32(d_last)
         d_depth = _f32(d_depth) if (want_depth and d_depth is not None) else None
-        check(lib.apn_composite_bwd(ptr(alpha), ptr(rgb), ptr(step_id) if want_depth else None, ptr(ray_start), R, thres, bg,
-                                    ptr(T_save), ptr(n_used), ptr(last), ptr(d_rgb_m), ptr(d_last), ptr(d_depth),
-                                    ptr(d_alpha), ptr(d_rgb), stream()), "apn_composite_bwd")
+        with stage("Alphas2Weights_bwd"):
+            check(lib.apn_composite_bwd(ptr(alpha), ptr(rgb), ptr(step_id) if want_depth else None, ptr(ray_start), R, thres, bg,
+                                        ptr(T_save), ptr(n_used), ptr(last), ptr(d_rgb_m), ptr(d_last), ptr(d_depth),
+                                        ptr(d_alpha), ptr(d_rgb), stream()), "apn_composite_bwd")
         return d_alpha, d_rgb, None, None, None, None, None, None, None
 
 
@@ -425,4 +437,5 @@ def adam_multi(entries, beta1: float, beta2: float, eps: float) -> None:
         arr[i].numel = p.numel()
         arr[i].step_size = ss
         arr[i].mode = mode
-    check(lib.apn_adam_multi(C.cast(arr, C.c_void_p), len(entries), beta1, beta2, eps, stream()), "apn_adam_multi")
+    with stage("adam"):
+        check(lib.apn_adam_multi(C.cast(arr, C.c_void_p), len(entries), beta1, beta2, eps, stream()), "apn_adam_multi")

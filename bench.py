@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the PCD hot path (BASELINE.json metric: rays/s, train fwd+bwd+Adam / render fwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4|c1|c3|c5] [--impl reference]
+
+Default workload = BASELINE.json configs[1] ("c2"): jumpingjacks-shaped stage-2 training step, 8192-ray batch,
+forward + render-loss backward + (masked) Adam over the reference's parameter groups.  Render workloads
+(c1/c3/c5) time one whole frame per step.  Data: seeded synthetic scene of the reference's shapes
+(articulated_point_nerf_b200/scene.py), random-init weights of the reference's architecture.
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step through the public
+Python surface with HOST (pinned) inputs, H2D copy + loss/frame D2H inside the timed region.
+L2 is flushed (256 MiB write) between timed steps; every step is bracketed by CUDA events on the launching
+stream; max over ranks.  `--impl reference` times the CPU port of the reference path (oracle/) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+TRAIN_WORKLOADS = {"c2": "c2", "c4": "c4", "tiny": "tiny", "small": "small"}
+RENDER_WORKLOADS = {"c1": "c1", "c3": "c3", "c5": "c5", "tiny_render": "tiny", "small_render": "small"}
+N_RAND = 8192                      # configs/nerf/default.py:114
+METRIC = {"train": "rays/sec (PCD train step: fwd+bwd+Adam)", "render": "rays/sec (PCD render fwd)"}
+
+
+# ----------------------------------------------------------------------------------------------
+# workload construction (CPU, seeded): identical for both arms
+# ----------------------------------------------------------------------------------------------
+def make_batches(scene, mode, n_steps, rank, n_rand=N_RAND):
+    """Per step: (t, rays_o, rays_d, viewdirs, target) on the host.  Train: n_rand random pixels of one view
+    (run.py:587-601: a D-NeRF time step is one image); render: every pixel of one view."""
+    out = []
+    n_views = len(scene.HW)
+    cache = {}
+    for i in range(n_steps):
+        v = (i + 3 * rank) % n_views
+        if v not in cache:
+            cache[v] = [x.reshape(-1, 3).contiguous() for x in scene.rays(v)]
+        ro, rd, vd = cache[v]
+        t = torch.tensor([v / max(n_views - 1, 1)], dtype=torch.float32)
+        if mode == "train":
+            g = torch.Generator().manual_seed(1000 * rank + i)
+            sel = torch.randint(0, len(ro), (n_rand,), generator=g)
+            tgt = torch.rand(n_rand, 3, generator=g)
+            out.append((t, ro[sel].contiguous(), rd[sel].contiguous(), vd[sel].contiguous(), tgt))
+        else:
+            out.append((t, ro, rd, vd, None))
+    return out
+
+
+def pack_host(batch, pin):
+    """One contiguous host buffer per step: [rays_o | rays_d | viewdirs | target] (R, 9 or 12) + t."""
+    t, ro, rd, vd, tgt = batch
+    parts = [ro, rd, vd] + ([tgt] if tgt is not None else [])
+    buf = torch.cat(parts, dim=1).contiguous()
+    if pin:
+        buf = buf.pin_memory()
+        t = t.pin_memory()
+    return t, buf
+
+
+def unpack_dev(t_dev, buf_dev):
+    ro, rd, vd = buf_dev[:, 0:3].contiguous(), buf_dev[:, 3:6].contiguous(), buf_dev[:, 6:9].contiguous()
+    tgt = buf_dev[:, 9:12].contiguous() if buf_dev.shape[1] >= 12 else None
+    return t_dev, ro, rd, vd, tgt
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, f"/tmp/apn_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+                for n, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(n)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# algorithmic work of the decoder, from measured counts
+# ----------------------------------------------------------------------------------------------
+def decoder_flops(M, d_in, train):
+    fwd = M * 8 * 2 * (d_in * 128 + 3 * 128 * 128) + M * 2 * (128 * 128 + 155 * 64 + 64 * 3 + 128)
+    return fwd * (3 if train else 1)        # backward = dgrad + wgrad = 2x forward
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (oracle/), all host threads
+# ----------------------------------------------------------------------------------------------
+class OracleArm:
+    def __init__(self, scene, model_state, mode):
+        from oracle.path_oracle import OraclePath
+        from oracle import dvgo_ops
+        self.dvgo = dvgo_ops
+        cfg = scene.cfg
+        self.scene, self.cfg, self.mode = scene, cfg, mode
+        state = {k: v.detach().cpu().clone() for k, v in model_state["state"].items()}
+        self.orc = OraclePath(state, scene.canonical_pcd, scene.bones, stepsize=cfg.stepsize, voxel_size=scene.voxel_size,
+                              fast_color_thres=cfg.fast_color_thres, act_shift=model_state["act_shift"],
+                              voxel_size_ratio=model_state["voxel_size_ratio"], pose_embedding_dim=cfg.pose_embedding_dim,
+                              mean_min_distance=model_state["mean_min_distance"])
+        from articulated_point_nerf_b200.train import STAGE2_LRATES
+        self.groups = []
+        for name in ("rgbnet", "densitynet", "canonical_feat", "gammas", "weights", "theta_weight", "forward_warp", "joints",
+                     "feat_net"):
+            ks = [k for k in state if (k == name or k.startswith(name + ".")) and state[k].is_floating_point()]
+            self.groups.append((STAGE2_LRATES[name], ks))
+        self.trainable = [k for _, ks in self.groups for k in ks]
+        self.adam = {k: (torch.zeros_like(state[k]), torch.zeros_like(state[k])) for k in self.trainable}
+        self.step_no = 0
+
+    def step(self, batch, n_rays=None):
+        t, ro, rd, vd, tgt = batch
+        if n_rays is not None and n_rays < len(ro):
+            ro, rd, vd = ro[:n_rays], rd[:n_rays], vd[:n_rays]
+            tgt = None if tgt is None else tgt[:n_rays]
+        cfg, orc = self.cfg, self.orc
+        kw = dict(rays_o=ro, rays_d=rd, viewdirs=vd, near=cfg.near, far=cfg.far, stepsize=cfg.stepsize, bg=cfg.bg)
+        if self.mode == "render":
+            with torch.no_grad():
+                # the reference renders a frame in 8192-ray chunks, re-warping per chunk (run.py:136-166)
+                outs = []
+                for s in range(0, len(ro), N_RAND):
+                    kwc = dict(kw, rays_o=ro[s:s + N_RAND], rays_d=rd[s:s + N_RAND], viewdirs=vd[s:s + N_RAND])
+                    outs.append(orc.forward(t, **kwc)["rgb_marched"])
+                return torch.cat(outs)
+        for k in self.trainable:
+            orc.s[k].requires_grad_(True)
+            orc.s[k].grad = None
+        out = orc.forward(t, **kw)
+        loss = 200.0 * torch.nn.functional.mse_loss(out["rgb_marched"], tgt)
+        if loss.requires_grad:
+            loss.backward()
+        self.step_no += 1
+        with torch.no_grad():
+            for lr, ks in self.groups:
+                for k in ks:
+                    p = orc.s[k]
+                    if p.grad is None:
+                        continue
+                    m, v = self.adam[k]
+                    self.dvgo.adam_upd(p, p.grad, m, v, self.step_no, 0.9, 0.99, lr, 1e-8)
+        return loss.detach()
+
+
+def time_oracle(arm, batches, steps, warmup, budget_s):
+    """Bounded sample: rays per step are cut so that warmup+steps fit the budget (calibrated on one step)."""
+    R = len(batches[0][1])
+    t0 = time.perf_counter()
+    arm.step(batches[0], min(R, 1024))
+    probe = time.perf_counter() - t0
+    # cost model: fixed (warp, tables) + per-ray; the 1024-ray probe over-estimates the per-ray part
+    n = int(min(R, max(512, 1024 * (budget_s / max(steps + warmup, 1)) / max(probe, 1e-3))))
+    for i in range(warmup):
+        arm.step(batches[i % len(batches)], n)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        arm.step(batches[(warmup + i) % len(batches)], n)
+    dt = time.perf_counter() - t0
+    return n, dt / max(steps, 1)
+
+
+# ----------------------------------------------------------------------------------------------
+def model_state_for_oracle(model):
+    return {"state": {k: v for k, v in model.state_dict().items() if not k.startswith("tineuvox.")},
+            "act_shift": float(model.tineuvox.act_shift), "voxel_size_ratio": float(model.tineuvox.voxel_size_ratio),
+            "mean_min_distance": None}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--decoder", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="print the per-stage CUDA-event breakdown to stderr")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    mode = "train" if args.workload in TRAIN_WORKLOADS else "render"
+    cfg_name = TRAIN_WORKLOADS.get(args.workload) or RENDER_WORKLOADS[args.workload]
+
+    from articulated_point_nerf_b200.scene import build_model, make_scene
+    scene = make_scene(cfg_name)
+    n_steps = args.steps + args.warmup
+    base_cfg = {"workload": f"{args.workload}: {mode}, N={len(scene.canonical_pcd)} points, J={len(scene.joints)}, "
+                            f"{'%d-ray batch of one %dx%d view' % (N_RAND, scene.cfg.H, scene.cfg.W) if mode == 'train' else 'one %dx%d frame' % (scene.cfg.H, scene.cfg.W)} per step per GPU",
+                "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"rays sharded, dp{args.gpus}"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 1)
+        model = build_model(scene, seed=0)
+        arm = OracleArm(scene, model_state_for_oracle(model), mode)
+        batches = make_batches(scene, mode, min(n_steps, 8), 0)
+        n, sec = time_oracle(arm, batches, args.steps, args.warmup, args.ref_budget)
+        val = n / sec
+        sample = f"{n} of {len(batches[0][1])} rays per step, {args.steps} steps, oracle port (torch-CPU fp32, brute-force k-NN)"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC[mode], "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg,
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from articulated_point_nerf_b200 import _lib
+    from articulated_point_nerf_b200.train import GradBucket, create_optimizer, train_step
+
+    model = build_model(scene, seed=0)
+    oracle_state = model_state_for_oracle(model) if (rank == 0 and not args.no_cpu_baseline and world == 1) else None
+    if oracle_state is not None:
+        oracle_state["state"] = {k: v.detach().clone() for k, v in oracle_state["state"].items()}
+    model = model.to(dev)
+    if args.decoder != "auto":
+        model.decoder = args.decoder
+    host = [pack_host(b, pin=True) for b in make_batches(scene, mode, n_steps, rank)]
+    rk = scene.render_kwargs()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    opt = bucket = None
+    if mode == "train":
+        opt = create_optimizer(model)
+        bucket = GradBucket(opt)
+    decay = 0.1 ** (1.0 / (160 * 1000))
+    counts = []
+
+    def run_step(t_dev, buf_dev):
+        t, ro, rd, vd, tgt = unpack_dev(t_dev, buf_dev)
+        kw = dict(rk, rays_o=ro, rays_d=rd, viewdirs=vd)
+        if mode == "train":
+            out = train_step(model, opt, bucket, t, kw, tgt, decay_factor=decay)
+        else:
+            with torch.no_grad():
+                out = model(t, render_depth=True, render_kwargs=kw)["rgb_marched"]
+        counts.append(dict(model.last_counts))
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(e2e: bool):
+        dev_in = None if e2e else [(t.to(dev), b.to(dev)) for t, b in host]
+        for i in range(args.warmup):
+            t_d, b_d = (host[i][0].to(dev, non_blocking=True), host[i][1].to(dev, non_blocking=True)) if e2e else dev_in[i]
+            o = run_step(t_d, b_d)
+            if e2e:
+                (o.item() if mode == "train" else o.cpu())
+        counts.clear()
+        barrier()
+        _lib.STAGES.reset(not e2e)
+        evs = []
+        n0 = _lib.launch_count()
+        for i in range(args.warmup, n_steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if e2e:
+                t_d, b_d = host[i][0].to(dev, non_blocking=True), host[i][1].to(dev, non_blocking=True)
+            else:
+                t_d, b_d = dev_in[i]
+            o = run_step(t_d, b_d)
+            if e2e:
+                (o.item() if mode == "train" else o.cpu())
+            b.record()
+            evs.append((a, b))
+        barrier()
+        launches = _lib.launch_count() - n0
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), launches
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    total_ms, launches = timed_loop(e2e=False)
+    clk = clocks.stop()
+    stage_tot = _lib.STAGES.totals()
+    _lib.STAGES.reset(False)
+    timed_counts = list(counts)
+    e2e_ms, _ = timed_loop(e2e=True)
+
+    rays_per_step = len(host[0][1])
+    value = rays_per_step * world * args.steps / (total_ms * 1e-3)
+    e2e_val = rays_per_step * world * args.steps / (e2e_ms * 1e-3)
+    h2d = host[0][1].numel() * 4 + 4
+    d2h = 4 if mode == "train" else rays_per_step * 3 * 4
+
+    # roofline of the dominant kernel group: the decoder (feat_net + heads; fwd [+ bwd]) — the only dense contraction
+    M_sum = sum(c.get("M", 0) for c in timed_counts[:args.steps])
+    d_in = 191 + scene.cfg.pose_embedding_dim
+    dec_ms = sum(ms for name, (n, ms) in stage_tot.items() if name.startswith("feat_net"))
+    dec_ms_timed = dec_ms          # stage events cover exactly the timed steps
+    flops = decoder_flops(M_sum, d_in, mode == "train")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    ach_tf = flops / max(dec_ms_timed * 1e-3, 1e-9) / 1e12
+    roofline = {"kernel": "decoder (feat_net + heads%s), %s path" % (" fwd+bwd" if mode == "train" else "", model.decoder),
+                "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else
+                "fallback 1.4 PFLOP/s sustained (of fallback)",
+                "decoder_ms_per_step": dec_ms_timed / args.steps, "kept_samples_per_step": M_sum / max(args.steps, 1)}
+    if args.stages and rank == 0:
+        for name, (n, ms) in sorted(stage_tot.items(), key=lambda kv: -kv[1][1]):
+            print(f"  stage {name:22s} calls {n:4d}  total {ms:9.3f} ms  avg {ms / n:8.4f} ms", file=sys.stderr)
+
+    cpu_baseline = None
+    if oracle_state is not None:
+        torch.set_num_threads(os.cpu_count() or 1)
+        arm = OracleArm(scene, oracle_state, mode)
+        batches = make_batches(scene, mode, 3, 0)
+        n, sec = time_oracle(arm, batches, 2, 0, args.cpu_budget)
+        cpu_baseline = {"value": n / sec, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{n} of {len(batches[0][1])} rays per step, 2 steps after a 1024-ray probe, oracle port "
+                                  f"(torch-CPU fp32, brute-force k-NN) of the same workload"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC[mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg, "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "counts": {"kept_samples_per_step": M_sum / max(args.steps, 1),
+                       "candidates_per_step": sum(c.get("candidates", 0) for c in timed_counts[:args.steps]) / max(args.steps, 1)},
+            "stages_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in stage_tot.items()}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
