@@ -337,88 +337,138 @@ extern "C" int apn_ray_candidates(const float* rays_o, const float* rays_d, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// k-NN
+// k-NN: one WARP per query.
+//   * the 27 neighbour cells of the current level are fetched by lanes 0..26 (two cell_start
+//     loads each), their point ranges are flattened with a warp prefix sum, and the warp then
+//     walks the concatenated list 32 points at a time (coalesced float4 loads of `sorted`);
+//   * the running top-8 lives in lanes 0..7 as sorted 64-bit keys (d2 bits << 32 | index, i.e.
+//     lexicographic (d2, index): the tie-break of the neighbour contract);
+//   * a point is inserted only if its key beats the current threshold.  The threshold starts
+//     at the level's certified radius (a farther point could not be certified at this level
+//     anyway) and tightens to the 8th best, so insertions become rare after the first chunk.
 // ---------------------------------------------------------------------------------------
 #define KEY_INF 0x7f800000ffffffffull  // (+inf, max index)
+#define FULL_MASK 0xffffffffu
 
-template <int K>
-__device__ __forceinline__ void topk_insert(unsigned long long (&b)[K], unsigned long long key) {
-  if (key < b[K - 1]) {
-    b[K - 1] = key;
-#pragma unroll
-    for (int i = K - 1; i > 0; --i) {
-      const unsigned long long lo = b[i - 1], hi = b[i];
-      const bool sw = hi < lo;
-      b[i - 1] = sw ? hi : lo;
-      b[i] = sw ? lo : hi;
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+  return __shfl_sync(FULL_MASK, v, src);
+}
+
+// lanes 0..7 hold the sorted best keys; inserts k (k < best[7] is the caller's business)
+__device__ __forceinline__ void warp_topk_insert(unsigned long long& best, unsigned long long k, int lane) {
+  const unsigned long long up = __shfl_up_sync(FULL_MASK, best, 1);
+  if (lane < APN_K && best > k) best = (lane > 0 && up > k) ? up : k;
+}
+
+// offers one key per lane (KEY_INF = nothing) to the warp's top-8
+__device__ __forceinline__ void warp_topk_offer(unsigned long long& best, unsigned long long& thr, unsigned long long key,
+                                                int lane) {
+  unsigned int m = __ballot_sync(FULL_MASK, key < thr);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const unsigned long long k = shfl_u64(key, src);
+    if (k < thr) {
+      warp_topk_insert(best, k, lane);
+      const unsigned long long b7 = shfl_u64(best, APN_K - 1);
+      thr = b7 < thr ? b7 : thr;
     }
   }
 }
 
-__device__ __forceinline__ void scan_range(const float4* __restrict__ sorted, int s, int e, float qx, float qy, float qz,
-                                           unsigned long long (&best)[APN_K]) {
-  for (int i = s; i < e; ++i) {
-    const float4 P = __ldg(sorted + i);
-    const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
-    const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
-    topk_insert<APN_K>(best, key);
+__device__ __forceinline__ void warp_scan_range(const float4* __restrict__ sorted, int s, int e, float qx, float qy, float qz,
+                                                unsigned long long& best, unsigned long long& thr, int lane) {
+  for (int base = s; base < e; base += 32) {
+    const int i = base + lane;
+    unsigned long long key = KEY_INF;
+    if (i < e) {
+      const float4 P = __ldg(sorted + i);
+      const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
+      key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
+    }
+    warp_topk_offer(best, thr, key, lane);
   }
 }
 
-// Exact K-NN of q.  If bounded, returns false as soon as it is certain that the K-th squared
-// distance exceeds r2.  Unbounded queries fall back to a full scan when the top level cannot
-// certify the result (never happens for queries inside a dense cloud).
-__device__ bool knn_search(const GridView& g, float qx, float qy, float qz, bool bounded,
-                           unsigned long long (&best)[APN_K]) {
+// Exact K-NN of q by one warp; the result (sorted keys) is left in `best` of lanes 0..7.  If bounded,
+// returns false as soon as it is certain that the K-th squared distance exceeds r2.  Unbounded
+// queries fall back to a full scan when the top level cannot certify the result (never happens
+// for queries inside a dense cloud).
+__device__ bool knn_search_warp(const GridView& g, float qx, float qy, float qz, bool bounded, unsigned long long& best,
+                                int lane) {
   const GridHeader* h = g.h;
   const int L = h->L, tx = h->top_dim[0], ty = h->top_dim[1], tz = h->top_dim[2];
   const float lx0 = qx - h->origin[0], ly0 = qy - h->origin[1], lz0 = qz - h->origin[2];
+  const float r2 = h->r2, cell = h->cell;
   int ix, iy, iz;
   point_cell(h, qx, qy, qz, ix, iy, iz);
+  // neighbour offset of this lane (lanes 27..31 idle during the gather)
+  const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
   int l = 0;
   while (true) {
-#pragma unroll
-    for (int k = 0; k < APN_K; ++k) best[k] = KEY_INF;
     const int cx = ix >> l, cy = iy >> l, cz = iz >> l;
     const int dxm = tx << (L - l), dym = ty << (L - l), dzm = tz << (L - l);
-    const int span = 1 << (3 * l);
-    for (int dz = -1; dz <= 1; ++dz) {
-      const int nz = cz + dz;
-      if (nz < 0 || nz >= dzm) continue;
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int ny = cy + dy;
-        if (ny < 0 || ny >= dym) continue;
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int nx = cx + dx;
-          if (nx < 0 || nx >= dxm) continue;
-          const int key = cell_key(nx << l, ny << l, nz << l, L, tx, ty);
-          const int s = __ldg(g.cell_start + key), e = __ldg(g.cell_start + key + span);
-          scan_range(g.sorted, s, e, qx, qy, qz, best);
-        }
-      }
-    }
-    const float d8 = __uint_as_float((unsigned int)(best[APN_K - 1] >> 32));
-    const float sl = h->cell * (float)(1 << l);
+    // certified radius of this level
+    const float sl = cell * (float)(1 << l);
     const float mx = fminf(lx0 - cx * sl, (cx + 1) * sl - lx0);
     const float my = fminf(ly0 - cy * sl, (cy + 1) * sl - ly0);
     const float mz = fminf(lz0 - cz * sl, (cz + 1) * sl - lz0);
     const float gr = (sl + fminf(mx, fminf(my, mz))) * 0.999f;
-    if (gr > 0.f && d8 <= gr * gr) return !bounded || d8 <= h->r2;
-    if (bounded && gr > 0.f && gr * gr > h->r2 && d8 > h->r2) return false;  // every unseen point is farther than rq
-    if (l == L) {
-      if (bounded) return false;
+    const float gr2 = gr > 0.f ? gr * gr : 0.f;
+    const bool last = (l == L);
+    // at the last level an unbounded query must keep everything it sees (it falls back to a full scan otherwise)
+    unsigned long long thr = ((unsigned long long)__float_as_uint(gr2) << 32) | 0xffffffffull;
+    best = KEY_INF;
+    // gather the (up to) 27 ranges
+    int s = 0, n = 0;
+    {
+      const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
+      if (lane < 27 && nx >= 0 && ny >= 0 && nz >= 0 && nx < dxm && ny < dym && nz < dzm) {
+        const int key = cell_key(nx << l, ny << l, nz << l, L, tx, ty);
+        s = __ldg(g.cell_start + key);
+        n = __ldg(g.cell_start + key + (1 << (3 * l))) - s;
+      }
+    }
+    int incl = n;
 #pragma unroll
-      for (int k = 0; k < APN_K; ++k) best[k] = KEY_INF;
-      scan_range(g.sorted, 0, h->n_points, qx, qy, qz, best);
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    for (int base = 0; base < total; base += 32) {
+      const int j = base + lane;
+      // cell holding flattened index j: number of cells with incl <= j
+      int c = 0;
+#pragma unroll
+      for (int st = 16; st > 0; st >>= 1) {
+        const int v = __shfl_sync(FULL_MASK, incl, c + st - 1);
+        if (j >= v) c += st;
+      }
+      c = min(c, 31);
+      const int cs = __shfl_sync(FULL_MASK, s, c);
+      const int ci = __shfl_sync(FULL_MASK, incl, c);
+      const int cn = __shfl_sync(FULL_MASK, n, c);
+      unsigned long long key = KEY_INF;
+      if (j < total) {
+        const float4 P = __ldg(g.sorted + cs + (j - (ci - cn)));
+        const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
+        key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
+      }
+      warp_topk_offer(best, thr, key, lane);
+    }
+    const unsigned long long b7 = shfl_u64(best, APN_K - 1);
+    const float d8 = __uint_as_float((unsigned int)(b7 >> 32));   // +inf when fewer than 8 points inside gr
+    if (gr > 0.f && d8 <= gr2) return !bounded || d8 <= r2;
+    if (bounded && gr > 0.f && gr2 > r2) return false;              // every unseen point is farther than sqrt(r2)
+    if (last) {
+      if (bounded) return false;
+      best = KEY_INF;
+      thr = KEY_INF;
+      warp_scan_range(g.sorted, 0, h->n_points, qx, qy, qz, best, thr, lane);
       return true;
     }
-    // next level: cell edge must cover the K-th distance found so far (if any)
-    int nl = l + 1;
-    if (d8 < INFINITY) {
-      const float need = sqrtf(d8) * 1.002f;
-      while (nl < L && h->cell * (float)(1 << nl) < need) ++nl;
-    }
-    l = nl;
+    ++l;
   }
 }
 
@@ -427,25 +477,20 @@ knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, f
            const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand,
            int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep) {
   const GridView g = grid_view(blob);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cand) return;
   const GridHeader* h = g.h;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
   const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
-  const RaySetup s = ray_setup(rays_o, rays_d, cand_ray[i], bmin, bmax, near, far, stepdist);
-  float px, py, pz;
-  ray_point(s, cand_step[i], stepdist, px, py, pz);
-  unsigned long long best[APN_K];
-  const bool ok = knn_search(g, px, py, pz, true, best);
-  keep[i] = ok ? 1 : 0;
-  if (ok) {
-    int4 a, b;
-    a.x = (int)(unsigned int)best[0]; a.y = (int)(unsigned int)best[1]; a.z = (int)(unsigned int)best[2]; a.w = (int)(unsigned int)best[3];
-    b.x = (int)(unsigned int)best[4]; b.y = (int)(unsigned int)best[5]; b.z = (int)(unsigned int)best[6]; b.w = (int)(unsigned int)best[7];
-    reinterpret_cast<int4*>(nn_idx)[2 * (size_t)i] = a;
-    reinterpret_cast<int4*>(nn_idx)[2 * (size_t)i + 1] = b;
-    if (nn_d2) {
-#pragma unroll
-      for (int k = 0; k < APN_K; ++k) nn_d2[(size_t)i * APN_K + k] = __uint_as_float((unsigned int)(best[k] >> 32));
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_cand; i += warps) {
+    const RaySetup s = ray_setup(rays_o, rays_d, __ldg(cand_ray + i), bmin, bmax, near, far, stepdist);
+    float px, py, pz;
+    ray_point(s, __ldg(cand_step + i), stepdist, px, py, pz);
+    unsigned long long best;
+    const bool ok = knn_search_warp(g, px, py, pz, true, best, lane);
+    if (lane == 0) keep[i] = ok ? 1 : 0;
+    if (ok && lane < APN_K) {
+      nn_idx[(size_t)i * APN_K + lane] = (int)(unsigned int)best;
+      if (nn_d2) nn_d2[(size_t)i * APN_K + lane] = __uint_as_float((unsigned int)(best >> 32));
     }
   }
 }
@@ -456,8 +501,9 @@ extern "C" int apn_knn(const float* rays_o, const float* rays_d, float near, flo
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_cand <= 0) return 0;
   APN_CHECK_ARG(rays_o && rays_d && grid && cand_ray && cand_step && nn_idx && keep, "null pointer");
-  knn_kernel<<<apn_div_up(n_cand, 128), 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand,
-                                                         nn_idx, nn_d2, keep);
+  const int blocks = min(apn_div_up(n_cand, 4), APN_SM_COUNT * 16);   // 4 warps (queries) per block, persistent grid-stride
+  knn_kernel<<<blocks, 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand, nn_idx, nn_d2,
+                                         keep);
   APN_LAUNCH_CHECK();
   return 0;
 }
@@ -506,20 +552,16 @@ __global__ void __launch_bounds__(128)
 knn_points_kernel(const float* __restrict__ query, int n_query, const void* __restrict__ blob, int k,
                   int* __restrict__ nn_idx, float* __restrict__ nn_d2) {
   const GridView g = grid_view(blob);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_query) return;
-  unsigned long long best[APN_K];
-  if (g.h->overflow) {
-#pragma unroll
-    for (int j = 0; j < APN_K; ++j) best[j] = KEY_INF;
-  } else {
-    knn_search(g, query[3 * i], query[3 * i + 1], query[3 * i + 2], false, best);
-  }
-#pragma unroll
-  for (int j = 0; j < APN_K; ++j) {
-    if (j < k) {
-      nn_idx[(size_t)i * k + j] = (int)(unsigned int)best[j];
-      if (nn_d2) nn_d2[(size_t)i * k + j] = __uint_as_float((unsigned int)(best[j] >> 32));
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_query; i += warps) {
+    unsigned long long best = KEY_INF;
+    if (!g.h->overflow)
+      knn_search_warp(g, __ldg(query + 3 * (size_t)i), __ldg(query + 3 * (size_t)i + 1), __ldg(query + 3 * (size_t)i + 2), false,
+                      best, lane);
+    if (lane < k) {
+      nn_idx[(size_t)i * k + lane] = (int)(unsigned int)best;
+      if (nn_d2) nn_d2[(size_t)i * k + lane] = __uint_as_float((unsigned int)(best >> 32));
     }
   }
 }
@@ -530,7 +572,7 @@ extern "C" int apn_knn_points(const float* query, int n_query, const void* grid,
   APN_CHECK_ARG(k >= 1 && k <= APN_K, "1 <= k <= 8");
   if (n_query <= 0) return 0;
   APN_CHECK_ARG(query && grid && nn_idx, "null pointer");
-  knn_points_kernel<<<apn_div_up(n_query, 128), 128, 0, stream>>>(query, n_query, grid, k, nn_idx, nn_d2);
+  knn_points_kernel<<<min(apn_div_up(n_query, 4), APN_SM_COUNT * 16), 128, 0, stream>>>(query, n_query, grid, k, nn_idx, nn_d2);
   APN_LAUNCH_CHECK();
   return 0;
 }
