@@ -100,6 +100,8 @@ agg_prep_kernel(const apn_agg_inputs in, int ld0, float* __restrict__ x0, float*
 // ---------------------------------------------------------------------------------------
 // K-reduce + densitynet + Raw2Alpha + view PE: one warp per sample
 // ---------------------------------------------------------------------------------------
+// FROM_H: `h` already holds the reduced feature (written by the tensor-core kernel); only the heads' inputs are built
+template <bool FROM_H>
 __global__ void __launch_bounds__(256)
 agg_reduce_kernel(const apn_agg_inputs in, const float* __restrict__ act3, const float* __restrict__ idw,
                   const float* __restrict__ density_w, const float* __restrict__ density_b, float* __restrict__ h,
@@ -110,13 +112,17 @@ agg_reduce_kernel(const apn_agg_inputs in, const float* __restrict__ act3, const
   const float bd = __ldg(density_b);
   for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < in.M; m += warps) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (FROM_H) {
+      acc = reinterpret_cast<const float4*>(h + (size_t)m * AGG_C)[lane];
+    } else {
 #pragma unroll
-    for (int k = 0; k < AGG_K; ++k) {
-      const float w = __ldg(idw + (size_t)m * AGG_K + k);
-      const float4 a = __ldg(reinterpret_cast<const float4*>(act3 + ((size_t)m * AGG_K + k) * AGG_C) + lane);
-      acc.x += a.x * w; acc.y += a.y * w; acc.z += a.z * w; acc.w += a.w * w;
+      for (int k = 0; k < AGG_K; ++k) {
+        const float w = __ldg(idw + (size_t)m * AGG_K + k);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(act3 + ((size_t)m * AGG_K + k) * AGG_C) + lane);
+        acc.x += a.x * w; acc.y += a.y * w; acc.z += a.z * w; acc.w += a.w * w;
+      }
+      reinterpret_cast<float4*>(h + (size_t)m * AGG_C)[lane] = acc;
     }
-    reinterpret_cast<float4*>(h + (size_t)m * AGG_C)[lane] = acc;
     const float dens = warp_sum(acc.x * wd.x + acc.y * wd.y + acc.z * wd.z + acc.w * wd.w) + bd;
     if (lane == 0) {
       // lib/cuda/render_utils_kernel.cu:358-370
@@ -160,6 +166,25 @@ __global__ void agg_rgb_out_kernel(const float* __restrict__ v0, const float* __
   rgb[3 * (size_t)m] = 1.f / (1.f + expf(-a0));
   rgb[3 * (size_t)m + 1] = 1.f / (1.f + expf(-a1));
   rgb[3 * (size_t)m + 2] = 1.f / (1.f + expf(-a2));
+}
+
+// K-reduce (unless act3 == NULL: h given) + densitynet/Raw2Alpha + RGBNet; shared by the fp32 and tensor-core paths
+int agg_heads_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const float* act3, const float* idw,
+                     float* h, float* exp_d, float* alpha, float* fv, float* v0, float* rgb) {
+  const int M = in->M;
+  const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 16);
+  if (act3)
+    agg_reduce_kernel<false><<<wblocks, 256, 0, st>>>(*in, act3, idw, w->density_w, w->density_b, h, exp_d, alpha, fv);
+  else
+    agg_reduce_kernel<true><<<wblocks, 256, 0, st>>>(*in, nullptr, idw, w->density_w, w->density_b, h, exp_d, alpha, fv);
+  APN_LAUNCH_CHECK();
+  // RGBNet (lib/tineuvox.py:77-88): feature_linears has no activation
+  APN_CHECK_ARG(gemm_forward(st, h, AGG_C, w->rgb_feat_w, AGG_C, w->rgb_feat_b, fv, AGG_FV_LD, M, AGG_C, AGG_C, 1.f) == 0, "gemm rgb feat");
+  APN_CHECK_ARG(gemm_forward(st, fv, AGG_FV_LD, w->rgb_v0_w, AGG_C + APN_PE_VIEW, w->rgb_v0_b, v0, AGG_V0, M, AGG_V0,
+                             AGG_C + APN_PE_VIEW, 0.f) == 0, "gemm rgb v0");
+  agg_rgb_out_kernel<<<apn_div_up(M, 128), 128, 0, st>>>(v0, w->rgb_v2_w, w->rgb_v2_b, M, rgb);
+  APN_LAUNCH_CHECK();
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -233,15 +258,7 @@ extern "C" int apn_aggregate_fwd(const apn_agg_inputs* in, const apn_mlp_weights
   APN_CHECK_ARG(gemm_forward(st, b.x0, ld0, w->w[0], in->d_in, w->b[0], b.act[0], AGG_C, rows, AGG_C, in->d_in, 0.01f) == 0, "gemm L0");
   for (int l = 1; l < 4; ++l)
     APN_CHECK_ARG(gemm_forward(st, b.act[l - 1], AGG_C, w->w[l], AGG_C, w->b[l], b.act[l], AGG_C, rows, AGG_C, AGG_C, 0.01f) == 0, "gemm L");
-  agg_reduce_kernel<<<wblocks, 256, 0, st>>>(*in, b.act[3], out->idw, w->density_w, w->density_b, b.h, b.exp_d, out->alpha, b.fv);
-  APN_LAUNCH_CHECK();
-  // RGBNet (lib/tineuvox.py:77-88): feature_linears has no activation
-  APN_CHECK_ARG(gemm_forward(st, b.h, AGG_C, w->rgb_feat_w, AGG_C, w->rgb_feat_b, b.fv, AGG_FV_LD, M, AGG_C, AGG_C, 1.f) == 0, "gemm rgb feat");
-  APN_CHECK_ARG(gemm_forward(st, b.fv, AGG_FV_LD, w->rgb_v0_w, AGG_C + APN_PE_VIEW, w->rgb_v0_b, b.v0, AGG_V0, M, AGG_V0,
-                             AGG_C + APN_PE_VIEW, 0.f) == 0, "gemm rgb v0");
-  agg_rgb_out_kernel<<<apn_div_up(M, 128), 128, 0, st>>>(b.v0, w->rgb_v2_w, w->rgb_v2_b, M, out->rgb);
-  APN_LAUNCH_CHECK();
-  return 0;
+  return agg_heads_launch(st, in, w, b.act[3], out->idw, b.h, b.exp_d, out->alpha, b.fv, b.v0, out->rgb);
 }
 
 // ---------------------------------------------------------------------------------------

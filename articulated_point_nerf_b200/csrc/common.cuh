@@ -11,6 +11,9 @@
 
 void apn_set_error(const char* fmt, ...);
 void apn_count_launch(int n = 1);
+// aggregate.cu: [K-reduce of act3 unless act3 == NULL] + densitynet/Raw2Alpha + RGBNet on the reduced feature h
+int agg_heads_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const float* act3, const float* idw,
+                     float* h, float* exp_d, float* alpha, float* fv, float* v0, float* rgb);
 
 #define APN_CHECK_ARG(cond, msg)                                   \
   do {                                                             \

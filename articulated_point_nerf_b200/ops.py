@@ -360,6 +360,57 @@ def aggregate(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch.Te
     return _Aggregate.apply(c, xyz, ginv, feat, pose_emb, *weights)
 
 
+class PackedDecoder:
+    """feat_net weights in the tensor-core kernel's shared-memory image (csrc/aggregate_tc.cu).  Re-packed
+    whenever a weight tensor changes (tracked through the tensors' version counters)."""
+
+    def __init__(self):
+        self.buf = None
+        self.key = None
+
+    def get(self, ws: Sequence[torch.Tensor], d_in: int) -> torch.Tensor:
+        key = tuple((w.data_ptr(), w._version) for w in ws[:8:2]) + (d_in,)
+        if self.key != key:
+            lib = _lib.load()
+            if self.buf is None:
+                self.buf = _empty((lib.apn_aggregate_tc_weights_bytes(d_in),), ws[0].device, torch.uint8)
+            w = _mlp_struct(ws)
+            check(lib.apn_aggregate_tc_pack_weights(C.byref(w), d_in, ptr(self.buf), stream()), "apn_aggregate_tc_pack_weights")
+            self.key = key
+        return self.buf
+
+
+def aggregate_tc(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch.Tensor], packed: PackedDecoder,
+                 precision: int = 1):
+    """Inference-only aggregation on the tcgen05 tensor cores (no autograd graph).
+    precision 0: fp16 operands; 1: split-fp16 (fp32-class).  -> alpha, rgb, alpha_direct, rgb_direct, idw."""
+    assert len(weights) == 16
+    lib = _lib.load()
+    with torch.no_grad():
+        xyz, ginv, feat = _f32(xyz.detach()), _f32(ginv.detach()), _f32(feat.detach())
+        pose_emb = None if pose_emb is None else _f32(pose_emb.detach()).reshape(-1)
+        ws = [_f32(w.detach()) for w in weights]
+        M = c.pts.shape[0]
+        dev = xyz.device
+        d_in = PE_POS + FEAT_DIM + (0 if pose_emb is None else pose_emb.numel())
+        alpha, rgb = _empty((M,), dev), _empty((M, 3), dev)
+        alpha_d = _empty((M,), dev) if c.direct else None
+        rgb_d = _empty((M, 3), dev) if c.direct else None
+        idw = _empty((M, K_NEIGHBOURS), dev)
+        if M > 0:
+            out = AggOutputs()
+            out.alpha, out.rgb, out.alpha_direct, out.rgb_direct, out.idw = ptr(alpha), ptr(rgb), ptr(alpha_d), ptr(rgb_d), ptr(idw)
+            a = _agg_inputs(c, xyz, ginv, feat, pose_emb, M, d_in)
+            w = _mlp_struct(ws)
+            pk = packed.get(ws, d_in)
+            sb = lib.apn_aggregate_tc_scratch_bytes(M)
+            scratch = _empty((sb,), dev, torch.uint8)
+            with stage("feat_net"):
+                check(lib.apn_aggregate_fwd_tc(C.byref(a), C.byref(w), ptr(pk), C.byref(out), int(precision), ptr(scratch), sb,
+                                               stream()), "apn_aggregate_fwd_tc")
+    return alpha, rgb, alpha_d, rgb_d, idw
+
+
 # --------------------------------------------------------------------------------------
 # K4: compositing
 # --------------------------------------------------------------------------------------

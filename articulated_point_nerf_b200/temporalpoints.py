@@ -139,7 +139,10 @@ class TemporalPoints(torch.nn.Module):
         self.beta_min = torch.nn.Parameter(torch.tensor([0.0001]), requires_grad=False)
         self._last_weights = None
         self.last_counts = {}
-        self.decoder = "fp32"      # "fp32" (exact, differentiable) | "tc" (tcgen05 bf16 inference path)
+        # decoder used when no gradient is needed: "tc" = tcgen05 split-fp16 (fp32-class), "tc_fast" = tcgen05 fp16
+        # operands, "fp32" = CUDA-core exact path (always used when autograd is recording)
+        self.decoder = "tc"
+        self._packed_decoder = ops.PackedDecoder()
 
     # ------------------------------------------------------------------------------------------
     def get_kwargs(self):
@@ -330,9 +333,10 @@ class TemporalPoints(torch.nn.Module):
                          canonical_alpha=self.canonical_alpha.detach(), canonical_rgbs=self.canonical_rgbs.detach(),
                          direct_eps=self.direct_eps.detach(), mean_min_distance=self._mmd_float, eps=float(self.eps),
                          act_shift=float(self.tineuvox.act_shift), interval=interval, direct=True)
-        if self.decoder == "tc" and not torch.is_grad_enabled():
+        if self.decoder in ("tc", "tc_fast") and not torch.is_grad_enabled():
             alpha, rgb, alpha_d, rgb_d, idw = ops.aggregate_tc(c, t_hat_pcd, warped['ginv'], self.canonical_feat, pose_embedding,
-                                                               self._mlp_weights())
+                                                               self._mlp_weights(), self._packed_decoder,
+                                                               precision=1 if self.decoder == "tc" else 0)
         else:
             alpha, rgb, alpha_d, rgb_d, idw = ops.aggregate(c, t_hat_pcd, warped['ginv'], self.canonical_feat, pose_embedding,
                                                             self._mlp_weights())

@@ -38,7 +38,7 @@ METRIC = {"train": "rays/sec (PCD train step: fwd+bwd+Adam)", "render": "rays/se
 # ----------------------------------------------------------------------------------------------
 # workload construction (CPU, seeded): identical for both arms
 # ----------------------------------------------------------------------------------------------
-def make_batches(scene, mode, n_steps, rank, n_rand=N_RAND):
+def make_batches(scene, mode, n_steps, rank, n_rand=N_RAND, repose=False):
     """Per step: (t, rays_o, rays_d, viewdirs, target) on the host.  Train: n_rand random pixels of one view
     (run.py:587-601: a D-NeRF time step is one image); render: every pixel of one view."""
     out = []
@@ -50,6 +50,12 @@ def make_batches(scene, mode, n_steps, rank, n_rand=N_RAND):
             cache[v] = [x.reshape(-1, 3).contiguous() for x in scene.rays(v)]
         ro, rd, vd = cache[v]
         t = torch.tensor([v / max(n_views - 1, 1)], dtype=torch.float32)
+        if repose:
+            # run.py:1364-1377: random bone rotations, root fixed, scaled along the clip
+            g = torch.Generator().manual_seed(77)
+            rp = torch.randn(len(scene.joints), 4, generator=g) * 0.2
+            rp[0] = 0
+            t = (rp * ((i % 30) / 29.0)).contiguous()
         if mode == "train":
             g = torch.Generator().manual_seed(1000 * rank + i)
             sel = torch.randint(0, len(ro), (n_rand,), generator=g)
@@ -172,7 +178,7 @@ class OracleArm:
                 outs = []
                 for s in range(0, len(ro), N_RAND):
                     kwc = dict(kw, rays_o=ro[s:s + N_RAND], rays_d=rd[s:s + N_RAND], viewdirs=vd[s:s + N_RAND])
-                    outs.append(orc.forward(t, **kwc)["rgb_marched"])
+                    outs.append((orc.forward(None, t, **kwc) if t.dim() == 2 else orc.forward(t, **kwc))["rgb_marched"])
                 return torch.cat(outs)
         for k in self.trainable:
             orc.s[k].requires_grad_(True)
@@ -242,6 +248,7 @@ def main():
 
     from articulated_point_nerf_b200.scene import build_model, make_scene
     scene = make_scene(cfg_name)
+    repose = mode == "render" and cfg_name in ("c3", "c5")          # --repose_pcd workloads (run.py:1355-1396)
     n_steps = args.steps + args.warmup
     base_cfg = {"workload": f"{args.workload}: {mode}, N={len(scene.canonical_pcd)} points, J={len(scene.joints)}, "
                             f"{'%d-ray batch of one %dx%d view' % (N_RAND, scene.cfg.H, scene.cfg.W) if mode == 'train' else 'one %dx%d frame' % (scene.cfg.H, scene.cfg.W)} per step per GPU",
@@ -254,7 +261,7 @@ def main():
         torch.set_num_threads(os.cpu_count() or 1)
         model = build_model(scene, seed=0)
         arm = OracleArm(scene, model_state_for_oracle(model), mode)
-        batches = make_batches(scene, mode, min(n_steps, 8), 0)
+        batches = make_batches(scene, mode, min(n_steps, 8), 0, repose=repose)
         n, sec = time_oracle(arm, batches, args.steps, args.warmup, args.ref_budget)
         val = n / sec
         sample = f"{n} of {len(batches[0][1])} rays per step, {args.steps} steps, oracle port (torch-CPU fp32, brute-force k-NN)"
@@ -283,7 +290,7 @@ def main():
     model = model.to(dev)
     if args.decoder != "auto":
         model.decoder = args.decoder
-    host = [pack_host(b, pin=True) for b in make_batches(scene, mode, n_steps, rank)]
+    host = [pack_host(b, pin=True) for b in make_batches(scene, mode, n_steps, rank, repose=repose)]
     rk = scene.render_kwargs()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     opt = bucket = None
@@ -300,7 +307,10 @@ def main():
             out = train_step(model, opt, bucket, t, kw, tgt, decay_factor=decay)
         else:
             with torch.no_grad():
-                out = model(t, render_depth=True, render_kwargs=kw)["rgb_marched"]
+                if t.dim() == 2:      # repose: rot_params instead of a time (run.py:287)
+                    out = model(None, render_depth=True, render_kwargs=kw, rot_params=t)["rgb_marched"]
+                else:
+                    out = model(t, render_depth=True, render_kwargs=kw)["rgb_marched"]
         counts.append(dict(model.last_counts))
         return out
 
@@ -383,7 +393,7 @@ def main():
     if oracle_state is not None:
         torch.set_num_threads(os.cpu_count() or 1)
         arm = OracleArm(scene, oracle_state, mode)
-        batches = make_batches(scene, mode, 3, 0)
+        batches = make_batches(scene, mode, 3, 0, repose=repose)
         n, sec = time_oracle(arm, batches, 2, 0, args.cpu_budget)
         cpu_baseline = {"value": n / sec, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"{n} of {len(batches[0][1])} rays per step, 2 steps after a 1024-ray probe, oracle port "

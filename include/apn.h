@@ -195,13 +195,18 @@ size_t apn_aggregate_bwd_scratch_bytes(int M, int d_in);
 int apn_aggregate_bwd(const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* saved,
                       const apn_agg_grads* g, void* scratch, size_t scratch_bytes, apn_stream_t stream);
 
-/* tcgen05 (5th-gen tensor core) fused inference path: same contract as apn_aggregate_fwd for
- * alpha / rgb / alpha_direct / rgb_direct / idw; nothing is saved for backward.
- * precision: 0 = bf16 operands (1 pass), 1 = bf16x3 split operands (fp32-class, parity mode). */
+/* tcgen05 (5th-gen tensor core, accumulators in tensor memory) fused inference path: same contract as
+ * apn_aggregate_fwd for alpha / rgb / alpha_direct / rgb_direct / idw; nothing is saved for backward.
+ * precision: 0 = fp16 operands, fp32 accumulate (one MMA per K step);
+ *            1 = split operands x = hi + lo (two fp16 terms), hi*hi + hi*lo + lo*hi in fp32: fp32-class (parity mode).
+ * packed_weights: apn_aggregate_tc_weights_bytes(d_in) bytes filled by apn_aggregate_tc_pack_weights (re-pack after
+ * every weight update); scratch >= apn_aggregate_tc_scratch_bytes(M). */
 size_t apn_aggregate_tc_weights_bytes(int d_in);
 int apn_aggregate_tc_pack_weights(const apn_mlp_weights* w, int d_in, void* packed, apn_stream_t stream);
+size_t apn_aggregate_tc_scratch_bytes(int M);
 int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_weights,
-                         const apn_agg_outputs* out, int precision, apn_stream_t stream);
+                         const apn_agg_outputs* out, int precision, void* scratch, size_t scratch_bytes,
+                         apn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4  Ray compositing.

@@ -364,3 +364,54 @@ def test_reference_compatible_render_utils(golden_tiny):
     # CPU tensors are rejected, like CHECK_INPUT
     with pytest.raises(RuntimeError):
         ru.raw2alpha(dens, -6.9, 0.5)
+
+
+# ----------------------------------------------------------------------------------------
+# K3 on the tcgen05 tensor cores
+# ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [(1, RTOL), (0, 3e-2)])
+def test_aggregate_tensor_core_path(golden_tiny, precision, tol):
+    """Split-fp16 tcgen05 decoder == oracle within the 1e-4 parity bar; the single-pass fp16 mode within its own bound."""
+    ops, orc, o, xyz, gi, smp, model, c = _agg_setup(golden_tiny, False)
+    rgb, alpha, rgb_d, alpha_d, _ = o
+    packed = ops.PackedDecoder()
+    k_alpha, k_rgb, k_ad, k_rd, k_idw = ops.aggregate_tc(c, xyz.cuda(), gi[:, :3, :3].reshape(-1, 9).contiguous().cuda(),
+                                                         model.canonical_feat, None, model._mlp_weights(), packed, precision)
+    assert rel_err(k_idw, orc.trace["idw"]) < 1e-5
+    assert rel_err(k_ad, alpha_d) < RTOL and rel_err(k_rd, rgb_d) < RTOL
+    assert rel_err(k_alpha, alpha) < tol, rel_err(k_alpha, alpha)
+    assert rel_err(k_rgb, rgb) < tol, rel_err(k_rgb, rgb)
+
+
+@pytest.mark.parametrize("M,pose", [(1, False), (15, False), (16, True), (17, False), (4099, True)])
+def test_aggregate_tensor_core_matches_fp32_kernel_on_ragged_sizes(M, pose):
+    """Tile tails (M not a multiple of 16), more tiles than SMs, and the pose-embedding fold (d_in = 255)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M)
+    N, d = 3000, "cuda"
+    xyz = torch.rand(N, 3, generator=g)
+    A = torch.eye(3) + 0.2 * torch.randn(N, 3, 3, generator=g)
+    feat = torch.relu(torch.randn(N, 128, generator=g)) * 0.5
+    nn_idx = torch.randint(0, N, (M, 8), generator=g).int()
+    pts = xyz[nn_idx[:, 0].long()] + 0.02 * torch.randn(M, 3, generator=g)
+    ray_id = torch.sort(torch.randint(0, 50, (M,), generator=g))[0].int()
+    vd = torch.nn.functional.normalize(torch.randn(50, 3, generator=g), dim=-1)
+    d_in = 255 if pose else 191
+    lin = [torch.nn.Linear(d_in, 128), torch.nn.Linear(128, 128), torch.nn.Linear(128, 128), torch.nn.Linear(128, 128),
+           torch.nn.Linear(128, 1), torch.nn.Linear(128, 128), torch.nn.Linear(155, 64), torch.nn.Linear(64, 3)]
+    ws = []
+    for l in lin:
+        ws += [l.weight.detach().to(d), l.bias.detach().to(d)]
+    pe = (torch.randn(64, generator=g) * 0.3).to(d) if pose else None
+    c = ops.AggConst(pts=pts.to(d), nn_idx=nn_idx.to(d), ray_id=ray_id.to(d), viewdirs=vd.to(d),
+                     canonical_alpha=torch.rand(N, generator=g).to(d), canonical_rgbs=torch.rand(N, 3, generator=g).to(d),
+                     direct_eps=torch.full((N,), 0.05).to(d), mean_min_distance=0.02, eps=1e-6, act_shift=0.0, interval=0.5)
+    # act_shift = 0 keeps alpha = 1 - (1 + e^d)^-0.5 away from the cancellation regime where one ulp of 1.0 is 1e-4 of alpha
+    args = (c, xyz.to(d), A.reshape(N, 9).contiguous().to(d), feat.to(d), pe)
+    with torch.no_grad():
+        ref = ops.aggregate(*args, ws)
+    got = ops.aggregate_tc(*args, ws, ops.PackedDecoder(), precision=1)
+    for a, b, name in zip(got, ref, ["alpha", "rgb", "alpha_direct", "rgb_direct", "idw"]):
+        assert rel_err(a, b) < RTOL, (name, rel_err(a, b))
+    fast = ops.aggregate_tc(*args, ws, ops.PackedDecoder(), precision=0)
+    assert rel_err(fast[0], ref[0]) < 3e-2 and rel_err(fast[1], ref[1]) < 3e-2
