@@ -80,7 +80,8 @@ SIGNATURES = {
     "apn_aggregate_tc_weights_bytes": (SZ, [I]),
     "apn_aggregate_tc_pack_weights": (I, [P, I, P, P]),
     "apn_aggregate_tc_scratch_bytes": (SZ, [I]),
-    "apn_aggregate_fwd_tc": (I, [P, P, P, P, I, P, SZ, P]),
+    "apn_aggregate_tc_point_table": (I, [P, P, I, I, P, P]),
+    "apn_aggregate_fwd_tc": (I, [P, P, P, P, P, I, P, SZ, P]),
     "apn_composite_fwd": (I, [P, P, P, P, I, P, I, F, F, P, P, P, P, P, P, P]),
     "apn_composite_bwd": (I, [P, P, P, P, I, F, F, P, P, P, P, P, P, P, P, P]),
     "apn_adam_step_size": (F, [I, F, F, F]),

@@ -5,40 +5,50 @@
 // Replaces lib/temporalpoints.py:446-494 and lib/tineuvox.py:872-878; the heads (densitynet / Raw2Alpha /
 // RGBNet, 4.5 % of the flops) run on the reduced feature through agg_heads_launch (aggregate.cu).
 //
+// Layer 0 is split algebraically: the feature columns of its input are a pure gather of per-point rows, so
+//   W0 [PE | feat[idx]] = W0_pe PE + (feat W0_feat^T)[idx]
+// and the second term is a per-point table P (N x 128 fp32, exact CUDA-core GEMM, rebuilt only when the
+// features or W0 change: apn_aggregate_tc_point_table).  The kernel adds P[idx] in the layer-0 epilogue; the
+// tensor cores only see K = 64 for layer 0 instead of 192.
+//
 // One persistent CTA per SM walks 128-row tiles (16 kept samples x 8 neighbours):
-//   warps 0-7  build the layer-0 operand tile in shared memory (fp16, K-major, 128-byte swizzle), and after every
-//              layer read the fp32 accumulator from tensor memory, apply bias + LeakyReLU and write the next
-//              layer's operand tile (layers 0-2) or do the weighted 8-row reduce and store h (layer 3);
-//   warp 8     streams the packed weight chunks ([128 out x 64 in] fp16 tiles, pre-swizzled by
+//   warps 0-15 "compute": build the PE operand tile (fp16, K-major, 128-byte swizzle); after every layer read
+//              the fp32 accumulator from tensor memory, add bias (+P row), LeakyReLU, write the next layer's
+//              operand tile — K-chunk 0 first, then K-chunk 1, each announced on its own mbarrier so the next
+//              layer's MMAs start on chunk 0 while chunk 1 is still being written (accumulators are double
+//              buffered in tensor memory); after layer 3 the weighted 8-row reduce produces h.
+//              The next tile's prologue runs between the layer-2 epilogue and the final epilogue, i.e. under
+//              the layer-3 MMAs, and the next tile's layer-0 MMAs run under the final epilogue.
+//   warp 16    streams the packed weight chunks ([128 out x 64 in] fp16 tiles, pre-swizzled by
 //              apn_aggregate_tc_pack_weights) with 1-D bulk async copies into a ring of shared-memory slots
-//              (precision 0: all 9 chunks stay resident);
-//   warp 9     one elected thread issues tcgen05.mma (M=128, N=128, K=16) and commits to mbarriers.
+//              (precision 0: all 7 chunks stay resident);
+//   warp 17    one elected thread issues tcgen05.mma (M=128, N=128, K=16) and commits to mbarriers.
 // Precision 0: fp16 operands, fp32 accumulate (1 MMA per K step).
 // Precision 1: every operand is split x = hi + lo (two fp16 terms, 22 mantissa bits) and the three products
 //              hi*hi + hi*lo + lo*hi are accumulated in fp32: fp32-class results (the parity mode).
-// Column order of the layer-0 operand: [feat 0..63 | feat 64..127 | rel_c(3) sin(30) cos(30) 0]; the packed
-// W0 uses the same permutation.  A pose embedding (d_in = 255) is constant over rows: W0[:,191:255] * pose is
-// folded into the layer-0 bias by every CTA at start-up.
-#include "common.cuh"
+// PE chunk columns: [rel_c(3) sin(30) cos(30) 0] (the reference's own order).  A pose embedding (d_in = 255) is
+// constant over rows: W0[:,191:255] * pose is folded into the layer-0 bias by every CTA at start-up.
+#include "sgemm.cuh"
 #include "tc05.cuh"
 
 using namespace tc05;
 
 #define TC_ROWS 128
 #define TC_SAMPLES 16
-#define TC_NCHUNKS 9                 // K chunks of 64: layer 0 has 3, layers 1-3 have 2
+#define TC_NCHUNKS 7                 // chunk 0: layer-0 PE columns; 1..6: layers 1-3, two K chunks of 64 each
 #define TC_TILE_BYTES 16384          // [128 x 64] fp16
 #define TC_CHUNK_GBYTES (2 * TC_TILE_BYTES)   // packed global: hi tile then lo tile
-#define TC_COMPUTE_WARPS 8
+#define TC_COMPUTE_WARPS 16
 #define TC_COMPUTE_THREADS (32 * TC_COMPUTE_WARPS)
 #define TC_THREADS (TC_COMPUTE_THREADS + 64)
-#define TC_TMEM_COLS 128
+#define TC_TMEM_COLS 256             // two 128-column fp32 accumulators
 
 struct TcParams {
   apn_agg_inputs in;
   const float* bias[4];
   const float* w0;            // fp32 W0 (128, d_in) for the pose-embedding fold
   const uint8_t* packed;
+  const float* ptable;        // (N,128) feat W0_feat^T
   float* h;                   // (M,128)
   float* idw;                 // (M,8)
   float* alpha_direct;        // (M) or NULL
@@ -51,15 +61,13 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------
 __global__ void tc_pack_kernel(const apn_mlp_weights w, int d_in, uint8_t* __restrict__ packed) {
   const int c = blockIdx.x;                                  // chunk
-  const int layer = c < 3 ? 0 : 1 + (c - 3) / 2;
-  const int kc = c < 3 ? c : (c - 3) % 2;
+  const int layer = c == 0 ? 0 : 1 + (c - 1) / 2;
+  const int kc = c == 0 ? 0 : (c - 1) % 2;
   const float* W = w.w[layer];
   const int ld = layer == 0 ? d_in : APN_C;
   for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
     const int n = e >> 6, k = e & 63;
-    int col;
-    if (layer == 0) col = (kc < 2) ? APN_PE_POS + kc * 64 + k : (k < APN_PE_POS ? k : -1);
-    else col = kc * 64 + k;
+    const int col = layer == 0 ? (k < APN_PE_POS ? k : -1) : kc * 64 + k;
     const float v = col >= 0 ? W[(size_t)n * ld + col] : 0.f;
     __half hi, lo;
     split_half(v, hi, lo);
@@ -86,29 +94,120 @@ extern "C" int apn_aggregate_tc_pack_weights(const apn_mlp_weights* w, int d_in,
   return 0;
 }
 
+// P = feat W0[:, 63:191]^T  (N x 128), exact fp32
+extern "C" int apn_aggregate_tc_point_table(const float* feat, const float* w0, int d_in, int N, float* ptable,
+                                            apn_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  APN_CHECK_ARG(feat && w0 && ptable, "null pointer");
+  APN_CHECK_ARG(d_in >= APN_PE_POS + APN_C && d_in <= 256 && N > 0, "bad sizes");
+  APN_CHECK_ARG(gemm_forward(st, feat, APN_C, w0 + APN_PE_POS, d_in, nullptr, ptable, APN_C, N, APN_C, APN_C, 1.f) == 0,
+                "point table gemm");
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------
 template <int NSPLIT>
 struct TcSmem {
   static constexpr int NSLOT = NSPLIT == 1 ? TC_NCHUNKS : 3;
-  static constexpr int A_BYTES = 3 * NSPLIT * TC_TILE_BYTES;
-  static constexpr int W_BYTES = NSLOT * NSPLIT * TC_TILE_BYTES;
-  static constexpr int OFF_A = 0;
-  static constexpr int OFF_W = A_BYTES;
-  static constexpr int OFF_BIAS = OFF_W + W_BYTES;          // 4 x 128 floats
-  static constexpr int OFF_IDW = OFF_BIAS + 4 * 128 * 4;     // 128 floats
-  static constexpr int OFF_IDX = OFF_IDW + 128 * 4;          // 128 ints
-  static constexpr int OFF_BAR = OFF_IDX + 128 * 4;          // barriers
-  static constexpr int N_BAR = 2 * NSLOT + 2;
+  static constexpr int OFF_PE = 0;                                           // NSPLIT tiles
+  static constexpr int OFF_ACT = OFF_PE + NSPLIT * TC_TILE_BYTES;            // 2 x NSPLIT tiles: (kc, split)
+  static constexpr int OFF_W = OFF_ACT + 2 * NSPLIT * TC_TILE_BYTES;         // NSLOT x NSPLIT tiles
+  static constexpr int OFF_BIAS = OFF_W + NSLOT * NSPLIT * TC_TILE_BYTES;    // 4 x 128 floats
+  static constexpr int OFF_IDW = OFF_BIAS + 4 * 128 * 4;                     // 2 x 128 floats
+  static constexpr int OFF_IDX = OFF_IDW + 2 * 128 * 4;                      // 2 x 128 ints
+  static constexpr int OFF_BAR = OFF_IDX + 2 * 128 * 4;
+  static constexpr int N_BAR = 2 * NSLOT + 5;
   static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
-  static constexpr int TOTAL = OFF_TMEM + 16 + 1024;         // + slack for the 1024-byte alignment of the base
+  static constexpr int TOTAL = OFF_TMEM + 16 + 1024;                         // + slack for the 1024-byte alignment
 };
 
-__device__ __forceinline__ float leaky(float y) { return y < 0.f ? y * 0.01f : y; }
+__device__ __forceinline__ float leaky(float y) { return fmaxf(y, 0.01f * y); }
 
 // bar.sync among the compute warps only
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE_THREADS) : "memory"); }
+
+// Builds the per-tile sample state (idw, neighbour indices, direct branch) and the PE operand tile.
+// 4 threads per row: part p owns the (dimension, frequency) pairs j = p, p+4, ...
+template <int NSPLIT>
+__device__ __forceinline__ void tc_prologue(const TcParams& p, int tile, int tid, uint8_t* sPE, float* sIdw, int* sIdx) {
+  const apn_agg_inputs& in = p.in;
+  const int r = tid & 127, part = tid >> 7;
+  const int s = r >> 3;
+  const int m0 = tile * TC_SAMPLES;
+  const int m = min(m0 + s, in.M - 1);
+  const bool valid = (m0 + s) < in.M;
+  const int idx = __ldg(in.nn_idx + (size_t)m * APN_K + (r & 7));
+  const float px = __ldg(in.pts + 3 * (size_t)m), py = __ldg(in.pts + 3 * (size_t)m + 1), pz = __ldg(in.pts + 3 * (size_t)m + 2);
+  const float rx = px - __ldg(in.xyz + 3 * (size_t)idx), ry = py - __ldg(in.xyz + 3 * (size_t)idx + 1),
+              rz = pz - __ldg(in.xyz + 3 * (size_t)idx + 2);
+  if (part == 0) {
+    const float d2 = (rx * rx + ry * ry) + rz * rz;
+    // inverse-distance weights (lib/temporalpoints.py:473-475): the 8 rows of a sample are 8 consecutive lanes
+    const float u = 1.0f / (d2 + in.eps);
+    float su = u;
+    su += __shfl_xor_sync(0xffffffffu, su, 1);
+    su += __shfl_xor_sync(0xffffffffu, su, 2);
+    su += __shfl_xor_sync(0xffffffffu, su, 4);
+    const float w = u / su;
+    sIdw[r] = w;
+    sIdx[r] = idx;
+    if (valid) p.idw[(size_t)m * APN_K + (r & 7)] = w;
+    if (p.alpha_direct) {
+      // direct branch (lib/temporalpoints.py:459-470)
+      const float sig = in.mean_min_distance * fmaxf(__ldg(in.direct_eps + idx), 0.f);
+      const float wd = expf(-(d2 * d2) / (2.f * sig * sig + 1e-12f));
+      float sw = wd;
+      sw += __shfl_xor_sync(0xffffffffu, sw, 1);
+      sw += __shfl_xor_sync(0xffffffffu, sw, 2);
+      sw += __shfl_xor_sync(0xffffffffu, sw, 4);
+      const float wn = wd / (sw + 1e-12f);
+      float a = (1.0f / APN_K) * wd * fminf(fmaxf(__ldg(in.canonical_alpha + idx), 0.f), 1.f);
+      float cr = wn * fminf(fmaxf(__ldg(in.canonical_rgbs + 3 * (size_t)idx), 0.f), 1.f);
+      float cg = wn * fminf(fmaxf(__ldg(in.canonical_rgbs + 3 * (size_t)idx + 1), 0.f), 1.f);
+      float cb = wn * fminf(fmaxf(__ldg(in.canonical_rgbs + 3 * (size_t)idx + 2), 0.f), 1.f);
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        cr += __shfl_xor_sync(0xffffffffu, cr, o);
+        cg += __shfl_xor_sync(0xffffffffu, cg, o);
+        cb += __shfl_xor_sync(0xffffffffu, cb, o);
+      }
+      if (valid && (r & 7) == 0) {
+        p.alpha_direct[m] = a;
+        p.rgb_direct[3 * (size_t)m] = cr; p.rgb_direct[3 * (size_t)m + 1] = cg; p.rgb_direct[3 * (size_t)m + 2] = cb;
+      }
+    }
+  }
+  // canonical-frame offset (lib/temporalpoints.py:478-480)
+  const float* G = in.ginv + 9 * (size_t)idx;
+  float rc[3];
+  rc[0] = __ldg(G) * rx + __ldg(G + 1) * ry + __ldg(G + 2) * rz;
+  rc[1] = __ldg(G + 3) * rx + __ldg(G + 4) * ry + __ldg(G + 5) * rz;
+  rc[2] = __ldg(G + 6) * rx + __ldg(G + 7) * ry + __ldg(G + 8) * rz;
+  auto put = [&](int col, float v) {
+    __half hi, lo;
+    split_half(v, hi, lo);
+    const uint32_t o = sw128_offset(r, col);
+    *reinterpret_cast<__half*>(sPE + o) = hi;
+    if (NSPLIT == 2) *reinterpret_cast<__half*>(sPE + TC_TILE_BYTES + o) = lo;
+  };
+  if (part < 3) put(part, part == 0 ? rc[0] : part == 1 ? rc[1] : rc[2]);
+  else put(63, 0.f);
+  // poc_fre (lib/tineuvox.py:872-878): column 3 + d*10 + i = sin(rel_c[d] * 2^i), column 33 + d*10 + i = cos(...)
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = part + 4 * jj;
+    if (j < 30) {
+      const int d = j / 10, i = j - d * 10;
+      float sn, cs;
+      sincosf((d == 0 ? rc[0] : d == 1 ? rc[1] : rc[2]) * (float)(1 << i), &sn, &cs);
+      put(3 + j, sn);
+      put(33 + j, cs);
+    }
+  }
+}
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParams p) {
@@ -117,16 +216,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParam
   constexpr bool RESIDENT = (NSPLIT == 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem + S::OFF_A;                 // tile (kc, split) at (kc * NSPLIT + split) * TC_TILE_BYTES
+  uint8_t* sPE = smem + S::OFF_PE;               // [hi tile][lo tile]
+  uint8_t* sAct = smem + S::OFF_ACT;             // tile (kc, split) at (kc * NSPLIT + split) * TC_TILE_BYTES
   uint8_t* sW = smem + S::OFF_W;                 // slot s: [hi tile][lo tile]
   float* sBias = (float*)(smem + S::OFF_BIAS);
-  float* sIdw = (float*)(smem + S::OFF_IDW);
-  int* sIdx = (int*)(smem + S::OFF_IDX);
+  float* sIdw = (float*)(smem + S::OFF_IDW);     // [2][128]
+  int* sIdx = (int*)(smem + S::OFF_IDX);         // [2][128]
   uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
   uint64_t* w_full = bars;                        // [NSLOT] weights landed
   uint64_t* w_free = bars + NSLOT;                // [NSLOT] MMAs reading the slot have completed
-  uint64_t* a_ready = bars + 2 * NSLOT;           // operand tile written (TC_COMPUTE_THREADS arrivals)
-  uint64_t* acc_ready = bars + 2 * NSLOT + 1;     // accumulator of the layer complete
+  uint64_t* pe_ready = bars + 2 * NSLOT;          // PE tile written (all compute threads)
+  uint64_t* a_ready = bars + 2 * NSLOT + 1;       // [2] activation K-chunk written (all compute threads)
+  uint64_t* acc_ready = bars + 2 * NSLOT + 3;     // [2] accumulator buffer complete
   uint32_t* sTmem = (uint32_t*)(smem + S::OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -137,8 +238,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParam
       mbar_init(w_full + i, 1);
       mbar_init(w_free + i, 1);
     }
+    mbar_init(pe_ready, TC_COMPUTE_THREADS);
     mbar_init(a_ready, TC_COMPUTE_THREADS);
+    mbar_init(a_ready + 1, TC_COMPUTE_THREADS);
     mbar_init(acc_ready, 1);
+    mbar_init(acc_ready + 1, 1);
     fence_barrier_init();
   }
   if (warp == TC_COMPUTE_WARPS + 1) tmem_alloc<TC_TMEM_COLS>(sTmem);
@@ -182,225 +286,173 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParam
     // ================================================================= MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(128, 128);
-      const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
-      uint32_t it = 0, ph_a = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        int c = 0;
-        for (int layer = 0; layer < 4; ++layer) {
-          mbar_wait(a_ready, ph_a);
-          ph_a ^= 1;
-          tc_fence_after();
-          const int nk = layer == 0 ? 3 : 2;
-          for (int kc = 0; kc < nk; ++kc, ++c, ++it) {
-            const uint32_t slot = RESIDENT ? (uint32_t)c : it % NSLOT;
-            mbar_wait(w_full + slot, RESIDENT ? 0u : ((it / NSLOT) & 1));
-            tc_fence_after();
-            const uint32_t a_hi = a_base + (uint32_t)(kc * NSPLIT) * TC_TILE_BYTES;
-            const uint32_t b_hi = w_base + slot * (uint32_t)(NSPLIT * TC_TILE_BYTES);
+      const uint32_t pe_base = smem_u32(sPE), act_base = smem_u32(sAct), w_base = smem_u32(sW);
+      uint32_t it = 0, ph_pe = 0, ph_a0 = 0, ph_a1 = 0;
+      // one K chunk of 64: 4 K steps, NSPLIT == 2 adds the two cross products
+      auto issue_chunk = [&](uint32_t a_hi, uint32_t acc, bool first_chunk, int c) {
+        const uint32_t slot = RESIDENT ? (uint32_t)c : it % NSLOT;
+        mbar_wait(w_full + slot, RESIDENT ? 0u : ((it / NSLOT) & 1));
+        tc_fence_after();
+        const uint32_t b_hi = w_base + slot * (uint32_t)(NSPLIT * TC_TILE_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t da = umma_desc_k_sw128(a_hi + ks * 32), db = umma_desc_k_sw128(b_hi + ks * 32);
-              umma_f16(tmem_base, da, db, idesc, (kc | ks) ? 1u : 0u);
-              if (NSPLIT == 2) {
-                const uint64_t da_lo = umma_desc_k_sw128(a_hi + TC_TILE_BYTES + ks * 32);
-                const uint64_t db_lo = umma_desc_k_sw128(b_hi + TC_TILE_BYTES + ks * 32);
-                umma_f16(tmem_base, da, db_lo, idesc, 1u);
-                umma_f16(tmem_base, da_lo, db, idesc, 1u);
-              }
-            }
-            if (!RESIDENT) umma_commit(w_free + slot);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t da = umma_desc_k_sw128(a_hi + ks * 32), db = umma_desc_k_sw128(b_hi + ks * 32);
+          umma_f16(acc, da, db, idesc, (first_chunk && ks == 0) ? 0u : 1u);
+          if (NSPLIT == 2) {
+            const uint64_t da_lo = umma_desc_k_sw128(a_hi + TC_TILE_BYTES + ks * 32);
+            const uint64_t db_lo = umma_desc_k_sw128(b_hi + TC_TILE_BYTES + ks * 32);
+            umma_f16(acc, da, db_lo, idesc, 1u);
+            umma_f16(acc, da_lo, db, idesc, 1u);
           }
-          umma_commit(acc_ready);
+        }
+        if (!RESIDENT) umma_commit(w_free + slot);
+        ++it;
+      };
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        // layer 0: PE chunk -> accumulator 0
+        mbar_wait(pe_ready, ph_pe);
+        ph_pe ^= 1;
+        tc_fence_after();
+        issue_chunk(pe_base, tmem_base, true, 0);
+        umma_commit(acc_ready);
+        // layers 1..3: activation chunks 0, 1 -> accumulator (layer & 1)
+        for (int layer = 1; layer < 4; ++layer) {
+          const uint32_t acc = tmem_base + (uint32_t)((layer & 1) * 128);
+          mbar_wait(a_ready, ph_a0);
+          ph_a0 ^= 1;
+          tc_fence_after();
+          issue_chunk(act_base, acc, true, 2 * layer - 1);
+          mbar_wait(a_ready + 1, ph_a1);
+          ph_a1 ^= 1;
+          tc_fence_after();
+          issue_chunk(act_base + NSPLIT * TC_TILE_BYTES, acc, false, 2 * layer);
+          umma_commit(acc_ready + (layer & 1));
         }
       }
     }
   } else {
     // ================================================================= compute warps
-    uint32_t ph_acc = 0;
-    const int q = warp & 3, chalf = warp >> 2;
-    const int erow = q * 32 + lane;                       // accumulator row owned in the epilogues
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int m0 = tile * TC_SAMPLES;
-      // ---------------------------------------------------------------- prologue 1: geometry + PE (2 threads per row)
-      {
-        const int r = tid & 127, half = tid >> 7;
-        const int s = r >> 3;
-        const int m = min(m0 + s, in.M - 1);
-        const bool valid = (m0 + s) < in.M;
-        const int idx = __ldg(in.nn_idx + (size_t)m * APN_K + (r & 7));
-        const float px = __ldg(in.pts + 3 * (size_t)m), py = __ldg(in.pts + 3 * (size_t)m + 1), pz = __ldg(in.pts + 3 * (size_t)m + 2);
-        const float rx = px - __ldg(in.xyz + 3 * (size_t)idx), ry = py - __ldg(in.xyz + 3 * (size_t)idx + 1),
-                    rz = pz - __ldg(in.xyz + 3 * (size_t)idx + 2);
-        const float d2 = (rx * rx + ry * ry) + rz * rz;
-        if (half == 0) {
-          // inverse-distance weights (lib/temporalpoints.py:473-475): the 8 rows of a sample are 8 consecutive lanes
-          const float u = 1.0f / (d2 + in.eps);
-          float su = u;
-          su += __shfl_xor_sync(0xffffffffu, su, 1);
-          su += __shfl_xor_sync(0xffffffffu, su, 2);
-          su += __shfl_xor_sync(0xffffffffu, su, 4);
-          const float w = u / su;
-          sIdw[r] = w;
-          sIdx[r] = idx;
-          if (valid) p.idw[(size_t)m * APN_K + (r & 7)] = w;
-          if (p.alpha_direct) {
-            // direct branch (lib/temporalpoints.py:459-470)
-            const float sig = in.mean_min_distance * fmaxf(__ldg(in.direct_eps + idx), 0.f);
-            const float wd = expf(-(d2 * d2) / (2.f * sig * sig + 1e-12f));
-            float sw = wd;
-            sw += __shfl_xor_sync(0xffffffffu, sw, 1);
-            sw += __shfl_xor_sync(0xffffffffu, sw, 2);
-            sw += __shfl_xor_sync(0xffffffffu, sw, 4);
-            const float wn = wd / (sw + 1e-12f);
-            float a = (1.0f / APN_K) * wd * fminf(fmaxf(__ldg(in.canonical_alpha + idx), 0.f), 1.f);
-            float cr = wn * fminf(fmaxf(__ldg(in.canonical_rgbs + 3 * (size_t)idx), 0.f), 1.f);
-            float cg = wn * fminf(fmaxf(__ldg(in.canonical_rgbs + 3 * (size_t)idx + 1), 0.f), 1.f);
-            float cb = wn * fminf(fmaxf(__ldg(in.canonical_rgbs + 3 * (size_t)idx + 2), 0.f), 1.f);
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-              a += __shfl_xor_sync(0xffffffffu, a, o);
-              cr += __shfl_xor_sync(0xffffffffu, cr, o);
-              cg += __shfl_xor_sync(0xffffffffu, cg, o);
-              cb += __shfl_xor_sync(0xffffffffu, cb, o);
-            }
-            if (valid && (r & 7) == 0) {
-              p.alpha_direct[m] = a;
-              p.rgb_direct[3 * (size_t)m] = cr; p.rgb_direct[3 * (size_t)m + 1] = cg; p.rgb_direct[3 * (size_t)m + 2] = cb;
-            }
-          }
-        }
-        // canonical-frame offset and its positional encoding -> chunk 2 of the operand tile
-        const float* G = in.ginv + 9 * (size_t)idx;
-        float rc[3];
-        rc[0] = __ldg(G) * rx + __ldg(G + 1) * ry + __ldg(G + 2) * rz;
-        rc[1] = __ldg(G + 3) * rx + __ldg(G + 4) * ry + __ldg(G + 5) * rz;
-        rc[2] = __ldg(G + 6) * rx + __ldg(G + 7) * ry + __ldg(G + 8) * rz;
-        uint8_t* t_hi = sA + (size_t)(2 * NSPLIT) * TC_TILE_BYTES;
-        uint8_t* t_lo = t_hi + TC_TILE_BYTES;
-        auto put = [&](int col, float v) {
-          __half hi, lo;
-          split_half(v, hi, lo);
-          const uint32_t o = sw128_offset(r, col);
-          *reinterpret_cast<__half*>(t_hi + o) = hi;
-          if (NSPLIT == 2) *reinterpret_cast<__half*>(t_lo + o) = lo;
-        };
-        if (half == 0) {
-          put(0, rc[0]); put(1, rc[1]); put(2, rc[2]);
-          put(63, 0.f);
-        }
-        // poc_fre: column 3 + d*10 + i = sin(rel_c[d] * 2^i), column 33 + d*10 + i = cos(...); half h owns i = 5h..5h+4
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-#pragma unroll
-          for (int ii = 0; ii < 5; ++ii) {
-            const int i = half * 5 + ii;
-            float sn, cs;
-            sincosf(rc[d] * (float)(1 << i), &sn, &cs);
-            put(3 + d * 10 + i, sn);
-            put(33 + d * 10 + i, cs);
-          }
-        }
-      }
-      compute_sync();     // sIdx visible
-      // ---------------------------------------------------------------- prologue 2: feature gather (one warp per row)
-      {
-#pragma unroll 4
-        for (int j = 0; j < TC_ROWS / TC_COMPUTE_WARPS; ++j) {
-          const int r = warp * (TC_ROWS / TC_COMPUTE_WARPS) + j;
-          const float4 f = __ldg(reinterpret_cast<const float4*>(in.feat + (size_t)sIdx[r] * APN_C) + lane);
-          __half h0, l0, h1, l1, h2, l2, h3, l3;
-          split_half(f.x, h0, l0); split_half(f.y, h1, l1); split_half(f.z, h2, l2); split_half(f.w, h3, l3);
-          const int kc = lane >> 4, unit = (lane & 15) >> 1;
-          const uint32_t o = (uint32_t)(r * 128 + (((unit ^ (r & 7)) & 7) << 4) + ((lane & 1) << 3));
-          uint8_t* t_hi = sA + (size_t)(kc * NSPLIT) * TC_TILE_BYTES;
-          *reinterpret_cast<uint2*>(t_hi + o) = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
-          if (NSPLIT == 2) *reinterpret_cast<uint2*>(t_hi + TC_TILE_BYTES + o) = make_uint2(pack_half2(l0, l1), pack_half2(l2, l3));
-        }
-      }
+    uint32_t ph_acc0 = 0, ph_acc1 = 0;
+    const int q = warp & 3, cq = warp >> 2;
+    const int erow = q * 32 + lane;                       // accumulator row (tensor-memory lane) owned in the epilogues
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    int n = 0;
+    if ((int)blockIdx.x < p.n_tiles) {
+      tc_prologue<NSPLIT>(p, blockIdx.x, tid, sPE, sIdw, sIdx);
       fence_proxy_async_smem();
-      mbar_arrive(a_ready);
-      // ---------------------------------------------------------------- layers
-      for (int layer = 0; layer < 4; ++layer) {
-        mbar_wait(acc_ready, ph_acc);
-        ph_acc ^= 1;
+      mbar_arrive(pe_ready);
+      compute_sync();
+    }
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++n) {
+      const int buf = n & 1;
+      const int m0 = tile * TC_SAMPLES;
+      // ---------------------------------------------------------------- epilogues of layers 0..2
+#pragma unroll
+      for (int layer = 0; layer < 3; ++layer) {
+        float4 pf[2][4];
+        if (layer == 0) {
+          // P[idx] rows for this thread's 2 x 16 columns, in flight while the layer-0 MMAs finish
+          const float* prow = p.ptable + (size_t)sIdx[buf * 128 + erow] * APN_C + cq * 16;
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pf[ph][u] = __ldg(reinterpret_cast<const float4*>(prow + ph * 64) + u);
+        }
+        if (layer & 1) {
+          mbar_wait(acc_ready + 1, ph_acc1);
+          ph_acc1 ^= 1;
+        } else {
+          mbar_wait(acc_ready, ph_acc0);
+          ph_acc0 ^= 1;
+        }
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chalf * 64);
-        const float* bias = sBias + layer * 128 + chalf * 64;
-        if (layer < 3) {
-          uint8_t* t_hi = sA + (size_t)(chalf * NSPLIT) * TC_TILE_BYTES + (size_t)erow * 128;
+        const uint32_t tacc = tmem_base + (uint32_t)((layer & 1) * 128) + tlane;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t v[32];
-            tmem_ld32(taddr + hh * 32, v);
-            tmem_ld_wait();
+        for (int ph = 0; ph < 2; ++ph) {                  // K chunk `ph` of the next layer's operand
+          uint32_t v[16];
+          tmem_ld16(tacc + ph * 64 + cq * 16, v);
+          tmem_ld_wait();
+          const float* bias = sBias + layer * 128 + ph * 64 + cq * 16;
+          uint8_t* t_hi = sAct + (size_t)(ph * NSPLIT) * TC_TILE_BYTES + (size_t)erow * 128;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint32_t ph[4], pl[4];
+          for (int u = 0; u < 2; ++u) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int cidx = hh * 32 + u * 8 + 2 * e;
-                const float y0 = leaky(__uint_as_float(v[u * 8 + 2 * e]) + bias[cidx]);
-                const float y1 = leaky(__uint_as_float(v[u * 8 + 2 * e + 1]) + bias[cidx + 1]);
-                __half a0, b0, a1, b1;
-                split_half(y0, a0, b0);
-                split_half(y1, a1, b1);
-                ph[e] = pack_half2(a0, a1);
-                pl[e] = pack_half2(b0, b1);
+            for (int e = 0; e < 4; ++e) {
+              float y0 = __uint_as_float(v[u * 8 + 2 * e]) + bias[u * 8 + 2 * e];
+              float y1 = __uint_as_float(v[u * 8 + 2 * e + 1]) + bias[u * 8 + 2 * e + 1];
+              if (layer == 0) {
+                const float4 f = pf[ph][u * 2 + (e >> 1)];
+                y0 += (e & 1) ? f.z : f.x;
+                y1 += (e & 1) ? f.w : f.y;
               }
-              const uint32_t o = (uint32_t)((((hh * 4 + u) ^ (erow & 7)) & 7) << 4);
-              *reinterpret_cast<uint4*>(t_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              if (NSPLIT == 2) *reinterpret_cast<uint4*>(t_hi + TC_TILE_BYTES + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              split_half2(leaky(y0), leaky(y1), hi[e], lo[e]);
             }
+            const uint32_t o = (uint32_t)((((cq * 2 + u) ^ (erow & 7)) & 7) << 4);
+            *reinterpret_cast<uint4*>(t_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (NSPLIT == 2) *reinterpret_cast<uint4*>(t_hi + TC_TILE_BYTES + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async_smem();
           tc_fence_before();
-          mbar_arrive(a_ready);
-        } else {
-          // out_k = LeakyReLU(acc + b3); h = sum_k idw_k out_k: reduce-scatter over the 8 lanes of a sample
-          float v[64];
-          {
-            uint32_t t0[32], t1[32];
-            tmem_ld32(taddr, t0);
-            tmem_ld32(taddr + 32, t1);
-            tmem_ld_wait();
-            const float w = sIdw[erow];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v[i] = w * leaky(__uint_as_float(t0[i]) + bias[i]);
-              v[32 + i] = w * leaky(__uint_as_float(t1[i]) + bias[32 + i]);
-            }
-          }
-          tc_fence_before();
-          const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-          float x32[32], x16[16], x8[8];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float send = b4 ? v[i] : v[32 + i];
-            const float keep = b4 ? v[32 + i] : v[i];
-            x32[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float send = b2 ? x32[i] : x32[16 + i];
-            const float keep = b2 ? x32[16 + i] : x32[i];
-            x16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float send = b1 ? x16[i] : x16[8 + i];
-            const float keep = b1 ? x16[8 + i] : x16[i];
-            x8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-          }
-          const int s = erow >> 3, m = m0 + s;
-          if (m < in.M) {
-            const int col = chalf * 64 + (b4 ? 32 : 0) + (b2 ? 16 : 0) + (b1 ? 8 : 0);
-            float4* dst = reinterpret_cast<float4*>(p.h + (size_t)m * APN_C + col);
-            dst[0] = make_float4(x8[0], x8[1], x8[2], x8[3]);
-            dst[1] = make_float4(x8[4], x8[5], x8[6], x8[7]);
-          }
+          mbar_arrive(a_ready + ph);
         }
       }
-      compute_sync();     // sIdw / sIdx are rewritten by the next tile's prologue
+      // ---------------------------------------------------------------- next tile's prologue (under the layer-3 MMAs)
+      const int next = tile + gridDim.x;
+      if (next < p.n_tiles) {
+        tc_prologue<NSPLIT>(p, next, tid, sPE, sIdw + (buf ^ 1) * 128, sIdx + (buf ^ 1) * 128);
+        fence_proxy_async_smem();
+        mbar_arrive(pe_ready);
+      }
+      // ---------------------------------------------------------------- layer 3: out_k = LeakyReLU(acc + b3); h = sum_k idw_k out_k
+      mbar_wait(acc_ready + 1, ph_acc1);
+      ph_acc1 ^= 1;
+      tc_fence_after();
+      {
+        float v[32];
+        {
+          uint32_t t0[16], t1[16];
+          const uint32_t tacc = tmem_base + 128u + tlane;
+          tmem_ld16(tacc + cq * 16, t0);
+          tmem_ld16(tacc + 64 + cq * 16, t1);
+          tmem_ld_wait();
+          const float w = sIdw[buf * 128 + erow];
+          const float* bias = sBias + 3 * 128 + cq * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = w * leaky(__uint_as_float(t0[i]) + bias[i]);
+            v[16 + i] = w * leaky(__uint_as_float(t1[i]) + bias[64 + i]);
+          }
+        }
+        tc_fence_before();
+        // reduce-scatter over the 8 lanes (rows) of a sample: 32 -> 16 -> 8 -> 4 columns per lane
+        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+        float x16[16], x8[8], x4[4];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float send = b4 ? v[i] : v[16 + i];
+          const float keep = b4 ? v[16 + i] : v[i];
+          x16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float send = b2 ? x16[i] : x16[8 + i];
+          const float keep = b2 ? x16[8 + i] : x16[i];
+          x8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = b1 ? x8[i] : x8[4 + i];
+          const float keep = b1 ? x8[4 + i] : x8[i];
+          x4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        const int m = m0 + (erow >> 3);
+        if (m < in.M) {
+          const int col = (b4 ? 64 : 0) + cq * 16 + (b2 ? 8 : 0) + (b1 ? 4 : 0);
+          *reinterpret_cast<float4*>(p.h + (size_t)m * APN_C + col) = make_float4(x4[0], x4[1], x4[2], x4[3]);
+        }
+      }
+      compute_sync();     // next tile's sIdx / sIdw visible to every compute thread; this tile's are free again
     }
   }
   tc_fence_before();
@@ -444,18 +496,18 @@ static int tc_launch(cudaStream_t st, const TcParams& p) {
 }
 
 extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_weights,
-                                    const apn_agg_outputs* out, int precision, void* scratch, size_t scratch_bytes,
-                                    apn_stream_t stream_) {
+                                    const float* point_table, const apn_agg_outputs* out, int precision, void* scratch,
+                                    size_t scratch_bytes, apn_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  APN_CHECK_ARG(in && w && out && packed_weights, "null pointer");
+  APN_CHECK_ARG(in && w && out && packed_weights && point_table, "null pointer");
   APN_CHECK_ARG(precision == 0 || precision == 1, "precision: 0 = fp16 operands, 1 = split fp16 (fp32-class)");
   APN_CHECK_ARG(in->d_in == APN_PE_POS + APN_C || (in->d_in > APN_PE_POS + APN_C && in->d_in <= 256 && in->pose_emb),
                 "d_in must be 191, or 192..256 with a pose embedding");
-  APN_CHECK_ARG(in->pts && in->nn_idx && in->ray_id && in->xyz && in->ginv && in->feat && in->viewdirs, "null input pointer");
+  APN_CHECK_ARG(in->pts && in->nn_idx && in->ray_id && in->xyz && in->ginv && in->viewdirs, "null input pointer");
   APN_CHECK_ARG(out->alpha && out->rgb && out->idw, "alpha, rgb and idw outputs are required");
   APN_CHECK_ARG((out->alpha_direct == nullptr) == (out->rgb_direct == nullptr), "direct outputs come as a pair");
   APN_CHECK_ARG(!out->alpha_direct || (in->canonical_alpha && in->canonical_rgbs && in->direct_eps), "direct branch inputs missing");
-  APN_CHECK_ARG((((uintptr_t)in->feat) & 15) == 0, "feat must be 16-byte aligned");
+  APN_CHECK_ARG((((uintptr_t)point_table) & 15) == 0, "point table must be 16-byte aligned");
   const int M = in->M;
   if (M <= 0) return 0;
   APN_CHECK_ARG(scratch && scratch_bytes >= apn_aggregate_tc_scratch_bytes(M), "scratch too small");
@@ -465,6 +517,7 @@ extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
   for (int l = 0; l < 4; ++l) p.bias[l] = w->b[l];
   p.w0 = w->w[0];
   p.packed = (const uint8_t*)packed_weights;
+  p.ptable = point_table;
   p.h = b.h;
   p.idw = out->idw;
   p.alpha_direct = out->alpha_direct;

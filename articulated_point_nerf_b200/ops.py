@@ -361,23 +361,31 @@ def aggregate(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch.Te
 
 
 class PackedDecoder:
-    """feat_net weights in the tensor-core kernel's shared-memory image (csrc/aggregate_tc.cu).  Re-packed
-    whenever a weight tensor changes (tracked through the tensors' version counters)."""
+    """Derived decoder state of the tensor-core kernel (csrc/aggregate_tc.cu): feat_net weights in the kernel's
+    shared-memory image and the per-point table canonical_feat @ W0_feat^T.  Rebuilt whenever a source tensor
+    changes (tracked through the tensors' version counters)."""
 
     def __init__(self):
-        self.buf = None
-        self.key = None
+        self.buf = self.table = None
+        self.key = self.table_key = None
 
-    def get(self, ws: Sequence[torch.Tensor], d_in: int) -> torch.Tensor:
+    def get(self, ws: Sequence[torch.Tensor], d_in: int, feat: torch.Tensor):
+        lib = _lib.load()
         key = tuple((w.data_ptr(), w._version) for w in ws[:8:2]) + (d_in,)
         if self.key != key:
-            lib = _lib.load()
             if self.buf is None:
                 self.buf = _empty((lib.apn_aggregate_tc_weights_bytes(d_in),), ws[0].device, torch.uint8)
             w = _mlp_struct(ws)
             check(lib.apn_aggregate_tc_pack_weights(C.byref(w), d_in, ptr(self.buf), stream()), "apn_aggregate_tc_pack_weights")
             self.key = key
-        return self.buf
+        tkey = (feat.data_ptr(), feat._version, feat.shape[0], ws[0].data_ptr(), ws[0]._version, d_in)
+        if self.table_key != tkey:
+            if self.table is None or self.table.shape[0] != feat.shape[0]:
+                self.table = _empty((feat.shape[0], FEAT_DIM), feat.device)
+            check(lib.apn_aggregate_tc_point_table(ptr(feat), ptr(ws[0]), d_in, feat.shape[0], ptr(self.table), stream()),
+                  "apn_aggregate_tc_point_table")
+            self.table_key = tkey
+        return self.buf, self.table
 
 
 def aggregate_tc(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch.Tensor], packed: PackedDecoder,
@@ -402,12 +410,12 @@ def aggregate_tc(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch
             out.alpha, out.rgb, out.alpha_direct, out.rgb_direct, out.idw = ptr(alpha), ptr(rgb), ptr(alpha_d), ptr(rgb_d), ptr(idw)
             a = _agg_inputs(c, xyz, ginv, feat, pose_emb, M, d_in)
             w = _mlp_struct(ws)
-            pk = packed.get(ws, d_in)
+            pk, table = packed.get(ws, d_in, feat)
             sb = lib.apn_aggregate_tc_scratch_bytes(M)
             scratch = _empty((sb,), dev, torch.uint8)
             with stage("feat_net"):
-                check(lib.apn_aggregate_fwd_tc(C.byref(a), C.byref(w), ptr(pk), C.byref(out), int(precision), ptr(scratch), sb,
-                                               stream()), "apn_aggregate_fwd_tc")
+                check(lib.apn_aggregate_fwd_tc(C.byref(a), C.byref(w), ptr(pk), ptr(table), C.byref(out), int(precision),
+                                               ptr(scratch), sb, stream()), "apn_aggregate_fwd_tc")
     return alpha, rgb, alpha_d, rgb_d, idw
 
 

@@ -203,10 +203,15 @@ int apn_aggregate_bwd(const apn_agg_inputs* in, const apn_mlp_weights* w, const 
  * every weight update); scratch >= apn_aggregate_tc_scratch_bytes(M). */
 size_t apn_aggregate_tc_weights_bytes(int d_in);
 int apn_aggregate_tc_pack_weights(const apn_mlp_weights* w, int d_in, void* packed, apn_stream_t stream);
+/* point_table (N,128) = canonical_feat * W0[:, 63:191]^T in exact fp32: the feature columns of feat_net's first
+ * layer are a gather of per-point rows, so their product with W0 is tabulated per point (rebuild when
+ * canonical_feat or feat_net.0.weight change) and added back in the layer-0 epilogue. */
+int apn_aggregate_tc_point_table(const float* feat, const float* w0, int d_in, int N, float* point_table,
+                                 apn_stream_t stream);
 size_t apn_aggregate_tc_scratch_bytes(int M);
 int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_weights,
-                         const apn_agg_outputs* out, int precision, void* scratch, size_t scratch_bytes,
-                         apn_stream_t stream);
+                         const float* point_table, const apn_agg_outputs* out, int precision, void* scratch,
+                         size_t scratch_bytes, apn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4  Ray compositing.
