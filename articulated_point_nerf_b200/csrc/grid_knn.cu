@@ -23,6 +23,8 @@
 
 #include "common.cuh"
 
+#define GRID_L 2      // Morton levels inside a top cell: leaf edge = top edge / 4, 64 leaves per top cell
+
 struct GridHeader {
   float origin[3];
   float cell;       // finest cell edge
@@ -113,8 +115,8 @@ __global__ void grid_header_kernel(void* blob, const float* __restrict__ bbox, i
   GridHeader* h = (GridHeader*)blob;
   const float rq = sqrtf(r2);
   const float top = rq * 1.01f;
-  int L = (int)rintf(log2f(top / fmaxf(cell_hint, 1e-9f)));
-  L = max(0, min(L, 6));
+  (void)cell_hint;
+  int L = GRID_L;                               // 4 x 4 x 4 leaves per top cell (see the k-NN section)
   float ext[3];
   int td[3];
   for (int c = 0; c < 3; ++c) {
@@ -134,9 +136,11 @@ __global__ void grid_header_kernel(void* blob, const float* __restrict__ bbox, i
     td[0] = td[1] = td[2] = 0;
     n_top = 0;
     L = 0;
-  } else {
-    while (L > 0 && (n_top << (3 * L)) > (long long)cap) --L;
-    cell = top / (float)(1 << L);
+  } else if ((n_top << (3 * L)) > (long long)cap) {
+    bad = true;
+    td[0] = td[1] = td[2] = 0;
+    n_top = 0;
+    L = 0;
   }
   for (int c = 0; c < 3; ++c) {
     h->origin[c] = bbox[c] - pad - 0.5f * cell;
@@ -337,21 +341,28 @@ extern "C" int apn_ray_candidates(const float* rays_o, const float* rays_d, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// k-NN: one WARP per query.
-//   * the 27 neighbour cells of the current level are fetched by lanes 0..26 (two cell_start
-//     loads each), their point ranges are flattened with a warp prefix sum, and the warp then
-//     walks the concatenated list 32 points at a time (coalesced float4 loads of `sorted`);
+// k-NN: one WARP per query, pruned two-level traversal.
+//   * a top cell (edge 1.01*sqrt(r2)) owns 64 leaves (4x4x4, Morton order) whose point ranges are
+//     contiguous in `sorted`; the 65 range boundaries of a top cell are two coalesced loads;
 //   * the running top-8 lives in lanes 0..7 as sorted 64-bit keys (d2 bits << 32 | index, i.e.
-//     lexicographic (d2, index): the tie-break of the neighbour contract);
-//   * a point is inserted only if its key beats the current threshold.  The threshold starts
-//     at the level's certified radius (a farther point could not be certified at this level
-//     anyway) and tightens to the 8th best, so insertions become rare after the first chunk.
+//     lexicographic (d2, index): the tie-break of the neighbour contract); `thr` is the key a point
+//     must beat: it starts at the search bound (r2 for ray samples, tightened by the previous
+//     sample of the same ray: |d8(p) - d8(p')| <= |p - p'|) and drops to the 8th best;
+//   * top cells are visited nearest-first and only while their box can still hold a point that
+//     beats thr; inside a top cell only leaves whose box passes the same test are scanned (the
+//     leaf containing the query first, to tighten thr early).  Boxes are inflated by `eps` so
+//     that the float rounding of the point -> cell assignment can never hide a point.
+// The result is the exact top-8 under the contract, independent of bounds and visiting order.
 // ---------------------------------------------------------------------------------------
 #define KEY_INF 0x7f800000ffffffffull  // (+inf, max index)
 #define FULL_MASK 0xffffffffu
 
 __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
   return __shfl_sync(FULL_MASK, v, src);
+}
+__device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as_float((unsigned int)(k >> 32)); }
+__device__ __forceinline__ unsigned long long bound_key(float d2) {
+  return ((unsigned long long)__float_as_uint(d2) << 32) | 0xffffffffull;
 }
 
 // lanes 0..7 hold the sorted best keys; inserts k (k < best[7] is the caller's business)
@@ -376,101 +387,166 @@ __device__ __forceinline__ void warp_topk_offer(unsigned long long& best, unsign
   }
 }
 
+__device__ __forceinline__ unsigned long long point_key(const float4* __restrict__ sorted, int i, float qx, float qy, float qz) {
+  const float4 P = __ldg(sorted + i);
+  const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
+  return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
+}
+
 __device__ __forceinline__ void warp_scan_range(const float4* __restrict__ sorted, int s, int e, float qx, float qy, float qz,
                                                 unsigned long long& best, unsigned long long& thr, int lane) {
   for (int base = s; base < e; base += 32) {
     const int i = base + lane;
-    unsigned long long key = KEY_INF;
-    if (i < e) {
-      const float4 P = __ldg(sorted + i);
-      const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
-      key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
-    }
-    warp_topk_offer(best, thr, key, lane);
+    warp_topk_offer(best, thr, i < e ? point_key(sorted, i, qx, qy, qz) : KEY_INF, lane);
   }
 }
 
-// Exact K-NN of q by one warp; the result (sorted keys) is left in `best` of lanes 0..7.  If bounded,
-// returns false as soon as it is certain that the K-th squared distance exceeds r2.  Unbounded
-// queries fall back to a full scan when the top level cannot certify the result (never happens
-// for queries inside a dense cloud).
-__device__ bool knn_search_warp(const GridView& g, float qx, float qy, float qz, bool bounded, unsigned long long& best,
-                                int lane) {
-  const GridHeader* h = g.h;
-  const int L = h->L, tx = h->top_dim[0], ty = h->top_dim[1], tz = h->top_dim[2];
-  const float lx0 = qx - h->origin[0], ly0 = qy - h->origin[1], lz0 = qz - h->origin[2];
-  const float r2 = h->r2, cell = h->cell;
-  int ix, iy, iz;
-  point_cell(h, qx, qy, qz, ix, iy, iz);
-  // neighbour offset of this lane (lanes 27..31 idle during the gather)
-  const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
-  int l = 0;
-  while (true) {
-    const int cx = ix >> l, cy = iy >> l, cz = iz >> l;
-    const int dxm = tx << (L - l), dym = ty << (L - l), dzm = tz << (L - l);
-    // certified radius of this level
-    const float sl = cell * (float)(1 << l);
-    const float mx = fminf(lx0 - cx * sl, (cx + 1) * sl - lx0);
-    const float my = fminf(ly0 - cy * sl, (cy + 1) * sl - ly0);
-    const float mz = fminf(lz0 - cz * sl, (cz + 1) * sl - lz0);
-    const float gr = (sl + fminf(mx, fminf(my, mz))) * 0.999f;
-    const float gr2 = gr > 0.f ? gr * gr : 0.f;
-    const bool last = (l == L);
-    // at the last level an unbounded query must keep everything it sees (it falls back to a full scan otherwise)
-    unsigned long long thr = ((unsigned long long)__float_as_uint(gr2) << 32) | 0xffffffffull;
-    best = KEY_INF;
-    // gather the (up to) 27 ranges
-    int s = 0, n = 0;
-    {
-      const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
-      if (lane < 27 && nx >= 0 && ny >= 0 && nz >= 0 && nx < dxm && ny < dym && nz < dzm) {
-        const int key = cell_key(nx << l, ny << l, nz << l, L, tx, ty);
-        s = __ldg(g.cell_start + key);
-        n = __ldg(g.cell_start + key + (1 << (3 * l))) - s;
-      }
-    }
-    int incl = n;
+// every lane contributes one range [s, s+n) (n may be 0); the warp walks the concatenation 32 points at a time
+__device__ __forceinline__ void warp_scan_ranges(const float4* __restrict__ sorted, int s, int n, float qx, float qy, float qz,
+                                                 unsigned long long& best, unsigned long long& thr, int lane) {
+  int incl = n;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(FULL_MASK, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(FULL_MASK, incl, 31);
-    for (int base = 0; base < total; base += 32) {
-      const int j = base + lane;
-      // cell holding flattened index j: number of cells with incl <= j
-      int c = 0;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(FULL_MASK, incl, 31);
+  for (int base = 0; base < total; base += 32) {
+    const int j = base + lane;
+    int c = 0;                                     // lane (range) holding flattened index j: #ranges with incl <= j
 #pragma unroll
-      for (int st = 16; st > 0; st >>= 1) {
-        const int v = __shfl_sync(FULL_MASK, incl, c + st - 1);
-        if (j >= v) c += st;
-      }
-      c = min(c, 31);
-      const int cs = __shfl_sync(FULL_MASK, s, c);
-      const int ci = __shfl_sync(FULL_MASK, incl, c);
-      const int cn = __shfl_sync(FULL_MASK, n, c);
-      unsigned long long key = KEY_INF;
-      if (j < total) {
-        const float4 P = __ldg(g.sorted + cs + (j - (ci - cn)));
-        const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
-        key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
-      }
-      warp_topk_offer(best, thr, key, lane);
+    for (int st = 16; st > 0; st >>= 1) {
+      const int v = __shfl_sync(FULL_MASK, incl, c + st - 1);
+      if (j >= v) c += st;
     }
-    const unsigned long long b7 = shfl_u64(best, APN_K - 1);
-    const float d8 = __uint_as_float((unsigned int)(b7 >> 32));   // +inf when fewer than 8 points inside gr
-    if (gr > 0.f && d8 <= gr2) return !bounded || d8 <= r2;
-    if (bounded && gr > 0.f && gr2 > r2) return false;              // every unseen point is farther than sqrt(r2)
-    if (last) {
-      if (bounded) return false;
-      best = KEY_INF;
-      thr = KEY_INF;
-      warp_scan_range(g.sorted, 0, h->n_points, qx, qy, qz, best, thr, lane);
-      return true;
-    }
-    ++l;
+    c = min(c, 31);
+    const int cs = __shfl_sync(FULL_MASK, s, c);
+    const int ci = __shfl_sync(FULL_MASK, incl, c);
+    const int cn = __shfl_sync(FULL_MASK, n, c);
+    warp_topk_offer(best, thr, j < total ? point_key(sorted, cs + (j - (ci - cn)), qx, qy, qz) : KEY_INF, lane);
   }
 }
+
+// squared distance from q to the axis-aligned box [lo, lo+size]^3 inflated by eps (0 inside)
+__device__ __forceinline__ float box_dist2(float qx, float qy, float qz, float lx, float ly, float lz, float size, float eps) {
+  const float dx = fmaxf(fmaxf(lx - eps - qx, qx - (lx + size + eps)), 0.f);
+  const float dy = fmaxf(fmaxf(ly - eps - qy, qy - (ly + size + eps)), 0.f);
+  const float dz = fmaxf(fmaxf(lz - eps - qz, qz - (lz + size + eps)), 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+struct KnnQuery {
+  float qx, qy, qz;      // query
+  float ox, oy, oz;      // grid origin
+  float T, cell, eps;
+  int tx, ty, tz;
+};
+
+// scans the leaves of top cell t that can still hold a point beating thr; seed >= 0: that leaf first
+__device__ __forceinline__ void knn_visit_top(const GridView& g, const KnnQuery& k, int t, int seed, unsigned long long& best,
+                                              unsigned long long& thr, int lane) {
+  const int* cs = g.cell_start + ((size_t)t << (3 * GRID_L));
+  const int s0 = __ldg(cs + lane), s1 = __ldg(cs + 32 + lane), end = __ldg(cs + 64);
+  int e0 = __shfl_down_sync(FULL_MASK, s0, 1), e1 = __shfl_down_sync(FULL_MASK, s1, 1);
+  const int s1_first = __shfl_sync(FULL_MASK, s1, 0);
+  if (lane == 31) {
+    e0 = s1_first;
+    e1 = end;
+  }
+  int n0 = e0 - s0, n1 = e1 - s1;
+  if (seed >= 0) {
+    const int sl = seed & 31;
+    const int ss = __shfl_sync(FULL_MASK, seed < 32 ? s0 : s1, sl), se = __shfl_sync(FULL_MASK, seed < 32 ? e0 : e1, sl);
+    warp_scan_range(g.sorted, ss, se, k.qx, k.qy, k.qz, best, thr, lane);
+    if (lane == sl) {
+      if (seed < 32) n0 = 0;
+      else n1 = 0;
+    }
+  }
+  const int tcx = t % k.tx, tcy = (t / k.tx) % k.ty, tcz = t / (k.tx * k.ty);
+  const float bx = k.ox + tcx * k.T, by = k.oy + tcy * k.T, bz = k.oz + tcz * k.T;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int l = lane + 32 * half;
+    const int lx = (l & 1) | ((l >> 2) & 2), ly = ((l >> 1) & 1) | ((l >> 3) & 2), lz = ((l >> 2) & 1) | ((l >> 4) & 2);
+    const int n = half ? n1 : n0;
+    const float md2 = box_dist2(k.qx, k.qy, k.qz, bx + lx * k.cell, by + ly * k.cell, bz + lz * k.cell, k.cell, k.eps);
+    const bool active = n > 0 && md2 <= key_d2(thr);
+    if (__any_sync(FULL_MASK, active))
+      warp_scan_ranges(g.sorted, half ? s1 : s0, active ? n : 0, k.qx, k.qy, k.qz, best, thr, lane);
+  }
+}
+
+// Exact K-NN of q by one warp; the result (sorted keys) is left in `best` of lanes 0..7.
+// bounded: only neighbours with d2 <= r2 matter; returns whether 8 of them exist.
+// bound_d2: a caller-supplied upper bound on the 8th squared distance (+inf if none).
+__device__ bool knn_search_warp(const GridView& g, float qx, float qy, float qz, bool bounded, float bound_d2,
+                                unsigned long long& best, int lane) {
+  const GridHeader* h = g.h;
+  KnnQuery k;
+  k.qx = qx; k.qy = qy; k.qz = qz;
+  k.ox = h->origin[0]; k.oy = h->origin[1]; k.oz = h->origin[2];
+  k.T = h->top_cell; k.cell = h->cell; k.eps = 1e-4f * h->cell + 1e-6f;
+  k.tx = h->top_dim[0]; k.ty = h->top_dim[1]; k.tz = h->top_dim[2];
+  const float lx0 = qx - k.ox, ly0 = qy - k.oy, lz0 = qz - k.oz;
+  const int cx = (int)floorf(lx0 / k.T), cy = (int)floorf(ly0 / k.T), cz = (int)floorf(lz0 / k.T);
+  best = KEY_INF;
+  unsigned long long thr = bound_key(bounded ? fminf(h->r2, bound_d2) : bound_d2);
+  // the 27 top cells around the query
+  int t = -1;
+  float md2 = INFINITY;
+  {
+    const int nx = cx + lane % 3 - 1, ny = cy + (lane / 3) % 3 - 1, nz = cz + lane / 9 - 1;
+    if (lane < 27 && nx >= 0 && ny >= 0 && nz >= 0 && nx < k.tx && ny < k.ty && nz < k.tz) {
+      t = (nz * k.ty + ny) * k.tx + nx;
+      const int cnt = __ldg(g.cell_start + (((size_t)t + 1) << (3 * GRID_L))) - __ldg(g.cell_start + ((size_t)t << (3 * GRID_L)));
+      if (cnt > 0) md2 = box_dist2(qx, qy, qz, k.ox + nx * k.T, k.oy + ny * k.T, k.oz + nz * k.T, k.T, k.eps);
+    }
+  }
+  // leaf containing the query, if its top cell is inside the grid
+  int seed = -1;
+  if (cx >= 0 && cy >= 0 && cz >= 0 && cx < k.tx && cy < k.ty && cz < k.tz) {
+    const int ix = min(max((int)floorf((lx0 - cx * k.T) / k.cell), 0), 3), iy = min(max((int)floorf((ly0 - cy * k.T) / k.cell), 0), 3),
+              iz = min(max((int)floorf((lz0 - cz * k.T) / k.cell), 0), 3);
+    seed = (int)(part1by2(ix) | (part1by2(iy) << 1) | (part1by2(iz) << 2));
+  }
+  const int t_centre = __shfl_sync(FULL_MASK, t, 13);
+  while (true) {
+    const float m = warp_min(md2);
+    if (m == INFINITY || !(m <= key_d2(thr))) break;
+    const int src = __ffs(__ballot_sync(FULL_MASK, md2 == m)) - 1;
+    const int tsel = __shfl_sync(FULL_MASK, t, src);
+    if (lane == src) md2 = INFINITY;
+    knn_visit_top(g, k, tsel, (tsel == t_centre) ? seed : -1, best, thr, lane);
+  }
+  if (bounded) return key_d2(shfl_u64(best, APN_K - 1)) <= h->r2;
+  // unbounded: certified if the 8th distance lies inside the 3x3x3 block; otherwise sweep the remaining top cells
+  const float mx = fminf(lx0 - cx * k.T, (cx + 1) * k.T - lx0), my = fminf(ly0 - cy * k.T, (cy + 1) * k.T - ly0),
+              mz = fminf(lz0 - cz * k.T, (cz + 1) * k.T - lz0);
+  const float gr = (k.T + fminf(mx, fminf(my, mz))) * 0.999f;
+  if (gr > 0.f && key_d2(shfl_u64(best, APN_K - 1)) <= gr * gr) return true;
+  for (int c0 = 0; c0 < h->n_top; c0 += 32) {
+    const int tt = c0 + lane;
+    bool cand = false;
+    if (tt < h->n_top) {
+      const int nx = tt % k.tx, ny = (tt / k.tx) % k.ty, nz = tt / (k.tx * k.ty);
+      const bool in_block = abs(nx - cx) <= 1 && abs(ny - cy) <= 1 && abs(nz - cz) <= 1;
+      if (!in_block) {
+        const int cnt = __ldg(g.cell_start + (((size_t)tt + 1) << (3 * GRID_L))) - __ldg(g.cell_start + ((size_t)tt << (3 * GRID_L)));
+        cand = cnt > 0 && box_dist2(qx, qy, qz, k.ox + nx * k.T, k.oy + ny * k.T, k.oz + nz * k.T, k.T, k.eps) <= key_d2(thr);
+      }
+    }
+    unsigned int mk = __ballot_sync(FULL_MASK, cand);
+    while (mk) {
+      const int src = __ffs(mk) - 1;
+      mk &= mk - 1;
+      knn_visit_top(g, k, c0 + src, -1, best, thr, lane);
+    }
+  }
+  return true;
+}
+
+#define KNN_GROUP 8     // consecutive candidates (ray-major order) handled by one warp, so bounds carry over along a ray
 
 __global__ void __launch_bounds__(128)
 knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
@@ -481,16 +557,33 @@ knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, f
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_cand; i += warps) {
-    const RaySetup s = ray_setup(rays_o, rays_d, __ldg(cand_ray + i), bmin, bmax, near, far, stepdist);
-    float px, py, pz;
-    ray_point(s, __ldg(cand_step + i), stepdist, px, py, pz);
-    unsigned long long best;
-    const bool ok = knn_search_warp(g, px, py, pz, true, best, lane);
-    if (lane == 0) keep[i] = ok ? 1 : 0;
-    if (ok && lane < APN_K) {
-      nn_idx[(size_t)i * APN_K + lane] = (int)(unsigned int)best;
-      if (nn_d2) nn_d2[(size_t)i * APN_K + lane] = __uint_as_float((unsigned int)(best >> 32));
+  const int n_groups = (n_cand + KNN_GROUP - 1) / KNN_GROUP;
+  for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
+    int prev_ray = -1, prev_step = 0;
+    float prev_d8 = -1.f;
+    const int i_end = min(n_cand, (grp + 1) * KNN_GROUP);
+    for (int i = grp * KNN_GROUP; i < i_end; ++i) {
+      const int r = __ldg(cand_ray + i), st = __ldg(cand_step + i);
+      const RaySetup s = ray_setup(rays_o, rays_d, r, bmin, bmax, near, far, stepdist);
+      float px, py, pz;
+      ray_point(s, st, stepdist, px, py, pz);
+      // |d8(p) - d8(p')| <= |p - p'| = (step - step') * stepdist along a ray (unit direction)
+      float bound = INFINITY;
+      if (r == prev_ray && prev_d8 >= 0.f) {
+        const float u = (prev_d8 + (float)(st - prev_step) * stepdist) * 1.0005f;
+        bound = u * u + 1e-12f;
+      }
+      unsigned long long best;
+      bool ok = knn_search_warp(g, px, py, pz, true, bound, best, lane);
+      if (!ok && bound < h->r2) ok = knn_search_warp(g, px, py, pz, true, INFINITY, best, lane);   // safety net, never taken
+      if (lane == 0) keep[i] = ok ? 1 : 0;
+      if (ok && lane < APN_K) {
+        nn_idx[(size_t)i * APN_K + lane] = (int)(unsigned int)best;
+        if (nn_d2) nn_d2[(size_t)i * APN_K + lane] = key_d2(best);
+      }
+      prev_ray = r;
+      prev_step = st;
+      prev_d8 = ok ? sqrtf(key_d2(shfl_u64(best, APN_K - 1))) : -1.f;
     }
   }
 }
@@ -501,7 +594,7 @@ extern "C" int apn_knn(const float* rays_o, const float* rays_d, float near, flo
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_cand <= 0) return 0;
   APN_CHECK_ARG(rays_o && rays_d && grid && cand_ray && cand_step && nn_idx && keep, "null pointer");
-  const int blocks = min(apn_div_up(n_cand, 4), APN_SM_COUNT * 16);   // 4 warps (queries) per block, persistent grid-stride
+  const int blocks = min(apn_div_up(n_cand, 4 * KNN_GROUP), APN_SM_COUNT * 16);   // 4 warps per block, persistent grid-stride
   knn_kernel<<<blocks, 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand, nn_idx, nn_d2,
                                          keep);
   APN_LAUNCH_CHECK();
@@ -558,7 +651,7 @@ knn_points_kernel(const float* __restrict__ query, int n_query, const void* __re
     unsigned long long best = KEY_INF;
     if (!g.h->overflow)
       knn_search_warp(g, __ldg(query + 3 * (size_t)i), __ldg(query + 3 * (size_t)i + 1), __ldg(query + 3 * (size_t)i + 2), false,
-                      best, lane);
+                      INFINITY, best, lane);
     if (lane < k) {
       nn_idx[(size_t)i * k + lane] = (int)(unsigned int)best;
       if (nn_d2) nn_d2[(size_t)i * k + lane] = __uint_as_float((unsigned int)(best >> 32));
