@@ -31,8 +31,36 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+_ITEMSIZE = {torch.float32: 4, torch.int32: 4, torch.uint8: 1, torch.int64: 8, torch.float16: 2}
+
+
+def _zeros_like_many(tensors):
+    """Zero gradients for a list of tensors as views of ONE flat buffer (one memset instead of one per tensor)."""
+    sizes = [(t.numel() + 3) // 4 * 4 for t in tensors]          # keep every view 16-byte aligned
+    flat = torch.zeros(sum(sizes), device=tensors[0].device, dtype=torch.float32)
+    out, o = [], 0
+    for t, n in zip(tensors, sizes):
+        out.append(flat[o:o + t.numel()].view(t.shape))
+        o += n
+    return out
+
+
 def _empty(shape, device, dtype=torch.float32):
-    return torch.empty(shape, device=device, dtype=dtype)
+    """torch.empty whose storage size is rounded up to quarter-octave buckets once it exceeds 256 KiB: the sizes
+    of the per-step buffers follow the (data-dependent) sample counts, and a handful of bucket sizes keeps them
+    inside the caching allocator instead of reaching cudaMalloc whenever a batch is a little larger than any
+    before it."""
+    if isinstance(shape, int):
+        shape = (shape,)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    itemsize = _ITEMSIZE.get(dtype) or torch.empty((), dtype=dtype).element_size()
+    if n * itemsize <= (1 << 18):
+        return torch.empty(shape, device=device, dtype=dtype)
+    q = 1 << max(n.bit_length() - 3, 0)
+    cap = (n + q - 1) // q * q
+    return torch.empty((cap,), device=device, dtype=dtype)[:n].view(shape)
 
 
 # --------------------------------------------------------------------------------------
@@ -303,8 +331,14 @@ class _Aggregate(torch.autograd.Function):
             with stage("feat_net"):
                 check(lib.apn_aggregate_fwd(C.byref(a), C.byref(w), C.byref(out), ptr(scratch), scratch_bytes, stream()),
                       "apn_aggregate_fwd")
-        ctx.c, ctx.saved, ctx.d_in = c, saved, d_in
-        ctx.tensors = (xyz, ginv, feat, pose_emb, ws, alpha, rgb, idw)
+        # every tensor goes through save_for_backward: keeping outputs (alpha, rgb, idw) as plain attributes of ctx
+        # would create a node -> tensor -> node reference cycle that only the Python GC frees, i.e. a slow leak of
+        # device memory between collections
+        ctx.c, ctx.d_in, ctx.has_pose, ctx.has_saved = c, d_in, pose_emb is not None, saved is not None
+        extra = []
+        if saved is not None:
+            extra = [saved["x0"], *saved["act"], saved["h"], saved["exp_d"], saved["fv"], saved["v0"]]
+        ctx.save_for_backward(xyz, ginv, feat, pose_emb if pose_emb is not None else xyz.new_empty(0), *ws, alpha, rgb, idw, *extra)
         ctx.mark_non_differentiable(idw)
         if c.direct:
             ctx.mark_non_differentiable(alpha_d, rgb_d)
@@ -314,25 +348,36 @@ class _Aggregate(torch.autograd.Function):
     def backward(ctx, d_alpha, d_rgb, *_):
         lib = _lib.load()
         c = ctx.c
-        xyz, ginv, feat, pose_emb, ws, alpha, rgb, idw = ctx.tensors
+        sv_all = ctx.saved_tensors
+        xyz, ginv, feat, pose_emb = sv_all[0:4]
+        if not ctx.has_pose:
+            pose_emb = None
+        ws = list(sv_all[4:20])
+        alpha, rgb, idw = sv_all[20:23]
         M = c.pts.shape[0]
         dev = xyz.device
         need = ctx.needs_input_grad      # (c, xyz, ginv, feat, pose_emb, *ws)
-        d_xyz = torch.zeros_like(xyz) if need[1] else None
-        d_ginv = torch.zeros_like(ginv) if need[2] else None
-        d_feat = torch.zeros_like(feat) if need[3] else None
-        d_pose = torch.zeros_like(pose_emb) if (pose_emb is not None and need[4]) else None
-        d_ws = [torch.zeros_like(w) for w in ws]
+        wanted = [t for t, n in ((xyz, need[1]), (ginv, need[2]), (feat, need[3])) if n]
+        if pose_emb is not None and need[4]:
+            wanted.append(pose_emb)
+        zs = _zeros_like_many(wanted + list(ws))
+        zi = iter(zs)
+        d_xyz = next(zi) if need[1] else None
+        d_ginv = next(zi) if need[2] else None
+        d_feat = next(zi) if need[3] else None
+        d_pose = next(zi) if (pose_emb is not None and need[4]) else None
+        d_ws = list(zi)
         if M > 0:
+            assert ctx.has_saved
             d_alpha = torch.zeros_like(alpha) if d_alpha is None else _f32(d_alpha)
             d_rgb = torch.zeros_like(rgb) if d_rgb is None else _f32(d_rgb)
-            sv = ctx.saved
+            x0, a0, a1, a2, a3, h, exp_d, fv, v0 = sv_all[23:32]
             out = AggOutputs()
             out.alpha, out.rgb, out.idw = ptr(alpha), ptr(rgb), ptr(idw)
-            out.x0 = ptr(sv["x0"])
-            for l in range(4):
-                out.act[l] = ptr(sv["act"][l])
-            out.h, out.exp_d, out.fv, out.v0 = ptr(sv["h"]), ptr(sv["exp_d"]), ptr(sv["fv"]), ptr(sv["v0"])
+            out.x0 = ptr(x0)
+            for l, a_ in enumerate((a0, a1, a2, a3)):
+                out.act[l] = ptr(a_)
+            out.h, out.exp_d, out.fv, out.v0 = ptr(h), ptr(exp_d), ptr(fv), ptr(v0)
             g = AggGrads()
             g.d_alpha, g.d_rgb = ptr(d_alpha), ptr(d_rgb)
             g.d_xyz, g.d_ginv, g.d_feat, g.d_pose_emb = ptr(d_xyz), ptr(d_ginv), ptr(d_feat), ptr(d_pose)
@@ -348,7 +393,6 @@ class _Aggregate(torch.autograd.Function):
             with stage("feat_net_bwd"):
                 check(lib.apn_aggregate_bwd(C.byref(a), C.byref(w), C.byref(out), C.byref(g), ptr(scratch), sb, stream()),
                       "apn_aggregate_bwd")
-        ctx.saved = None
         if d_pose is not None and pose_emb is not None:
             d_pose = d_pose.reshape(pose_emb.shape)
         return (None, d_xyz, d_ginv, d_feat, d_pose, *[dw if need[5 + i] else None for i, dw in enumerate(d_ws)])

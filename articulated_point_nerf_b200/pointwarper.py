@@ -117,9 +117,9 @@ class PointWarper(torch.nn.Module):
         J = R_t.shape[0]
         pivot = joints[pj]
         top = torch.cat((R_t, pivot[..., None] - R_t @ pivot[..., None]), -1)                      # (J,3,4)
-        hom = torch.tensor([0., 0., 0., 1.], device=joints.device, dtype=joints.dtype).expand(J, 1, 4)
-        M = torch.cat((top, hom), -2)
-        M = torch.cat((torch.eye(4, device=joints.device, dtype=joints.dtype)[None], M), 0)         # slot 0 = identity pad
+        eye = torch.eye(4, device=joints.device, dtype=joints.dtype)     # built on the device: CUDA-graph capturable
+        M = torch.cat((top, eye[3:4].expand(J, 1, 4)), -2)
+        M = torch.cat((eye[None], M), 0)                                                            # slot 0 = identity pad
         return self.matrix_chain_product(M[pi + 1])[:, 0]
 
     def get_thetas(self, ts_embed):

@@ -30,6 +30,23 @@ class NoPointsException(Exception):
     pass
 
 
+class _PoseChain(torch.nn.Module):
+    """t_embed, joints -> bone transforms: TransformNet + Rodrigues + kinematic chain (lib/pointwarper.py:217-236)
+    as ONE unit, so that the ~250 tiny launches of its forward + backward can be replayed as two CUDA graphs
+    (torch.cuda.make_graphed_callables) inside the training step.  Never registered as a sub-module of
+    TemporalPoints: the parameters stay under `forward_warp.*`."""
+
+    def __init__(self, warper: PointWarper):
+        super().__init__()
+        self.warper = warper
+
+    def forward(self, t_embed, joints):
+        bone_Ts, global_t = self.warper.pose(joints, t=t_embed)
+        jh = torch.cat([joints, torch.ones((len(joints), 1), device=joints.device, dtype=joints.dtype)], dim=-1)
+        joints_rel = torch.bmm(bone_Ts, jh.unsqueeze(-1)).squeeze(-1)[:, :3]
+        return bone_Ts, global_t, self.warper.prev_thetas, joints_rel
+
+
 def hls_palette(n: int):
     """seaborn.color_palette('hls', n) (lib/temporalpoints.py:692) without the seaborn dependency."""
     hues = np.linspace(0, 1, int(n) + 1)[:-1] + 0.01
@@ -143,6 +160,10 @@ class TemporalPoints(torch.nn.Module):
         # operands, "fp32" = CUDA-core exact path (always used when autograd is recording)
         self.decoder = "tc"
         self._packed_decoder = ops.PackedDecoder()
+        # replay the pose chain (fwd + bwd) as CUDA graphs while training on a CUDA device
+        self.graph_pose = True
+        object.__setattr__(self, '_pose_graph', None)
+        object.__setattr__(self, '_pose_graph_key', None)
 
     # ------------------------------------------------------------------------------------------
     def get_kwargs(self):
@@ -276,14 +297,34 @@ class TemporalPoints(torch.nn.Module):
         """forward_warp stage: -> dict(xyz, ginv, weights, bbox, bone_Ts, global_t, joints_rel)."""
         self._ensure_neighbourhood()
         t_embed = poc_fre(t, self.time_poc) if rot_params is None else None
-        bone_Ts, global_t = self.forward_warp.pose(self.joints, t=t_embed, rot_params=rot_params)
+        joints_rel = None
+        if (self.graph_pose and rot_params is None and torch.is_grad_enabled() and self.joints.is_cuda
+                and self.joints.requires_grad):
+            bone_Ts, global_t, joints_rel = self._pose_graphed(t_embed)
+        else:
+            bone_Ts, global_t = self.forward_warp.pose(self.joints, t=t_embed, rot_params=rot_params)
         rules = self._merge_rules_i32()
         xyz, ginv, w, bbox = ops.lbs(self.weights, self.theta_weight, bone_Ts, global_t, self.canonical_pcd, rules=rules,
                                      eps=float(self.eps))
         self._last_weights = w
-        jh = torch.cat([self.joints, torch.ones((len(self.joints), 1), device=self.joints.device)], dim=-1)
-        joints_rel = torch.bmm(bone_Ts, jh.unsqueeze(-1)).squeeze(-1)[:, :3]
+        if joints_rel is None:
+            jh = torch.cat([self.joints, torch.ones((len(self.joints), 1), device=self.joints.device)], dim=-1)
+            joints_rel = torch.bmm(bone_Ts, jh.unsqueeze(-1)).squeeze(-1)[:, :3]
         return dict(xyz=xyz, ginv=ginv, weights=w, bbox=bbox, bone_Ts=bone_Ts, global_t=global_t, joints_rel=joints_rel)
+
+    def _pose_graphed(self, t_embed):
+        """Pose chain through CUDA graphs (captured on first use, re-captured when the masks change)."""
+        fw = self.forward_warp
+        key = (id(fw.rot_mask), fw.rot_mask._version, id(fw.sibling_mask), fw.sibling_mask._version, self.joints.data_ptr())
+        if self._pose_graph is None or self._pose_graph_key != key:
+            chain = _PoseChain(fw)
+            sample = (t_embed.detach().clone(), self.joints)
+            graphed = torch.cuda.make_graphed_callables(chain, sample)
+            object.__setattr__(self, '_pose_graph', graphed)
+            object.__setattr__(self, '_pose_graph_key', key)
+        bone_Ts, global_t, thetas, joints_rel = self._pose_graph(t_embed.detach(), self.joints)
+        fw.prev_thetas, fw.prev_global_t = thetas, global_t
+        return bone_Ts, global_t, joints_rel
 
     def build_grid(self, warped, query_radius=0.01):
         return ops.Grid(warped['xyz'], warped['bbox'], query_radius=query_radius, bbox_pad=query_radius,

@@ -288,6 +288,8 @@ def main():
     if oracle_state is not None:
         oracle_state["state"] = {k: v.detach().clone() for k, v in oracle_state["state"].items()}
     model = model.to(dev)
+    if os.environ.get("APN_NO_POSE_GRAPH"):
+        model.graph_pose = False
     if args.decoder != "auto":
         model.decoder = args.decoder
     host = [pack_host(b, pin=True) for b in make_batches(scene, mode, n_steps, rank, repose=repose)]
@@ -345,6 +347,11 @@ def main():
             b.record()
             evs.append((a, b))
         barrier()
+        if os.environ.get("APN_ALLOC_STATS") and rank == 0:
+            st = torch.cuda.memory_stats()
+            print(f"  alloc stats ({'e2e' if e2e else 'value'}): device_alloc={st.get('num_device_alloc')} "
+                  f"device_free={st.get('num_device_free')} retries={st.get('num_alloc_retries')} "
+                  f"reserved={st.get('reserved_bytes.all.current', 0) / 1e6:.0f} MB", file=sys.stderr)
         launches = _lib.launch_count() - n0
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
