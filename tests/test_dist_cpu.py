@@ -37,7 +37,7 @@ def _worker(rank, world, port, q):
     for p in bucket.params:                     # autograd accumulated in place into the bucket views
         assert p.grad.data_ptr() >= bucket.flat.data_ptr()
     bucket.all_reduce_avg()
-    q.put((rank, bucket.flat.clone()))
+    q.put((rank, bucket.flat.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,7 +53,7 @@ def test_flat_bucket_allreduce_reproduces_single_process_gradient():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert torch.equal(got[0], got[1])
+    assert got[0] == got[1]
     # single-process reference: equal shards + AVG == gradient of the mean over the whole batch
     torch.manual_seed(0)
     lin = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
@@ -61,7 +61,7 @@ def test_flat_bucket_allreduce_reproduces_single_process_gradient():
     x = torch.arange(40, dtype=torch.float32).reshape(8, 5) / 10
     (lin(x).pow(2).mean(dim=1) + (extra * x[:, :1]).sum(dim=1)).mean().backward()
     ref = torch.cat([p.grad.reshape(-1) for p in list(lin.parameters()) + [extra]])
-    flat = got[0]
+    flat = torch.tensor(got[0])
     # strip the 64-element alignment padding between slices
     vals, o = [], 0
     for p in list(lin.parameters()) + [extra]:
