@@ -61,6 +61,9 @@ SIGNATURES = {
     "apn_version": (I, []),
     "apn_last_error": (C.c_char_p, []),
     "apn_launch_count": (C.c_ulonglong, []),
+    "apn_pose_saved_bytes": (SZ, [I]),
+    "apn_pose_fwd": (I, [P, I, P, P, P, P, P, P, P, I, P, P, P, P, P]),
+    "apn_pose_bwd": (I, [P, I, P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P]),
     "apn_lbs_fwd": (I, [P, P, F, P, P, P, P, I, I, P, P, P, P, P, P]),
     "apn_lbs_bwd_workspace_bytes": (SZ, [I, I]),
     "apn_lbs_bwd": (I, [P, P, F, P, P, P, I, I, P, P, P, P, P, P, P, P, P, P, SZ, P]),
@@ -81,7 +84,12 @@ SIGNATURES = {
     "apn_aggregate_tc_pack_weights": (I, [P, I, P, P]),
     "apn_aggregate_tc_scratch_bytes": (SZ, [I]),
     "apn_aggregate_tc_point_table": (I, [P, P, I, I, P, P]),
-    "apn_aggregate_fwd_tc": (I, [P, P, P, P, P, I, P, SZ, P]),
+    "apn_aggregate_tc_tape_bytes": (SZ, [I]),
+    "apn_aggregate_fwd_tc": (I, [P, P, P, P, P, I, P, SZ, P, SZ, P]),
+    "apn_aggregate_tc_bwd_weights_bytes": (SZ, []),
+    "apn_aggregate_tc_pack_weights_bwd": (I, [P, I, P, P]),
+    "apn_aggregate_tc_bwd_scratch_bytes": (SZ, [I, I]),
+    "apn_aggregate_bwd_tc": (I, [P, P, P, P, P, P, P, SZ, P]),
     "apn_composite_fwd": (I, [P, P, P, P, I, P, I, F, F, P, P, P, P, P, P, P]),
     "apn_composite_bwd": (I, [P, P, P, P, I, F, F, P, P, P, P, P, P, P, P, P]),
     "apn_adam_step_size": (F, [I, F, F, F]),

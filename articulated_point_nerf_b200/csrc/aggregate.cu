@@ -333,6 +333,24 @@ static int colsum(cudaStream_t st, const float* A, int lda, int rows, int N, flo
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+// RGBNet backward (lib/tineuvox.py:77-88): d_rgb -> weight gradients of the three Linear layers and d_h (M,128) of
+// the rgb branch; shared by the fp32 and tensor-core backward paths
+int agg_rgbnet_bwd_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* sv,
+                          const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h) {
+  const int M = in->M;
+  const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 8);
+  const int KV = AGG_C + APN_PE_VIEW;   // 155
+  agg_rgb_out_bwd_kernel<<<wblocks, 256, 0, st>>>(g->d_rgb, sv->rgb, sv->v0, w->rgb_v2_w, M, d_v0, g->d_rgb_v2_w, g->d_rgb_v2_b);
+  APN_LAUNCH_CHECK();
+  APN_CHECK_ARG(gemm_wgrad(st, d_v0, AGG_V0, sv->fv, AGG_FV_LD, g->d_rgb_v0_w, KV, M, AGG_V0, KV) == 0, "wgrad v0");
+  APN_CHECK_ARG(colsum(st, d_v0, AGG_V0, M, AGG_V0, g->d_rgb_v0_b) == 0, "colsum v0");
+  APN_CHECK_ARG(gemm_dgrad(st, d_v0, AGG_V0, w->rgb_v0_w, KV, d_fv, AGG_FV_LD, M, KV, AGG_V0, nullptr, 0, 1.f) == 0, "dgrad v0");
+  APN_CHECK_ARG(gemm_wgrad(st, d_fv, AGG_FV_LD, sv->h, AGG_C, g->d_rgb_feat_w, AGG_C, M, AGG_C, AGG_C) == 0, "wgrad rgb feat");
+  APN_CHECK_ARG(colsum(st, d_fv, AGG_FV_LD, M, AGG_C, g->d_rgb_feat_b) == 0, "colsum rgb feat");
+  APN_CHECK_ARG(gemm_dgrad(st, d_fv, AGG_FV_LD, w->rgb_feat_w, AGG_C, d_h, AGG_C, M, AGG_C, AGG_C, nullptr, 0, 1.f) == 0, "dgrad rgb feat");
+  return 0;
+}
+
 // one warp per sample: raw2alpha/densitynet backward, d_h -> d_act3 (masked), idw backward -> d_d2
 __global__ void __launch_bounds__(256)
 agg_reduce_bwd_kernel(const apn_agg_inputs in, const float* __restrict__ act3, const float* __restrict__ idw,
@@ -500,14 +518,7 @@ extern "C" int apn_aggregate_bwd(const apn_agg_inputs* in, const apn_mlp_weights
   const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 8);
   const int KV = AGG_C + APN_PE_VIEW;   // 155
   // RGBNet
-  agg_rgb_out_bwd_kernel<<<wblocks, 256, 0, st>>>(g->d_rgb, sv->rgb, sv->v0, w->rgb_v2_w, M, b.d_v0, g->d_rgb_v2_w, g->d_rgb_v2_b);
-  APN_LAUNCH_CHECK();
-  APN_CHECK_ARG(gemm_wgrad(st, b.d_v0, AGG_V0, sv->fv, AGG_FV_LD, g->d_rgb_v0_w, KV, M, AGG_V0, KV) == 0, "wgrad v0");
-  APN_CHECK_ARG(colsum(st, b.d_v0, AGG_V0, M, AGG_V0, g->d_rgb_v0_b) == 0, "colsum v0");
-  APN_CHECK_ARG(gemm_dgrad(st, b.d_v0, AGG_V0, w->rgb_v0_w, KV, b.d_fv, AGG_FV_LD, M, KV, AGG_V0, nullptr, 0, 1.f) == 0, "dgrad v0");
-  APN_CHECK_ARG(gemm_wgrad(st, b.d_fv, AGG_FV_LD, sv->h, AGG_C, g->d_rgb_feat_w, AGG_C, M, AGG_C, AGG_C) == 0, "wgrad rgb feat");
-  APN_CHECK_ARG(colsum(st, b.d_fv, AGG_FV_LD, M, AGG_C, g->d_rgb_feat_b) == 0, "colsum rgb feat");
-  APN_CHECK_ARG(gemm_dgrad(st, b.d_fv, AGG_FV_LD, w->rgb_feat_w, AGG_C, b.d_h, AGG_C, M, AGG_C, AGG_C, nullptr, 0, 1.f) == 0, "dgrad rgb feat");
+  if (agg_rgbnet_bwd_launch(st, in, w, sv, g, b.d_v0, b.d_fv, b.d_h)) return -1;
   // densitynet + K-reduce
   agg_reduce_bwd_kernel<<<wblocks, 256, 0, st>>>(*in, sv->act[3], sv->idw, sv->h, sv->exp_d, w->density_w, g->d_alpha, b.d_h, in->xyz,
                                                  b.d_act_a, b.d_d2, g->d_density_w, g->d_density_b);

@@ -29,19 +29,7 @@
 // PE chunk columns: [rel_c(3) sin(30) cos(30) 0] (the reference's own order).  A pose embedding (d_in = 255) is
 // constant over rows: W0[:,191:255] * pose is folded into the layer-0 bias by every CTA at start-up.
 #include "sgemm.cuh"
-#include "tc05.cuh"
-
-using namespace tc05;
-
-#define TC_ROWS 128
-#define TC_SAMPLES 16
-#define TC_NCHUNKS 7                 // chunk 0: layer-0 PE columns; 1..6: layers 1-3, two K chunks of 64 each
-#define TC_TILE_BYTES 16384          // [128 x 64] fp16
-#define TC_CHUNK_GBYTES (2 * TC_TILE_BYTES)   // packed global: hi tile then lo tile
-#define TC_COMPUTE_WARPS 16
-#define TC_COMPUTE_THREADS (32 * TC_COMPUTE_WARPS)
-#define TC_THREADS (TC_COMPUTE_THREADS + 64)
-#define TC_TMEM_COLS 256             // two 128-column fp32 accumulators
+#include "aggregate_tc.cuh"
 
 struct TcParams {
   apn_agg_inputs in;
@@ -53,6 +41,7 @@ struct TcParams {
   float* idw;                 // (M,8)
   float* alpha_direct;        // (M) or NULL
   float* rgb_direct;          // (M,3) or NULL
+  uint8_t* tape;              // training: n_tiles * TC_TAPE_TILE_BYTES, NULL in inference
   int n_tiles;
 };
 
@@ -123,15 +112,11 @@ struct TcSmem {
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;                         // + slack for the 1024-byte alignment
 };
 
-__device__ __forceinline__ float leaky(float y) { return fmaxf(y, 0.01f * y); }
-
-// bar.sync among the compute warps only
-__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE_THREADS) : "memory"); }
-
 // Builds the per-tile sample state (idw, neighbour indices, direct branch) and the PE operand tile.
 // 4 threads per row: part p owns the (dimension, frequency) pairs j = p, p+4, ...
 template <int NSPLIT>
 __device__ __forceinline__ void tc_prologue(const TcParams& p, int tile, int tid, uint8_t* sPE, float* sIdw, int* sIdx) {
+  uint8_t* tape_pe = p.tape ? p.tape + (size_t)tile * TC_TAPE_TILE_BYTES + TC_TAPE_PE(0) : nullptr;
   const apn_agg_inputs& in = p.in;
   const int r = tid & 127, part = tid >> 7;
   const int s = r >> 3;
@@ -192,6 +177,10 @@ __device__ __forceinline__ void tc_prologue(const TcParams& p, int tile, int tid
     const uint32_t o = sw128_offset(r, col);
     *reinterpret_cast<__half*>(sPE + o) = hi;
     if (NSPLIT == 2) *reinterpret_cast<__half*>(sPE + TC_TILE_BYTES + o) = lo;
+    if (tape_pe) {
+      *reinterpret_cast<__half*>(tape_pe + o) = hi;
+      *reinterpret_cast<__half*>(tape_pe + TC_TILE_BYTES + o) = lo;
+    }
   };
   if (part < 3) put(part, part == 0 ? rc[0] : part == 1 ? rc[1] : rc[2]);
   else put(63, 0.f);
@@ -374,6 +363,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParam
           tmem_ld_wait();
           const float* bias = sBias + layer * 128 + ph * 64 + cq * 16;
           uint8_t* t_hi = sAct + (size_t)(ph * NSPLIT) * TC_TILE_BYTES + (size_t)erow * 128;
+          uint8_t* tp = p.tape ? p.tape + (size_t)tile * TC_TAPE_TILE_BYTES : nullptr;
+          uint32_t mbits = 0;
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             uint32_t hi[4], lo[4];
@@ -386,12 +377,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParam
                 y0 += (e & 1) ? f.z : f.x;
                 y1 += (e & 1) ? f.w : f.y;
               }
+              mbits |= (y0 > 0.f ? 1u : 0u) << (u * 8 + 2 * e);
+              mbits |= (y1 > 0.f ? 1u : 0u) << (u * 8 + 2 * e + 1);
               split_half2(leaky(y0), leaky(y1), hi[e], lo[e]);
             }
             const uint32_t o = (uint32_t)((((cq * 2 + u) ^ (erow & 7)) & 7) << 4);
             *reinterpret_cast<uint4*>(t_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (NSPLIT == 2) *reinterpret_cast<uint4*>(t_hi + TC_TILE_BYTES + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (tp) {
+              uint8_t* g = tp + TC_TAPE_ACT(layer, ph, 0) + (size_t)erow * 128 + o;
+              *reinterpret_cast<uint4*>(g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(g + TC_TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
           }
+          if (tp) *reinterpret_cast<uint16_t*>(tp + TC_TAPE_MASK(layer) + ((size_t)erow * 8 + ph * 4 + cq) * 2) = (uint16_t)mbits;
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(a_ready + ph);
@@ -420,9 +419,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParam
           const float* bias = sBias + 3 * 128 + cq * 16;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            v[i] = w * leaky(__uint_as_float(t0[i]) + bias[i]);
-            v[16 + i] = w * leaky(__uint_as_float(t1[i]) + bias[64 + i]);
+            v[i] = leaky(__uint_as_float(t0[i]) + bias[i]);
+            v[16 + i] = leaky(__uint_as_float(t1[i]) + bias[64 + i]);
           }
+          if (p.tape) {
+            uint8_t* tp = p.tape + (size_t)tile * TC_TAPE_TILE_BYTES + (size_t)erow * 128;
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_half2(v[ph * 16 + u * 8 + 2 * e], v[ph * 16 + u * 8 + 2 * e + 1], hi[e], lo[e]);
+                uint8_t* g = tp + TC_TAPE_ACT(3, ph, 0) + (uint32_t)((((cq * 2 + u) ^ (erow & 7)) & 7) << 4);
+                *reinterpret_cast<uint4*>(g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(g + TC_TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= w;
         }
         tc_fence_before();
         // reduce-scatter over the 8 lanes (rows) of a sample: 32 -> 16 -> 8 -> 4 columns per lane
@@ -495,9 +510,13 @@ static int tc_launch(cudaStream_t st, const TcParams& p) {
   return 0;
 }
 
+extern "C" size_t apn_aggregate_tc_tape_bytes(int M) {
+  return M > 0 ? (size_t)apn_div_up(M, TC_SAMPLES) * TC_TAPE_TILE_BYTES : 0;
+}
+
 extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_weights,
-                                    const float* point_table, const apn_agg_outputs* out, int precision, void* scratch,
-                                    size_t scratch_bytes, apn_stream_t stream_) {
+                                    const float* point_table, const apn_agg_outputs* out, int precision, void* tape,
+                                    size_t tape_bytes, void* scratch, size_t scratch_bytes, apn_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   APN_CHECK_ARG(in && w && out && packed_weights && point_table, "null pointer");
   APN_CHECK_ARG(precision == 0 || precision == 1, "precision: 0 = fp16 operands, 1 = split fp16 (fp32-class)");
@@ -510,8 +529,17 @@ extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
   APN_CHECK_ARG((((uintptr_t)point_table) & 15) == 0, "point table must be 16-byte aligned");
   const int M = in->M;
   if (M <= 0) return 0;
-  APN_CHECK_ARG(scratch && scratch_bytes >= apn_aggregate_tc_scratch_bytes(M), "scratch too small");
-  const TcScratch b = tc_scratch_layout((char*)scratch, M);
+  TcScratch b;
+  if (tape) {
+    // training: the split-precision kernel records the tape; the heads' intermediates are kept by the caller
+    APN_CHECK_ARG(precision == 1, "the training forward runs in split precision");
+    APN_CHECK_ARG(tape_bytes >= apn_aggregate_tc_tape_bytes(M) && (((uintptr_t)tape) & 1023) == 0, "tape too small or not 1 KiB aligned");
+    APN_CHECK_ARG(out->h && out->exp_d && out->fv && out->v0, "training needs the h / exp_d / fv / v0 buffers");
+    b.h = out->h; b.exp_d = out->exp_d; b.fv = out->fv; b.v0 = out->v0;
+  } else {
+    APN_CHECK_ARG(scratch && scratch_bytes >= apn_aggregate_tc_scratch_bytes(M), "scratch too small");
+    b = tc_scratch_layout((char*)scratch, M);
+  }
   TcParams p;
   p.in = *in;
   for (int l = 0; l < 4; ++l) p.bias[l] = w->b[l];
@@ -522,6 +550,7 @@ extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
   p.idw = out->idw;
   p.alpha_direct = out->alpha_direct;
   p.rgb_direct = out->rgb_direct;
+  p.tape = (uint8_t*)tape;
   p.n_tiles = apn_div_up(M, TC_SAMPLES);
   const int rc = precision == 0 ? tc_launch<1>(st, p) : tc_launch<2>(st, p);
   if (rc) return rc;

@@ -104,6 +104,22 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
          | (0u << 15) | (0u << 16)     // A, B K-major
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same, with either operand read MN-major (the [row][col] tile is traversed with the reduction over rows)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_major(int M, int N, bool a_mn, bool b_mn) {
+  return umma_idesc_f16(M, N) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16);
+}
+// MN-major view of the same swizzled tiles: 64 contiguous elements (128 bytes) of the M/N dimension per row, 8 rows
+// (K) per 1024-byte atom; the next 64 M/N elements are `lbo_bytes` away, the next 8 K rows 1024 bytes away.
+// A K step of 16 rows advances the start address by 2048 bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -64,6 +64,71 @@ def _empty(shape, device, dtype=torch.float32):
 
 
 # --------------------------------------------------------------------------------------
+# K0: pose chain (TransformNet + Rodrigues + kinematic chain)
+# --------------------------------------------------------------------------------------
+@dataclass
+class PoseTables:
+    """Static int tables of the kinematic tree on the device (lib/pointwarper.py:95-116, 232-234)."""
+    parent_node: torch.Tensor   # (J) int32, -1 for the root
+    pivot: torch.Tensor         # (J) int32
+    sibling: torch.Tensor       # (J) int32
+    rot_mask: Optional[torch.Tensor]   # (J) uint8 or None
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = ptr(t)
+    return arr
+
+
+class _Pose(torch.autograd.Function):
+    """t_embed, joints, TransformNet weights -> bone_Ts (J,4,4), global_t (3), thetas (J) in one launch
+    (csrc/pose.cu); backward in one launch."""
+
+    @staticmethod
+    def forward(ctx, tb: PoseTables, t_embed, joints, *wb):
+        lib = _lib.load()
+        t_embed, joints = _f32(t_embed).reshape(-1), _f32(joints)
+        wb = [_f32(x) for x in wb]                    # w0, b0, w1, b1, w2, b2, w3, b3, w4
+        ws, bs = [wb[0], wb[2], wb[4], wb[6], wb[8]], [wb[1], wb[3], wb[5], wb[7]]
+        J, dev = joints.shape[0], joints.device
+        bone_T, global_t, thetas = _empty((J, 4, 4), dev), _empty((3,), dev), _empty((J,), dev)
+        saved = _empty((lib.apn_pose_saved_bytes(J) // 4,), dev)
+        with stage("transform_net"):
+            check(lib.apn_pose_fwd(ptr(t_embed), t_embed.numel(), _ptr_array(ws), _ptr_array(bs), ptr(joints), ptr(tb.parent_node),
+                                   ptr(tb.pivot), ptr(tb.sibling), ptr(tb.rot_mask), J, ptr(bone_T), ptr(global_t), ptr(thetas),
+                                   ptr(saved), stream()), "apn_pose_fwd")
+        ctx.tb = tb
+        ctx.save_for_backward(t_embed, joints, saved, *wb)
+        return bone_T, global_t, thetas
+
+    @staticmethod
+    def backward(ctx, d_bone_T, d_global_t, d_thetas):
+        lib = _lib.load()
+        tb = ctx.tb
+        t_embed, joints, saved, *wb = ctx.saved_tensors
+        ws, bs = [wb[0], wb[2], wb[4], wb[6], wb[8]], [wb[1], wb[3], wb[5], wb[7]]
+        J, dev = joints.shape[0], joints.device
+        d_bone_T = torch.zeros(J, 4, 4, device=dev) if d_bone_T is None else _f32(d_bone_T)
+        d_global_t = None if d_global_t is None else _f32(d_global_t)
+        d_thetas = None if d_thetas is None else _f32(d_thetas)
+        d_wb = [torch.empty_like(x) for x in wb]
+        d_ws, d_bs = [d_wb[0], d_wb[2], d_wb[4], d_wb[6], d_wb[8]], [d_wb[1], d_wb[3], d_wb[5], d_wb[7]]
+        d_joints = torch.empty_like(joints)
+        with stage("transform_net_bwd"):
+            check(lib.apn_pose_bwd(ptr(t_embed), t_embed.numel(), _ptr_array(ws), _ptr_array(bs), ptr(joints), ptr(tb.parent_node),
+                                   ptr(tb.pivot), ptr(tb.sibling), ptr(tb.rot_mask), J, ptr(saved), ptr(d_bone_T), ptr(d_global_t),
+                                   ptr(d_thetas), _ptr_array(d_ws), _ptr_array(d_bs), ptr(d_joints), stream()), "apn_pose_bwd")
+        return (None, None, d_joints, *d_wb)
+
+
+def pose_chain(tb: PoseTables, t_embed, joints, weights_and_biases):
+    """-> bone_Ts (J,4,4), global_t (3), thetas (J).  weights_and_biases = [w0,b0,w1,b1,w2,b2,w3,b3,w4]."""
+    return _Pose.apply(tb, t_embed, joints, *weights_and_biases)
+
+
+# --------------------------------------------------------------------------------------
 # K1: linear blend skinning
 # --------------------------------------------------------------------------------------
 class _LBS(torch.autograd.Function):
@@ -410,8 +475,21 @@ class PackedDecoder:
     changes (tracked through the tensors' version counters)."""
 
     def __init__(self):
-        self.buf = self.table = None
-        self.key = self.table_key = None
+        self.buf = self.table = self.buf_bwd = None
+        self.key = self.table_key = self.key_bwd = None
+
+    def get_bwd(self, ws: Sequence[torch.Tensor], d_in: int) -> torch.Tensor:
+        """Transposed weight tiles of the dgrad kernel."""
+        lib = _lib.load()
+        key = tuple((w.data_ptr(), w._version) for w in ws[:8:2]) + (d_in,)
+        if self.key_bwd != key:
+            if self.buf_bwd is None:
+                self.buf_bwd = _empty((lib.apn_aggregate_tc_bwd_weights_bytes(),), ws[0].device, torch.uint8)
+            w = _mlp_struct(ws)
+            check(lib.apn_aggregate_tc_pack_weights_bwd(C.byref(w), d_in, ptr(self.buf_bwd), stream()),
+                  "apn_aggregate_tc_pack_weights_bwd")
+            self.key_bwd = key
+        return self.buf_bwd
 
     def get(self, ws: Sequence[torch.Tensor], d_in: int, feat: torch.Tensor):
         lib = _lib.load()
@@ -459,8 +537,100 @@ def aggregate_tc(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch
             scratch = _empty((sb,), dev, torch.uint8)
             with stage("feat_net"):
                 check(lib.apn_aggregate_fwd_tc(C.byref(a), C.byref(w), ptr(pk), ptr(table), C.byref(out), int(precision),
-                                               ptr(scratch), sb, stream()), "apn_aggregate_fwd_tc")
+                                               None, 0, ptr(scratch), sb, stream()), "apn_aggregate_fwd_tc")
     return alpha, rgb, alpha_d, rgb_d, idw
+
+
+def _aligned_bytes(n: int, device, align: int = 1024) -> torch.Tensor:
+    t = _empty((n + align,), device, torch.uint8)
+    off = (-t.data_ptr()) % align
+    return t[off:off + n]
+
+
+class _AggregateTC(torch.autograd.Function):
+    """Training aggregation on the tcgen05 tensor cores: split-fp16 forward that records a tape, tensor-core dgrad
+    + wgrad backward (csrc/aggregate_tc.cu, csrc/aggregate_tc_bwd.cu).  Same contract as _Aggregate; d_in = 191."""
+
+    @staticmethod
+    def forward(ctx, c: AggConst, packed: PackedDecoder, xyz, ginv, feat, *ws):
+        lib = _lib.load()
+        xyz, ginv, feat = _f32(xyz), _f32(ginv), _f32(feat)
+        ws = [_f32(w) for w in ws]
+        M = c.pts.shape[0]
+        dev = xyz.device
+        d_in = PE_POS + FEAT_DIM
+        alpha, rgb = _empty((M,), dev), _empty((M, 3), dev)
+        alpha_d = _empty((M,), dev) if c.direct else None
+        rgb_d = _empty((M, 3), dev) if c.direct else None
+        idw = _empty((M, K_NEIGHBOURS), dev)
+        h, exp_d = _empty((M, FEAT_DIM), dev), _empty((M,), dev)
+        fv, v0 = _empty((M, FV_LD), dev), _empty((M, V0_DIM), dev)
+        tape_bytes = lib.apn_aggregate_tc_tape_bytes(M)
+        tape = _aligned_bytes(max(tape_bytes, 1), dev)
+        if M > 0:
+            out = AggOutputs()
+            out.alpha, out.rgb, out.alpha_direct, out.rgb_direct, out.idw = ptr(alpha), ptr(rgb), ptr(alpha_d), ptr(rgb_d), ptr(idw)
+            out.h, out.exp_d, out.fv, out.v0 = ptr(h), ptr(exp_d), ptr(fv), ptr(v0)
+            a = _agg_inputs(c, xyz, ginv, feat, None, M, d_in)
+            w = _mlp_struct(ws)
+            pk, table = packed.get(ws, d_in, feat)
+            with stage("feat_net"):
+                check(lib.apn_aggregate_fwd_tc(C.byref(a), C.byref(w), ptr(pk), ptr(table), C.byref(out), 1, ptr(tape),
+                                               tape_bytes, None, 0, stream()), "apn_aggregate_fwd_tc(train)")
+        ctx.c, ctx.packed, ctx.d_in = c, packed, d_in
+        ctx.save_for_backward(xyz, ginv, feat, *ws, alpha, rgb, idw, h, exp_d, fv, v0, tape)
+        ctx.mark_non_differentiable(idw)
+        if c.direct:
+            ctx.mark_non_differentiable(alpha_d, rgb_d)
+        return alpha, rgb, alpha_d, rgb_d, idw
+
+    @staticmethod
+    def backward(ctx, d_alpha, d_rgb, *_):
+        lib = _lib.load()
+        c = ctx.c
+        sv = ctx.saved_tensors
+        xyz, ginv, feat = sv[0:3]
+        ws = list(sv[3:19])
+        alpha, rgb, idw, h, exp_d, fv, v0, tape = sv[19:27]
+        M = c.pts.shape[0]
+        dev = xyz.device
+        need = ctx.needs_input_grad      # (c, packed, xyz, ginv, feat, *ws)
+        wanted = [t for t, n in ((xyz, need[2]), (ginv, need[3]), (feat, need[4])) if n]
+        zs = _zeros_like_many(wanted + list(ws))
+        zi = iter(zs)
+        d_xyz = next(zi) if need[2] else None
+        d_ginv = next(zi) if need[3] else None
+        d_feat = next(zi) if need[4] else None
+        d_ws = list(zi)
+        if M > 0:
+            d_alpha = torch.zeros_like(alpha) if d_alpha is None else _f32(d_alpha)
+            d_rgb = torch.zeros_like(rgb) if d_rgb is None else _f32(d_rgb)
+            out = AggOutputs()
+            out.alpha, out.rgb, out.idw = ptr(alpha), ptr(rgb), ptr(idw)
+            out.h, out.exp_d, out.fv, out.v0 = ptr(h), ptr(exp_d), ptr(fv), ptr(v0)
+            g = AggGrads()
+            g.d_alpha, g.d_rgb = ptr(d_alpha), ptr(d_rgb)
+            g.d_xyz, g.d_ginv, g.d_feat, g.d_pose_emb = ptr(d_xyz), ptr(d_ginv), ptr(d_feat), None
+            for l in range(4):
+                g.d_w[l] = ptr(d_ws[2 * l])
+                g.d_b[l] = ptr(d_ws[2 * l + 1])
+            (g.d_density_w, g.d_density_b, g.d_rgb_feat_w, g.d_rgb_feat_b, g.d_rgb_v0_w, g.d_rgb_v0_b, g.d_rgb_v2_w,
+             g.d_rgb_v2_b) = [ptr(t) for t in d_ws[8:16]]
+            a = _agg_inputs(c, xyz, ginv, feat, None, M, ctx.d_in)
+            w = _mlp_struct(ws)
+            pk = ctx.packed.get_bwd(ws, ctx.d_in)
+            sb = lib.apn_aggregate_tc_bwd_scratch_bytes(M, xyz.shape[0])
+            scratch = _aligned_bytes(sb, dev)
+            with stage("feat_net_bwd"):
+                check(lib.apn_aggregate_bwd_tc(C.byref(a), C.byref(w), ptr(pk), C.byref(out), ptr(tape), C.byref(g),
+                                               ptr(scratch), sb, stream()), "apn_aggregate_bwd_tc")
+        return (None, None, d_xyz, d_ginv, d_feat, *[dw if need[5 + i] else None for i, dw in enumerate(d_ws)])
+
+
+def aggregate_tc_train(c: AggConst, xyz, ginv, feat, weights: Sequence[torch.Tensor], packed: PackedDecoder):
+    """Differentiable aggregation on the tensor cores (d_in = 191). -> alpha, rgb, alpha_direct, rgb_direct, idw."""
+    assert len(weights) == 16
+    return _AggregateTC.apply(c, packed, xyz, ginv, feat, *weights)
 
 
 # --------------------------------------------------------------------------------------

@@ -74,6 +74,7 @@ class PointWarper(torch.nn.Module):
         self.register_buffer('rot_mask', torch.zeros(len(joints), dtype=torch.bool))
         self.register_buffer('sibling_mask', torch.arange(0, len(joints)).long())
         self.prev_params = self.prev_thetas = self.prev_global_t = None
+        self.fused_pose = True       # one-launch pose kernel (csrc/pose.cu) when the tree / MLP shape allows it
 
     # -- kinematic tree tables (lib/pointwarper.py:95-116, old=False branch) --------------------
     def init_tree(self, joints, bones, old=False):
@@ -140,11 +141,47 @@ class PointWarper(torch.nn.Module):
 
     Rodrigues = staticmethod(rodrigues)
 
+    # -- fused pose chain (csrc/pose.cu) -----------------------------------------------------
+    def _fused_tables(self, device):
+        """Device tables for the one-launch pose kernel, or None when the tree / MLP shape is outside what it covers
+        (then the PyTorch ops below are used: same maths, more launches)."""
+        key = (device, id(self.rot_mask), self.rot_mask._version, id(self.sibling_mask), self.sibling_mask._version)
+        if getattr(self, '_fused_key', None) != key:
+            self._fused_key, self._fused = key, None
+            J = len(self.parent_joint_ex)
+            parent_node = [self.parent_joint.get(i, -1) for i in range(J)]
+            lin = [m for m in self.transform_net.net if isinstance(m, torch.nn.Linear)]
+            ok = (J <= 128 and all(p < i for i, p in enumerate(parent_node)) and len(lin) == 5
+                  and lin[0].in_features <= 64 and all(l.out_features == 256 for l in lin[:4]) and lin[4].bias is None
+                  and lin[4].out_features == (J + 1) * 4)
+            if ok:
+                i32 = dict(dtype=torch.int32, device=device)
+                rm = self.rot_mask
+                self._fused = ops.PoseTables(
+                    parent_node=torch.tensor(parent_node, **i32), pivot=self.parent_joint_ex.to(**i32),
+                    sibling=self.sibling_mask.to(**i32),
+                    rot_mask=rm.to(device=device, dtype=torch.uint8) if rm is not None else None)
+        return self._fused
+
+    def _mlp_params(self):
+        lin = [m for m in self.transform_net.net if isinstance(m, torch.nn.Linear)]
+        out = []
+        for l in lin[:4]:
+            out += [l.weight, l.bias]
+        return out + [lin[4].weight]
+
     # -- pose -> bone transforms -------------------------------------------------------------
     def pose(self, joints, t=None, rot_params=None, global_t=None):
         """-> bone_Ts (J,4,4), global_t (3) or None.  Sets prev_params / prev_thetas / prev_global_t like
         lib/pointwarper.py:217-228."""
         assert (t is None) ^ (rot_params is None)
+        if rot_params is None and joints.is_cuda and self.fused_pose:
+            tb = self._fused_tables(joints.device)
+            if tb is not None:
+                bone_Ts, global_t, thetas = ops.pose_chain(tb, t, joints, self._mlp_params())
+                self.prev_params = None
+                self.prev_thetas, self.prev_global_t = thetas, global_t
+                return bone_Ts, global_t
         if rot_params is None:
             params = self.transform_net(t.unsqueeze(0))
             self.prev_params = params

@@ -159,8 +159,12 @@ class TemporalPoints(torch.nn.Module):
         # decoder used when no gradient is needed: "tc" = tcgen05 split-fp16 (fp32-class), "tc_fast" = tcgen05 fp16
         # operands, "fp32" = CUDA-core exact path (always used when autograd is recording)
         self.decoder = "tc"
+        # decoder used while autograd records: "tc" = tensor-core forward + backward (split-fp16; d_in = 191 only),
+        # "fp32" = CUDA-core exact path
+        self.decoder_train = "fp32"
         self._packed_decoder = ops.PackedDecoder()
-        # replay the pose chain (fwd + bwd) as CUDA graphs while training on a CUDA device
+        # replay the PyTorch pose chain (fwd + bwd) as CUDA graphs while training; only used when the fused pose
+        # kernel (forward_warp.fused_pose) does not cover the tree / MLP shape
         self.graph_pose = True
         object.__setattr__(self, '_pose_graph', None)
         object.__setattr__(self, '_pose_graph_key', None)
@@ -298,7 +302,9 @@ class TemporalPoints(torch.nn.Module):
         self._ensure_neighbourhood()
         t_embed = poc_fre(t, self.time_poc) if rot_params is None else None
         joints_rel = None
-        if (self.graph_pose and rot_params is None and torch.is_grad_enabled() and self.joints.is_cuda
+        fused = (rot_params is None and self.joints.is_cuda and self.forward_warp.fused_pose
+                 and self.forward_warp._fused_tables(self.joints.device) is not None)
+        if (not fused and self.graph_pose and rot_params is None and torch.is_grad_enabled() and self.joints.is_cuda
                 and self.joints.requires_grad):
             bone_Ts, global_t, joints_rel = self._pose_graphed(t_embed)
         else:
@@ -378,6 +384,9 @@ class TemporalPoints(torch.nn.Module):
             alpha, rgb, alpha_d, rgb_d, idw = ops.aggregate_tc(c, t_hat_pcd, warped['ginv'], self.canonical_feat, pose_embedding,
                                                                self._mlp_weights(), self._packed_decoder,
                                                                precision=1 if self.decoder == "tc" else 0)
+        elif self.decoder_train == "tc" and pose_embedding is None and torch.is_grad_enabled():
+            alpha, rgb, alpha_d, rgb_d, idw = ops.aggregate_tc_train(c, t_hat_pcd, warped['ginv'], self.canonical_feat,
+                                                                     self._mlp_weights(), self._packed_decoder)
         else:
             alpha, rgb, alpha_d, rgb_d, idw = ops.aggregate(c, t_hat_pcd, warped['ginv'], self.canonical_feat, pose_embedding,
                                                             self._mlp_weights())

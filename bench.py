@@ -230,7 +230,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--decoder", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--decoder", default="auto", choices=["auto", "fp32", "tc", "tc_fast"], help="inference decoder")
+    ap.add_argument("--decoder-train", default="tc", choices=["tc", "fp32"], help="decoder of the training step")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -292,6 +293,7 @@ def main():
         model.graph_pose = False
     if args.decoder != "auto":
         model.decoder = args.decoder
+    model.decoder_train = args.decoder_train
     host = [pack_host(b, pin=True) for b in make_batches(scene, mode, n_steps, rank, repose=repose)]
     rk = scene.render_kwargs()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -387,7 +389,8 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     ach_tf = flops / max(dec_ms_timed * 1e-3, 1e-9) / 1e12
-    roofline = {"kernel": "decoder (feat_net + heads%s), %s path" % (" fwd+bwd" if mode == "train" else "", model.decoder),
+    roofline = {"kernel": "decoder (feat_net + heads%s), %s path" % (" fwd+bwd" if mode == "train" else "",
+                                                                      model.decoder_train if mode == "train" else model.decoder),
                 "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else
                 "fallback 1.4 PFLOP/s sustained (of fallback)",

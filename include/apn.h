@@ -35,6 +35,25 @@ const char* apn_last_error(void);
 unsigned long long apn_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
+ * K0  Pose chain.  Replaces lib/pointwarper.py:217-236: TransformNet (lib/pointwarper.py:5-37; 256-wide, 4 hidden
+ * layers, bias-free output layer), 4-parameter Rodrigues (:118-143), per-joint pivot transforms and the kinematic
+ * chain product (:145-193), forward and backward, one single-CTA launch each.
+ *   w5 / b4: HOST arrays of device pointers to the Linear weights (torch layout) / biases
+ *   parent_node (J): chain parent of node i (-1 for the root; must be < i)   pivot (J): joint rotated about
+ *   sibling (J): node whose rotation node i uses (:232)   rot_mask (J) uint8 or NULL: rotation frozen to identity
+ *   bone_T (J,4,4)  global_t (3)  thetas (J)  saved: apn_pose_saved_bytes(J) bytes kept for the backward (or NULL)
+ * ------------------------------------------------------------------------------------- */
+size_t apn_pose_saved_bytes(int J);
+int apn_pose_fwd(const float* t_embed, int t_dim, const float* const* w5, const float* const* b4, const float* joints,
+                 const int32_t* parent_node, const int32_t* pivot, const int32_t* sibling, const uint8_t* rot_mask, int J,
+                 float* bone_T, float* global_t, float* thetas, void* saved, apn_stream_t stream);
+/* d_w5 / d_b4 / d_joints are overwritten; d_global_t / d_thetas may be NULL */
+int apn_pose_bwd(const float* t_embed, int t_dim, const float* const* w5, const float* const* b4, const float* joints,
+                 const int32_t* parent_node, const int32_t* pivot, const int32_t* sibling, const uint8_t* rot_mask, int J,
+                 const void* saved, const float* d_bone_T, const float* d_global_t, const float* d_thetas,
+                 float* const* d_w5, float* const* d_b4, float* d_joints, apn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * K1  Linear blend skinning.
  * Replaces lib/temporalpoints.py:401-414 (get_weights: softmax(raw/max(eps,theta)) + merge),
  * lib/pointwarper.py:241-266 (blend of bone 4x4s, point transform, + global_t),
@@ -209,8 +228,23 @@ int apn_aggregate_tc_pack_weights(const apn_mlp_weights* w, int d_in, void* pack
 int apn_aggregate_tc_point_table(const float* feat, const float* w0, int d_in, int N, float* point_table,
                                  apn_stream_t stream);
 size_t apn_aggregate_tc_scratch_bytes(int M);
+/* tape == NULL: inference (scratch required).  tape != NULL (training, precision 1 only): the kernel also records
+ * what the tensor-core backward needs (post-activations, PE operand, LeakyReLU masks; apn_aggregate_tc_tape_bytes(M)
+ * bytes, 1 KiB aligned) and out->h / exp_d / fv / v0 must be given (kept by the caller for the backward). */
+size_t apn_aggregate_tc_tape_bytes(int M);
 int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_weights,
-                         const float* point_table, const apn_agg_outputs* out, int precision, void* scratch,
+                         const float* point_table, const apn_agg_outputs* out, int precision, void* tape,
+                         size_t tape_bytes, void* scratch, size_t scratch_bytes, apn_stream_t stream);
+
+/* Tensor-core backward of the same op (replaces autograd through lib/temporalpoints.py:446-515): split-fp16 dgrad chain
+ * + wgrad with accumulators in tensor memory; heads in fp32.  Same gradient contract as apn_aggregate_bwd (all
+ * outgoing buffers accumulated into; caller zeroes).  Covers d_in = 191 (no pose embedding).
+ * packed_bwd: apn_aggregate_tc_bwd_weights_bytes() bytes filled by apn_aggregate_tc_pack_weights_bwd. */
+size_t apn_aggregate_tc_bwd_weights_bytes(void);
+int apn_aggregate_tc_pack_weights_bwd(const apn_mlp_weights* w, int d_in, void* packed_bwd, apn_stream_t stream);
+size_t apn_aggregate_tc_bwd_scratch_bytes(int M, int N);
+int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_bwd,
+                         const apn_agg_outputs* saved, const void* tape, const apn_agg_grads* g, void* scratch,
                          size_t scratch_bytes, apn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@ from articulated_point_nerf_b200 import ops, _lib
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 scene = make_scene(wl)
 model = build_model(scene, seed=0).cuda()
+model.decoder_train = os.environ.get("DT", "tc")
 host = [pack_host(b, True) for b in make_batches(scene, "train", 12, 0)]
 dev_in = [(t.cuda(), b.cuda()) for t, b in host]
 opt = create_optimizer(model); bucket = GradBucket(opt)
@@ -39,5 +40,5 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for i in range(3): step(i)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=30, max_name_column_width=70))
 print(prof.key_averages().table(sort_by="cpu_time_total", row_limit=25, max_name_column_width=60))

@@ -415,3 +415,139 @@ def test_aggregate_tensor_core_matches_fp32_kernel_on_ragged_sizes(M, pose):
         assert rel_err(a, b) < RTOL, (name, rel_err(a, b))
     fast = ops.aggregate_tc(*args, ws, ops.PackedDecoder(), precision=0)
     assert rel_err(fast[0], ref[0]) < 3e-2 and rel_err(fast[1], ref[1]) < 3e-2
+
+
+def _kink_free_sample_mask(orc, xyz, gi, smp, tol=1e-5):
+    """Samples none of whose 8 x 384 feat_net pre-activations (layers 0-2) lies within `tol` of the LeakyReLU kink.
+    A kernel that is not bit-identical to the reference cannot agree on the derivative AT the kink (a 1e-7 rounding
+    difference flips 1 <-> 0.01); everywhere else it must meet the 1e-4 bar."""
+    from oracle.path_oracle import poc_fre
+    with torch.no_grad():
+        s_i, pts = smp["s_i"], smp["pts"]
+        rel_p = pts[:, None, :] - xyz.detach()[s_i, :]
+        frames = gi.detach()[s_i]
+        rel_c = torch.bmm(frames[..., :3, :3].reshape(-1, 3, 3), rel_p.reshape(-1, 3).unsqueeze(-1)).squeeze(-1)
+        x = torch.cat([poc_fre(rel_c, orc.pos_poc), orc.s["canonical_feat"][s_i, :].reshape(-1, 128)], -1)
+        near = torch.zeros(len(x), dtype=torch.bool)
+        for name in ["feat_net.0", "feat_net.2.0", "feat_net.3.0", "feat_net.4"]:
+            pre = torch.nn.functional.linear(x, orc.s[name + ".weight"], orc.s[name + ".bias"])
+            near |= (pre.abs() < tol).any(dim=1)
+            x = torch.nn.functional.leaky_relu(pre, 0.01)
+    return ~near.view(-1, 8).any(dim=1)
+
+
+def test_aggregate_tensor_core_backward(golden_tiny):
+    """Tensor-core training path (split-fp16 forward with tape + dgrad/wgrad kernels) against the oracle's autograd:
+    1e-4 on every gradient for upstream gradients supported on kink-free samples."""
+    ops, orc, o, xyz, gi, smp, model, c = _agg_setup(golden_tiny, True)
+    rgb, alpha, _, _, _ = o
+    ok = _kink_free_sample_mask(orc, xyz, gi, smp)
+    assert ok.float().mean() > 0.5
+    gen = torch.Generator().manual_seed(2)
+    ca = torch.randn(alpha.shape, generator=gen) * ok
+    cr = torch.randn(rgb.shape, generator=gen) * ok[:, None]
+    ((alpha * ca).sum() + (rgb * cr).sum()).backward()
+    kx = xyz.detach().cuda().requires_grad_(True)
+    kg = gi.detach()[:, :3, :3].reshape(-1, 9).contiguous().cuda().requires_grad_(True)
+    model.zero_grad()
+    k_alpha, k_rgb, *_ = ops.aggregate_tc_train(c, kx, kg, model.canonical_feat, model._mlp_weights(), ops.PackedDecoder())
+    assert rel_err(k_alpha, alpha) < RTOL and rel_err(k_rgb, rgb) < RTOL
+    ((k_alpha * ca.cuda()).sum() + (k_rgb * cr.cuda()).sum()).backward()
+    errs = {"d_xyz": rel_err(kx.grad, xyz.grad), "d_ginv": rel_err(kg.grad.view(-1, 3, 3), gi.grad[:, :3, :3])}
+    named = dict(model.named_parameters())
+    for k in ["canonical_feat", "feat_net.0.weight", "feat_net.0.bias", "feat_net.2.0.weight", "feat_net.2.0.bias",
+              "feat_net.3.0.weight", "feat_net.3.0.bias", "feat_net.4.weight", "feat_net.4.bias", "densitynet.weight",
+              "densitynet.bias", "rgbnet.feature_linears.weight", "rgbnet.feature_linears.bias",
+              "rgbnet.views_linears.0.weight", "rgbnet.views_linears.0.bias", "rgbnet.views_linears.2.weight",
+              "rgbnet.views_linears.2.bias"]:
+        assert named[k].grad is not None, k
+        errs[k] = rel_err(named[k].grad, orc.s[k].grad)
+    bad = {k: v for k, v in errs.items() if not v < RTOL}
+    assert not bad, (bad, errs)
+
+
+@pytest.mark.parametrize("M", [1, 17, 2500])
+def test_aggregate_tensor_core_backward_matches_fp32_kernels_on_ragged_sizes(M):
+    """Tile tails and multi-tile accumulation (CTAs that walk several tiles; slab reduction of the wgrad) of the
+    tensor-core backward against the fp32 CUDA-core backward on random weights: every entry within 5e-4 of the tensor's
+    scale (split-fp16 carries 22 mantissa bits; the PE backward multiplies its rounding by up to 2^9).
+    The weights are seeded so that no LeakyReLU kink flip separates the two forwards (scripts/debug_tc_bwd2.py measures
+    what a flip in a dominant row does: ~1e-2 on that step's layer-0 gradients, in either implementation)."""
+    ops = _ops()
+    torch.manual_seed(1)
+    g = torch.Generator().manual_seed(100 + M)
+    N, d = 2000, "cuda"
+    xyz = torch.rand(N, 3, generator=g)
+    A = torch.eye(3) + 0.2 * torch.randn(N, 3, 3, generator=g)
+    feat = torch.relu(torch.randn(N, 128, generator=g)) * 0.5
+    nn_idx = torch.randint(0, N, (M, 8), generator=g).int()
+    pts = xyz[nn_idx[:, 0].long()] + 0.02 * torch.randn(M, 3, generator=g)
+    ray_id = torch.sort(torch.randint(0, 50, (M,), generator=g))[0].int()
+    vd = torch.nn.functional.normalize(torch.randn(50, 3, generator=g), dim=-1)
+    lin = [torch.nn.Linear(191, 128), torch.nn.Linear(128, 128), torch.nn.Linear(128, 128), torch.nn.Linear(128, 128),
+           torch.nn.Linear(128, 1), torch.nn.Linear(128, 128), torch.nn.Linear(155, 64), torch.nn.Linear(64, 3)]
+    c = ops.AggConst(pts=pts.to(d), nn_idx=nn_idx.to(d), ray_id=ray_id.to(d), viewdirs=vd.to(d),
+                     canonical_alpha=torch.rand(N, generator=g).to(d), canonical_rgbs=torch.rand(N, 3, generator=g).to(d),
+                     direct_eps=torch.full((N,), 0.05).to(d), mean_min_distance=0.02, eps=1e-6, act_shift=0.0, interval=0.5)
+    ca, cr = torch.randn(M, generator=g).to(d), torch.randn(M, 3, generator=g).to(d)
+
+    def run(tc):
+        leaves = [xyz.to(d).requires_grad_(True), A.reshape(N, 9).contiguous().to(d).requires_grad_(True),
+                  feat.to(d).requires_grad_(True)]
+        ws = []
+        for l in lin:
+            ws += [l.weight.detach().to(d).requires_grad_(True), l.bias.detach().to(d).requires_grad_(True)]
+        if tc:
+            out = ops.aggregate_tc_train(c, *leaves, ws, ops.PackedDecoder())
+        else:
+            out = ops.aggregate(c, *leaves, None, ws)
+        ((out[0] * ca).sum() + (out[1] * cr).sum()).backward()
+        return [t.grad for t in leaves + ws]
+
+    names = ["xyz", "ginv", "feat"] + [f"w{i}" for i in range(16)]
+    report = {}
+    for name, a, b in zip(names, run(True), run(False)):
+        err = ((a - b).abs() / (b.abs().max() + 1e-30))[b != 0]
+        if err.numel():
+            report[name] = (float(err.max()), float((err > 5e-4).float().mean()))
+    bad = {k: v for k, v in report.items() if v[0] > 2e-3 or v[1] > 1e-3}
+    assert not bad, (bad, report)
+
+
+# ----------------------------------------------------------------------------------------
+# K0 pose chain (one launch) against the PyTorch ops that restate lib/pointwarper.py:217-236
+# ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("masks", [False, True])
+def test_fused_pose_chain_matches_pytorch_chain(golden_tiny, masks):
+    from articulated_point_nerf_b200 import poc_fre
+    g = golden_tiny
+    model, scene = model_from_golden(g)
+    fw = model.forward_warp
+    J = len(model.joints)
+    if masks:
+        m = torch.zeros(J, dtype=torch.bool)
+        m[[3, 11]] = True
+        fw.set_rotation_mask(~m.cuda())
+        sib = torch.arange(J)
+        sib[6], sib[14] = 5, 13
+        fw.set_sibling_mask(sib.cuda())
+    t_embed = poc_fre(g["train"]["t"].cuda(), model.time_poc)
+    gen = torch.Generator().manual_seed(0)
+    c1, c2, c3 = torch.randn(J, 4, 4, generator=gen).cuda(), torch.randn(3, generator=gen).cuda(), torch.randn(J, generator=gen).cuda()
+    c1[:, 3] = 0          # the last row of a bone transform is constant
+
+    def run(fused):
+        fw.fused_pose = fused
+        model.zero_grad(set_to_none=True)
+        bone_Ts, global_t = fw.pose(model.joints, t=t_embed)
+        ((bone_Ts * c1).sum() + (global_t * c2).sum() + (fw.prev_thetas * c3).sum()).backward()
+        grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        return bone_Ts.detach(), global_t.detach(), fw.prev_thetas.detach(), grads
+
+    ref, got = run(False), run(True)
+    assert fw._fused_tables(model.joints.device) is not None
+    for a, b in zip(got[:3], ref[:3]):
+        assert rel_err(a, b) < 1e-5
+    assert set(got[3]) == set(ref[3]) and "joints" in got[3]
+    for k in ref[3]:
+        assert rel_err(got[3][k], ref[3][k]) < RTOL, k

@@ -61,10 +61,34 @@ PE_AMPLIFIED = ("weights", "joints", "theta_weight", "canonical_feat", "feat_net
 GOLDEN_LOOSE = 5e-2
 
 
-def test_train_step_gradients_match_reference_golden(golden_tiny):
+@pytest.mark.parametrize("decoder", ["tc", "tc_fast", "fp32"])
+def test_render_with_fused_pose_matches_oracle_on_the_same_cloud(golden_tiny, decoder):
+    """Default product configuration (one-launch pose kernel): everything downstream of the warp against the oracle on the
+    kernel's own warped cloud; the warp itself against the golden file."""
+    from conftest import oracle_from_golden, oracle_render_on_cloud
+    g = golden_tiny
+    model, scene = model_from_golden(g, fused_pose=True)
+    model.decoder = decoder
+    rk = _rk(scene, g)
+    with torch.no_grad():
+        warped = model.warp(g["render"]["t"].cuda())
+        out = model(g["render"]["t"].cuda(), render_depth=True, render_kwargs=rk, warped=warped)
+    assert rel_err(out["t_hat_pcd"], g["render"]["out"]["t_hat_pcd"]) < 2e-6
+    assert rel_err(model.forward_warp.prev_thetas, g["render"]["prev_thetas"]) < 1e-5
+    orc, cfg = oracle_from_golden(g)
+    with torch.no_grad():
+        ref = oracle_render_on_cloud(orc, cfg, g, warped["xyz"].cpu(), warped["ginv"].cpu().view(-1, 3, 3))
+    assert model.last_counts["M"] == ref["M"]
+    tol = RTOL if decoder != "tc_fast" else 3e-2
+    for k in ["rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "alphainv_last_direct"]:
+        assert rel_err(out[k], ref[k]) < tol, k
+
+
+@pytest.mark.parametrize("fused_pose", [False, True])
+def test_train_step_gradients_match_reference_golden(golden_tiny, fused_pose):
     from conftest import oracle_from_golden
     g = golden_tiny
-    model, scene = model_from_golden(g)
+    model, scene = model_from_golden(g, fused_pose=fused_pose)
     rk = _rk(scene, g)
     model.zero_grad(set_to_none=True)
     warped = model.warp(g["train"]["t"].cuda())
@@ -72,14 +96,15 @@ def test_train_step_gradients_match_reference_golden(golden_tiny):
                 warped=warped)
     loss = F.mse_loss(res["rgb_marched"], g["train"]["target"].cuda()) * 200.0
     loss.backward()
-    assert abs(loss.item() - g["train"]["loss"].item()) < RTOL * g["train"]["loss"].item()
-    assert rel_err(res["rgb_marched"], g["train"]["rgb_marched"]) < RTOL
     named = dict(model.named_parameters())
-    # (1) against the reference's golden gradients
-    for k, ref in g["train"]["grads"].items():
-        assert named[k].grad is not None, k
-        tol = GOLDEN_LOOSE if k.startswith(PE_AMPLIFIED) else RTOL
-        assert rel_err(named[k].grad, ref) < tol, k
+    if not fused_pose:
+        # (1) against the reference's golden file (bit-compatible pose path, see conftest.model_from_golden)
+        assert abs(loss.item() - g["train"]["loss"].item()) < RTOL * g["train"]["loss"].item()
+        assert rel_err(res["rgb_marched"], g["train"]["rgb_marched"]) < RTOL
+        for k, ref in g["train"]["grads"].items():
+            assert named[k].grad is not None, k
+            tol = GOLDEN_LOOSE if k.startswith(PE_AMPLIFIED) else RTOL
+            assert rel_err(named[k].grad, ref) < tol, k
     # (2) every gradient at 1e-4 against the oracle run on the kernel's own warped cloud: the oracle's warp keeps
     # its autograd graph, its VALUES are replaced by the kernel's (straight-through)
     orc, cfg = oracle_from_golden(g)
@@ -97,7 +122,10 @@ def test_train_step_gradients_match_reference_golden(golden_tiny):
     smp = orc.sample_and_knn(xyz, g["rays_o"], g["rays_d"], cfg.near, cfg.far, cfg.stepsize, 0.01)
     rgb, alpha, *_ = orc.aggregate(xyz, Ginv, smp, g["viewdirs"], cfg.stepsize)
     rgb_m, *_ = orc.composite(alpha, rgb, smp["ray_id"], smp["step_id"], len(g["rays_o"]), cfg.bg)
-    (F.mse_loss(rgb_m, g["train"]["target"]) * 200.0).backward()
+    loss_o = F.mse_loss(rgb_m, g["train"]["target"]) * 200.0
+    loss_o.backward()
+    assert abs(loss.item() - loss_o.item()) < RTOL * loss_o.item()
+    assert rel_err(res["rgb_marched"], rgb_m) < RTOL
     for k in g["train"]["grads"]:
         assert rel_err(named[k].grad, orc.s[k].grad) < RTOL, k
 
