@@ -116,7 +116,7 @@ struct TcSmem {
 // 4 threads per row: part p owns the (dimension, frequency) pairs j = p, p+4, ...
 template <int NSPLIT>
 __device__ __forceinline__ void tc_prologue(const TcParams& p, int tile, int tid, uint8_t* sPE, float* sIdw, int* sIdx) {
-  uint8_t* tape_pe = p.tape ? p.tape + (size_t)tile * TC_TAPE_TILE_BYTES + TC_TAPE_PE(0) : nullptr;
+
   const apn_agg_inputs& in = p.in;
   const int r = tid & 127, part = tid >> 7;
   const int s = r >> 3;
@@ -177,10 +177,6 @@ __device__ __forceinline__ void tc_prologue(const TcParams& p, int tile, int tid
     const uint32_t o = sw128_offset(r, col);
     *reinterpret_cast<__half*>(sPE + o) = hi;
     if (NSPLIT == 2) *reinterpret_cast<__half*>(sPE + TC_TILE_BYTES + o) = lo;
-    if (tape_pe) {
-      *reinterpret_cast<__half*>(tape_pe + o) = hi;
-      *reinterpret_cast<__half*>(tape_pe + TC_TILE_BYTES + o) = lo;
-    }
   };
   if (part < 3) put(part, part == 0 ? rc[0] : part == 1 ? rc[1] : rc[2]);
   else put(63, 0.f);
@@ -302,6 +298,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParam
         mbar_wait(pe_ready, ph_pe);
         ph_pe ^= 1;
         tc_fence_after();
+        // training: the operand tiles ARE the tape (same layout): stream them out with bulk stores from shared memory
+        uint8_t* tape_tile = p.tape ? p.tape + (size_t)tile * TC_TAPE_TILE_BYTES : nullptr;
+        if (NSPLIT == 2 && tape_tile) {
+          bulk_s2g(tape_tile + TC_TAPE_PE(0), sPE, 2 * TC_TILE_BYTES);
+          bulk_commit();
+        }
         issue_chunk(pe_base, tmem_base, true, 0);
         umma_commit(acc_ready);
         // layers 1..3: activation chunks 0, 1 -> accumulator (layer & 1)
@@ -310,14 +312,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParam
           mbar_wait(a_ready, ph_a0);
           ph_a0 ^= 1;
           tc_fence_after();
+          if (NSPLIT == 2 && tape_tile) {
+            bulk_s2g(tape_tile + TC_TAPE_ACT(layer - 1, 0, 0), sAct, 2 * TC_TILE_BYTES);
+            bulk_commit();
+          }
           issue_chunk(act_base, acc, true, 2 * layer - 1);
           mbar_wait(a_ready + 1, ph_a1);
           ph_a1 ^= 1;
           tc_fence_after();
+          if (NSPLIT == 2 && tape_tile) {
+            bulk_s2g(tape_tile + TC_TAPE_ACT(layer - 1, 1, 0), sAct + 2 * TC_TILE_BYTES, 2 * TC_TILE_BYTES);
+            bulk_commit();
+            bulk_wait_read();      // the epilogue released by the commit below overwrites these tiles (and, later, sPE)
+          }
           issue_chunk(act_base + NSPLIT * TC_TILE_BYTES, acc, false, 2 * layer);
           umma_commit(acc_ready + (layer & 1));
         }
       }
+      if (NSPLIT == 2 && p.tape) bulk_wait_all();
     }
   } else {
     // ================================================================= compute warps
@@ -384,11 +396,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tc_fwd_kernel(const TcParam
             const uint32_t o = (uint32_t)((((cq * 2 + u) ^ (erow & 7)) & 7) << 4);
             *reinterpret_cast<uint4*>(t_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (NSPLIT == 2) *reinterpret_cast<uint4*>(t_hi + TC_TILE_BYTES + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            if (tp) {
-              uint8_t* g = tp + TC_TAPE_ACT(layer, ph, 0) + (size_t)erow * 128 + o;
-              *reinterpret_cast<uint4*>(g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(g + TC_TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
           }
           if (tp) *reinterpret_cast<uint16_t*>(tp + TC_TAPE_MASK(layer) + ((size_t)erow * 8 + ph * 4 + cq) * 2) = (uint16_t)mbits;
           fence_proxy_async_smem();

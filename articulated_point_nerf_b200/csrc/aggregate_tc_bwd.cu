@@ -156,6 +156,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
               ph_a1 ^= 1;
             }
             tc_fence_after();
+            // the dY operand tile is also the wgrad kernel's input: stream it out from shared memory
+            bulk_s2g(p.dy + (size_t)tile * TC_DY_TILE_BYTES + TC_TAPE_ACT(3 - g, kc, 0), sA + (size_t)(kc * 2) * TC_TILE_BYTES,
+                     2 * TC_TILE_BYTES);
+            bulk_commit();
+            if (kc == 1) bulk_wait_read();      // the epilogue released by this group's commit overwrites both tiles
             const uint32_t slot = it % TCB_SLOTS;
             mbar_wait(w_full + slot, (it / TCB_SLOTS) & 1);
             tc_fence_after();
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
           umma_commit(acc_ready + (g & 1));
         }
       }
+      bulk_wait_all();
     }
   } else {
     // ================================================================= compute warps
@@ -186,7 +192,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int m0 = tile * TC_SAMPLES;
       const uint8_t* tp = p.tape + (size_t)tile * TC_TAPE_TILE_BYTES;
-      uint8_t* dyt = p.dy + (size_t)tile * TC_DY_TILE_BYTES;
       const int ms = m0 + (erow >> 3);
       const bool valid = ms < in.M;
       const int mc = min(ms, in.M - 1);
@@ -226,9 +231,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
             uint8_t* t = sA + (size_t)(ph * 2) * TC_TILE_BYTES + o;
             *reinterpret_cast<uint4*>(t) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(t + TC_TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            uint8_t* g = dyt + TC_TAPE_ACT(3, ph, 0) + o;
-            *reinterpret_cast<uint4*>(g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(g + TC_TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async_smem();
           mbar_arrive(a_ready + ph);
@@ -261,7 +263,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
             // feature columns of layer 0: gradient of the per-point table row
             float* dp = p.d_ptable + (size_t)sIdx[erow] * APN_C + ph * 64 + cq * 16;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(dp + i, y[i] * inv_gscale);
+            for (int i = 0; i < 16; i += 4)
+              red_add_v4(dp + i, y[i] * inv_gscale, y[i + 1] * inv_gscale, y[i + 2] * inv_gscale, y[i + 3] * inv_gscale);
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -272,9 +275,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
             uint8_t* t = sA + (size_t)(ph * 2) * TC_TILE_BYTES + o;
             *reinterpret_cast<uint4*>(t) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(t + TC_TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            uint8_t* gg = dyt + TC_TAPE_ACT(l, ph, 0) + o;
-            *reinterpret_cast<uint4*>(gg) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(gg + TC_TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async_smem();
           tc_fence_before();

@@ -36,18 +36,31 @@ __device__ __forceinline__ void rodrigues4(const float p[4], float R[9], float n
   R[6] = x * z * C - y * sn;       R[7] = y * z * C + x * sn;       R[8] = z * z + (1.f - z * z) * cs;
 }
 
-// y[n] = act(dot(W[n,:K], x) + b[n]) for n < n_out: one warp per output row, coalesced weight reads
+// y[n] = act(dot(W[n,:K], x) + b[n]) for n < n_out: one warp per output row, coalesced weight reads; 8 rows are in
+// flight per warp so that the (cold, DRAM-latency) weight loads overlap instead of serialising row after row
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ b, const float* x, float* y,
                                             int n_out, int K, bool relu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int n = warp; n < n_out; n += nw) {
-    const float* wr = W + (size_t)n * K;
-    float s = 0.f;
-    for (int k = lane; k < K; k += 32) s = fmaf(__ldg(wr + k), x[k], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      s += b ? __ldg(b + n) : 0.f;
-      y[n] = relu ? fmaxf(s, 0.f) : s;
+  constexpr int RB = 8;
+  for (int n0 = warp * RB; n0 < n_out; n0 += nw * RB) {
+    float s[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) s[r] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      float wv[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) wv[r] = (n0 + r < n_out) ? __ldg(W + (size_t)(n0 + r) * K + k) : 0.f;
+      const float xv = x[k];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) s[r] = fmaf(wv[r], xv, s[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const float t = warp_sum(s[r]);
+      if (lane == 0 && n0 + r < n_out) {
+        const float v = t + (b ? __ldg(b + n0 + r) : 0.f);
+        y[n0 + r] = relu ? fmaxf(v, 0.f) : v;
+      }
     }
   }
 }
@@ -243,6 +256,7 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_bwd_kernel(const PoseArgs a
   for (int i = tid; i < n_out * POSE_H; i += blockDim.x) g.d_w[4][i] = sdP[i / POSE_H] * h[3 * POSE_H + (i % POSE_H)];
   {
     float s = 0.f;
+#pragma unroll 16
     for (int r = 0; r < n_out; ++r) s = fmaf(__ldg(a.w[4] + (size_t)r * POSE_H + tid), sdP[r], s);
     sd[0][tid] = h[3 * POSE_H + tid] > 0.f ? s : 0.f;
   }
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_bwd_kernel(const PoseArgs a
     g.d_b[l][tid] = sd[cur][tid];
     for (int i = tid; i < POSE_H * POSE_H; i += blockDim.x) g.d_w[l][i] = sd[cur][i / POSE_H] * x[i % POSE_H];
     float s = 0.f;
+#pragma unroll 32
     for (int n = 0; n < POSE_H; ++n) s = fmaf(__ldg(a.w[l] + (size_t)n * POSE_H + tid), sd[cur][n], s);
     sd[cur ^ 1][tid] = x[tid] > 0.f ? s : 0.f;
     __syncthreads();

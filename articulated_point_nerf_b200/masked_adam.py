@@ -32,12 +32,15 @@ class MaskedAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self):
-        batches = {}
+        """One multi-tensor launch per (betas, eps) class.  The descriptor table (device pointers of param / grad /
+        moments) is cached and rebuilt only when a pointer changes; per step only the step sizes are refreshed."""
+        plan = []
         for group in self.param_groups:
             lr = group['lr']
             beta1, beta2 = group['betas']
             eps = group['eps']
             skip_zero_grad = group.get('skip_zero_grad', False)
+            ss_cache = {}
             for param in group['params']:
                 if param.grad is None:
                     continue
@@ -54,8 +57,20 @@ class MaskedAdam(torch.optim.Optimizer):
                     mode, perlr = 1, None
                 else:
                     mode, perlr = 0, None
-                ss = ops.adam_step_size(state['step'], beta1, beta2, lr)
-                batches.setdefault((beta1, beta2, eps), []).append(
-                    (param.data, grad, state['exp_avg'], state['exp_avg_sq'], perlr, ss, mode))
-        for (beta1, beta2, eps), entries in batches.items():
-            ops.adam_multi(entries, beta1, beta2, eps)
+                st = state['step']
+                ss = ss_cache.get(st)
+                if ss is None:
+                    ss = ss_cache[st] = ops.adam_step_size(st, beta1, beta2, lr)
+                plan.append(((beta1, beta2, eps), param, grad, state, perlr, ss, mode))
+        if not plan:
+            return
+        key = tuple((cls, p.data_ptr(), g.data_ptr(), mode, None if pl is None else pl.data_ptr())
+                    for cls, p, g, _, pl, _, mode in plan)
+        if getattr(self, '_plan_key', None) != key:
+            batches = {}
+            for cls, p, g, state, pl, ss, mode in plan:
+                batches.setdefault(cls, []).append((p.data, g, state['exp_avg'], state['exp_avg_sq'], pl, ss, mode))
+            self._plan = [(cls, ops.AdamPlan(entries)) for cls, entries in batches.items()]
+            self._plan_key = key
+        for cls, ap in self._plan:
+            ap.launch([e[5] for e in plan if e[0] == cls], *cls)

@@ -695,6 +695,32 @@ def adam_step_size(step: int, beta1: float, beta2: float, lr: float) -> float:
     return float(_lib.load().apn_adam_step_size(int(step), beta1, beta2, lr))
 
 
+class AdamPlan:
+    """A cached descriptor table for apn_adam_multi: the device pointers stay fixed across steps (parameters, gradient
+    bucket views, moments), only the step sizes change."""
+
+    def __init__(self, entries):
+        self.n = len(entries)
+        self.arr = (AdamTensor * self.n)()
+        self.keep = entries                      # keeps the tensors alive
+        for i, (p, g, m, v, pl, ss, mode) in enumerate(entries):
+            for t in (p, g, m, v):
+                if t.dtype != torch.float32:
+                    raise _lib.ApnError("Adam tensors must be fp32")
+            self.arr[i].param, self.arr[i].grad, self.arr[i].exp_avg, self.arr[i].exp_avg_sq = ptr(p), ptr(g), ptr(m), ptr(v)
+            self.arr[i].perlr = ptr(pl)
+            self.arr[i].numel = p.numel()
+            self.arr[i].step_size = ss
+            self.arr[i].mode = mode
+        self.cptr = C.cast(self.arr, C.c_void_p)
+
+    def launch(self, step_sizes, beta1, beta2, eps):
+        for i, ss in enumerate(step_sizes):
+            self.arr[i].step_size = ss
+        with stage("adam"):
+            check(_lib.load().apn_adam_multi(self.cptr, self.n, beta1, beta2, eps, stream()), "apn_adam_multi")
+
+
 def adam_multi(entries, beta1: float, beta2: float, eps: float) -> None:
     """entries: list of (param, grad, exp_avg, exp_avg_sq, perlr|None, step_size, mode)."""
     if not entries:
