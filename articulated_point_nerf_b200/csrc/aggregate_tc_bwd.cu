@@ -27,9 +27,9 @@ __global__ void tc_pack_bwd_kernel(const apn_mlp_weights w, int d_in, uint8_t* _
   const int ld = layer == 0 ? d_in : APN_C;
   for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
     const int n = e >> 6, k = e & 63;                 // n: input feature (row of the B tile), k: output feature
-    float v = 0.f;
-    if (layer > 0 || n < APN_PE_POS) v = W[(size_t)(kc * 64 + k) * ld + n];
-    if (layer == 0 && n >= 64) continue;              // the layer-0 tile has 64 rows
+    if (layer == 0 && n >= 64) continue;              // the layer-0 tile has 64 rows (the PE tile's column order)
+    const int col = layer == 0 ? tc_pe_ref_col(n) : n;
+    const float v = col >= 0 ? W[(size_t)(kc * 64 + k) * ld + col] : 0.f;
     __half hi, lo;
     split_half(v, hi, lo);
     uint8_t* base = packed + (size_t)c * TC_CHUNK_GBYTES;
@@ -299,29 +299,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
         const float rc0 = __ldg(G) * rx + __ldg(G + 1) * ry + __ldg(G + 2) * rz;
         const float rc1 = __ldg(G + 3) * rx + __ldg(G + 4) * ry + __ldg(G + 5) * rz;
         const float rc2 = __ldg(G + 6) * rx + __ldg(G + 7) * ry + __ldg(G + 8) * rz;
+        // d rel_c[d] = g_x[d] + sum_i 2^i (cos_i g_sin_i - sin_i g_cos_i), in the PE tile's column layout (aggregate_tc.cuh)
         float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        if (cq < 3) {                                       // columns 16 d + [sin i = 0..7 | cos i = 0..7]
+          float sn[8], cs[8];
+          tc_pe_octaves<0, 8>(cq == 0 ? rc0 : cq == 1 ? rc1 : rc2, sn, cs);
+          float acc = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = cq * 16 + i;                      // PE column: [x(3) | sin 30 | cos 30 | pad]
-          const float gv = __uint_as_float(v[i]) * inv_gscale;
-          float contrib = 0.f;
-          int d;
-          if (col < 3) {
-            d = col;
-            contrib = gv;
-          } else if (col < 63) {
-            const int j = (col - 3) % 30, is_cos = (col - 3) / 30;
-            d = j / 10;
-            const float f = (float)(1 << (j - d * 10));
-            float sn, cs;
-            sincosf((d == 0 ? rc0 : d == 1 ? rc1 : rc2) * f, &sn, &cs);
-            contrib = is_cos ? -f * sn * gv : f * cs * gv;
-          } else {
-            d = 0;
+          for (int i = 0; i < 8; ++i)
+            acc += (float)(1 << i) * (cs[i] * __uint_as_float(v[i]) - sn[i] * __uint_as_float(v[8 + i]));
+          acc *= inv_gscale;
+          d0 = cq == 0 ? acc : 0.f;
+          d1 = cq == 1 ? acc : 0.f;
+          d2 = cq == 2 ? acc : 0.f;
+        } else {                                            // 4 d + [sin 8, sin 9 | cos 8, cos 9], then rel_c
+          float dd[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            float sn[2], cs[2];
+            tc_pe_octaves<8, 2>(d == 0 ? rc0 : d == 1 ? rc1 : rc2, sn, cs);
+            dd[d] = 256.f * (cs[0] * __uint_as_float(v[4 * d]) - sn[0] * __uint_as_float(v[4 * d + 2])) +
+                    512.f * (cs[1] * __uint_as_float(v[4 * d + 1]) - sn[1] * __uint_as_float(v[4 * d + 3])) +
+                    __uint_as_float(v[12 + d]);
           }
-          d0 += d == 0 ? contrib : 0.f;
-          d1 += d == 1 ? contrib : 0.f;
-          d2 += d == 2 ? contrib : 0.f;
+          d0 = dd[0] * inv_gscale;
+          d1 = dd[1] * inv_gscale;
+          d2 = dd[2] * inv_gscale;
         }
         atomicAdd(&sDrc[3 * erow], d0);
         atomicAdd(&sDrc[3 * erow + 1], d1);
@@ -538,7 +541,8 @@ tc_wgrad_reduce_kernel(const float* __restrict__ partial, int n_slabs, const flo
     dw[e & (128 * 128 - 1)] += s;
   } else if (e < TCW_SLAB_BIAS) {
     const int r = (e - 3 * 128 * 128) >> 6, c = (e - 3 * 128 * 128) & 63;
-    if (c < APN_PE_POS) dw0[(size_t)r * d_in + c] += s;
+    const int col = tc_pe_ref_col(c);
+    if (col >= 0) dw0[(size_t)r * d_in + col] += s;
   } else {
     const int l = (e - TCW_SLAB_BIAS) >> 7, n = (e - TCW_SLAB_BIAS) & 127;
     float* db = l == 0 ? db0 : l == 1 ? db1 : l == 2 ? db2 : db3;
