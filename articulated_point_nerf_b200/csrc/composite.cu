@@ -18,6 +18,34 @@
 
 #define COMP_MAX_EXTRA 4
 
+// Every lane walks its own segment, so a scalar access costs one L1 tag look-up per lane and instruction (32 distinct
+// sectors): the walk is bound by the L1 tag stage, not by DRAM.  Samples are therefore fetched and stored four at a time
+// with 16-byte accesses wherever the segment allows (scalar head up to the first multiple of four, scalar tail), and
+// consumed strictly in order; loads past an early stop stay inside the ray's own segment and are simply unused.
+struct CompState {
+  float Tc, cr, cg, cb, dep;
+  float ex[COMP_MAX_EXTRA];
+  bool stopped;
+};
+
+// one sample of the chain (render_utils_kernel.cu:445-457); returns the value saved for the backward
+__device__ __forceinline__ float comp_step(CompState& st, int i, float a, float r, float g, float b, float stepf, bool has_step,
+                                           float thres, const float* __restrict__ extra, int n_extra) {
+  if (!(a > thres)) return 1.f;       // dropped by the pre-mask: not part of the chain
+  const float T = st.Tc;
+  const float w = __fmul_rn(T, a);
+  if (w > thres) {
+    st.cr = __fadd_rn(st.cr, __fmul_rn(w, r));
+    st.cg = __fadd_rn(st.cg, __fmul_rn(w, g));
+    st.cb = __fadd_rn(st.cb, __fmul_rn(w, b));
+    if (has_step) st.dep = __fadd_rn(st.dep, __fmul_rn(w, stepf));
+    for (int c = 0; c < n_extra; ++c) st.ex[c] = __fadd_rn(st.ex[c], __fmul_rn(w, extra[(size_t)i * n_extra + c]));
+  }
+  st.Tc = (float)((double)T * (1.0 - (double)a));
+  if ((double)st.Tc < 1e-3) st.stopped = true;
+  return T;
+}
+
 __global__ void __launch_bounds__(128)
 composite_fwd_kernel(const float* __restrict__ alpha, const float* __restrict__ rgb, const int* __restrict__ step_id,
                      const float* __restrict__ extra, int n_extra, const int* __restrict__ ray_start, int R, float thres,
@@ -26,40 +54,54 @@ composite_fwd_kernel(const float* __restrict__ alpha, const float* __restrict__ 
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   const int s = ray_start[r], e = ray_start[r + 1];
-  float Tc = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f;
-  float ex[COMP_MAX_EXTRA] = {0.f, 0.f, 0.f, 0.f};
-  int i = s;
-  for (; i < e; ++i) {
-    const float a = alpha[i];
-    if (!(a > thres)) {               // dropped by the pre-mask: not part of the chain
-      if (T_save) T_save[i] = 1.f;
-      continue;
-    }
-    if (T_save) T_save[i] = Tc;
-    const float w = __fmul_rn(Tc, a);
-    if (w > thres) {
-      cr = __fadd_rn(cr, __fmul_rn(w, rgb[3 * (size_t)i]));
-      cg = __fadd_rn(cg, __fmul_rn(w, rgb[3 * (size_t)i + 1]));
-      cb = __fadd_rn(cb, __fmul_rn(w, rgb[3 * (size_t)i + 2]));
-      if (step_id) dep = __fadd_rn(dep, __fmul_rn(w, (float)step_id[i]));
-      for (int c = 0; c < n_extra; ++c) ex[c] = __fadd_rn(ex[c], __fmul_rn(w, extra[(size_t)i * n_extra + c]));
-    }
-    Tc = (float)((double)Tc * (1.0 - (double)a));
-    if ((double)Tc < 1e-3) {
-      ++i;
-      break;
-    }
+  CompState st;
+  st.Tc = 1.f; st.cr = st.cg = st.cb = st.dep = 0.f; st.stopped = false;
+#pragma unroll
+  for (int c = 0; c < COMP_MAX_EXTRA; ++c) st.ex[c] = 0.f;
+  const bool has_step = step_id != nullptr;
+  int i = s, visited = 0;
+  // scalar head
+  for (; i < e && (i & 3) && !st.stopped; ++i, ++visited) {
+    const float T = comp_step(st, i, alpha[i], rgb[3 * (size_t)i], rgb[3 * (size_t)i + 1], rgb[3 * (size_t)i + 2],
+                              has_step ? (float)step_id[i] : 0.f, has_step, thres, extra, n_extra);
+    if (T_save) T_save[i] = T;
   }
-  if (n_used) n_used[r] = i - s;      // samples visited before the early stop
-  if (T_save)
-    for (int k = i; k < e; ++k) T_save[k] = 1.f;
-  rgb_marched[3 * (size_t)r] = __fadd_rn(cr, __fmul_rn(Tc, bg));
-  rgb_marched[3 * (size_t)r + 1] = __fadd_rn(cg, __fmul_rn(Tc, bg));
-  rgb_marched[3 * (size_t)r + 2] = __fadd_rn(cb, __fmul_rn(Tc, bg));
+  // 16-byte body
+  for (; i + 4 <= e && !st.stopped; i += 4) {
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(alpha + i));
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(rgb + 3 * (size_t)i));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(rgb + 3 * (size_t)i) + 1);
+    const float4 c2 = __ldg(reinterpret_cast<const float4*>(rgb + 3 * (size_t)i) + 2);
+    int4 s4 = make_int4(0, 0, 0, 0);
+    if (has_step) s4 = __ldg(reinterpret_cast<const int4*>(step_id + i));
+    float4 tv = make_float4(1.f, 1.f, 1.f, 1.f);
+    tv.x = comp_step(st, i, a4.x, c0.x, c0.y, c0.z, (float)s4.x, has_step, thres, extra, n_extra);
+    ++visited;
+    if (!st.stopped) { tv.y = comp_step(st, i + 1, a4.y, c0.w, c1.x, c1.y, (float)s4.y, has_step, thres, extra, n_extra); ++visited; }
+    if (!st.stopped) { tv.z = comp_step(st, i + 2, a4.z, c1.z, c1.w, c2.x, (float)s4.z, has_step, thres, extra, n_extra); ++visited; }
+    if (!st.stopped) { tv.w = comp_step(st, i + 3, a4.w, c2.y, c2.z, c2.w, (float)s4.w, has_step, thres, extra, n_extra); ++visited; }
+    if (T_save) *reinterpret_cast<float4*>(T_save + i) = tv;
+  }
+  // scalar tail
+  for (; i < e && !st.stopped; ++i, ++visited) {
+    const float T = comp_step(st, i, alpha[i], rgb[3 * (size_t)i], rgb[3 * (size_t)i + 1], rgb[3 * (size_t)i + 2],
+                              has_step ? (float)step_id[i] : 0.f, has_step, thres, extra, n_extra);
+    if (T_save) T_save[i] = T;
+  }
+  if (n_used) n_used[r] = visited;    // samples visited before the early stop
+  if (T_save) {                       // never visited (i is past every group already written)
+    for (; i < e && (i & 3); ++i) T_save[i] = 1.f;
+    for (; i + 4 <= e; i += 4) *reinterpret_cast<float4*>(T_save + i) = make_float4(1.f, 1.f, 1.f, 1.f);
+    for (; i < e; ++i) T_save[i] = 1.f;
+  }
+  const float Tc = st.Tc;
+  rgb_marched[3 * (size_t)r] = __fadd_rn(st.cr, __fmul_rn(Tc, bg));
+  rgb_marched[3 * (size_t)r + 1] = __fadd_rn(st.cg, __fmul_rn(Tc, bg));
+  rgb_marched[3 * (size_t)r + 2] = __fadd_rn(st.cb, __fmul_rn(Tc, bg));
   alphainv_last[r] = Tc;
-  if (depth) depth[r] = dep;
+  if (depth) depth[r] = st.dep;
   if (extra_marched)
-    for (int c = 0; c < n_extra; ++c) extra_marched[(size_t)r * n_extra + c] = __fadd_rn(ex[c], __fmul_rn(Tc, bg));
+    for (int c = 0; c < n_extra; ++c) extra_marched[(size_t)r * n_extra + c] = __fadd_rn(st.ex[c], __fmul_rn(Tc, bg));
 }
 
 // Backward of the fused op.  With gw[i] = d(rgb_marched)·rgb[i] + d(depth)*step[i] for samples
@@ -67,6 +109,25 @@ composite_fwd_kernel(const float* __restrict__ alpha, const float* __restrict__ 
 //   back = gl*alphainv_last;  for i reversed over the chain:
 //     d_alpha[i] = gw[i]*T[i] - back/(1-alpha[i]+1e-10);  back += gw[i]*w[i]
 // (render_utils_kernel.cu:520-531, same float/double mixing).  d_rgb[i] = w[i]*d(rgb_marched).
+struct CompGrad {
+  float gr, gg, gb, gd, back;
+};
+__device__ __forceinline__ void comp_bwd_step(CompGrad& G, float a, float T, float r, float g, float b, float stepf, bool has_step,
+                                              float thres, float& da, float& dr, float& dg, float& db) {
+  da = dr = dg = db = 0.f;
+  if (a > thres) {
+    const float w = __fmul_rn(T, a);
+    float gw = 0.f;
+    if (w > thres) {
+      gw = G.gr * r + G.gg * g + G.gb * b;
+      if (has_step) gw += G.gd * stepf;
+      dr = w * G.gr; dg = w * G.gg; db = w * G.gb;
+    }
+    da = (float)((double)__fmul_rn(gw, T) - (double)G.back / ((double)(1.f - a) + 1e-10));
+    G.back = __fadd_rn(G.back, __fmul_rn(gw, w));
+  }
+}
+
 __global__ void __launch_bounds__(128)
 composite_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ rgb, const int* __restrict__ step_id,
                      const int* __restrict__ ray_start, int R, float thres, float bg, const float* __restrict__ T_save,
@@ -77,35 +138,61 @@ composite_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ 
   if (r >= R) return;
   const int s = ray_start[r], e = ray_start[r + 1];
   const int stop = s + n_used[r];
-  const float gr = d_rgb_marched ? d_rgb_marched[3 * (size_t)r] : 0.f;
-  const float gg = d_rgb_marched ? d_rgb_marched[3 * (size_t)r + 1] : 0.f;
-  const float gb = d_rgb_marched ? d_rgb_marched[3 * (size_t)r + 2] : 0.f;
-  const float gd = d_depth ? d_depth[r] : 0.f;
+  CompGrad G;
+  G.gr = d_rgb_marched ? d_rgb_marched[3 * (size_t)r] : 0.f;
+  G.gg = d_rgb_marched ? d_rgb_marched[3 * (size_t)r + 1] : 0.f;
+  G.gb = d_rgb_marched ? d_rgb_marched[3 * (size_t)r + 2] : 0.f;
+  G.gd = d_depth ? d_depth[r] : 0.f;
   float gl = d_alphainv_last ? d_alphainv_last[r] : 0.f;
-  gl += bg * (gr + gg + gb);
-  for (int i = stop; i < e; ++i) {    // never visited: no gradient
-    d_alpha[i] = 0.f;
-    d_rgb[3 * (size_t)i] = 0.f; d_rgb[3 * (size_t)i + 1] = 0.f; d_rgb[3 * (size_t)i + 2] = 0.f;
-  }
-  float back = __fmul_rn(gl, alphainv_last[r]);
-  for (int i = stop - 1; i >= s; --i) {
-    const float a = alpha[i];
-    float da = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
-    if (a > thres) {
-      const float T = T_save[i];
-      const float w = __fmul_rn(T, a);
-      float gw = 0.f;
-      if (w > thres) {
-        gw = gr * rgb[3 * (size_t)i] + gg * rgb[3 * (size_t)i + 1] + gb * rgb[3 * (size_t)i + 2];
-        if (step_id) gw += gd * (float)step_id[i];
-        dr = w * gr; dg = w * gg; db = w * gb;
-      }
-      da = (float)((double)__fmul_rn(gw, T) - (double)back / ((double)(1.f - a) + 1e-10));
-      back = __fadd_rn(back, __fmul_rn(gw, w));
+  gl += bg * (G.gr + G.gg + G.gb);
+  const bool has_step = step_id != nullptr;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  {                                   // never visited: no gradient
+    int i = stop;
+    for (; i < e && (i & 3); ++i) {
+      d_alpha[i] = 0.f;
+      d_rgb[3 * (size_t)i] = 0.f; d_rgb[3 * (size_t)i + 1] = 0.f; d_rgb[3 * (size_t)i + 2] = 0.f;
     }
+    for (; i + 4 <= e; i += 4) {
+      *reinterpret_cast<float4*>(d_alpha + i) = z4;
+      float4* o = reinterpret_cast<float4*>(d_rgb + 3 * (size_t)i);
+      o[0] = z4; o[1] = z4; o[2] = z4;
+    }
+    for (; i < e; ++i) {
+      d_alpha[i] = 0.f;
+      d_rgb[3 * (size_t)i] = 0.f; d_rgb[3 * (size_t)i + 1] = 0.f; d_rgb[3 * (size_t)i + 2] = 0.f;
+    }
+  }
+  G.back = __fmul_rn(gl, alphainv_last[r]);
+  auto scalar = [&](int i) {
+    float da, dr, dg, db;
+    comp_bwd_step(G, alpha[i], T_save[i], rgb[3 * (size_t)i], rgb[3 * (size_t)i + 1], rgb[3 * (size_t)i + 2],
+                  has_step ? (float)step_id[i] : 0.f, has_step, thres, da, dr, dg, db);
     d_alpha[i] = da;
     d_rgb[3 * (size_t)i] = dr; d_rgb[3 * (size_t)i + 1] = dg; d_rgb[3 * (size_t)i + 2] = db;
+  };
+  int i = stop - 1;
+  for (; i >= s && (i & 3) != 3; --i) scalar(i);                    // scalar head (top of the range)
+  for (; i - 3 >= s; i -= 4) {                                       // 16-byte body: samples i-3 .. i, consumed i first
+    const int j = i - 3;
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(alpha + j));
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(T_save + j));
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(rgb + 3 * (size_t)j));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(rgb + 3 * (size_t)j) + 1);
+    const float4 c2 = __ldg(reinterpret_cast<const float4*>(rgb + 3 * (size_t)j) + 2);
+    int4 s4 = make_int4(0, 0, 0, 0);
+    if (has_step) s4 = __ldg(reinterpret_cast<const int4*>(step_id + j));
+    float4 da;
+    float4 o0, o1, o2;
+    comp_bwd_step(G, a4.w, t4.w, c2.y, c2.z, c2.w, (float)s4.w, has_step, thres, da.w, o2.y, o2.z, o2.w);
+    comp_bwd_step(G, a4.z, t4.z, c1.z, c1.w, c2.x, (float)s4.z, has_step, thres, da.z, o1.z, o1.w, o2.x);
+    comp_bwd_step(G, a4.y, t4.y, c0.w, c1.x, c1.y, (float)s4.y, has_step, thres, da.y, o0.w, o1.x, o1.y);
+    comp_bwd_step(G, a4.x, t4.x, c0.x, c0.y, c0.z, (float)s4.x, has_step, thres, da.x, o0.x, o0.y, o0.z);
+    *reinterpret_cast<float4*>(d_alpha + j) = da;
+    float4* o = reinterpret_cast<float4*>(d_rgb + 3 * (size_t)j);
+    o[0] = o0; o[1] = o1; o[2] = o2;
   }
+  for (; i >= s; --i) scalar(i);                                     // scalar tail (bottom of the range)
 }
 
 extern "C" int apn_composite_fwd(const float* alpha, const float* rgb, const int32_t* step_id, const float* extra,

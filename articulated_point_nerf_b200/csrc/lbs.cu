@@ -3,35 +3,17 @@
 // Replaces lib/temporalpoints.py:401-414,424,569 and lib/pointwarper.py:241-266.
 //
 // Bandwidth-bound: algorithmic bytes fwd = N*(4J + 12 + 12 + 36) (+4J when merged weights are
-// written); bwd = N*(8J + 12 + 12 + 36 + 36).  One tile = 128 points; the (128 x J) weight tile
-// is staged through shared memory with float4-coalesced global access and an odd row stride so
-// that the per-point passes are bank-conflict free; bone matrices live in shared memory and
-// are read as warp broadcasts.  Persistent grid (multiple of the SM count).
+// written); bwd = N*(8J + 12 + 12 + 36 + 36).  Warp-centric: a warp owns 32 points at a time, reads and writes
+// the (N x J) weight rows coalesced with its lanes over the bones, and switches to lane = point (rows in a
+// warp-private shared tile with an odd stride, bone matrices as warp broadcasts) for the per-point algebra.
+// No block-wide barriers inside the loop; persistent grid (multiple of the SM count).
 #include "common.cuh"
 
-#define LBS_TILE 128
 #define LBS_MAX_J 128
 
 __global__ void lbs_init_bbox_kernel(float* bbox) {
   if (threadIdx.x < 3) bbox[threadIdx.x] = __int_as_float(0x7f800000);       // +inf
   else if (threadIdx.x < 6) bbox[threadIdx.x] = __int_as_float(0xff800000);  // -inf
-}
-
-// cooperative (LBS_TILE x J) global <-> shared copy; global rows are contiguous (stride J),
-// shared rows have stride JP.
-__device__ __forceinline__ void tile_load(float* __restrict__ s, const float* __restrict__ g, int n_valid, int J, int JP) {
-  const int total = n_valid * J;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = i / J, j = i - p * J;
-    s[p * JP + j] = __ldg(g + i);
-  }
-}
-__device__ __forceinline__ void tile_store(float* __restrict__ g, const float* __restrict__ s, int n_valid, int J, int JP) {
-  const int total = n_valid * J;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = i / J, j = i - p * J;
-    g[i] = s[p * JP + j];
-  }
 }
 
 __device__ __forceinline__ void inverse3x3(const float a[9], float inv[9]) {
@@ -69,7 +51,39 @@ __device__ __forceinline__ void softmax_row(float* row, int J, float theta) {
   for (int j = 0; j < J; ++j) row[j] *= inv;
 }
 
-__global__ void __launch_bounds__(LBS_TILE)
+// softmax(raw / theta) of one shared-memory row by ONE thread, in place (three passes over the row).
+// x / theta is evaluated as q = x * (1/theta) followed by one residual correction, q + (x - q theta) * (1/theta):
+// the correctly rounded quotient for all but a vanishing fraction of operands, at 3 instructions instead of the
+// ~10 of the IEEE division sequence.
+__device__ __forceinline__ void softmax_row(float* row, int J, float theta, float inv_theta) {
+  float mx = -INFINITY;
+  for (int j = 0; j < J; ++j) {
+    const float x = row[j];
+    const float q = x * inv_theta;
+    const float z = fmaf(fmaf(-q, theta, x), inv_theta, q);
+    row[j] = z;
+    mx = fmaxf(mx, z);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < J; ++j) {
+    const float e = expf(row[j] - mx);
+    row[j] = e;
+    sum += e;
+  }
+  const float inv = 1.0f / sum;
+  for (int j = 0; j < J; ++j) row[j] *= inv;
+}
+
+// Forward: warp-centric, no block-wide barriers.  A warp owns 32 consecutive points per step:
+//   phase 1  lanes run over the bones of one point at a time: coalesced row read straight from global memory,
+//            softmax with two warp reductions, the weights go to the warp's shared-memory tile (odd row stride) and
+//            — when no merge rules apply — straight back to global memory, again coalesced;
+//   phase 2  lane = point: merge rules, blend of the bone 3x4s (broadcast reads), transform, closed-form inverse, bbox.
+#define LBS_WARPS 4
+#define LBS_MAX_K (LBS_MAX_J / 32)
+
+template <int K>          // K = ceil(J / 32) registers per lane and row
+__global__ void __launch_bounds__(32 * LBS_WARPS)
 lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_weight, float eps,
                const int* __restrict__ rules, const float* __restrict__ bone_T, const float* __restrict__ xyz,
                const float* __restrict__ global_t, int N, int J, float* __restrict__ xyz_out,
@@ -77,28 +91,67 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
                float* __restrict__ bbox) {
   extern __shared__ float smem[];
   const int JP = J | 1;
-  float* sT = smem;                    // J*12
-  int* sR = (int*)(sT + J * 12);       // J
-  float* sW = (float*)(sR + J);        // LBS_TILE*JP
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sT = smem;                                  // J*12
+  int* sR = (int*)(sT + J * 12);                     // J
+  float* sW = (float*)(sR + J) + warp * 32 * JP;     // this warp's 32 x JP tile
   for (int i = threadIdx.x; i < J * 12; i += blockDim.x) {
     const int j = i / 12, c = i - j * 12;
     sT[i] = bone_T[j * 16 + c];        // rows 0..2 of the 4x4
   }
   for (int j = threadIdx.x; j < J; j += blockDim.x) sR[j] = rules ? rules[j] : j;
+  __syncthreads();
   const float theta = theta_weight ? fmaxf(eps, theta_weight[0]) : 1.f;
+  const float inv_theta = 1.0f / theta;
   const float gx = global_t ? global_t[0] : 0.f, gy = global_t ? global_t[1] : 0.f, gz = global_t ? global_t[2] : 0.f;
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mxv[3] = {-INFINITY, -INFINITY, -INFINITY};
-  const int n_tiles = (N + LBS_TILE - 1) / LBS_TILE;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int base = tile * LBS_TILE;
-    const int n_valid = min(LBS_TILE, N - base);
-    __syncthreads();
-    tile_load(sW, raw_w + (size_t)base * J, n_valid, J, JP);
-    __syncthreads();
-    const int p = threadIdx.x;
-    if (p < n_valid) {
-      float* row = sW + p * JP;
-      if (theta_weight) softmax_row(row, J, theta);   // NULL: the caller passes final weights
+  const int n_chunks = (N + 31) / 32;
+  const int n_warps = gridDim.x * LBS_WARPS;
+  // rows are fetched four at a time, one batch ahead of their use (across chunk boundaries too)
+  auto load_rows = [&](int chunk, int p0, float (&v)[4][K]) {
+    const int base = chunk * 32;
+    const int last = min(32, N - base) - 1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t row = (size_t)(base + min(p0 + u, last)) * J;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k;
+        v[u][k] = j < J ? __ldg(raw_w + row + j) : -INFINITY;
+      }
+    }
+  };
+  float vn[4][K];
+  int chunk = blockIdx.x * LBS_WARPS + warp;
+  if (chunk < n_chunks) load_rows(chunk, 0, vn);
+  for (; chunk < n_chunks; chunk += n_warps) {
+    const int base = chunk * 32;
+    const int n_valid = min(32, N - base);
+    // ---------------------------------------------------------------- phase 1: rows -> warp tile, lanes over bones
+    for (int p0 = 0; p0 < n_valid; p0 += 4) {
+      float v[4][K];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[u][k] = vn[u][k];
+      if (p0 + 4 < n_valid) load_rows(chunk, p0 + 4, vn);
+      else if (chunk + n_warps < n_chunks) load_rows(chunk + n_warps, 0, vn);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p0 + u >= n_valid) break;
+        float* srow = sW + (p0 + u) * JP;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int j = lane + 32 * k;
+          if (j < J) srow[j] = v[u][k];
+        }
+      }
+    }
+    __syncwarp();
+    // ---------------------------------------------------------------- phase 2: lane = point
+    if (lane < n_valid) {
+      float* row = sW + lane * JP;
+      if (theta_weight) softmax_row(row, J, theta, inv_theta);   // NULL: the caller passes final weights
       if (rules) {
         for (int j = 0; j < J; ++j) {
           const int t = sR[j];
@@ -113,11 +166,13 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
       for (int c = 0; c < 12; ++c) G[c] = 0.f;
       for (int j = 0; j < J; ++j) {
         const float w = row[j];
-        const float* T = sT + j * 12;
-#pragma unroll
-        for (int c = 0; c < 12; ++c) G[c] = fmaf(w, T[c], G[c]);
+        const float4* T = reinterpret_cast<const float4*>(sT + j * 12);
+        const float4 t0 = T[0], t1 = T[1], t2 = T[2];
+        G[0] = fmaf(w, t0.x, G[0]); G[1] = fmaf(w, t0.y, G[1]); G[2] = fmaf(w, t0.z, G[2]); G[3] = fmaf(w, t0.w, G[3]);
+        G[4] = fmaf(w, t1.x, G[4]); G[5] = fmaf(w, t1.y, G[5]); G[6] = fmaf(w, t1.z, G[6]); G[7] = fmaf(w, t1.w, G[7]);
+        G[8] = fmaf(w, t2.x, G[8]); G[9] = fmaf(w, t2.y, G[9]); G[10] = fmaf(w, t2.z, G[10]); G[11] = fmaf(w, t2.w, G[11]);
       }
-      const size_t n = (size_t)base + p;
+      const size_t n = (size_t)base + lane;
       const float x = xyz[3 * n], y = xyz[3 * n + 1], z = xyz[3 * n + 2];
       const float ox = G[0] * x + G[1] * y + G[2] * z + G[3] + gx;
       const float oy = G[4] * x + G[5] * y + G[6] * z + G[7] + gy;
@@ -140,15 +195,24 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
         go[3] = make_float4(0.f, 0.f, 0.f, 1.f);
       }
     }
-    if (w_out) {
-      __syncthreads();
-      tile_store(w_out + (size_t)base * J, sW, n_valid, J, JP);
+    __syncwarp();
+    if (w_out) {                                       // (merged) weights: the tile, row by row, coalesced
+      for (int p = 0; p < n_valid; ++p) {
+        const float* srow = sW + p * JP;
+        float* grow = w_out + (size_t)(base + p) * J;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int j = lane + 32 * k;
+          if (j < J) grow[j] = srow[j];
+        }
+      }
     }
+    __syncwarp();
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float a = warp_min(mn[c]), b = warp_max(mxv[c]);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
       if (a < INFINITY) atomic_min_float(bbox + c, a);
       if (b > -INFINITY) atomic_max_float(bbox + 3 + c, b);
     }
@@ -158,8 +222,15 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
 // ---------------------------------------------------------------------------------------
 // backward
 // partial layout per block: [J*12 dT | 1 dtheta | 3 dglobal_t]
+// Warp-centric like the forward; per 32-point chunk:
+//   phase 1  lanes over bones: raw row -> softmax weights w (warp tile sW), incoming d_w row (warp tile sDM);
+//   phase 2  lane = point: dA = -B^T dB B^T, dG (registers + warp tile sDG), merged weights (sM, only with merge
+//            rules), dm_j = d_w_j + <dG, T_j> (sDM, in place);
+//   phase 3  lanes over bones: softmax backward -> d_raw row (coalesced store) and the theta gradient;
+//            dT_j += sum_p m[p][j] dG[p][:] in registers (12 K accumulators per lane, kept across chunks).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LBS_TILE)
+template <int K>
+__global__ void __launch_bounds__(32 * LBS_WARPS)
 lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_weight, float eps,
                const int* __restrict__ rules, const float* __restrict__ bone_T, const float* __restrict__ xyz, int N,
                int J, const float* __restrict__ ginv, const float* __restrict__ d_xyz,
@@ -168,38 +239,91 @@ lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
   extern __shared__ float smem[];
   const int JP = J | 1;
   const int n_out = J * 12;
-  float* sT = smem;                          // J*12
-  int* sR = (int*)(sT + n_out);              // J
-  float* sW = (float*)(sR + J);              // softmax weights, later d_raw          TILE*JP
-  float* sM = sW + LBS_TILE * JP;            // merged weights                         TILE*JP
-  float* sDW = sM + LBS_TILE * JP;           // incoming d_w tile                      TILE*JP
-  float* sDG = sDW + LBS_TILE * JP;          // dG per point                           TILE*13
-  float* sAcc = sDG + LBS_TILE * 13;         // dT accumulators                        J*12
-  __shared__ float sRed[4][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // every float4-read array starts on a 16-byte boundary: sT, sAcc, then per warp [sDG | sW | sM | sDM], sR last
+  float* sT = smem;                                        // J*12
+  float* sAcc = sT + n_out;                                // J*12 + 4 block accumulators
+  const int n_tiles_w = rules ? 3 : 2;                     // the merged-weight tile exists only with merge rules
+  const int wstride = n_tiles_w * 32 * JP + 32 * 12;
+  float* wbase = sAcc + n_out + 4 + warp * wstride;
+  float* sDG = wbase;                                      // dG per point                 32*12
+  float* sW = sDG + 32 * 12;                               // softmax weights              32*JP
+  float* sDM = sW + 32 * JP;                               // d_w in, dm out               32*JP
+  float* sM = sDM + 32 * JP;                               // merged weights (rules only)  32*JP
+  int* sR = (int*)(sAcc + n_out + 4 + LBS_WARPS * wstride);                   // J
   for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
     const int j = i / 12, c = i - j * 12;
     sT[i] = bone_T[j * 16 + c];
-    sAcc[i] = 0.f;
   }
+  for (int i = threadIdx.x; i < n_out + 4; i += blockDim.x) sAcc[i] = 0.f;
   for (int j = threadIdx.x; j < J; j += blockDim.x) sR[j] = rules ? rules[j] : j;
+  __syncthreads();
   const float theta = theta_weight ? fmaxf(eps, theta_weight[0]) : 1.f;
-  float acc_theta = 0.f, acc_g[3] = {0.f, 0.f, 0.f};
-  const int n_tiles = (N + LBS_TILE - 1) / LBS_TILE;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int base = tile * LBS_TILE;
-    const int n_valid = min(LBS_TILE, N - base);
-    __syncthreads();
-    tile_load(sW, raw_w + (size_t)base * J, n_valid, J, JP);
-    if (d_w) tile_load(sDW, d_w + (size_t)base * J, n_valid, J, JP);
-    __syncthreads();
-    const int p = threadIdx.x;
-    float* dg = sDG + p * 13;
-    if (p < n_valid) {
-      float* row = sW + p * JP;
-      float* mrow = sM + p * JP;
-      if (theta_weight) softmax_row(row, J, theta);
-      for (int j = 0; j < J; ++j) mrow[j] = row[j];
+  const float inv_theta = 1.0f / theta;
+  double acc_theta = 0.0;                                  // heavy cancellation over N*J terms: accumulated in fp64
+  float acc_g[3] = {0.f, 0.f, 0.f};
+  float accT[K][12];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int c = 0; c < 12; ++c) accT[k][c] = 0.f;
+  const float* sMm = rules ? sM : sW;                      // weights that multiplied T_j in the forward
+  const int n_chunks = (N + 31) / 32;
+  const int n_warps = gridDim.x * LBS_WARPS;
+  auto load_rows = [&](int chunk, int p0, float (&v)[4][K], float (&dwv)[4][K]) {
+    const int base = chunk * 32;
+    const int last = min(32, N - base) - 1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t row = (size_t)(base + min(p0 + u, last)) * J;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k;
+        v[u][k] = j < J ? __ldg(raw_w + row + j) : -INFINITY;
+        dwv[u][k] = (d_w && j < J) ? __ldg(d_w + row + j) : 0.f;
+      }
+    }
+  };
+  float vn[4][K], dwn[4][K];
+  int chunk = blockIdx.x * LBS_WARPS + warp;
+  if (chunk < n_chunks) load_rows(chunk, 0, vn, dwn);
+  for (; chunk < n_chunks; chunk += n_warps) {
+    const int base = chunk * 32;
+    const int n_valid = min(32, N - base);
+    // ---------------------------------------------------------------- phase 1: raw and d_w rows -> warp tiles
+    for (int p0 = 0; p0 < n_valid; p0 += 4) {
+      float v[4][K], dwv[4][K];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          v[u][k] = vn[u][k];
+          dwv[u][k] = dwn[u][k];
+        }
+      if (p0 + 4 < n_valid) load_rows(chunk, p0 + 4, vn, dwn);
+      else if (chunk + n_warps < n_chunks) load_rows(chunk + n_warps, 0, vn, dwn);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p0 + u >= n_valid) break;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int j = lane + 32 * k;
+          if (j < J) {
+            sW[(p0 + u) * JP + j] = v[u][k];
+            sDM[(p0 + u) * JP + j] = dwv[u][k];
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---------------------------------------------------------------- phase 2: lane = point
+    float* dg = sDG + lane * 12;
+    if (lane < n_valid) {
+      if (theta_weight) softmax_row(sW + lane * JP, J, theta, inv_theta);
       if (rules) {
+        float* mrow = sM + lane * JP;
+        const float* row = sW + lane * JP;
+        for (int j = 0; j < J; ++j) mrow[j] = row[j];
         for (int j = 0; j < J; ++j) {
           const int t = sR[j];
           if (t != j) {
@@ -208,7 +332,7 @@ lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
           }
         }
       }
-      const size_t n = (size_t)base + p;
+      const size_t n = (size_t)base + lane;
       float B[9], dB[9], dA[9];
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
@@ -229,64 +353,105 @@ lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
       const float gx = d_xyz ? d_xyz[3 * n] : 0.f, gy = d_xyz ? d_xyz[3 * n + 1] : 0.f, gz = d_xyz ? d_xyz[3 * n + 2] : 0.f;
       acc_g[0] += gx; acc_g[1] += gy; acc_g[2] += gz;
       // dG rows: [dA row | db]
-      dg[0] = dA[0] + gx * x; dg[1] = dA[1] + gx * y; dg[2] = dA[2] + gx * z; dg[3] = gx;
-      dg[4] = dA[3] + gy * x; dg[5] = dA[4] + gy * y; dg[6] = dA[5] + gy * z; dg[7] = gy;
-      dg[8] = dA[6] + gz * x; dg[9] = dA[7] + gz * y; dg[10] = dA[8] + gz * z; dg[11] = gz;
+      float g12[12] = {dA[0] + gx * x, dA[1] + gx * y, dA[2] + gx * z, gx, dA[3] + gy * x, dA[4] + gy * y, dA[5] + gy * z, gy,
+                       dA[6] + gz * x, dA[7] + gz * y, dA[8] + gz * z, gz};
       if (d_g) {
 #pragma unroll
-        for (int c = 0; c < 12; ++c) dg[c] += d_g[16 * n + c];
+        for (int c = 0; c < 12; ++c) g12[c] += d_g[16 * n + c];
       }
-      // dm_j, then dw_j = dm_{rules[j]}, softmax backward
-      float* dwrow = sDW + p * JP;
-      for (int j = 0; j < J; ++j) {
-        const float* T = sT + j * 12;
-        float s = d_w ? dwrow[j] : 0.f;
 #pragma unroll
-        for (int c = 0; c < 12; ++c) s = fmaf(dg[c], T[c], s);
-        dwrow[j] = s;  // dm_j
-      }
-      if (theta_weight) {
-        float dot = 0.f;
-        for (int j = 0; j < J; ++j) dot = fmaf(row[j], dwrow[sR[j]], dot);
-        float th = 0.f;
-        for (int j = 0; j < J; ++j) {
-          const float dz = row[j] * (dwrow[sR[j]] - dot);
-          const float rawv = __ldg(raw_w + n * J + j);
-          th = fmaf(-dz, rawv, th);
-          row[j] = dz / theta;  // d_raw
-        }
-        acc_theta += th / (theta * theta);
-      } else {
-        for (int j = 0; j < J; ++j) row[j] = dwrow[sR[j]];
+      for (int c = 0; c < 12; ++c) dg[c] = g12[c];
+      // dm_j = d_w_j + <dG, T_j>
+      float* dmrow = sDM + lane * JP;
+      for (int j = 0; j < J; ++j) {
+        const float4* T = reinterpret_cast<const float4*>(sT + j * 12);
+        const float4 t0 = T[0], t1v = T[1], t2 = T[2];
+        float sacc = dmrow[j];
+        sacc = fmaf(g12[0], t0.x, sacc); sacc = fmaf(g12[1], t0.y, sacc); sacc = fmaf(g12[2], t0.z, sacc); sacc = fmaf(g12[3], t0.w, sacc);
+        sacc = fmaf(g12[4], t1v.x, sacc); sacc = fmaf(g12[5], t1v.y, sacc); sacc = fmaf(g12[6], t1v.z, sacc); sacc = fmaf(g12[7], t1v.w, sacc);
+        sacc = fmaf(g12[8], t2.x, sacc); sacc = fmaf(g12[9], t2.y, sacc); sacc = fmaf(g12[10], t2.z, sacc); sacc = fmaf(g12[11], t2.w, sacc);
+        dmrow[j] = sacc;
       }
     } else {
 #pragma unroll
       for (int c = 0; c < 12; ++c) dg[c] = 0.f;
-      float* mrow = sM + p * JP;
-      for (int j = 0; j < J; ++j) mrow[j] = 0.f;
     }
-    __syncthreads();
-    tile_store(d_raw + (size_t)base * J, sW, n_valid, J, JP);
-    // dT_j += sum_p m[p][j] * dG[p][:]
-    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-      const int j = o / 12, c = o - j * 12;
-      float a = 0.f;
-#pragma unroll 8
-      for (int q = 0; q < LBS_TILE; ++q) a = fmaf(sM[q * JP + j], sDG[q * 13 + c], a);
-      sAcc[o] += a;
+    __syncwarp();
+    // ---------------------------------------------------------------- phase 3: lanes over bones
+    for (int p = 0; p < n_valid; ++p) {
+      const float* wrow = sW + p * JP;
+      const float* dmrow = sDM + p * JP;
+      const size_t row = (size_t)(base + p) * J;
+      float wv[K], dmr[K];
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k;
+        wv[k] = j < J ? wrow[j] : 0.f;
+        dmr[k] = j < J ? dmrow[sR[j]] : 0.f;
+        dot = fmaf(wv[k], dmr[k], dot);
+      }
+      if (theta_weight) {
+        dot = warp_sum(dot);
+        float th = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int j = lane + 32 * k;
+          if (j < J) {
+            const float dz = wv[k] * (dmr[k] - dot);
+            th = fmaf(-dz, __ldg(raw_w + row + j), th);
+            d_raw[row + j] = dz * inv_theta;
+          }
+        }
+        acc_theta += (double)th;
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int j = lane + 32 * k;
+          if (j < J) d_raw[row + j] = dmr[k];
+        }
+      }
+      // dT_j += m[p][j] * dG[p][:]
+      const float4* gp = reinterpret_cast<const float4*>(sDG + p * 12);
+      const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
+      const float* mrow = sMm + p * JP;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k;
+        const float m = j < J ? mrow[j] : 0.f;
+        accT[k][0] = fmaf(m, g0.x, accT[k][0]); accT[k][1] = fmaf(m, g0.y, accT[k][1]); accT[k][2] = fmaf(m, g0.z, accT[k][2]);
+        accT[k][3] = fmaf(m, g0.w, accT[k][3]); accT[k][4] = fmaf(m, g1.x, accT[k][4]); accT[k][5] = fmaf(m, g1.y, accT[k][5]);
+        accT[k][6] = fmaf(m, g1.z, accT[k][6]); accT[k][7] = fmaf(m, g1.w, accT[k][7]); accT[k][8] = fmaf(m, g2.x, accT[k][8]);
+        accT[k][9] = fmaf(m, g2.y, accT[k][9]); accT[k][10] = fmaf(m, g2.z, accT[k][10]); accT[k][11] = fmaf(m, g2.w, accT[k][11]);
+      }
+    }
+    __syncwarp();
+  }
+  // block reduction (4 warps, shared-memory atomics: the order varies, the values are 4 partial sums per output)
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int j = lane + 32 * k;
+    if (j < J) {
+#pragma unroll
+      for (int c = 0; c < 12; ++c) atomicAdd(&sAcc[j * 12 + c], accT[k][c]);
+    }
+  }
+  {
+    double t = acc_theta;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    const float th = (float)(t / ((double)theta * (double)theta));
+    const float a0 = warp_sum(acc_g[0]), a1 = warp_sum(acc_g[1]), a2 = warp_sum(acc_g[2]);
+    if (lane == 0) {
+      atomicAdd(&sAcc[n_out], th);
+      atomicAdd(&sAcc[n_out + 1], a0);
+      atomicAdd(&sAcc[n_out + 2], a1);
+      atomicAdd(&sAcc[n_out + 3], a2);
     }
   }
   __syncthreads();
   float* out = partial + (size_t)blockIdx.x * (n_out + 4);
-  for (int o = threadIdx.x; o < n_out; o += blockDim.x) out[o] = sAcc[o];
-  float v[4] = {acc_theta, acc_g[0], acc_g[1], acc_g[2]};
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float s = warp_sum(v[c]);
-    if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5][c] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < 4) out[n_out + threadIdx.x] = sRed[0][threadIdx.x] + sRed[1][threadIdx.x] + sRed[2][threadIdx.x] + sRed[3][threadIdx.x];
+  for (int o = threadIdx.x; o < n_out + 4; o += blockDim.x) out[o] = sAcc[o];
 }
 
 // fixed-order reduction of the per-block partials (deterministic)
@@ -309,12 +474,6 @@ __global__ void lbs_bwd_reduce_kernel(const float* __restrict__ partial, int n_b
   }
 }
 
-static int lbs_grid(int N) {
-  const int tiles = (N + LBS_TILE - 1) / LBS_TILE;
-  const int cap = APN_SM_COUNT * 8;
-  return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
-}
-
 extern "C" int apn_lbs_fwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
                            const float* bone_T, const float* xyz, const float* global_t, int N, int J, float* xyz_out,
                            float* ginv_out, float* w_out, float* g_out, float* bbox, apn_stream_t stream_) {
@@ -322,24 +481,42 @@ extern "C" int apn_lbs_fwd(const float* raw_w, const float* theta_weight, float 
   APN_CHECK_ARG(N > 0 && J > 0 && J <= LBS_MAX_J, "need N > 0 and 0 < J <= 128");
   APN_CHECK_ARG(raw_w && bone_T && xyz && xyz_out && ginv_out && bbox, "null pointer");
   const int JP = J | 1;
-  const size_t smem = sizeof(float) * (J * 12 + J + (size_t)LBS_TILE * JP);
-  APN_CUDA(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = sizeof(float) * (J * 12 + J + (size_t)LBS_WARPS * 32 * JP);
   lbs_init_bbox_kernel<<<1, 32, 0, stream>>>(bbox);
   APN_LAUNCH_CHECK();
-  lbs_fwd_kernel<<<lbs_grid(N), LBS_TILE, smem, stream>>>(raw_w, theta_weight, eps, merge_rules, bone_T, xyz, global_t, N,
-                                                         J, xyz_out, ginv_out, w_out, g_out, bbox);
+  const int blocks_needed = apn_div_up(apn_div_up(N, 32), LBS_WARPS);
+  const int per_sm = (int)((200 * 1024) / (smem + 1024));
+  const int cap = APN_SM_COUNT * (per_sm < 1 ? 1 : per_sm > 12 ? 12 : per_sm);
+  const int grid = blocks_needed < cap ? blocks_needed : cap;
+#define LBS_FWD_LAUNCH(KK)                                                                                              \
+  do {                                                                                                                   \
+    APN_CUDA(cudaFuncSetAttribute(lbs_fwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    lbs_fwd_kernel<KK><<<grid, 32 * LBS_WARPS, smem, stream>>>(raw_w, theta_weight, eps, merge_rules, bone_T, xyz,       \
+                                                              global_t, N, J, xyz_out, ginv_out, w_out, g_out, bbox);   \
+  } while (0)
+  const int K = (J + 31) / 32;
+  if (K == 1) LBS_FWD_LAUNCH(1);
+  else if (K == 2) LBS_FWD_LAUNCH(2);
+  else if (K == 3) LBS_FWD_LAUNCH(3);
+  else LBS_FWD_LAUNCH(4);
+#undef LBS_FWD_LAUNCH
   APN_LAUNCH_CHECK();
   return 0;
 }
 
-static int lbs_bwd_grid(int N) {
-  const int tiles = (N + LBS_TILE - 1) / LBS_TILE;
-  const int cap = APN_SM_COUNT * 4;
-  return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
+static size_t lbs_bwd_smem(int J, bool rules) {
+  const int JP = J | 1;
+  return sizeof(float) * (J * 12 + J + J * 12 + 4 + (size_t)LBS_WARPS * ((rules ? 3 : 2) * 32 * JP + 32 * 12));
+}
+static int lbs_bwd_grid(int N, int J) {
+  const int blocks_needed = apn_div_up(apn_div_up(N, 32), LBS_WARPS);
+  const int per_sm = (int)((200 * 1024) / (lbs_bwd_smem(J, false) + 1024));   // workspace sizing: the larger grid
+  const int cap = APN_SM_COUNT * (per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm);
+  return blocks_needed < cap ? (blocks_needed > 0 ? blocks_needed : 1) : cap;
 }
 
 extern "C" size_t apn_lbs_bwd_workspace_bytes(int N, int J) {
-  return sizeof(float) * (size_t)lbs_bwd_grid(N) * (J * 12 + 4);
+  return sizeof(float) * (size_t)lbs_bwd_grid(N, J) * (J * 12 + 4);
 }
 
 extern "C" int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
@@ -352,13 +529,21 @@ extern "C" int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float 
   APN_CHECK_ARG(raw_w && bone_T && xyz && ginv && d_raw && d_bone_T && workspace, "null pointer");
   APN_CHECK_ARG(!theta_weight || d_theta, "d_theta is required when theta_weight is given");
   APN_CHECK_ARG(workspace_bytes >= apn_lbs_bwd_workspace_bytes(N, J), "workspace too small");
-  const int JP = J | 1;
-  const size_t smem = sizeof(float) * (J * 12 + J + 3 * (size_t)LBS_TILE * JP + LBS_TILE * 13 + J * 12);
+  const size_t smem = lbs_bwd_smem(J, merge_rules != nullptr);
   APN_CHECK_ARG(smem <= 227 * 1024, "J too large for the backward tile");
-  APN_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = lbs_bwd_grid(N);
-  lbs_bwd_kernel<<<grid, LBS_TILE, smem, stream>>>(raw_w, theta_weight, eps, merge_rules, bone_T, xyz, N, J, ginv, d_xyz,
-                                                  d_ginv, d_w, d_g, d_raw, (float*)workspace);
+  const int grid = lbs_bwd_grid(N, J);
+#define LBS_BWD_LAUNCH(KK)                                                                                               \
+  do {                                                                                                                    \
+    APN_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    lbs_bwd_kernel<KK><<<grid, 32 * LBS_WARPS, smem, stream>>>(raw_w, theta_weight, eps, merge_rules, bone_T, xyz, N, J,  \
+                                                              ginv, d_xyz, d_ginv, d_w, d_g, d_raw, (float*)workspace);  \
+  } while (0)
+  const int K = (J + 31) / 32;
+  if (K == 1) LBS_BWD_LAUNCH(1);
+  else if (K == 2) LBS_BWD_LAUNCH(2);
+  else if (K == 3) LBS_BWD_LAUNCH(3);
+  else LBS_BWD_LAUNCH(4);
+#undef LBS_BWD_LAUNCH
   APN_LAUNCH_CHECK();
   const int n = J * 12 + 4;
   lbs_bwd_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const float*)workspace, grid, J, theta_weight, eps, d_theta,

@@ -101,8 +101,17 @@ def main():
     # ---------------------------------------------------------------- compositing
     R = args.rays
     spr = args.samples_per_ray
-    hit = torch.rand(R, device=dev, generator=g) < 0.3            # ~30 % of the rays hit the cloud
-    cnt = (hit * torch.randint(1, 8 * spr, (R,), device=dev, generator=g)).to(torch.int32)
+    # image-space coherent sample counts, as a rendered object produces them: a disc covering ~30 % of the frame whose
+    # per-ray count follows the chord length through a sphere (max 8 * spr samples), +-1 sample of noise
+    side = int(round(R ** 0.5))
+    yy, xx = torch.meshgrid(torch.arange(side, device=dev), torch.arange(side, device=dev), indexing="ij")
+    rad = (0.3 / 3.14159) ** 0.5 * side
+    d2 = ((xx - side / 2) ** 2 + (yy - side / 2) ** 2).float() / (rad * rad)
+    chord = torch.sqrt(torch.clamp(1.0 - d2, min=0.0))
+    cnt = torch.round(chord * 8 * spr + (chord > 0) * (torch.rand(side, side, device=dev, generator=g) * 2 - 1)).clamp(min=0)
+    cnt = cnt.reshape(-1)[:R].to(torch.int32)
+    if cnt.numel() < R:
+        cnt = torch.cat([cnt, torch.zeros(R - cnt.numel(), dtype=torch.int32, device=dev)])
     ray_start = torch.zeros(R + 1, dtype=torch.int32, device=dev)
     ray_start[1:] = torch.cumsum(cnt, 0)
     M = int(ray_start[-1].item())
