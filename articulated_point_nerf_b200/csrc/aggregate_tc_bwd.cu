@@ -675,8 +675,8 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
   }
   // feature columns of layer 0 through the per-point table: d_feat = dP W0_feat, dW0_feat += dP^T feat
   if (g->d_feat)
-    APN_CHECK_ARG(gemm_dgrad(st, b.d_ptable, APN_C, w->w[0] + APN_PE_POS, in->d_in, g->d_feat, APN_C, N, APN_C, APN_C, nullptr, 0, 1.f) == 0,
-                  "dgrad point table");
+    APN_CHECK_ARG(gemm_dgrad_accum(st, b.d_ptable, APN_C, w->w[0] + APN_PE_POS, in->d_in, g->d_feat, APN_C, N, APN_C, APN_C) == 0,
+                  "dgrad point table");      // accumulates, like every other gradient of this entry point
   APN_CHECK_ARG(gemm_wgrad(st, b.d_ptable, APN_C, in->feat, APN_C, g->d_w[0] + APN_PE_POS, in->d_in, N, APN_C, APN_C) == 0,
                 "wgrad point table");
   return 0;

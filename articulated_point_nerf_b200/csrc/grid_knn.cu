@@ -546,25 +546,28 @@ __device__ bool knn_search_warp(const GridView& g, float qx, float qy, float qz,
   return true;
 }
 
-#define KNN_GROUP 8     // consecutive candidates (ray-major order) handled by one warp, so bounds carry over along a ray
+// consecutive candidates (ray-major order) handled by one warp, so bounds and the ray setup carry over along a ray:
+// 16 when there is enough work to fill the machine anyway, down to 2 for small batches (latency)
+#define KNN_GROUP_MAX 16
 
 __global__ void __launch_bounds__(128)
 knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
            const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand,
-           int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep) {
+           int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep, int group) {
   const GridView g = grid_view(blob);
   const GridHeader* h = g.h;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
-  const int n_groups = (n_cand + KNN_GROUP - 1) / KNN_GROUP;
+  const int n_groups = (n_cand + group - 1) / group;
   for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
     int prev_ray = -1, prev_step = 0;
     float prev_d8 = -1.f;
-    const int i_end = min(n_cand, (grp + 1) * KNN_GROUP);
-    for (int i = grp * KNN_GROUP; i < i_end; ++i) {
+    RaySetup s;
+    const int i_end = min(n_cand, (grp + 1) * group);
+    for (int i = grp * group; i < i_end; ++i) {
       const int r = __ldg(cand_ray + i), st = __ldg(cand_step + i);
-      const RaySetup s = ray_setup(rays_o, rays_d, r, bmin, bmax, near, far, stepdist);
+      if (r != prev_ray) s = ray_setup(rays_o, rays_d, r, bmin, bmax, near, far, stepdist);   // 9 divisions + sqrt: once per ray
       float px, py, pz;
       ray_point(s, st, stepdist, px, py, pz);
       // |d8(p) - d8(p')| <= |p - p'| = (step - step') * stepdist along a ray (unit direction)
@@ -594,9 +597,12 @@ extern "C" int apn_knn(const float* rays_o, const float* rays_d, float near, flo
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_cand <= 0) return 0;
   APN_CHECK_ARG(rays_o && rays_d && grid && cand_ray && cand_step && nn_idx && keep, "null pointer");
-  const int blocks = min(apn_div_up(n_cand, 4 * KNN_GROUP), APN_SM_COUNT * 16);   // 4 warps per block, persistent grid-stride
+  const int resident_warps = APN_SM_COUNT * 16 * 4;
+  int group = n_cand / resident_warps;
+  group = group < 2 ? 2 : group > KNN_GROUP_MAX ? KNN_GROUP_MAX : group;
+  const int blocks = min(apn_div_up(n_cand, 4 * group), APN_SM_COUNT * 16);   // 4 warps per block, persistent grid-stride
   knn_kernel<<<blocks, 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand, nn_idx, nn_d2,
-                                         keep);
+                                         keep, group);
   APN_LAUNCH_CHECK();
   return 0;
 }

@@ -12,7 +12,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { GEMM_EPI_BIAS_ACT = 0, GEMM_EPI_MASK = 1, GEMM_EPI_ATOMIC = 2 };
+enum { GEMM_EPI_BIAS_ACT = 0, GEMM_EPI_MASK = 1, GEMM_EPI_ATOMIC = 2, GEMM_EPI_ACCUM = 3 };   // ACCUM: C += A B (one writer per element)
 
 struct GemmArgs {
   const float* A; int lda;
@@ -169,6 +169,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
               v[j] = (y < 0.f) ? y * g.slope : y;
             }
           }
+        } else if (EPI == GEMM_EPI_ACCUM) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < g.N) v[j] += c[j];
         } else if (g.mask) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -203,6 +207,16 @@ static inline int gemm_dgrad(cudaStream_t st, const float* dY, int lda, const fl
   GemmArgs g = {dY, lda, W, ldw, dX, ldc, M, N, K, nullptr, slope, mask, ldm, 0};
   dim3 grid(apn_div_up(M, GEMM_BM), apn_div_up(N, GEMM_BN), 1);
   sgemm_kernel<true, false, GEMM_EPI_MASK><<<grid, 256, 0, st>>>(g);
+  apn_count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+// dX += dY W (no activation mask): the accumulating form, for gradients that land in a caller-owned buffer
+static inline int gemm_dgrad_accum(cudaStream_t st, const float* dY, int lda, const float* W, int ldw, float* dX, int ldc, int M,
+                                   int N, int K) {
+  if (M <= 0) return 0;
+  GemmArgs g = {dY, lda, W, ldw, dX, ldc, M, N, K, nullptr, 1.f, nullptr, 0, 0};
+  dim3 grid(apn_div_up(M, GEMM_BM), apn_div_up(N, GEMM_BN), 1);
+  sgemm_kernel<true, false, GEMM_EPI_ACCUM><<<grid, 256, 0, st>>>(g);
   apn_count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -25,6 +25,10 @@ FV_LD = 160
 V0_DIM = 64
 
 
+# set by train.GradBucket: backward kernels that accumulate may write straight into an existing leaf .grad
+DIRECT_GRAD_ACCUM = False
+
+
 def _f32(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -595,13 +599,20 @@ class _AggregateTC(torch.autograd.Function):
         M = c.pts.shape[0]
         dev = xyz.device
         need = ctx.needs_input_grad      # (c, packed, xyz, ginv, feat, *ws)
-        wanted = [t for t, n in ((xyz, need[2]), (ginv, need[3]), (feat, need[4])) if n]
-        zs = _zeros_like_many(wanted + list(ws))
+        # The backward kernels ACCUMULATE into caller-provided buffers.  With DIRECT_GRAD_ACCUM (set by
+        # train.GradBucket) a leaf parameter whose .grad already exists (a slice of the flat gradient bucket) receives
+        # its gradient in place and autograd is handed None: no temporary, no memset, no AccumulateGrad add kernel.
+        direct = [DIRECT_GRAD_ACCUM and n and t.is_leaf and t.grad is not None and t.grad.is_contiguous()
+                  and t.grad.dtype == torch.float32 for t, n in zip([feat] + list(ws), need[4:])]
+        wanted = [t for t, n in ((xyz, need[2]), (ginv, need[3])) if n]
+        wanted += [t for t, dr in zip([feat] + list(ws), direct) if not dr]
+        zs = _zeros_like_many(wanted) if wanted else []
         zi = iter(zs)
         d_xyz = next(zi) if need[2] else None
         d_ginv = next(zi) if need[3] else None
-        d_feat = next(zi) if need[4] else None
-        d_ws = list(zi)
+        d_all = [t.grad if dr else next(zi) for t, dr in zip([feat] + list(ws), direct)]
+        d_feat = d_all[0] if need[4] else None
+        d_ws = d_all[1:]
         if M > 0:
             d_alpha = torch.zeros_like(alpha) if d_alpha is None else _f32(d_alpha)
             d_rgb = torch.zeros_like(rgb) if d_rgb is None else _f32(d_rgb)
@@ -624,7 +635,8 @@ class _AggregateTC(torch.autograd.Function):
             with stage("feat_net_bwd"):
                 check(lib.apn_aggregate_bwd_tc(C.byref(a), C.byref(w), ptr(pk), C.byref(out), ptr(tape), C.byref(g),
                                                ptr(scratch), sb, stream()), "apn_aggregate_bwd_tc")
-        return (None, None, d_xyz, d_ginv, d_feat, *[dw if need[5 + i] else None for i, dw in enumerate(d_ws)])
+        return (None, None, d_xyz, d_ginv, (None if direct[0] else d_feat),
+                *[dw if (need[5 + i] and not direct[1 + i]) else None for i, dw in enumerate(d_ws)])
 
 
 def aggregate_tc_train(c: AggConst, xyz, ginv, feat, weights: Sequence[torch.Tensor], packed: PackedDecoder):

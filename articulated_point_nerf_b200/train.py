@@ -64,6 +64,9 @@ class GradBucket:
         for p, o in zip(params, offs):
             p.grad = self.flat[o:o + p.numel()].view_as(p)
         self.numel = sum(p.numel() for p in params)
+        # gradients of the decoder parameters are accumulated by the backward kernels directly into these slices
+        from . import ops
+        ops.DIRECT_GRAD_ACCUM = True
 
     def zero(self):
         self.flat.zero_()
