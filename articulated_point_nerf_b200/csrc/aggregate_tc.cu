@@ -631,22 +631,19 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) agg_tc_fwd_kernel(const TcP
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+// inference scratch: the reduced feature h and the packed head weights (heads_tc.cu)
 struct TcScratch {
-  float *h, *exp_d, *fv, *v0;
+  float* h;
+  void* heads_packed;
   size_t total;
 };
 static TcScratch tc_scratch_layout(char* base, int M) {
   TcScratch b;
   size_t o = 0;
-  auto take = [&](size_t n_float) {
-    float* p = (float*)(base + o);
-    o = apn_align(o + n_float * sizeof(float));
-    return p;
-  };
-  b.h = take((size_t)M * APN_C);
-  b.exp_d = take(M);
-  b.fv = take((size_t)M * 160);
-  b.v0 = take((size_t)M * 64);
+  b.h = (float*)(base + o);
+  o = apn_align(o + (size_t)M * APN_C * sizeof(float));
+  b.heads_packed = base + o;
+  o = apn_align(o + heads_tc_weights_bytes());
   b.total = o;
   return b;
 }
@@ -688,9 +685,11 @@ extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
     APN_CHECK_ARG(precision == 1, "the training forward runs in split precision");
     APN_CHECK_ARG(tape_bytes >= apn_aggregate_tc_tape_bytes(M) && (((uintptr_t)tape) & 1023) == 0, "tape too small or not 1 KiB aligned");
     APN_CHECK_ARG(out->h && out->exp_d && out->fv && out->v0, "training needs the h / exp_d / fv / v0 buffers");
-    b.h = out->h; b.exp_d = out->exp_d; b.fv = out->fv; b.v0 = out->v0;
+    b.h = out->h;
+    b.heads_packed = nullptr;
   } else {
-    APN_CHECK_ARG(scratch && scratch_bytes >= apn_aggregate_tc_scratch_bytes(M), "scratch too small");
+    APN_CHECK_ARG(scratch && scratch_bytes >= apn_aggregate_tc_scratch_bytes(M) && (((uintptr_t)scratch) & 15) == 0,
+                  "scratch too small or not 16-byte aligned");
     b = tc_scratch_layout((char*)scratch, M);
   }
   TcParams p;
@@ -707,5 +706,7 @@ extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
   p.n_tiles = apn_div_up(M, TC_SAMPLES);
   const int rc = precision == 0 ? tc_launch<1, false>(st, p) : tape ? tc_launch<2, true>(st, p) : tc_launch<2, false>(st, p);
   if (rc) return rc;
-  return agg_heads_launch(st, in, w, nullptr, out->idw, b.h, b.exp_d, out->alpha, b.fv, b.v0, out->rgb);
+  if (tape)     // fp32 heads: their intermediates are the backward's tape
+    return agg_heads_launch(st, in, w, nullptr, out->idw, b.h, out->exp_d, out->alpha, out->fv, out->v0, out->rgb);
+  return agg_heads_tc_launch(st, in, w, b.h, b.heads_packed, out->alpha, out->rgb);
 }

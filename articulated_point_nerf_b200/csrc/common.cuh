@@ -14,6 +14,10 @@ void apn_count_launch(int n = 1);
 // aggregate.cu: [K-reduce of act3 unless act3 == NULL] + densitynet/Raw2Alpha + RGBNet on the reduced feature h
 int agg_heads_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const float* act3, const float* idw,
                      float* h, float* exp_d, float* alpha, float* fv, float* v0, float* rgb);
+// heads_tc.cu: densitynet / Raw2Alpha + RGBNet on the tensor cores (inference); `packed` >= heads_tc_weights_bytes()
+size_t heads_tc_weights_bytes();
+int agg_heads_tc_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const float* h, void* packed,
+                        float* alpha, float* rgb);
 // aggregate.cu: RGBNet backward: weight gradients + d_h (M,128) of the rgb branch
 int agg_rgbnet_bwd_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* sv,
                           const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h);
