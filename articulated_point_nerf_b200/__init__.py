@@ -9,5 +9,7 @@ from .pointwarper import PointWarper, TransformNet                     # noqa: F
 from .render_utils import (Alphas2Weights, Raw2Alpha, adam_upd_cuda,   # noqa: F401
                            render_utils_cuda)
 from .temporalpoints import NoPointsException, TemporalPoints          # noqa: F401
+from .render import (PoseCache, load_checkpoint, render_repose,        # noqa: F401
+                     render_viewpoints, save_checkpoint)
 
 __version__ = "0.1.0"

@@ -1,0 +1,191 @@
+"""Whole-frame render entry points: the callers of the hot path.
+
+`render_viewpoints` / `render_repose` keep the call signatures and return values of `run.py:82-260` / `run.py:262-340`
+(the reference renders a frame as 8192-ray chunks and re-warps the cloud for every chunk, `run.py:136-166,283-298`).
+Here a frame is ONE pass of the hot path:
+
+  * the pose chain, LBS and the grid run once per distinct pose (`PoseCache`: consecutive views of the same time step
+    or the same `rot_params` — WIM / ZJU multi-view sets — reuse the warped cloud and its grid);
+  * all rays of the frame go through sampling / k-NN / decoder / compositing in one call (`chunk_rays` bounds the
+    number of rays per call for very large frames; results are identical either way because rays are independent);
+  * frames are assembled on the device and leave it with one D2H copy per frame.
+
+Image metrics other than PSNR, PNG writing and the skeleton overlay (`cv2`) belong to the reference's CLI, not to the
+hot path: PSNR is computed here, the others raise if requested.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .scene import get_rays_of_a_view
+from .temporalpoints import TemporalPoints
+
+
+class PoseCache:
+    """warp() + build_grid() once per distinct pose."""
+
+    def __init__(self, model: TemporalPoints, query_radius: float = 0.01):
+        self.model, self.query_radius = model, query_radius
+        self.key, self.warped, self.grid = None, None, None
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _key(t, rot_params):
+        x = t if rot_params is None else rot_params
+        x = x.detach().reshape(-1).float().cpu()
+        return ("t" if rot_params is None else "rot", tuple(x.tolist()))
+
+    def get(self, t=None, rot_params=None):
+        k = self._key(t, rot_params)
+        if k != self.key:
+            self.warped = self.model.warp(t, rot_params)
+            self.grid = self.model.build_grid(self.warped, self.query_radius)
+            self.key = k
+            self.misses += 1
+        else:
+            self.hits += 1
+        return self.warped, self.grid
+
+
+def _scale_cameras(HW, Ks, render_factor):
+    if render_factor == 0:
+        return HW, Ks
+    HW = np.copy(HW) // render_factor
+    Ks = torch.as_tensor(Ks).clone()
+    Ks[:, :2, :3] = Ks[:, :2, :3] // render_factor
+    return HW, Ks
+
+
+def _render_frame(model, cache, H, W, K, c2w, render_kwargs, *, t=None, rot_params=None, render_pcd_direct=False,
+                  fixed_viewdirs=None, chunk_rays=None, inverse_y=False, flip_x=False, flip_y=False, Ks_i=None):
+    dev = model.device
+    rays_o, rays_d, viewdirs = get_rays_of_a_view(H, W, K.to(torch.float32), c2w, inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y)
+    if fixed_viewdirs is not None:
+        viewdirs = fixed_viewdirs
+    rays_o = rays_o.reshape(-1, 3).to(dev).contiguous()
+    rays_d = rays_d.reshape(-1, 3).to(dev).contiguous()
+    viewdirs = viewdirs.reshape(-1, 3).to(dev).contiguous()
+    warped, grid = cache.get(t=t, rot_params=rot_params)
+    R = rays_o.shape[0]
+    step = R if not chunk_rays else int(chunk_rays)
+    outs = []
+    for s in range(0, R, step):
+        rk = dict(render_kwargs, rays_o=rays_o[s:s + step], rays_d=rays_d[s:s + step], viewdirs=viewdirs[s:s + step])
+        out = model(t, render_depth=True, render_kwargs=rk, render_weights=True, rot_params=rot_params,
+                    render_pcd_direct=render_pcd_direct, poses=c2w[None].to(dev), Ks=(K if Ks_i is None else Ks_i)[None].to(dev),
+                    get_skeleton=True, warped=warped, grid=grid)
+        if render_pcd_direct:
+            out['rgb_marched'] = out['rgb_marched_direct']
+        outs.append(out)
+    cat = {k: (outs[0][k] if len(outs) == 1 else torch.cat([o[k] for o in outs])).reshape(H, W, -1)
+           for k in ('rgb_marched', 'depth', 'weights')}
+    return cat, outs[0]['joints'], outs[0]['bones']
+
+
+def _finish(rgbs, depths, weights, joints, gt_imgs, render_factor, eval_psnr, other_metrics, savedir):
+    if other_metrics:
+        raise NotImplementedError("SSIM / LPIPS belong to the reference's evaluation CLI (lib/utils.py), not to the render path")
+    if savedir is not None:
+        raise NotImplementedError("image writing belongs to the reference's CLI (imageio / cv2 are not part of this path)")
+    psnrs = []
+    if gt_imgs is not None and render_factor == 0 and eval_psnr:
+        for i, rgb in enumerate(rgbs):
+            psnrs.append(-10. * np.log10(np.mean(np.square(rgb - np.asarray(gt_imgs[i])))))
+        print('Testing psnr', np.mean(psnrs), '(avg)')
+    return np.array(rgbs), np.array(depths), np.array(weights), psnrs
+
+
+@torch.no_grad()
+def render_viewpoints(model, render_poses, HW, Ks, ndc, render_kwargs, gt_imgs=None, savedir=None, test_times=None,
+                      render_factor=0, eval_psnr=False, eval_ssim=False, eval_lpips_alex=False, eval_lpips_vgg=False,
+                      inverse_y=False, flip_x=False, flip_y=False, batch_size=None, verbose=True, render_pcd_direct=False,
+                      render_flow=False, fixed_viewdirs=None, return_joints=False):
+    """run.py:82-260.  -> rgbs (V,H,W,3), depths (V,H,W,1), weights (V,H,W,3), flows (empty) as numpy arrays.
+    `batch_size=None` renders each frame in one pass; an integer reproduces the reference's ray chunking (same result)."""
+    assert len(render_poses) == len(HW) and len(HW) == len(Ks)
+    assert isinstance(model, TemporalPoints), "this entry point drives the point-cloud model"
+    assert not ndc, "the PCD path never uses NDC rays (configs keep ndc=False)"
+    assert not render_flow, "scene flow is not part of the PCD hot path"
+    HW, Ks = _scale_cameras(HW, Ks, render_factor)
+    cache = PoseCache(model)
+    rgbs, depths, weights, joints = [], [], [], {}
+    bones = None
+    for i, c2w in enumerate(render_poses):
+        H, W = int(HW[i][0]), int(HW[i][1])
+        t = torch.as_tensor(test_times[i], dtype=torch.float32, device=model.device).reshape(1)
+        frame, jt, bn = _render_frame(model, cache, H, W, torch.as_tensor(Ks[i]), torch.as_tensor(c2w), render_kwargs, t=t,
+                                      render_pcd_direct=render_pcd_direct, fixed_viewdirs=fixed_viewdirs, chunk_rays=batch_size,
+                                      inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y)
+        if jt is not None and i not in joints:
+            jt = jt.clone()
+            if not render_kwargs['inverse_y']:
+                jt[:, :, 0] = (int(HW[0][0]) - 1) - jt[:, :, 0]
+            joints[i] = jt[0].cpu().numpy()
+            bones = bn
+        host = torch.cat([frame['rgb_marched'], frame['depth'], frame['weights']], dim=-1).cpu().numpy()   # one D2H per frame
+        rgbs.append(host[..., 0:3])
+        depths.append(host[..., 3:4])
+        weights.append(host[..., 4:7])
+    rgbs, depths, weights, _ = _finish(rgbs, depths, weights, joints, gt_imgs, render_factor, eval_psnr,
+                                       eval_ssim or eval_lpips_alex or eval_lpips_vgg, savedir)
+    if verbose:
+        print(f'render_viewpoints: {len(rgbs)} frames, {cache.misses} warps ({cache.hits} reused)')
+    flows = np.array([])
+    if return_joints:
+        return rgbs, depths, weights, flows, [joints[i] for i in sorted(joints)], bones
+    return rgbs, depths, weights, flows
+
+
+@torch.no_grad()
+def render_repose(rot_params, render_poses, HW, Ks, ndc, model, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
+                  eval_psnr=False, eval_ssim=False, eval_lpips_alex=False, eval_lpips_vgg=False, inverse_y=False,
+                  flip_x=False, flip_y=False, batch_size=None):
+    """run.py:262-340: one frame per (rot_params[i], render_poses[i]).  -> rgbs, depths, weights (numpy)."""
+    assert len(render_poses) == len(HW) and len(HW) == len(Ks)
+    assert isinstance(model, TemporalPoints)
+    assert not ndc
+    HW, Ks = _scale_cameras(HW, Ks, render_factor)
+    cache = PoseCache(model)
+    rgbs, depths, weights = [], [], []
+    for i, c2w in enumerate(render_poses):
+        H, W = int(HW[i][0]), int(HW[i][1])
+        rp = torch.as_tensor(rot_params[i], dtype=torch.float32, device=model.device)
+        frame, _, _ = _render_frame(model, cache, H, W, torch.as_tensor(Ks[i]), torch.as_tensor(c2w), render_kwargs, rot_params=rp,
+                                    chunk_rays=batch_size, inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y)
+        host = torch.cat([frame['rgb_marched'], frame['depth'], frame['weights']], dim=-1).cpu().numpy()
+        rgbs.append(host[..., 0:3])
+        depths.append(host[..., 3:4])
+        weights.append(host[..., 4:7])
+    rgbs, depths, weights, _ = _finish(rgbs, depths, weights, {}, gt_imgs, render_factor, eval_psnr,
+                                       eval_ssim or eval_lpips_alex or eval_lpips_vgg, savedir)
+    return rgbs, depths, weights
+
+
+# ----------------------------------------------------------------------------------------------
+# On-disk formats: the reference's checkpoints are torch.save dicts
+#   temporalpoints_last.tar : {'global_step', 'model_kwargs', 'model_state_dict', 'optimizer_state_dict'}  (run.py:1234-1235,
+#                             lib/utils.py:519-523 load_model: model_class(**ckpt['model_kwargs']); load_state_dict)
+#   pcds/canonical.tar, pcds/skeleton.tar : point-cloud / skeleton dicts written by export_point_cloud (run.py:1091-1103)
+# ----------------------------------------------------------------------------------------------
+def save_checkpoint(path: str, model: TemporalPoints, optimizer=None, global_step: int = 0) -> None:
+    """Writes the reference's `temporalpoints_last.tar` layout (run.py:1234-1235)."""
+    kw = model.get_kwargs()
+    torch.save({'global_step': int(global_step), 'model_kwargs': kw, 'model_state_dict': model.state_dict(),
+                'optimizer_state_dict': None if optimizer is None else optimizer.state_dict()}, path)
+
+
+def load_checkpoint(path: str, tineuvox=None, device='cuda', strict: bool = False):
+    """lib/utils.py:519-523 `load_model` for the point-cloud model: rebuilds `TemporalPoints(**model_kwargs)` and loads
+    the state dict (`strict=False`, as the reference does).  `tineuvox` supplies the frozen stage-1 heads the constructor
+    needs (the reference passes the loaded TiNeuVox; `heads.TiNeuVoxHeads` here).  -> (model, checkpoint dict)."""
+    ckpt = torch.load(path, map_location='cpu', weights_only=False)
+    kw = dict(ckpt['model_kwargs'])
+    if tineuvox is not None:            # default: the heads object pickled inside model_kwargs, as the reference does
+        kw['tineuvox'] = tineuvox
+    model = TemporalPoints(**kw)
+    missing, unexpected = model.load_state_dict(ckpt['model_state_dict'], strict=strict)
+    model = model.to(device)
+    return model, ckpt

@@ -156,3 +156,29 @@ def test_reference_gradients_are_ill_conditioned_in_the_warped_cloud(golden_tiny
     assert rel_err(b["canonical_feat"], a["canonical_feat"]) > 1e-4
     assert rel_err(b["feat_net.0.bias"], a["feat_net.0.bias"]) > 1e-4
     assert rel_err(b["rgbnet.views_linears.0.weight"], a["rgbnet.views_linears.0.weight"]) < 1e-5
+
+
+def test_checkpoint_round_trip_keeps_the_reference_layout(tmp_path):
+    """temporalpoints_last.tar: {'global_step', 'model_kwargs', 'model_state_dict', 'optimizer_state_dict'} (run.py:1234-1235);
+    load = model_class(**model_kwargs) + load_state_dict (lib/utils.py:519-523)."""
+    import torch
+    from articulated_point_nerf_b200 import load_checkpoint, save_checkpoint
+    from articulated_point_nerf_b200.scene import build_model, make_scene
+    scene = make_scene("tiny")
+    model = build_model(scene, seed=3)
+    with torch.no_grad():
+        model.theta_weight.fill_(0.123)
+        model.flat_merging_rules[2] = 1
+    path = str(tmp_path / "temporalpoints_last.tar")
+    save_checkpoint(path, model, optimizer=None, global_step=42)
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(raw) == {"global_step", "model_kwargs", "model_state_dict", "optimizer_state_dict"} and raw["global_step"] == 42
+    for k in ("canonical_pcd", "skeleton_pcd", "bones", "joints", "weights", "xyz_min", "xyz_max", "tineuvox", "stepsize",
+              "voxel_size", "fast_color_thres", "feat_depth", "pose_embedding_dim"):
+        assert k in raw["model_kwargs"], k
+    loaded, ckpt = load_checkpoint(path, device="cpu")
+    a, b = model.state_dict(), loaded.state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(loaded.canonical_pcd, model.canonical_pcd) and loaded.bones == model.bones

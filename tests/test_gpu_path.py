@@ -231,3 +231,44 @@ def test_pointwarper_forward_contract(golden_tiny):
     assert rel_err(xyz, g["render"]["out"]["t_hat_pcd"]) < 1e-5
     assert G.shape == (len(xyz), 4, 4) and xyz.is_contiguous()
     assert torch.equal(G[:, 3].cpu(), torch.tensor([0., 0., 0., 1.]).expand(len(xyz), 4))
+
+
+def test_render_viewpoints_whole_frame_equals_reference_chunk_loop(golden_tiny):
+    """render.render_viewpoints (one pass per frame, warp + grid cached per pose) against the reference's caller loop
+    (run.py:136-166: 8192-ray chunks, re-warp per chunk), here with small chunks; and the per-pose cache on a multi-view set."""
+    from articulated_point_nerf_b200 import render_repose, render_viewpoints
+    g = golden_tiny
+    model, scene = model_from_golden(g)
+    rk = scene.render_kwargs()
+    V = len(scene.HW)
+    times = [0.25] * V                                   # multi-view: every view shows the same time step
+    rgbs, depths, weights, flows = render_viewpoints(model, scene.poses, scene.HW, scene.Ks, False, dict(rk), test_times=times,
+                                                     inverse_y=scene.cfg.inverse_y, verbose=False)
+    assert rgbs.shape == (V, scene.cfg.H, scene.cfg.W, 3) and depths.shape[-1] == 1 and weights.shape == rgbs.shape
+    # the reference's loop: per view, per chunk, a full forward (warps again for every chunk)
+    for i in range(V):
+        ro, rd, vd = [x.reshape(-1, 3).contiguous().cuda() for x in scene.rays(i)]
+        chunks = []
+        for s in range(0, len(ro), 97):
+            kw = dict(rk, rays_o=ro[s:s + 97], rays_d=rd[s:s + 97], viewdirs=vd[s:s + 97])
+            with torch.no_grad():
+                out = model(torch.tensor([0.25]).cuda(), render_depth=True, render_kwargs=kw, render_weights=True,
+                            poses=scene.poses[i][None].cuda(), Ks=scene.Ks[i][None].cuda(), get_skeleton=True)
+            chunks.append(torch.cat([out["rgb_marched"], out["depth"][:, None], out["weights"]], dim=-1))
+        ref = torch.cat(chunks).reshape(scene.cfg.H, scene.cfg.W, 7).cpu().numpy()
+        assert abs(rgbs[i] - ref[..., 0:3]).max() < 1e-6
+        assert abs(depths[i] - ref[..., 3:4]).max() < 1e-4
+        assert abs(weights[i] - ref[..., 4:7]).max() < 1e-6
+    # chunked mode of the same entry point gives the same frames
+    rgbs_c, depths_c, _, _ = render_viewpoints(model, scene.poses, scene.HW, scene.Ks, False, dict(rk), test_times=times,
+                                               inverse_y=scene.cfg.inverse_y, verbose=False, batch_size=1000)
+    assert abs(rgbs_c - rgbs).max() < 1e-6 and abs(depths_c - depths).max() < 1e-4
+    # repose: rot_params per frame
+    gen = torch.Generator().manual_seed(5)
+    rp = torch.randn(2, len(scene.joints), 4, generator=gen) * 0.2
+    rp[:, 0] = 0
+    r2, d2, w2 = render_repose(rp, scene.poses[:2], scene.HW[:2], scene.Ks[:2], False, model, dict(rk), inverse_y=scene.cfg.inverse_y)
+    ro, rd, vd = [x.reshape(-1, 3).contiguous().cuda() for x in scene.rays(1)]
+    with torch.no_grad():
+        out = model(None, render_depth=True, render_kwargs=dict(rk, rays_o=ro, rays_d=rd, viewdirs=vd), rot_params=rp[1].cuda())
+    assert abs(r2[1].reshape(-1, 3) - out["rgb_marched"].cpu().numpy()).max() < 1e-6
