@@ -1,0 +1,154 @@
+"""GPU checks at BASELINE.json's FULL sizes (c1: 30k points, one 400x400 frame; c5-sized kernels) through
+size-independent properties — the oracle finishes only small cases in seconds, so at scale the kernels are checked
+against invariants of the domain and against an independent brute force on random subsets:
+
+  k-NN          ascending (d2, index) order, radius rule, distinct valid indices, exact match with a GPU brute force
+                (torch.cdist-free, same fp32 contract) on a random subset of the kept samples
+  LBS           partition of unity of the skinning weights, identity bones leave the cloud unchanged (ginv = I),
+                a rigid transform shared by all bones moves the cloud rigidly
+  compositing   sum of weights + alphainv_last = 1 on every ray (rgb == 1, bg == 1  =>  rgb_marched == 1)
+  render        bit-identical frames from two runs and from whole-frame vs chunked evaluation
+  Adam          bit-exact against the reference's update rule in torch at 4M parameters
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from articulated_point_nerf_b200 import ops
+    return ops
+
+
+@pytest.fixture(scope="module")
+def c1_model():
+    from articulated_point_nerf_b200.scene import build_model, make_scene
+    scene = make_scene("c1")
+    model = build_model(scene, seed=0).cuda()
+    return scene, model
+
+
+def test_knn_at_full_size_sorted_within_radius_and_exact_on_a_subset(c1_model):
+    ops = _ops()
+    scene, model = c1_model
+    ro, rd, vd = [x.reshape(-1, 3).contiguous().cuda() for x in scene.rays(2)]
+    with torch.no_grad():
+        warped = model.warp(torch.tensor([0.4], device="cuda"))
+        grid = model.build_grid(warped)
+        cfg = scene.cfg
+        smp, dbg = ops.sample_and_knn(grid, ro, rd, cfg.near, cfg.far, cfg.stepsize * scene.voxel_size, return_d2=True)
+    M, N = smp.M, len(warped["xyz"])
+    assert M > 100_000, "the c1 frame keeps > 1e5 samples"
+    idx = smp.nn_idx.long()
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
+    s_idx = torch.sort(idx, dim=1).values
+    assert bool((s_idx[:, 1:] != s_idx[:, :-1]).all()), "neighbours of a sample are distinct points"
+    # recompute d2 under the contract ((dx*dx + dy*dy) + dz*dz, no FMA): ascending by (d2, index); 8th within the radius
+    xyz = warped["xyz"]
+    d = smp.pts[:, None, :] - xyz[idx]
+    dx2, dy2, dz2 = d[..., 0] * d[..., 0], d[..., 1] * d[..., 1], d[..., 2] * d[..., 2]
+    d2 = (dx2 + dy2) + dz2
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all())
+    ties = d2[:, 1:] == d2[:, :-1]
+    assert bool((idx[:, 1:][ties] > idx[:, :-1][ties]).all()), "ties are broken by the lower index"
+    assert bool((d2[:, -1] <= 0.01).all())
+    # ray-major, near-to-far order and CSR consistency
+    assert bool((smp.ray_id[1:] >= smp.ray_id[:-1]).all())
+    same = smp.ray_id[1:] == smp.ray_id[:-1]
+    assert bool((smp.step_id[1:][same] > smp.step_id[:-1][same]).all())
+    counts = torch.bincount(smp.ray_id.long(), minlength=len(ro))
+    assert torch.equal(counts.int(), (smp.ray_start[1:] - smp.ray_start[:-1]))
+    # independent brute force on a random subset: the 8 nearest of ALL points, same arithmetic, stable tie-break
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sel = torch.randint(0, M, (2048,), device="cuda", generator=g)
+    q = smp.pts[sel]
+    dd = q[:, None, :] - xyz[None, :, :]
+    full = (dd[..., 0] * dd[..., 0] + dd[..., 1] * dd[..., 1]) + dd[..., 2] * dd[..., 2]
+    key = (full.view(torch.int32).long() << 32) | torch.arange(N, device="cuda")[None, :]     # (d2 bits, index): lexicographic
+    ref = torch.topk(key, 8, dim=1, largest=False, sorted=True).indices
+    assert torch.equal(ref, idx[sel])
+
+
+def test_lbs_invariants_at_one_million_points():
+    ops = _ops()
+    N, J = 1_000_000, 65
+    g = torch.Generator(device="cuda").manual_seed(1)
+    raw = torch.randn(N, J, device="cuda", generator=g)
+    theta = torch.tensor([0.1], device="cuda")
+    xyz = torch.rand(N, 3, device="cuda", generator=g) * 2 - 1
+    eye = torch.eye(4, device="cuda").repeat(J, 1, 1)
+    out, ginv, w, bbox = ops.lbs(raw, theta, eye, None, xyz)
+    assert float((w.sum(1) - 1).abs().max()) < 2e-6 and float(w.min()) >= 0.0
+    assert float((out - xyz).abs().max()) < 1e-6          # sum_j w_j I = I up to the rounding of sum w
+    assert float((ginv.view(N, 3, 3) - torch.eye(3, device="cuda")).abs().max()) < 2e-6
+    assert torch.equal(bbox.cpu(), torch.cat([out.min(0).values, out.max(0).values]).cpu())
+    # one rigid transform on every bone moves the cloud rigidly, whatever the weights
+    A = torch.linalg.qr(torch.randn(3, 3, device="cuda", generator=g))[0]
+    A = A * torch.sign(torch.linalg.det(A))
+    T = eye.clone()
+    T[:, :3, :3] = A
+    T[:, :3, 3] = torch.tensor([0.1, -0.2, 0.3], device="cuda")
+    gt = torch.tensor([0.5, 0.0, -0.25], device="cuda")
+    out2, ginv2, _, _ = ops.lbs(raw, theta, T, gt, xyz)
+    ref = xyz @ A.T + T[0, :3, 3] + gt
+    assert float((out2 - ref).abs().max()) < 5e-6
+    assert float((ginv2.view(N, 3, 3) - A.T).abs().max()) < 5e-6
+
+
+def test_compositing_conserves_transmittance_on_every_ray():
+    ops = _ops()
+    R = 1_000_000
+    g = torch.Generator(device="cuda").manual_seed(2)
+    cnt = (torch.rand(R, device="cuda", generator=g) < 0.4) * torch.randint(1, 40, (R,), device="cuda", generator=g)
+    ray_start = torch.zeros(R + 1, dtype=torch.int32, device="cuda")
+    ray_start[1:] = torch.cumsum(cnt, 0)
+    M = int(ray_start[-1])
+    alpha = torch.rand(M, device="cuda", generator=g) * 0.6
+    alpha[torch.rand(M, device="cuda", generator=g) < 0.1] = 0.0          # some samples fail the pre-mask
+    rgb = torch.ones(M, 3, device="cuda")
+    step = torch.zeros(M, dtype=torch.int32, device="cuda")
+    # thres = 0: no sample is dropped by the weight mask, so sum_i w_i + T_last telescopes to exactly 1 in exact
+    # arithmetic (the early stop only truncates the sum at T < 1e-3: what is left over is alphainv_last itself)
+    rgb_m, last, depth, _ = ops.composite(alpha, rgb, step, ray_start, R, 0.0, 1.0, want_depth=True)
+    assert float((rgb_m - 1.0).abs().max()) < 5e-6
+    assert float(last.min()) >= 0.0 and float(last.max()) <= 1.0
+    assert bool((last[cnt == 0] == 1.0).all()) and bool((depth == 0).all())
+
+
+def test_render_is_deterministic_and_independent_of_ray_chunking(c1_model):
+    scene, model = c1_model
+    ro, rd, vd = [x.reshape(-1, 3).contiguous().cuda() for x in scene.rays(1)]
+    rk = scene.render_kwargs()
+    t = torch.tensor([0.7], device="cuda")
+    with torch.no_grad():
+        warped = model.warp(t)
+        grid = model.build_grid(warped)
+        full = [model(t, render_depth=True, render_kwargs=dict(rk, rays_o=ro, rays_d=rd, viewdirs=vd), warped=warped, grid=grid)
+                for _ in range(2)]
+        assert torch.equal(full[0]["rgb_marched"], full[1]["rgb_marched"]) and torch.equal(full[0]["depth"], full[1]["depth"])
+        parts = []
+        for s in range(0, len(ro), 8192):                 # the reference's chunk size (run.py:84)
+            kw = dict(rk, rays_o=ro[s:s + 8192], rays_d=rd[s:s + 8192], viewdirs=vd[s:s + 8192])
+            parts.append(model(t, render_depth=True, render_kwargs=kw, warped=warped, grid=grid)["rgb_marched"])
+        assert torch.equal(torch.cat(parts), full[0]["rgb_marched"])
+        assert float((full[0]["rgb_marched"] - 1.0).abs().max()) > 1e-3, "the frame shows the object, not only background"
+
+
+def test_adam_bit_exact_at_four_million_parameters():
+    from articulated_point_nerf_b200 import MaskedAdam
+    from oracle import dvgo_ops
+    n = 4_000_003
+    gen = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=gen)
+    grad = torch.randn(n, generator=gen)
+    grad[torch.rand(n, generator=gen) < 0.3] = 0.0
+    param = torch.nn.Parameter(p0.clone().cuda())
+    opt = MaskedAdam([{"params": [param], "lr": 1e-3, "skip_zero_grad": True}])
+    p_ref, m_ref, v_ref = p0.clone(), torch.zeros(n), torch.zeros(n)
+    for step in (1, 2, 3):
+        param.grad = (grad * step).cuda()
+        opt.step()
+        dvgo_ops.masked_adam_upd(p_ref, grad * step, m_ref, v_ref, step, 0.9, 0.99, 1e-3, 1e-8)   # lib/cuda/adam_upd_kernel.cu:44-60
+    assert torch.equal(param.detach().cpu(), p_ref)
+    assert torch.equal(opt.state[param]["exp_avg"].cpu(), m_ref) and torch.equal(opt.state[param]["exp_avg_sq"].cpu(), v_ref)
