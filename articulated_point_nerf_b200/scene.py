@@ -325,7 +325,7 @@ def make_scene(cfg: SceneConfig | str) -> Scene:
 # model construction on top of a scene (tests, bench.py, smoke())
 # --------------------------------------------------------------------------------------
 def build_model(scene: Scene, seed: int = 0, density_bias: float = 7.0, theta_std: float = 0.2,
-                density_gain: float = 300.0, rgb_gain: float = 8.0, device=None):
+                density_gain: float = 300.0, rgb_gain: float = 8.0, device=None, density_std: float = 2.5):
     """TemporalPoints on random-init weights of the reference's architecture, with the output heads rescaled so
     that kept-sample alpha spreads over (0,1) and early ray termination triggers."""
     from .heads import TiNeuVoxHeads, poc_fre
@@ -341,8 +341,21 @@ def build_model(scene: Scene, seed: int = 0, density_bias: float = 7.0, theta_st
         xyz_min=scene.xyz_min.numpy(), xyz_max=scene.xyz_max.numpy(), tineuvox=heads, stepsize=cfg.stepsize,
         voxel_size=scene.voxel_size, fast_color_thres=cfg.fast_color_thres, pose_embedding_dim=cfg.pose_embedding_dim)
     with torch.no_grad():
-        model.densitynet.bias.fill_(density_bias)
-        model.densitynet.weight.mul_(density_gain)
+        # density head calibrated on a CPU sample of decoder features (random points, offsets of the size the k-NN
+        # produces): pre-activation density + act_shift ~ N(0, density_std) => median kept-sample alpha ~ 0.3, a spread over
+        # (0.02, 0.9) and early ray termination on the thicker parts; `density_gain` is the fallback scale
+        gcal = torch.Generator().manual_seed(seed + 1234)
+        sel = torch.randint(0, len(scene.canonical_pcd), (512,), generator=gcal)
+        rel = torch.randn(512, 3, generator=gcal) * (0.7 * float(scene.lattice_h))
+        x = torch.cat([poc_fre(rel, model.pos_poc), model.canonical_feat[sel]], dim=-1)
+        if x.shape[-1] == model.feat_net[0].in_features:
+            z = model.densitynet(model.feat_net(x)).reshape(-1)
+            gain = density_std / max(float(z.std()), 1e-6)
+            model.densitynet.weight.mul_(gain)
+            model.densitynet.bias.fill_(-float(heads.act_shift) - gain * float(z.mean() - model.densitynet.bias.reshape(-1)[0]))
+        else:                      # pose-embedding configs: the decoder input has extra columns
+            model.densitynet.bias.fill_(density_bias)
+            model.densitynet.weight.mul_(density_gain)
         model.rgbnet.views_linears[2].weight.mul_(rgb_gain)
         t_embed = poc_fre(torch.tensor([0.37]), model.time_poc)
         out = model.forward_warp.transform_net(t_embed.unsqueeze(0))
