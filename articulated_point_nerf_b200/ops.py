@@ -117,9 +117,11 @@ class _Pose(torch.autograd.Function):
         d_bone_T = torch.zeros(J, 4, 4, device=dev) if d_bone_T is None else _f32(d_bone_T)
         d_global_t = None if d_global_t is None else _f32(d_global_t)
         d_thetas = None if d_thetas is None else _f32(d_thetas)
-        d_wb = [torch.empty_like(x) for x in wb]
+        # the kernel OVERWRITES its outputs; a caller that owns zeroed gradient storage (train.FusedTrainStep) passes it in
+        out = getattr(ctx, "grad_out", None)
+        d_wb = out["wb"] if out else [torch.empty_like(x) for x in wb]
         d_ws, d_bs = [d_wb[0], d_wb[2], d_wb[4], d_wb[6], d_wb[8]], [d_wb[1], d_wb[3], d_wb[5], d_wb[7]]
-        d_joints = torch.empty_like(joints)
+        d_joints = out["joints"] if out else torch.empty_like(joints)
         with stage("transform_net_bwd"):
             check(lib.apn_pose_bwd(ptr(t_embed), t_embed.numel(), _ptr_array(ws), _ptr_array(bs), ptr(joints), ptr(tb.parent_node),
                                    ptr(tb.pivot), ptr(tb.sibling), ptr(tb.rot_mask), J, ptr(saved), ptr(d_bone_T), ptr(d_global_t),
@@ -172,8 +174,9 @@ class _LBS(torch.autograd.Function):
         d_ginv = None if d_ginv is None else _f32(d_ginv)
         d_w = None if d_w is None else _f32(d_w)
         d_g = _f32(d_g) if (ctx.want_frames and d_g is not None) else None
-        d_raw = _empty((N, J), dev)
-        d_theta = _empty((1,), dev) if theta_weight is not None else None
+        out = getattr(ctx, "grad_out", None)          # see _Pose.backward
+        d_raw = out["raw"] if out else _empty((N, J), dev)
+        d_theta = (out["theta"] if out else _empty((1,), dev)) if theta_weight is not None else None
         d_bone = _empty((J, 4, 4), dev)
         d_gt = _empty((3,), dev)
         ws_bytes = lib.apn_lbs_bwd_workspace_bytes(N, J)

@@ -86,8 +86,117 @@ def shard_rays(n_rays: int, rank: int, world: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
-def train_step(model, optimizer: MaskedAdam, bucket: GradBucket, t, render_kwargs, target, *, decay_factor: float = 1.0):
+class _Ctx:
+    """Stand-in for the autograd context: runs the autograd.Function bodies of ops.py outside the autograd engine."""
+    __slots__ = ("needs_input_grad", "saved_tensors", "__dict__")
+
+    def __init__(self, needs):
+        self.needs_input_grad = tuple(needs)
+        self.saved_tensors = ()
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+    def mark_non_differentiable(self, *a):
+        pass
+
+
+class FusedTrainStep:
+    """The render-loss training step as one explicit forward + backward chain over the kernels (no autograd engine, no
+    AccumulateGrad, every gradient written by its kernel straight into the flat bucket).  Same arithmetic as
+    `loss.backward()` through TemporalPoints.forward: it calls the very same forward/backward bodies (ops._Pose, _LBS,
+    _AggregateTC, _Composite) in the order autograd would.  Covers the configuration the stage-2 loop runs in
+    (time input, fused pose kernel, tensor-core decoder, no pose embedding); `eligible()` says whether it applies."""
+
+    def __init__(self, model, optimizer: MaskedAdam, bucket: GradBucket):
+        self.model, self.opt, self.bucket = model, optimizer, bucket
+        model._ensure_neighbourhood()
+
+    @staticmethod
+    def eligible(model) -> bool:
+        fw = model.forward_warp
+        return (model.decoder_train == "tc" and model.pose_embedding_dim == 0 and model.joints.is_cuda and fw.fused_pose
+                and fw._fused_tables(model.joints.device) is not None)
+
+    @torch.no_grad()
+    def run(self, t, render_kwargs, target):
+        """-> loss (device scalar), or None when the batch keeps no sample (the caller falls back to autograd)."""
+        from . import ops
+        from .heads import poc_fre
+        m, fw = self.model, self.model.forward_warp
+        dev = m.joints.device
+        self.bucket.zero()
+        # ---- forward
+        t_embed = poc_fre(t, m.time_poc)
+        wb = fw._mlp_params()
+        cp = _Ctx((False, False, m.joints.requires_grad, *[w.requires_grad for w in wb]))
+        bone_Ts, global_t, thetas = ops._Pose.forward(cp, fw._fused_tables(dev), t_embed, m.joints, *wb)
+        fw.prev_params, fw.prev_thetas, fw.prev_global_t = None, thetas, global_t
+        cl = _Ctx((m.weights.requires_grad, m.theta_weight.requires_grad, True, True, False, False, False, False))
+        xyz, ginv, w, bbox, _ = ops._LBS.forward(cl, m.weights, m.theta_weight, bone_Ts, global_t, m.canonical_pcd,
+                                                 m._merge_rules_i32(), float(m.eps), False)
+        m._last_weights = w
+        warped = dict(xyz=xyz, ginv=ginv, weights=w, bbox=bbox, bone_Ts=bone_Ts, global_t=global_t, joints_rel=None)
+        grid = m.build_grid(warped, 0.01)
+        rays_o, rays_d, viewdirs = render_kwargs['rays_o'], render_kwargs['rays_d'], render_kwargs['viewdirs']
+        R = len(rays_o)
+        stepdist = float(render_kwargs['stepsize']) * float(m.voxel_size)
+        smp = ops.sample_and_knn(grid, rays_o, rays_d, float(render_kwargs['near']), float(render_kwargs['far']), stepdist)
+        m.last_counts = dict(R=R, candidates=smp.n_candidates, M=smp.M, N=len(xyz))
+        if smp.M == 0:
+            return None
+        c = ops.AggConst(pts=smp.pts, nn_idx=smp.nn_idx, ray_id=smp.ray_id, viewdirs=ops._f32(viewdirs),
+                         canonical_alpha=m.canonical_alpha, canonical_rgbs=m.canonical_rgbs, direct_eps=m.direct_eps,
+                         mean_min_distance=m._mmd_float, eps=float(m.eps), act_shift=float(m.tineuvox.act_shift),
+                         interval=float(render_kwargs['stepsize']) * float(m.tineuvox.voxel_size_ratio), direct=False)
+        ws = m._mlp_weights()
+        ca = _Ctx((False, False, True, True, m.canonical_feat.requires_grad, *[x.requires_grad for x in ws]))
+        alpha, rgb, _, _, _ = ops._AggregateTC.forward(ca, c, m._packed_decoder, xyz, ginv, m.canonical_feat, *ws)
+        cc = _Ctx((True, True, False, False, False, False, False, False, False))
+        rgb_m, last, _, _ = ops._Composite.forward(cc, alpha, rgb, smp.step_id, None, smp.ray_start, R, m.fast_color_thres,
+                                                   float(render_kwargs['bg']), False)
+        # ---- loss (run.py:617-621: img2mse weighted by weight_render) and its gradient
+        diff = rgb_m - target
+        loss = WEIGHT_RENDER * (diff * diff).mean()
+        d_rgb_m = diff * (2.0 * WEIGHT_RENDER / diff.numel())
+        # ---- backward, in autograd's order
+        d_alpha, d_rgb = ops._Composite.backward(cc, d_rgb_m, None, None, None)[:2]
+        ga = ops._AggregateTC.backward(ca, d_alpha, d_rgb)
+        self._accumulate([m.canonical_feat] + list(ws), ga[4:])            # None where the kernels wrote into .grad directly
+        if m.weights.grad is not None and m.theta_weight.grad is not None:
+            cl.grad_out = dict(raw=m.weights.grad, theta=m.theta_weight.grad.reshape(1))
+        gl = ops._LBS.backward(cl, ga[2], ga[3], None, None, None)
+        if not hasattr(cl, "grad_out"):
+            self._accumulate([m.weights, m.theta_weight], gl[0:2])
+        if all(p.grad is not None for p in [m.joints] + list(wb)):
+            cp.grad_out = dict(wb=[p.grad for p in wb], joints=m.joints.grad)
+        gp = ops._Pose.backward(cp, gl[2], gl[3], None)
+        if not hasattr(cp, "grad_out"):
+            self._accumulate([m.joints] + list(wb), gp[2:])
+        return loss
+
+    @staticmethod
+    def _accumulate(params, grads):
+        for p, g in zip(params, grads):
+            if g is not None and p.requires_grad and p.grad is not None:
+                p.grad.add_(g.reshape(p.grad.shape))
+
+
+def train_step(model, optimizer: MaskedAdam, bucket: GradBucket, t, render_kwargs, target, *, decay_factor: float = 1.0,
+               fused: bool = True):
     """One stage-2 iteration on one rank's ray batch.  Returns the (device) loss tensor."""
+    if fused and FusedTrainStep.eligible(model):
+        fs = getattr(bucket, "_fused_step", None)
+        if fs is None or fs.model is not model:
+            fs = bucket._fused_step = FusedTrainStep(model, optimizer, bucket)
+        loss = fs.run(t, render_kwargs, target)
+        if loss is not None:
+            bucket.all_reduce_avg()
+            optimizer.step()
+            if decay_factor != 1.0:
+                for g in optimizer.param_groups:                  # run.py:718-721
+                    g['lr'] = g['lr'] * decay_factor
+            return loss
     bucket.zero()
     res = model(t, False, render_kwargs, render_pcd_direct=False)
     loss = WEIGHT_RENDER * F.mse_loss(res['rgb_marched'], target)

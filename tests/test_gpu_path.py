@@ -158,13 +158,46 @@ def test_bucketed_train_step_equals_plain_autograd(golden_tiny):
         named = dict(model.named_parameters())
         for k, ref in plain.items():
             if named[k].requires_grad:
-                assert rel_err(named[k].grad, ref) < 1e-5, k
+                assert rel_err(named[k].grad, ref) < RTOL, k
         backward_once()                                   # accumulation semantics of .grad
         for k, ref in plain.items():
             if named[k].requires_grad:
-                assert rel_err(named[k].grad, 2 * ref) < 1e-5, k
+                assert rel_err(named[k].grad, 2 * ref) < RTOL, k
     finally:
         ops.DIRECT_GRAD_ACCUM = False
+
+
+def test_fused_train_step_equals_autograd_step(golden_tiny):
+    """train.FusedTrainStep (explicit kernel chain, gradients written straight into the bucket) against the same step
+    through autograd: same loss, same gradients, same parameters after Adam."""
+    import copy
+    from articulated_point_nerf_b200 import ops
+    from articulated_point_nerf_b200.train import FusedTrainStep, GradBucket, create_optimizer, train_step
+    g = golden_tiny
+    rk_base = None
+    results = []
+    try:
+        for fused in (False, True):
+            model, scene = model_from_golden(g, fused_pose=True)
+            model.decoder_train = "tc"
+            rk = _rk(scene, g)
+            opt = create_optimizer(model)
+            bucket = GradBucket(opt)
+            assert FusedTrainStep.eligible(model)
+            t, tgt = g["train"]["t"].cuda(), g["train"]["target"].cuda()
+            loss = train_step(model, opt, bucket, t, rk, tgt, fused=fused)
+            assert (getattr(bucket, "_fused_step", None) is not None) == fused
+            results.append((float(loss.detach()), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None},
+                            {k: p.detach().clone() for k, p in model.named_parameters()}))
+    finally:
+        ops.DIRECT_GRAD_ACCUM = False
+    (l0, g0, p0), (l1, g1, p1) = results
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)
+    assert set(g0) == set(g1)
+    for k in g0:       # atomics make run-to-run differences of ~1e-6; theta_weight (a heavily cancelling sum) ~1e-5
+        assert rel_err(g1[k], g0[k]) < RTOL, k
+    for k in p0:       # Adam's first step moves every element by ~lr * sign(g): elements with g ~ 0 may differ by one lr
+        assert rel_err(p1[k], p0[k]) < 1e-3, k
 
 
 def test_regulariser_losses_match_reference_golden(golden_tiny):
