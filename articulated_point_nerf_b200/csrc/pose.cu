@@ -1,13 +1,19 @@
 // Pose chain in one launch: TransformNet MLP -> 4-parameter Rodrigues -> per-joint pivot transform -> kinematic chain
 // (lib/pointwarper.py:5-37,118-193,217-236), forward and backward.  J <= 128 joints and a 256-wide, 5-layer MLP on a
-// single time sample are a few hundred tiny PyTorch launches per training step; here they are two single-CTA kernels
-// (the work is ~2 MB of weight traffic, latency-bound by construction).
+// single time sample are a few hundred tiny PyTorch launches per training step; here they are two kernels, each ONE
+// thread-block cluster of 8 CTAs: the work is ~1-2 MB of weight traffic whose latency is the whole cost, so every layer's
+// rows are split over the 8 SMs of the cluster (8x the loads in flight) and the 256-float activations / partial sums are
+// exchanged through distributed shared memory with one cluster barrier per layer.
 //
 // Conventions (checked by the Python wrapper): node i's parent node index is smaller than i (bone i = [parent, i+1],
 // lib/pointwarper.py:105-111), so  T_i = T_parent(i) * M_i  can be evaluated in index order and differentiated in
 // reverse order;  M_i = [R_i | p - R_i p] with p = joints[pivot(i)] (the parent joint; the root pivots on itself).
-#include "common.cuh"
+#include <cooperative_groups.h>
 
+#include "common.cuh"
+namespace cg = cooperative_groups;
+
+#define POSE_CLUSTER 8        // CTAs per launch (one cluster)
 #define POSE_H 256            // hidden width of TransformNet (lib/pointwarper.py:6)
 #define POSE_MAX_J 128
 #define POSE_MAX_T 64
@@ -36,20 +42,25 @@ __device__ __forceinline__ void rodrigues4(const float p[4], float R[9], float n
   R[6] = x * z * C - y * sn;       R[7] = y * z * C + x * sn;       R[8] = z * z + (1.f - z * z) * cs;
 }
 
-// y[n] = act(dot(W[n,:K], x) + b[n]) for n < n_out: one warp per output row, coalesced weight reads; 8 rows are in
-// flight per warp so that the (cold, DRAM-latency) weight loads overlap instead of serialising row after row
-__device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ b, const float* x, float* y,
-                                            int n_out, int K, bool relu) {
+// y[n] = act(dot(W[n,:K], x) + b[n]) for the rows n of THIS CTA's slice of [0, n_out); every result is stored into the
+// shared memory of all CTAs of the cluster (lane r of the writing warp stores to rank r), so after the next
+// cluster barrier each CTA holds the complete activation vector.  One warp per row, 4 rows in flight per warp.
+__device__ __forceinline__ void dense_layer_cluster(cg::cluster_group& cluster, const float* __restrict__ W,
+                                                    const float* __restrict__ b, const float* x, float* y, int n_out, int K,
+                                                    bool relu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  constexpr int RB = 8;
-  for (int n0 = warp * RB; n0 < n_out; n0 += nw * RB) {
+  const int per = (n_out + POSE_CLUSTER - 1) / POSE_CLUSTER;
+  const int r0 = (int)cluster.block_rank() * per, r1 = min(n_out, r0 + per);
+  constexpr int RB = 4;
+  float* y_remote = lane < POSE_CLUSTER ? cluster.map_shared_rank(y, lane) : nullptr;
+  for (int n0 = r0 + warp * RB; n0 < r1; n0 += nw * RB) {
     float s[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) s[r] = 0.f;
     for (int k = lane; k < K; k += 32) {
       float wv[RB];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) wv[r] = (n0 + r < n_out) ? __ldg(W + (size_t)(n0 + r) * K + k) : 0.f;
+      for (int r = 0; r < RB; ++r) wv[r] = (n0 + r < r1) ? __ldg(W + (size_t)(n0 + r) * K + k) : 0.f;
       const float xv = x[k];
 #pragma unroll
       for (int r = 0; r < RB; ++r) s[r] = fmaf(wv[r], xv, s[r]);
@@ -57,9 +68,10 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       const float t = warp_sum(s[r]);
-      if (lane == 0 && n0 + r < n_out) {
-        const float v = t + (b ? __ldg(b + n0 + r) : 0.f);
-        y[n0 + r] = relu ? fmaxf(v, 0.f) : v;
+      if (n0 + r < r1) {
+        float v = t + (b ? __ldg(b + n0 + r) : 0.f);
+        v = relu ? fmaxf(v, 0.f) : v;
+        if (lane < POSE_CLUSTER) y_remote[n0 + r] = v;
       }
     }
   }
@@ -68,25 +80,27 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
 // saved layout (floats): h1..h4 (4 x 256) | params ((J+1)*4) | R_raw (J*9) | M (J*12) | T (J*12)
 __host__ __device__ inline int pose_saved_floats(int J) { return 4 * POSE_H + (J + 1) * 4 + J * 9 + J * 12 + J * 12; }
 
-__global__ void __launch_bounds__(POSE_THREADS) pose_fwd_kernel(const PoseArgs a, float* __restrict__ bone_T,
-                                                               float* __restrict__ global_t, float* __restrict__ thetas,
-                                                               float* __restrict__ saved) {
+__global__ void __cluster_dims__(POSE_CLUSTER, 1, 1) __launch_bounds__(POSE_THREADS)
+pose_fwd_kernel(const PoseArgs a, float* __restrict__ bone_T, float* __restrict__ global_t, float* __restrict__ thetas,
+                float* __restrict__ saved) {
   __shared__ float sh[5][POSE_H];
   __shared__ float sP[(POSE_MAX_J + 1) * 4];
   __shared__ float sR[POSE_MAX_J * 9];
   __shared__ float sM[POSE_MAX_J * 12];
   __shared__ float sT[POSE_MAX_J * 12];
+  cg::cluster_group cluster = cg::this_cluster();
   const int J = a.J, tid = threadIdx.x;
   for (int i = tid; i < a.t_dim; i += blockDim.x) sh[0][i] = a.t_embed[i];
-  __syncthreads();
-  dense_layer(a.w[0], a.b[0], sh[0], sh[1], POSE_H, a.t_dim, true);
-  __syncthreads();
+  cluster.sync();                                   // every CTA's shared memory exists before the first remote store
+  dense_layer_cluster(cluster, a.w[0], a.b[0], sh[0], sh[1], POSE_H, a.t_dim, true);
+  cluster.sync();
   for (int l = 1; l < 4; ++l) {
-    dense_layer(a.w[l], a.b[l], sh[l], sh[l + 1], POSE_H, POSE_H, true);
-    __syncthreads();
+    dense_layer_cluster(cluster, a.w[l], a.b[l], sh[l], sh[l + 1], POSE_H, POSE_H, true);
+    cluster.sync();
   }
-  dense_layer(a.w[4], nullptr, sh[4], sP, (J + 1) * 4, POSE_H, false);
-  __syncthreads();
+  dense_layer_cluster(cluster, a.w[4], nullptr, sh[4], sP, (J + 1) * 4, POSE_H, false);
+  cluster.sync();                                   // last remote store done: from here on only rank 0 works
+  if (cluster.block_rank() != 0) return;
   // raw rotations
   if (tid < J) {
     float R[9], n[3], rl, cs, sn;
@@ -161,13 +175,21 @@ struct PoseGrads {
   float* d_joints;            // (J,3)
 };
 
-__global__ void __launch_bounds__(POSE_THREADS) pose_bwd_kernel(const PoseArgs a, const float* __restrict__ saved, const PoseGrads g) {
+// The tree part (chain, pivots, Rodrigues: a few thousand flops) is evaluated redundantly by every CTA of the cluster, so
+// that all of them hold dP; the MLP part splits every layer's rows over the CTAs: each CTA writes its rows of dW_l and a
+// partial W_l^T d over its rows, the partials are all-gathered through distributed shared memory and summed in rank order.
+__global__ void __cluster_dims__(POSE_CLUSTER, 1, 1) __launch_bounds__(POSE_THREADS)
+pose_bwd_kernel(const PoseArgs a, const float* __restrict__ saved, const PoseGrads g) {
   __shared__ float sdT[POSE_MAX_J * 12];
   __shared__ float sdR[POSE_MAX_J * 9];      // gradient on the RAW rotations (after the sibling gather)
   __shared__ float sdJ[POSE_MAX_J * 3];
   __shared__ float sdP[(POSE_MAX_J + 1) * 4];
   __shared__ float sd[2][POSE_H];
+  __shared__ float sPart[2][POSE_CLUSTER][POSE_H];   // [layer parity][source rank][column]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   const int J = a.J, tid = threadIdx.x;
+  cluster.sync();                                   // every CTA's shared memory exists before the first remote store
   const float* h = saved;                        // h[l-1] = activation of hidden layer l (1..4)
   const float* sP = saved + 4 * POSE_H;
   const float* sR = sP + (J + 1) * 4;
@@ -249,32 +271,53 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_bwd_kernel(const PoseArgs a
     sdP[4 * tid + 3] = -sn * gc + cs * gs + (g.d_thetas ? g.d_thetas[tid] : 0.f);
   }
   if (tid < 4) sdP[4 * J + tid] = (tid < 3 && g.d_global_t) ? g.d_global_t[tid] : 0.f;
-  for (int i = tid; i < J * 3; i += blockDim.x) g.d_joints[i] = sdJ[i];
+  if (rank == 0)
+    for (int i = tid; i < J * 3; i += blockDim.x) g.d_joints[i] = sdJ[i];
   __syncthreads();
-  // output layer (no bias): dW4[r,:] = dP[r] h4 ; dh4 = W4^T dP
-  const int n_out = (J + 1) * 4;
-  for (int i = tid; i < n_out * POSE_H; i += blockDim.x) g.d_w[4][i] = sdP[i / POSE_H] * h[3 * POSE_H + (i % POSE_H)];
-  {
+  // all-gather of this CTA's partial column sums + rank-ordered reduction: -> full vector in every CTA
+  auto allreduce_cols = [&](int par, float partial) -> float {
+#pragma unroll
+    for (int r = 0; r < POSE_CLUSTER; ++r) cluster.map_shared_rank(&sPart[par][rank][0], r)[tid] = partial;
+    cluster.sync();
     float s = 0.f;
-#pragma unroll 16
-    for (int r = 0; r < n_out; ++r) s = fmaf(__ldg(a.w[4] + (size_t)r * POSE_H + tid), sdP[r], s);
+#pragma unroll
+    for (int r = 0; r < POSE_CLUSTER; ++r) s += sPart[par][r][tid];
+    return s;
+  };
+  // output layer (no bias): dW4[r,:] = dP[r] h4 ; dh4 = W4^T dP, rows split over the cluster
+  const int n_out = (J + 1) * 4;
+  {
+    const int per = (n_out + POSE_CLUSTER - 1) / POSE_CLUSTER;
+    const int r0 = rank * per, r1 = min(n_out, r0 + per);
+    for (int i = r0 * POSE_H + tid; i < r1 * POSE_H; i += blockDim.x) g.d_w[4][i] = sdP[i / POSE_H] * h[3 * POSE_H + (i % POSE_H)];
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) s = fmaf(__ldg(a.w[4] + (size_t)r * POSE_H + tid), sdP[r], s);
+    s = allreduce_cols(0, s);
     sd[0][tid] = h[3 * POSE_H + tid] > 0.f ? s : 0.f;
   }
   __syncthreads();
   int cur = 0;
+  constexpr int ROWS = POSE_H / POSE_CLUSTER;      // 32 rows of every hidden layer per CTA
   for (int l = 3; l >= 1; --l) {                 // hidden layers 3..1: input h[l-1] (activation of layer l)
     const float* x = h + (size_t)(l - 1) * POSE_H;
-    g.d_b[l][tid] = sd[cur][tid];
-    for (int i = tid; i < POSE_H * POSE_H; i += blockDim.x) g.d_w[l][i] = sd[cur][i / POSE_H] * x[i % POSE_H];
+    const int n0 = rank * ROWS;
+    if (tid >= n0 && tid < n0 + ROWS) g.d_b[l][tid] = sd[cur][tid];
+    for (int i = n0 * POSE_H + tid; i < (n0 + ROWS) * POSE_H; i += blockDim.x) g.d_w[l][i] = sd[cur][i / POSE_H] * x[i % POSE_H];
     float s = 0.f;
 #pragma unroll 32
-    for (int n = 0; n < POSE_H; ++n) s = fmaf(__ldg(a.w[l] + (size_t)n * POSE_H + tid), sd[cur][n], s);
+    for (int n = n0; n < n0 + ROWS; ++n) s = fmaf(__ldg(a.w[l] + (size_t)n * POSE_H + tid), sd[cur][n], s);
+    s = allreduce_cols((4 - l) & 1, s);
     sd[cur ^ 1][tid] = x[tid] > 0.f ? s : 0.f;
     __syncthreads();
     cur ^= 1;
   }
-  g.d_b[0][tid] = sd[cur][tid];
-  for (int i = tid; i < POSE_H * a.t_dim; i += blockDim.x) g.d_w[0][i] = sd[cur][i / a.t_dim] * a.t_embed[i % a.t_dim];
+  {
+    const int n0 = rank * ROWS;
+    if (tid >= n0 && tid < n0 + ROWS) g.d_b[0][tid] = sd[cur][tid];
+    for (int i = n0 * a.t_dim + tid; i < (n0 + ROWS) * a.t_dim; i += blockDim.x) g.d_w[0][i] = sd[cur][i / a.t_dim] * a.t_embed[i % a.t_dim];
+  }
+  cluster.sync();                                   // no CTA leaves while its shared memory can still be written remotely
 }
 
 static int pose_check(const PoseArgs& a) {
@@ -299,7 +342,7 @@ extern "C" int apn_pose_fwd(const float* t_embed, int t_dim, const float* const*
   for (int l = 0; l < 4; ++l) a.b[l] = b4[l];
   if (pose_check(a)) return -1;
   APN_CHECK_ARG(bone_T && global_t && thetas, "null output");
-  pose_fwd_kernel<<<1, POSE_THREADS, 0, st>>>(a, bone_T, global_t, thetas, (float*)saved);
+  pose_fwd_kernel<<<POSE_CLUSTER, POSE_THREADS, 0, st>>>(a, bone_T, global_t, thetas, (float*)saved);
   APN_LAUNCH_CHECK();
   return 0;
 }
@@ -327,7 +370,7 @@ extern "C" int apn_pose_bwd(const float* t_embed, int t_dim, const float* const*
     APN_CHECK_ARG(d_b4[l], "null bias gradient");
     g.d_b[l] = d_b4[l];
   }
-  pose_bwd_kernel<<<1, POSE_THREADS, 0, st>>>(a, (const float*)saved, g);
+  pose_bwd_kernel<<<POSE_CLUSTER, POSE_THREADS, 0, st>>>(a, (const float*)saved, g);
   APN_LAUNCH_CHECK();
   return 0;
 }
