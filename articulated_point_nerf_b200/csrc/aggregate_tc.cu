@@ -660,9 +660,9 @@ static int tc_launch(cudaStream_t st, const TcParams& p) {
   return 0;
 }
 
-extern "C" size_t apn_aggregate_tc_tape_bytes(int M) {
-  return M > 0 ? (size_t)apn_div_up(M, TC_SAMPLES) * TC_TAPE_TILE_BYTES : 0;
-}
+// per-tile tape of the decoder + (at the end) the packed head weights of this step (heads_tc.cu)
+static size_t tc_tape_tiles_bytes(int M) { return (size_t)apn_div_up(M, TC_SAMPLES) * TC_TAPE_TILE_BYTES; }
+extern "C" size_t apn_aggregate_tc_tape_bytes(int M) { return M > 0 ? tc_tape_tiles_bytes(M) + apn_align(heads_tc_weights_bytes()) : 0; }
 
 extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_weights,
                                     const float* point_table, const apn_agg_outputs* out, int precision, void* tape,
@@ -686,7 +686,7 @@ extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
     APN_CHECK_ARG(tape_bytes >= apn_aggregate_tc_tape_bytes(M) && (((uintptr_t)tape) & 1023) == 0, "tape too small or not 1 KiB aligned");
     APN_CHECK_ARG(out->h && out->exp_d && out->fv && out->v0, "training needs the h / exp_d / fv / v0 buffers");
     b.h = out->h;
-    b.heads_packed = nullptr;
+    b.heads_packed = (char*)tape + tc_tape_tiles_bytes(M);
   } else {
     APN_CHECK_ARG(scratch && scratch_bytes >= apn_aggregate_tc_scratch_bytes(M) && (((uintptr_t)scratch) & 15) == 0,
                   "scratch too small or not 16-byte aligned");
@@ -706,7 +706,7 @@ extern "C" int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
   p.n_tiles = apn_div_up(M, TC_SAMPLES);
   const int rc = precision == 0 ? tc_launch<1, false>(st, p) : tape ? tc_launch<2, true>(st, p) : tc_launch<2, false>(st, p);
   if (rc) return rc;
-  if (tape)     // fp32 heads: their intermediates are the backward's tape
-    return agg_heads_launch(st, in, w, nullptr, out->idw, b.h, out->exp_d, out->alpha, out->fv, out->v0, out->rgb);
-  return agg_heads_tc_launch(st, in, w, b.h, b.heads_packed, out->alpha, out->rgb);
+  // tensor-core heads; in training they also leave exp_d / fv / v0, the tape of the (fp32) heads backward
+  return agg_heads_tc_launch(st, in, w, b.h, b.heads_packed, out->alpha, out->rgb, tape ? out->exp_d : nullptr,
+                             tape ? out->fv : nullptr, tape ? out->v0 : nullptr);
 }

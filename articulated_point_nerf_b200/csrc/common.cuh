@@ -16,8 +16,9 @@ int agg_heads_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_we
                      float* h, float* exp_d, float* alpha, float* fv, float* v0, float* rgb);
 // heads_tc.cu: densitynet / Raw2Alpha + RGBNet on the tensor cores (inference); `packed` >= heads_tc_weights_bytes()
 size_t heads_tc_weights_bytes();
+// exp_d / fv / v0: the tape of the fp32 heads backward (training), or NULL
 int agg_heads_tc_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const float* h, void* packed,
-                        float* alpha, float* rgb);
+                        float* alpha, float* rgb, float* exp_d, float* fv, float* v0);
 // aggregate.cu: RGBNet backward: weight gradients + d_h (M,128) of the rgb branch
 int agg_rgbnet_bwd_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* sv,
                           const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h);

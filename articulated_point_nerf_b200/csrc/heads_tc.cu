@@ -60,6 +60,10 @@ struct HtParams {
   float act_shift, interval;
   float* alpha;                // (M)
   float* rgb;                  // (M,3)
+  // training tape of the fp32 heads backward (aggregate.cu: agg_rgbnet_bwd_launch, density backward), or NULL
+  float* exp_d;                // (M)      exp(density + act_shift)
+  float* fv;                   // (M,160)  [f (128) | view PE (27) | 0 (5)]
+  float* v0;                   // (M,64)   ReLU(views_linears.0)
   int M, n_tiles;
 };
 
@@ -160,7 +164,10 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
     {
       // lib/cuda/render_utils_kernel.cu:358-370 on this lane's row of the warp
       const float e = expf(my_dens + bd + p.act_shift);
-      if (mrow < p.M) p.alpha[mrow] = 1.f - powf(1.f + e, -p.interval);
+      if (mrow < p.M) {
+        p.alpha[mrow] = 1.f - powf(1.f + e, -p.interval);
+        if (p.exp_d) p.exp_d[mrow] = e;
+      }
       // lib/tineuvox.py:872-878 with 4 frequencies: [v(3) | sin(v_d 2^i) d-major | cos(...)], zero padded to 32 columns
       const int ray = __ldg(p.ray_id + mc);
       float pe[32];
@@ -172,6 +179,11 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
         pe[d] = v;
 #pragma unroll
         for (int i = 0; i < 4; ++i) sincosf(v * (float)(1 << i), &pe[3 + d * 4 + i], &pe[15 + d * 4 + i]);
+      }
+      if (p.fv && mrow < p.M) {
+        float4* dst = reinterpret_cast<float4*>(p.fv + (size_t)mrow * 160 + APN_C);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dst[u] = make_float4(pe[4 * u], pe[4 * u + 1], pe[4 * u + 2], pe[4 * u + 3]);
       }
       const uint32_t t = sA + 2 * 2 * TC_TILE_BYTES + (uint32_t)tid * 128u;
 #pragma unroll
@@ -197,11 +209,18 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         uint32_t hi[4], lo[4];
+        float fr[8];
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
           const int col = pc * 16 + u * 8 + 2 * e2;
-          split_half2(make_float2(__uint_as_float(v[u * 8 + 2 * e2]) + sBf[col], __uint_as_float(v[u * 8 + 2 * e2 + 1]) + sBf[col + 1]),
-                      hi[e2], lo[e2]);
+          fr[2 * e2] = __uint_as_float(v[u * 8 + 2 * e2]) + sBf[col];
+          fr[2 * e2 + 1] = __uint_as_float(v[u * 8 + 2 * e2 + 1]) + sBf[col + 1];
+          split_half2(make_float2(fr[2 * e2], fr[2 * e2 + 1]), hi[e2], lo[e2]);
+        }
+        if (p.fv && mrow < p.M) {
+          float4* dst = reinterpret_cast<float4*>(p.fv + (size_t)mrow * 160 + pc * 16 + u * 8);
+          dst[0] = make_float4(fr[0], fr[1], fr[2], fr[3]);
+          dst[1] = make_float4(fr[4], fr[5], fr[6], fr[7]);
         }
         const uint32_t o = (uint32_t)(((((pc & 3) * 2 + u) ^ (tid & 7)) & 7) << 4);
         sts128(t + o, hi[0], hi[1], hi[2], hi[3]);
@@ -238,12 +257,20 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
       tmem_ld16(tacc + 128u + pc * 16, v);
       tmem_ld_wait();
 #pragma unroll
+      float xr[16];
+#pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int col = pc * 16 + i;
         const float x = fmaxf(__uint_as_float(v[i]) + sBv[col], 0.f);
+        xr[i] = x;
         a0 = fmaf(x, sW2[col], a0);
         a1 = fmaf(x, sW2[64 + col], a1);
         a2 = fmaf(x, sW2[128 + col], a2);
+      }
+      if (p.v0 && mrow < p.M) {
+        float4* dst = reinterpret_cast<float4*>(p.v0 + (size_t)mrow * 64 + pc * 16);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[u] = make_float4(xr[4 * u], xr[4 * u + 1], xr[4 * u + 2], xr[4 * u + 3]);
       }
     }
     if (mrow < p.M) {
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
 
 // packs the head weights into `packed` (HT_PACKED_BYTES, 16-byte aligned) and runs the heads on h
 int agg_heads_tc_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const float* h, void* packed,
-                        float* alpha, float* rgb) {
+                        float* alpha, float* rgb, float* exp_d, float* fv, float* v0) {
   const int M = in->M;
   if (M <= 0) return 0;
   heads_tc_pack_kernel<<<5, 256, 0, st>>>(w->rgb_feat_w, w->rgb_v0_w, (uint8_t*)packed);
@@ -271,7 +298,7 @@ int agg_heads_tc_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp
   p.h = h; p.ray_id = in->ray_id; p.viewdirs = in->viewdirs; p.packed = (const uint8_t*)packed;
   p.bf = w->rgb_feat_b; p.bv0 = w->rgb_v0_b; p.W2 = w->rgb_v2_w; p.b2 = w->rgb_v2_b; p.wd = w->density_w; p.bd = w->density_b;
   p.act_shift = in->act_shift; p.interval = in->interval;
-  p.alpha = alpha; p.rgb = rgb; p.M = M; p.n_tiles = apn_div_up(M, 128);
+  p.alpha = alpha; p.rgb = rgb; p.exp_d = exp_d; p.fv = fv; p.v0 = v0; p.M = M; p.n_tiles = apn_div_up(M, 128);
   static_assert(HtSmem::TOTAL <= 227 * 1024, "shared memory budget");
   APN_CUDA(cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HtSmem::TOTAL));
   const int grid = p.n_tiles < APN_SM_COUNT ? p.n_tiles : APN_SM_COUNT;

@@ -228,7 +228,7 @@ static inline int gemm_wgrad(cudaStream_t st, const float* dY, int ldy, const fl
   int splits = (2 * APN_SM_COUNT + tiles - 1) / tiles;
   int k_chunk = apn_div_up(rows, splits);
   k_chunk = ((k_chunk + GEMM_BK - 1) / GEMM_BK) * GEMM_BK;
-  if (k_chunk < 256) k_chunk = 256;
+  if (k_chunk < 64) k_chunk = 64;        // enough splits to fill the machine on the 8192-ray training batches (K ~ 1e4)
   splits = apn_div_up(rows, k_chunk);
   GemmArgs g = {dY, ldy, X, ldx, dW, ldw, n_out, n_in, rows, nullptr, 1.f, nullptr, 0, k_chunk};
   dim3 grid(apn_div_up(n_out, GEMM_BM), apn_div_up(n_in, GEMM_BN), splits);
