@@ -454,15 +454,18 @@ lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
   for (int o = threadIdx.x; o < n_out + 4; o += blockDim.x) out[o] = sAcc[o];
 }
 
-// fixed-order reduction of the per-block partials (deterministic)
-__global__ void lbs_bwd_reduce_kernel(const float* __restrict__ partial, int n_blocks, int J, const float* theta_weight,
-                                      float eps, float* __restrict__ d_theta, float* __restrict__ d_bone_T,
-                                      float* __restrict__ d_global_t) {
+// fixed-order reduction of the per-block partials (deterministic): one warp per output, lanes stride over the blocks
+// and a fixed shuffle tree combines them
+__global__ void __launch_bounds__(128)
+lbs_bwd_reduce_kernel(const float* __restrict__ partial, int n_blocks, int J, const float* theta_weight, float eps,
+                      float* __restrict__ d_theta, float* __restrict__ d_bone_T, float* __restrict__ d_global_t) {
   const int n_out = J * 12;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (o >= n_out + 4) return;
   float s = 0.f;
-  for (int b = 0; b < n_blocks; ++b) s += partial[(size_t)b * (n_out + 4) + o];
+  for (int b = lane; b < n_blocks; b += 32) s += partial[(size_t)b * (n_out + 4) + o];
+  s = warp_sum(s);
+  if (lane != 0) return;
   if (o < n_out) {
     const int j = o / 12, c = o - j * 12;
     d_bone_T[j * 16 + c] = s;
@@ -546,7 +549,7 @@ extern "C" int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float 
 #undef LBS_BWD_LAUNCH
   APN_LAUNCH_CHECK();
   const int n = J * 12 + 4;
-  lbs_bwd_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const float*)workspace, grid, J, theta_weight, eps, d_theta,
+  lbs_bwd_reduce_kernel<<<(n + 3) / 4, 128, 0, stream>>>((const float*)workspace, grid, J, theta_weight, eps, d_theta,
                                                             d_bone_T, d_global_t);
   APN_LAUNCH_CHECK();
   return 0;
