@@ -19,6 +19,8 @@
 // 64-bit keys (d2 bits << 32 | index, i.e. lexicographic (d2, index)); the result is exact as soon
 // as the 8th distance is inside the neighbourhood's guaranteed radius; otherwise jump to the
 // level whose cell edge covers the 8th distance found so far.
+#include <stdlib.h>
+
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -43,7 +45,8 @@ struct GridHeader {
   int top_capacity;
   long long off_cell_start, off_top, off_sorted, off_key, off_rank, off_scan;
   long long scan_bytes;
-  int pad_[16];
+  float occupancy;  // expected points per leaf, from the caller's spacing hint (cell_hint = 1.5 x mean point spacing)
+  int pad_[15];
 };
 static_assert(sizeof(GridHeader) <= 256, "header must fit 256 bytes");
 
@@ -115,7 +118,6 @@ __global__ void grid_header_kernel(void* blob, const float* __restrict__ bbox, i
   GridHeader* h = (GridHeader*)blob;
   const float rq = sqrtf(r2);
   const float top = rq * 1.01f;
-  (void)cell_hint;
   int L = GRID_L;                               // 4 x 4 x 4 leaves per top cell (see the k-NN section)
   float ext[3];
   int td[3];
@@ -155,6 +157,10 @@ __global__ void grid_header_kernel(void* blob, const float* __restrict__ bbox, i
   h->r2 = r2;
   h->n_points = N;
   h->overflow = bad ? 1 : 0;
+  {
+    const float ratio = h->cell / fmaxf(cell_hint / 1.5f, 1e-12f);
+    h->occupancy = ratio * ratio * ratio;
+  }
   h->cell_capacity = cap;
   h->top_capacity = lay.top_capacity;
   h->off_cell_start = lay.off_cell_start;
@@ -546,6 +552,109 @@ __device__ bool knn_search_warp(const GridView& g, float qx, float qy, float qz,
   return true;
 }
 
+// ---------------------------------------------------------------------------------------
+// k-NN of the ray samples, one THREAD per query (apn_knn).
+// The warp-per-query search above spends ~1800 warp instructions per query on cross-lane coordination (flattened
+// range scans, ballot-driven insertion into a top-8 spread over 8 lanes).  For ray samples the work per query is
+// small and regular — the 8th neighbour sits within one or two leaf edges — so here every thread owns a query and a
+// sorted top-8 of 64-bit (d2, index) keys in registers, and walks the leaves around its own leaf ring by ring
+// (Chebyshev distance 0, 1, 2, ...), skipping leaves whose inflated box cannot beat the current 8th key.  After ring k
+// every unscanned point is farther than  k * cell + (distance of q to the nearest face of its own leaf),  which
+// certifies the result as soon as the 8th distance is below that bound, and ends the search once the bound passes
+// the query radius (the sample is then dropped by the radius rule).  Lanes of a warp are consecutive samples of a ray,
+// i.e. neighbours in space: they walk the same leaves in the same order, so their loads largely coincide.
+// Same contract as the warp search: exact top-8 by (d2, index), d2 = (dx*dx + dy*dy) + dz*dz without FMA.
+// ---------------------------------------------------------------------------------------
+// Which search runs is decided ON THE DEVICE from the grid header (no host read-back): with fewer than this many
+// points per leaf the per-thread walk wins (the warp search wastes its lanes on one- and two-point leaves), with dense
+// leaves and for small batches (latency) the warp search does.  Large batches launch both kernels; the one that is
+// not selected returns at once.
+#define KNN_SPARSE_OCCUPANCY 6.0f
+#define KNN_THREAD_MIN_QUERIES 200000
+
+__device__ __forceinline__ void top8_insert(unsigned long long (&b)[APN_K], unsigned long long k) {   // k < b[7]
+#pragma unroll
+  for (int i = APN_K - 1; i > 0; --i) {
+    const unsigned long long lo = b[i - 1];
+    b[i] = (lo > k) ? lo : ((b[i] > k) ? k : b[i]);
+  }
+  b[0] = (b[0] > k) ? k : b[0];
+}
+
+__global__ void __launch_bounds__(128)
+knn_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
+                  const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand,
+                  int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep, bool force) {
+  const GridView g = grid_view(blob);
+  const GridHeader* h = g.h;
+  if (!force && !(h->occupancy < KNN_SPARSE_OCCUPANCY)) return;   // dense leaves: knn_kernel (warp per query) handles this launch
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand) return;
+  const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
+  const int r = __ldg(cand_ray + i), st = __ldg(cand_step + i);
+  const RaySetup rs = ray_setup(rays_o, rays_d, r, bmin, bmax, near, far, stepdist);
+  float qx, qy, qz;
+  ray_point(rs, st, stepdist, qx, qy, qz);
+  const float cell = h->cell, ox = h->origin[0], oy = h->origin[1], oz = h->origin[2];
+  const float eps = 1e-4f * cell + 1e-6f;
+  const int L = h->L, tx = h->top_dim[0], ty = h->top_dim[1];
+  const int nx = tx << L, ny = ty << L, nz = h->top_dim[2] << L;
+  int cx, cy, cz;
+  point_cell(h, qx, qy, qz, cx, cy, cz);
+  // distance of q to the nearest face of its own leaf (0 when q lies outside the grid and was clamped)
+  const float fx = qx - (ox + cx * cell), fy = qy - (oy + cy * cell), fz = qz - (oz + cz * cell);
+  const float m = fmaxf(fminf(fminf(fminf(fx, cell - fx), fminf(fy, cell - fy)), fminf(fz, cell - fz)), 0.f);
+  const float r2 = h->r2;
+  unsigned long long best[APN_K];
+#pragma unroll
+  for (int k = 0; k < APN_K; ++k) best[k] = KEY_INF;
+  unsigned long long thr = bound_key(r2);                 // a point must beat this key: (r2, max index), then the 8th best
+  const int max_ring = (int)ceilf(sqrtf(r2) / cell) + 1;
+  bool done = false;
+  for (int ring = 0; ring <= max_ring && !done; ++ring) {
+    for (int dz = -ring; dz <= ring; ++dz) {
+      const int iz = cz + dz;
+      if (iz < 0 || iz >= nz) continue;
+      for (int dy = -ring; dy <= ring; ++dy) {
+        const int iy = cy + dy;
+        if (iy < 0 || iy >= ny) continue;
+        const bool shell_zy = (dz == -ring) | (dz == ring) | (dy == -ring) | (dy == ring);
+        for (int dx = -ring; dx <= ring; dx += (shell_zy || ring == 0) ? 1 : 2 * ring) {   // interior rows: only the two end cells
+          const int ix = cx + dx;
+          if (ix < 0 || ix >= nx) continue;
+          const float md2 = box_dist2(qx, qy, qz, ox + ix * cell, oy + iy * cell, oz + iz * cell, cell, eps);
+          if (!(md2 <= key_d2(thr))) continue;
+          const int key = cell_key(ix, iy, iz, L, tx, ty);
+          const int s = __ldg(g.cell_start + key), e = __ldg(g.cell_start + key + 1);
+          for (int p = s; p < e; ++p) {
+            const float4 P = __ldg(g.sorted + p);
+            const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
+            const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
+            if (k < thr) {
+              top8_insert(best, k);
+              thr = best[APN_K - 1] < thr ? best[APN_K - 1] : thr;
+            }
+          }
+        }
+      }
+    }
+    // every unscanned point lies beyond  ring * cell + m  (minus the rounding slack of the point -> cell assignment)
+    const float reach = fmaxf((float)ring * cell + m - 3.f * eps, 0.f);
+    const float reach2 = reach * reach;
+    if (best[APN_K - 1] != KEY_INF && key_d2(best[APN_K - 1]) < reach2) done = true;     // certified
+    else if (reach2 > r2) done = true;                                                    // nothing within the radius is left
+  }
+  const bool ok = best[APN_K - 1] != KEY_INF && key_d2(best[APN_K - 1]) <= r2;
+  keep[i] = ok ? 1 : 0;
+  if (ok) {
+#pragma unroll
+    for (int k = 0; k < APN_K; ++k) {
+      nn_idx[(size_t)i * APN_K + k] = (int)(unsigned int)best[k];
+      if (nn_d2) nn_d2[(size_t)i * APN_K + k] = key_d2(best[k]);
+    }
+  }
+}
+
 // consecutive candidates (ray-major order) handled by one warp, so bounds and the ray setup carry over along a ray:
 // 16 when there is enough work to fill the machine anyway, down to 2 for small batches (latency)
 #define KNN_GROUP_MAX 16
@@ -553,12 +662,13 @@ __device__ bool knn_search_warp(const GridView& g, float qx, float qy, float qz,
 __global__ void __launch_bounds__(128)
 knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
            const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand,
-           int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep, int group) {
+           int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep, int group, bool both) {
   const GridView g = grid_view(blob);
   const GridHeader* h = g.h;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
+  if (both && h->occupancy < KNN_SPARSE_OCCUPANCY) return;   // sparse leaves: knn_thread_kernel handles this launch
   const int n_groups = (n_cand + group - 1) / group;
   for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
     int prev_ray = -1, prev_step = 0;
@@ -597,12 +707,22 @@ extern "C" int apn_knn(const float* rays_o, const float* rays_d, float near, flo
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_cand <= 0) return 0;
   APN_CHECK_ARG(rays_o && rays_d && grid && cand_ray && cand_step && nn_idx && keep, "null pointer");
+  // APN_KNN_FORCE=thread|warp pins the search (tests exercise both on the same inputs)
+  const char* forced = getenv("APN_KNN_FORCE");
+  const bool force_thread = forced && forced[0] == 't', force_warp = forced && forced[0] == 'w';
+  const bool both = !force_warp && !force_thread && n_cand >= KNN_THREAD_MIN_QUERIES;
+  if (both || force_thread) {
+    knn_thread_kernel<<<apn_div_up(n_cand, 128), 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step,
+                                                                   n_cand, nn_idx, nn_d2, keep, force_thread);
+    APN_LAUNCH_CHECK();
+    if (force_thread) return 0;
+  }
   const int resident_warps = APN_SM_COUNT * 16 * 4;
   int group = n_cand / resident_warps;
   group = group < 2 ? 2 : group > KNN_GROUP_MAX ? KNN_GROUP_MAX : group;
   const int blocks = min(apn_div_up(n_cand, 4 * group), APN_SM_COUNT * 16);   // 4 warps per block, persistent grid-stride
   knn_kernel<<<blocks, 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand, nn_idx, nn_d2,
-                                         keep, group);
+                                         keep, group, both);
   APN_LAUNCH_CHECK();
   return 0;
 }

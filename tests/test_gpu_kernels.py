@@ -94,9 +94,11 @@ def _cloud_and_rays(config="tiny", view=0):
     return scene, ro, rd, vd
 
 
+@pytest.mark.parametrize("search", ["warp", "thread"])
 @pytest.mark.parametrize("config", ["tiny", "small"])
-def test_sample_and_knn_bit_exact(config):
+def test_sample_and_knn_bit_exact(config, search, monkeypatch):
     """pts / ray_id / step_id / neighbour indices identical to the oracle's brute force (ties -> lower index)."""
+    monkeypatch.setenv("APN_KNN_FORCE", search)          # both k-NN searches (csrc/grid_knn.cu) against the same oracle
     ops = _ops()
     from oracle.path_oracle import OraclePath
     scene, ro, rd, vd = _cloud_and_rays(config)

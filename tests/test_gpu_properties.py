@@ -29,7 +29,10 @@ def c1_model():
     return scene, model
 
 
-def test_knn_at_full_size_sorted_within_radius_and_exact_on_a_subset(c1_model):
+@pytest.mark.parametrize("search", ["auto", "thread"])
+def test_knn_at_full_size_sorted_within_radius_and_exact_on_a_subset(c1_model, search, monkeypatch):
+    if search != "auto":
+        monkeypatch.setenv("APN_KNN_FORCE", search)       # the per-thread search too (auto picks the warp search on c1)
     ops = _ops()
     scene, model = c1_model
     ro, rd, vd = [x.reshape(-1, 3).contiguous().cuda() for x in scene.rays(2)]
