@@ -570,6 +570,7 @@ __device__ bool knn_search_warp(const GridView& g, float qx, float qy, float qz,
 // leaves and for small batches (latency) the warp search does.  Large batches launch both kernels; the one that is
 // not selected returns at once.
 #define KNN_SPARSE_OCCUPANCY 6.0f
+#define KNN_COARSE_OCCUPANCY 2.5f     // below this many points per leaf the per-thread search walks 2x2x2 leaf blocks
 #define KNN_THREAD_MIN_QUERIES 200000
 
 __device__ __forceinline__ void top8_insert(unsigned long long (&b)[APN_K], unsigned long long k) {   // k < b[7]
@@ -584,7 +585,7 @@ __device__ __forceinline__ void top8_insert(unsigned long long (&b)[APN_K], unsi
 __global__ void __launch_bounds__(128)
 knn_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
                   const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand,
-                  int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep, bool force) {
+                  int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep, bool force, int force_lvl) {
   const GridView g = grid_view(blob);
   const GridHeader* h = g.h;
   if (!force && !(h->occupancy < KNN_SPARSE_OCCUPANCY)) return;   // dense leaves: knn_kernel (warp per query) handles this launch
@@ -595,12 +596,17 @@ knn_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
   const RaySetup rs = ray_setup(rays_o, rays_d, r, bmin, bmax, near, far, stepdist);
   float qx, qy, qz;
   ray_point(rs, st, stepdist, qx, qy, qz);
-  const float cell = h->cell, ox = h->origin[0], oy = h->origin[1], oz = h->origin[2];
-  const float eps = 1e-4f * cell + 1e-6f;
+  // walk level: leaves (lvl 0) or, for very sparse clouds, their 2x2x2 parents (lvl 1) — every level-l cell is one
+  // contiguous range of `sorted` (Morton order inside a top cell), so a coarser walk tests 8x fewer boxes per point
+  const int lvl = force_lvl >= 0 ? force_lvl : ((h->occupancy < KNN_COARSE_OCCUPANCY && h->L >= 1) ? 1 : 0);
+  const float cell = h->cell * (float)(1 << lvl), ox = h->origin[0], oy = h->origin[1], oz = h->origin[2];
+  const float eps = 1e-4f * h->cell + 1e-6f;
   const int L = h->L, tx = h->top_dim[0], ty = h->top_dim[1];
-  const int nx = tx << L, ny = ty << L, nz = h->top_dim[2] << L;
+  const int nx = (tx << L) >> lvl, ny = (ty << L) >> lvl, nz = (h->top_dim[2] << L) >> lvl;
+  const int span = 1 << (3 * lvl);
   int cx, cy, cz;
   point_cell(h, qx, qy, qz, cx, cy, cz);
+  cx >>= lvl; cy >>= lvl; cz >>= lvl;
   // distance of q to the nearest face of its own leaf (0 when q lies outside the grid and was clamped)
   const float fx = qx - (ox + cx * cell), fy = qy - (oy + cy * cell), fz = qz - (oz + cz * cell);
   const float m = fmaxf(fminf(fminf(fminf(fx, cell - fx), fminf(fy, cell - fy)), fminf(fz, cell - fz)), 0.f);
@@ -624,8 +630,8 @@ knn_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
           if (ix < 0 || ix >= nx) continue;
           const float md2 = box_dist2(qx, qy, qz, ox + ix * cell, oy + iy * cell, oz + iz * cell, cell, eps);
           if (!(md2 <= key_d2(thr))) continue;
-          const int key = cell_key(ix, iy, iz, L, tx, ty);
-          const int s = __ldg(g.cell_start + key), e = __ldg(g.cell_start + key + 1);
+          const int key = cell_key(ix << lvl, iy << lvl, iz << lvl, L, tx, ty);
+          const int s = __ldg(g.cell_start + key), e = __ldg(g.cell_start + key + span);
           for (int p = s; p < e; ++p) {
             const float4 P = __ldg(g.sorted + p);
             const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
@@ -707,13 +713,14 @@ extern "C" int apn_knn(const float* rays_o, const float* rays_d, float near, flo
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_cand <= 0) return 0;
   APN_CHECK_ARG(rays_o && rays_d && grid && cand_ray && cand_step && nn_idx && keep, "null pointer");
-  // APN_KNN_FORCE=thread|warp pins the search (tests exercise both on the same inputs)
+  // APN_KNN_FORCE=warp|thread|thread0|thread1 pins the search (and its walk level): tests exercise all on the same inputs
   const char* forced = getenv("APN_KNN_FORCE");
   const bool force_thread = forced && forced[0] == 't', force_warp = forced && forced[0] == 'w';
+  const int force_lvl = (force_thread && (forced[6] == '0' || forced[6] == '1')) ? forced[6] - '0' : -1;
   const bool both = !force_warp && !force_thread && n_cand >= KNN_THREAD_MIN_QUERIES;
   if (both || force_thread) {
     knn_thread_kernel<<<apn_div_up(n_cand, 128), 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step,
-                                                                   n_cand, nn_idx, nn_d2, keep, force_thread);
+                                                                   n_cand, nn_idx, nn_d2, keep, force_thread, force_lvl);
     APN_LAUNCH_CHECK();
     if (force_thread) return 0;
   }

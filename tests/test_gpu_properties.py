@@ -29,7 +29,7 @@ def c1_model():
     return scene, model
 
 
-@pytest.mark.parametrize("search", ["auto", "thread"])
+@pytest.mark.parametrize("search", ["auto", "thread0", "thread1"])
 def test_knn_at_full_size_sorted_within_radius_and_exact_on_a_subset(c1_model, search, monkeypatch):
     if search != "auto":
         monkeypatch.setenv("APN_KNN_FORCE", search)       # the per-thread search too (auto picks the warp search on c1)
