@@ -245,6 +245,18 @@ class Grid:
         return idx, d2
 
 
+def nn1_batched(query: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """(B, Nq, D), (B, Nt, D), D in {2, 3} -> int64 (B, Nq): nearest target of every query inside its batch item
+    (KeOps argKmin K=1 of lib/temporalpoints.py:783-787); ties -> lowest index."""
+    lib = _lib.load()
+    q, t = query.detach().float().contiguous(), target.detach().float().contiguous()
+    assert q.dim() == 3 and t.dim() == 3 and q.shape[0] == t.shape[0] and q.shape[2] == t.shape[2]
+    B, nq, d = q.shape
+    idx = _empty((B, nq), q.device, torch.int32)
+    check(lib.apn_nn1_batched(ptr(q), ptr(t), B, nq, t.shape[1], d, ptr(idx), stream()), "apn_nn1_batched")
+    return idx.long()
+
+
 def exclusive_scan(x: torch.Tensor) -> torch.Tensor:
     """int32 (n) -> int32 (n+1), out[n] = total."""
     lib = _lib.load()

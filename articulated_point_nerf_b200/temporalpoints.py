@@ -275,6 +275,86 @@ class TemporalPoints(torch.nn.Module):
                     break
         return endpoints
 
+    @staticmethod
+    def _rotation_angle(rel):
+        """Rotation angle in [0, pi] of (..., 3, 3) rotation matrices — the norm of roma.rotmat_to_rotvec
+        (lib/temporalpoints.py:358-361) — as atan2(|axial vector|, (trace - 1) / 2)."""
+        vx = rel[..., 2, 1] - rel[..., 1, 2]
+        vy = rel[..., 0, 2] - rel[..., 2, 0]
+        vz = rel[..., 1, 0] - rel[..., 0, 1]
+        s = 0.5 * torch.sqrt(vx * vx + vy * vy + vz * vz)
+        c = 0.5 * (rel[..., 0, 0] + rel[..., 1, 1] + rel[..., 2, 2] - 1.0)
+        return torch.atan2(s, c)
+
+    def _are_rotations_similar(self, rot1, rot2, deg_threshold=20, five_percent_heuristic=False):
+        """lib/temporalpoints.py:356-369 for (T, ..., 3, 3) stacks; reduces over the leading (time) axis."""
+        angle = self._rotation_angle(rot1 @ rot2.transpose(-1, -2))
+        if not five_percent_heuristic:
+            return torch.rad2deg(torch.sqrt((angle ** 2).mean(dim=0))) <= deg_threshold
+        th = int(len(rot1) * 0.05)
+        return (torch.rad2deg(angle) >= deg_threshold).sum(dim=0) <= th
+
+    @torch.no_grad()
+    def simplify_skeleton(self, times, deg_threshold=10, mass_threshold=0.0, update_skeleton=False,
+                          five_percent_heuristic=False, visualise_canonical=False):
+        """lib/temporalpoints.py:256-343 (run.py:1302-1308, --degree_threshold): evaluate the pose network at every
+        training time, freeze joints that never rotate by more than the threshold, merge siblings that rotate alike,
+        and install the result as `forward_warp.rot_mask`, `forward_warp.sibling_mask` and `flat_merging_rules`
+        (the skinning-weight column merge done inside the LBS kernel).  Same return tuple as the reference.
+        Reference quirks kept: the 'average' heuristic thresholds the mean SQUARED angle converted to degrees
+        (no square root, :288); the last returned item is whatever the reference's `res` held last."""
+        from .treeprune import merge_joints
+        J = len(self.joints)
+        times = torch.as_tensor(times, dtype=torch.float32, device=self.time_poc.device).reshape(-1, 1)
+        assert len(times) > 1, "simplify_skeleton needs more than one time step (TransformNet drops the batch axis for one)"
+        params = self.forward_warp.transform_net(poc_fre(times, self.time_poc))          # (T, J+1, 4)
+        T = len(times)
+        if self.over_parameterized_rot:
+            rot_angles = params[:, :J, -1]
+            R, _ = self.forward_warp.Rodrigues(params[:, :J, :].reshape(T * J, 4))
+        else:
+            rot_angles = (params[:, :J, :3] ** 2).sum(-1).sqrt() % (2 * np.pi)
+            R, _ = self.forward_warp.Rodrigues(params[:, :J, :3].reshape(T * J, 3))
+        R = R.reshape(T, J, 3, 3)
+        # all joint pairs at once (the reference loops over the lower triangle and mirrors it)
+        pair = self._are_rotations_similar(R[:, :, None], R[:, None, :], deg_threshold=deg_threshold,
+                                           five_percent_heuristic=five_percent_heuristic)    # (J, J)
+        low = torch.tril(pair, diagonal=-1)
+        rotation_similarity_mat = (low | low.T | torch.eye(J, dtype=torch.bool, device=pair.device)).cpu()
+        if five_percent_heuristic:
+            th = int(T * 0.05)
+            res = (torch.rad2deg(rot_angles).abs() >= deg_threshold).sum(dim=0)
+            zero_motion = res <= th
+        else:
+            res = pair[J - 1, J - 2] if J > 1 else None
+            zero_motion = torch.rad2deg((rot_angles ** 2).mean(dim=0)) <= deg_threshold
+        prune_bones = zero_motion
+        prune_bones[0] = False                                   # the (imaginary) root bone is never pruned
+
+        joints = self.joints.detach().cpu().numpy()
+        bones = self.bones
+        new_joints, new_bones, merging_rules, joints_to_keep, rotations_to_keep, _, sibling_transfer_rules = \
+            merge_joints(joints, bones, prune_bones.cpu().numpy(), rotation_similarity_mat.numpy(),
+                         convert_merging_rules=False)
+        rotations_to_keep = torch.tensor(rotations_to_keep)
+        self.merging_rules = merging_rules
+        self.joints_to_keep = joints_to_keep
+        self.new_bones = new_bones
+
+        dev = self.forward_warp.rot_mask.device
+        self.forward_warp.set_rotation_mask(~prune_bones.to(dev))
+        self.forward_warp.set_sibling_mask(torch.tensor(sibling_transfer_rules).to(dev))
+        flat = [int(v) for v in self.flatten_merging_rules(merging_rules)]
+        self.flat_merging_rules = torch.tensor(flat, dtype=torch.long, device=self.flat_merging_rules.device)
+        self.sibling_merging_rules = torch.tensor(sibling_transfer_rules).to(self.sibling_merging_rules.device)
+        object.__setattr__(self, '_pose_graph', None)            # masks changed: captured pose graphs are stale
+        object.__setattr__(self, '_pose_graph_key', None)
+
+        print(f"Frozen joints/weights: {int(prune_bones.sum())} of {len(prune_bones)} ")
+        print(f"Joints kept: {[i for i, v in enumerate(~prune_bones) if v]}")
+        print(f"Actually pruned joints: {len(joints) - len(new_joints)} of {len(joints)}")
+        return joints, bones, new_joints, new_bones, prune_bones, merging_rules, rotations_to_keep, res
+
     # ------------------------------------------------------------------------------------------
     def _mlp_weights(self):
         fn, rn = self.feat_net, self.rgbnet
@@ -463,6 +543,22 @@ class TemporalPoints(torch.nn.Module):
         if c is None:
             return d1.mean() + d2.mean()
         return self._rho(d1, c).mean() + self._rho(d2, c).mean()
+
+    def get_batch_chamfer_loss(self, pcd1, pcd2, N=None, M=None):
+        """lib/temporalpoints.py:765-795 (2-D chamfer of the projected cloud against mask pixels, run.py:659-690):
+        (B, N, D) vs (B, M, D); gradients flow through the gathered coordinates, the indices come from
+        `apn_nn1_batched`."""
+        assert len(pcd1) == len(pcd2)
+        if N is not None:
+            pcd1 = pcd1[:, torch.randint(0, pcd1.shape[1], (N,), device=pcd1.device)]
+        if M is not None:
+            pcd2 = pcd2[:, torch.randint(0, pcd2.shape[1], (M,), device=pcd1.device)]
+        D = pcd1.shape[-1]
+        i12 = ops.nn1_batched(pcd1, pcd2)[..., None].expand(-1, -1, D)
+        i21 = ops.nn1_batched(pcd2, pcd1)[..., None].expand(-1, -1, D)
+        d1 = (pcd1 - torch.gather(pcd2, 1, i12)).pow(2)
+        d2 = (pcd2 - torch.gather(pcd1, 1, i21)).pow(2)
+        return d1.sum(-1).mean() + d2.sum(-1).mean()
 
     def get_transformation_regularisation_loss(self, d=0.0873):
         t = self.forward_warp.prev_global_t.abs()

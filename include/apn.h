@@ -124,6 +124,11 @@ int apn_compact_samples(const float* rays_o, const float* rays_d, float near, fl
  * lib/temporalpoints.py:104-111; chamfer K=1, :747-751). max_d2 <= 0: unbounded. */
 int apn_knn_points(const float* query, int n_query, const void* grid, int k, int32_t* nn_idx, float* nn_d2,
                    apn_stream_t stream);
+/* batched exact nearest neighbour, K = 1, dim 2 or 3 (batch chamfer loss, lib/temporalpoints.py:783-787: KeOps
+ * D_ij.argKmin(dim=2, K=1) / argKmin(dim=1, K=1) over (B, N, M); run.py:659-690).  query (B, n_query, dim),
+ * target (B, n_target, dim) -> nn_idx (B, n_query), index into that batch item's targets; ties -> lowest index. */
+int apn_nn1_batched(const float* query, const float* target, int n_batch, int n_query, int n_target, int dim,
+                    int32_t* nn_idx, apn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3  Aggregation: gather + positional encoding + feature MLP + inverse-distance reduce + heads.

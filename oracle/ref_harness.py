@@ -5,7 +5,8 @@ oracle/make_golden.py to produce tests/golden/*.pt, which pin oracle/path_oracle
 
 Third-party modules the reference imports but that are absent here are shimmed exactly as
 specified in SURVEY.md Appendix A:
-  tkinter.W, roma, seaborn.color_palette, matplotlib(.pyplot)     -> inert stand-ins
+  tkinter.W, seaborn.color_palette, matplotlib(.pyplot)           -> inert stand-ins
+  roma.rotmat_to_rotvec                                          -> axis * angle in float64 (only its norm is used)
   torch_scatter.segment_coo                                      -> out.index_add_
   pykeops.torch.LazyTensor                                       -> dense blocked brute force,
         d2 = (dx*dx + dy*dy) + dz*dz, K smallest ascending by (d2, index)
@@ -76,8 +77,10 @@ class _Lazy:
                 aa, bb = a, b[..., sl, :]
             dx = aa[..., 0] - bb[..., 0]
             dy = aa[..., 1] - bb[..., 1]
-            dz = aa[..., 2] - bb[..., 2]
-            d2 = (dx * dx + dy * dy) + dz * dz          # (..., i, j)
+            d2 = dx * dx + dy * dy                      # (..., i, j)
+            if aa.shape[-1] == 3:
+                dz = aa[..., 2] - bb[..., 2]
+                d2 = d2 + dz * dz
             if not reduce_j:
                 d2 = d2.transpose(-1, -2)               # (..., j_block, i)
             idx = torch.arange(n_red, dtype=torch.int64)
@@ -107,7 +110,17 @@ def install_shims():
         return m
 
     mod("tkinter", W="w")
-    mod("roma")
+    def rotmat_to_rotvec(R):
+        """roma.rotmat_to_rotvec restated from its documented semantics (rotation vector = unit axis * angle,
+        angle in [0, pi]); evaluated in float64.  Only its norm is consumed (lib/temporalpoints.py:358-361)."""
+        Rd = R.double()
+        cos = ((Rd[..., 0, 0] + Rd[..., 1, 1] + Rd[..., 2, 2]) - 1.0) / 2.0
+        angle = torch.acos(cos.clamp(-1.0, 1.0))
+        axis = torch.stack([Rd[..., 2, 1] - Rd[..., 1, 2], Rd[..., 0, 2] - Rd[..., 2, 0], Rd[..., 1, 0] - Rd[..., 0, 1]], -1)
+        axis = axis / axis.norm(dim=-1, keepdim=True).clamp_min(1e-300)
+        return (axis * angle[..., None]).to(R.dtype)
+
+    mod("roma", rotmat_to_rotvec=rotmat_to_rotvec)
     mod("seaborn", color_palette=lambda name, n: hls_palette(int(n)))
     mpl = mod("matplotlib")
     mpl.pyplot = mod("matplotlib.pyplot")

@@ -182,3 +182,65 @@ def test_checkpoint_round_trip_keeps_the_reference_layout(tmp_path):
     for k in a:
         assert torch.equal(a[k], b[k]), k
     assert torch.equal(loaded.canonical_pcd, model.canonical_pcd) and loaded.bones == model.bones
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# skeleton simplification: lib/treeprune.py merge_joints and lib/temporalpoints.py simplify_skeleton
+# against the reference's own outputs (tests/golden/ref_skeleton.pt, oracle/make_golden_skeleton.py)
+@pytest.fixture(scope="module")
+def golden_skeleton():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "ref_skeleton.pt"), weights_only=False)
+
+
+def test_merge_joints_matches_reference_on_its_fixture_and_random_trees(golden_skeleton):
+    import numpy as np
+    from articulated_point_nerf_b200.treeprune import merge_joints
+    names = ["new_joints", "new_bones", "merging_rules", "joints_to_keep", "rotations_to_keep", "rotation_switch_mask",
+             "sibling_transfer_rules"]
+    n_ok = n_sibling = 0
+    for c in golden_skeleton["merge_joints"]:
+        if not c["ok"]:
+            with pytest.raises(Exception):         # degenerate trees the reference itself cannot handle
+                merge_joints(c["joints"], c["bones"], c["prune"].copy(), c["sim"], convert_merging_rules=c["convert"])
+            continue
+        out = merge_joints(c["joints"], c["bones"], c["prune"].copy(), c["sim"], convert_merging_rules=c["convert"])
+        for name, ours, ref in zip(names, out, c["out"]):
+            assert np.array_equal(np.asarray(ours), ref), (c["name"], name)
+            assert np.asarray(ours).dtype == ref.dtype, (c["name"], name)
+        n_ok += 1
+        n_sibling += int((c["out"][6] != np.arange(len(c["out"][6]))).any())
+    assert n_ok > 100 and n_sibling > 20           # the sibling-merge branch is exercised
+
+
+def test_simplify_skeleton_matches_reference(golden_tiny, golden_skeleton):
+    import numpy as np
+    for s in golden_skeleton["simplify"]:
+        model, scene = model_from_golden(golden_tiny, device="cpu")
+        joints, bones, new_joints, new_bones, prune_bones, merging_rules, rot_keep, res = model.simplify_skeleton(
+            s["times"], deg_threshold=s["deg_threshold"], five_percent_heuristic=s["five_percent"])
+        assert torch.equal(prune_bones.cpu(), s["prune_bones"])
+        assert np.array_equal(merging_rules, s["merging_rules"])
+        assert np.array_equal(new_joints, s["new_joints"]) and np.array_equal(new_bones, s["new_bones"])
+        assert torch.equal(rot_keep, s["rotations_to_keep"])
+        assert torch.equal(model.flat_merging_rules.long(), s["flat_merging_rules"])
+        assert torch.equal(model.sibling_merging_rules.long(), s["sibling_merging_rules"])
+        assert torch.equal(model.forward_warp.rot_mask, s["rot_mask"])
+        assert torch.equal(model.forward_warp.sibling_mask, s["sibling_mask"])
+        # merged skinning weights (the reference's (J,J,J) merging_mat bmm, lib/temporalpoints.py:405-414)
+        assert rel_err(model.get_weights(), s["last_weights"]) < 1e-5
+        # a checkpoint written after the simplification loads back (load_model path, lib/utils.py:519-523)
+        fresh, _ = model_from_golden(golden_tiny, device="cpu")
+        fresh.load_state_dict(model.state_dict(), strict=False)
+        assert torch.equal(fresh.flat_merging_rules.long(), s["flat_merging_rules"])
+        assert torch.equal(fresh.forward_warp.rot_mask, s["rot_mask"])
+
+
+def test_rotation_angle_of_relative_rotations():
+    from articulated_point_nerf_b200 import TemporalPoints
+    from articulated_point_nerf_b200.pointwarper import rodrigues
+    torch.manual_seed(0)
+    axis = torch.randn(64, 3)
+    ang = torch.linspace(0.0, 3.1, 64)
+    R, _ = rodrigues(torch.cat([axis, ang[:, None]], -1))
+    # the 1e-5 inside the axis normalisation (lib/pointwarper.py:127) makes R slightly non-orthogonal: loose bound
+    assert (TemporalPoints._rotation_angle(R) - ang).abs().max() < 1e-3

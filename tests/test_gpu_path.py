@@ -305,3 +305,63 @@ def test_render_viewpoints_whole_frame_equals_reference_chunk_loop(golden_tiny):
     with torch.no_grad():
         out = model(None, render_depth=True, render_kwargs=dict(rk, rays_o=ro, rays_d=rd, viewdirs=vd), rot_params=rp[1].cuda())
     assert abs(r2[1].reshape(-1, 3) - out["rgb_marched"].cpu().numpy()).max() < 1e-6
+
+
+def test_render_after_simplify_skeleton_matches_reference():
+    """--degree_threshold path (run.py:1302-1308): simplify_skeleton, then the render through the merged skinning
+    weights / frozen rotations, against the reference's own run (tests/golden/ref_skeleton.pt)."""
+    import os
+    from conftest import GOLDEN_DIR, oracle_from_golden, oracle_render_on_cloud
+    g = torch.load(os.path.join(GOLDEN_DIR, "ref_tiny.pt"), weights_only=False)
+    sk = torch.load(os.path.join(GOLDEN_DIR, "ref_skeleton.pt"), weights_only=False)
+    for s in sk["simplify"]:
+        model, scene = model_from_golden(g)
+        model.simplify_skeleton(s["times"].cuda(), deg_threshold=s["deg_threshold"], five_percent_heuristic=s["five_percent"])
+        assert torch.equal(model.flat_merging_rules.cpu().long(), s["flat_merging_rules"])
+        assert torch.equal(model.forward_warp.rot_mask.cpu(), s["rot_mask"])
+        rk = _rk(scene, g)
+        with torch.no_grad():
+            warped = model.warp(s["t"].cuda())
+            out = model(s["t"].cuda(), render_depth=True, render_kwargs=rk, render_weights=True, warped=warped,
+                        poses=scene.poses[0][None].cuda(), Ks=scene.Ks[0][None].cuda(), get_skeleton=True)
+        # the warp (merged weights, frozen rotations) against the reference's run
+        for k in ["t_hat_pcd", "joints"]:
+            assert rel_err(out[k], s["out"][k]) < RTOL, (s["deg_threshold"], k)
+        assert rel_err(model._last_weights, s["last_weights"]) < 1e-5
+        # downstream of the warp: the kernel merges the weight columns in a different order than the reference's
+        # (J,J,J) bmm, so the cloud differs in the last bits and the bbox-face samples flip (conftest.model_from_golden):
+        # exact comparison against the oracle on the kernel's own cloud, loose one against the reference's images
+        orc, cfg = oracle_from_golden(g)
+        with torch.no_grad():
+            ref = oracle_render_on_cloud(orc, cfg, g, warped["xyz"].cpu(), warped["ginv"].cpu().view(-1, 3, 3))
+        assert model.last_counts["M"] == ref["M"]
+        for k in ["rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "alphainv_last_direct"]:
+            assert rel_err(out[k], ref[k]) < RTOL, (s["deg_threshold"], k)
+            assert (out[k].cpu() - s["out"][k]).abs().mean() < 2e-3 * s["out"][k].abs().max(), (s["deg_threshold"], k)
+
+
+def test_batch_chamfer_loss_matches_reference():
+    """lib/temporalpoints.py:765-795 through apn_nn1_batched (ties on the integer pixel grid -> lowest index)."""
+    import os
+    from conftest import GOLDEN_DIR
+    g = torch.load(os.path.join(GOLDEN_DIR, "ref_tiny.pt"), weights_only=False)
+    sk = torch.load(os.path.join(GOLDEN_DIR, "ref_skeleton.pt"), weights_only=False)
+    model, _ = model_from_golden(g)
+    for c in sk["batch_chamfer"]:
+        p1 = c["pcd1"].cuda().requires_grad_(True)
+        loss = model.get_batch_chamfer_loss(p1, c["pcd2"].cuda())
+        loss.backward()
+        assert rel_err(loss, c["loss"]) < 1e-5
+        assert rel_err(p1.grad, c["grad1"]) < 1e-5
+        # the indices themselves against a brute force with the (d2, index) rule
+        from articulated_point_nerf_b200 import ops
+        a, b = c["pcd1"].cuda(), c["pcd2"].cuda()
+        diff = a[:, :, None, :] - b[:, None, :, :]
+        d2 = (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1])
+        if a.shape[-1] == 3:
+            d2 = d2 + diff[..., 2] * diff[..., 2]
+        key = (d2.contiguous().view(torch.int32).long() << 32) | torch.arange(b.shape[1], device="cuda")
+        assert torch.equal(ops.nn1_batched(a, b), key.min(-1).values & 0xFFFFFFFF)
+    with pytest.raises(Exception):
+        from articulated_point_nerf_b200 import ops
+        ops.nn1_batched(torch.rand(1, 4, 4).cuda(), torch.rand(1, 4, 4).cuda())
