@@ -128,71 +128,138 @@ __device__ __forceinline__ void comp_bwd_step(CompGrad& G, float a, float T, flo
   }
 }
 
-__global__ void __launch_bounds__(128)
-composite_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ rgb, const int* __restrict__ step_id,
-                     const int* __restrict__ ray_start, int R, float thres, float bg, const float* __restrict__ T_save,
-                     const int* __restrict__ n_used, const float* __restrict__ alphainv_last,
-                     const float* __restrict__ d_rgb_marched, const float* __restrict__ d_alphainv_last,
-                     const float* __restrict__ d_depth, float* __restrict__ d_alpha, float* __restrict__ d_rgb) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R) return;
-  const int s = ray_start[r], e = ray_start[r + 1];
-  const int stop = s + n_used[r];
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward, staged through shared memory by the TMA.  A warp owns 32 consecutive rays, i.e. ONE contiguous span of the
+// sample arrays.  The span (CS_CHUNK samples at a time, last chunk first; longer spans take several passes) is brought
+// into shared memory by 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx, issued by one elected lane; the warp
+// waits once on its mbarrier), every lane then walks its own segment backwards out of shared memory (the arithmetic and
+// order of comp_bwd_step: bit-identical to a per-ray walk over global memory), leaves d_alpha / d_rgb in place of
+// alpha / rgb, and the span goes back to global memory with coalesced 16-byte stores.  Global traffic is one streaming
+// pass instead of 32 scattered sectors per warp instruction (the backward touches 10 arrays-worth of 16-byte accesses
+// per four samples; a per-ray walk was bound by the L1 tag stage at 37 % of the HBM peak, this one reaches 57 %).
+// The forward keeps the per-ray walk: it stops loading at the early stop (92 % of the hit rays on the repose scene).
+// ---------------------------------------------------------------------------------------------------------------------
+#include "tc05.cuh"
+#define CS_CHUNK 512
+#define CS_WARPS 4
+
+// lane 0: bulk copy of the 16-byte groups of [base, base+n) that lie inside the allocation; returns the element count
+// covered (multiple of 4).  `base` is a multiple of 4 elements.
+__device__ __forceinline__ int cs_bulk_count(long long base, int n, long long limit) {
+  const long long full = min((long long)((n + 3) & ~3), (limit - base) & ~3LL);
+  return (int)max(full, 0LL);
+}
+// the (at most 3) elements of [base, base+n) beyond the bulk part, guarded against the end of the data
+__device__ __forceinline__ void cs_load_tail(float* __restrict__ dst, const float* __restrict__ src, long long base, int n,
+                                             int n_bulk, long long limit, int lane) {
+  const int k = n_bulk + lane;
+  if (k < ((n + 3) & ~3)) dst[k] = (base + k < limit) ? __ldg(src + base + k) : 0.f;
+}
+// coalesced copy shared -> global of the elements of [base, base + n) that lie inside [lo, hi)
+__device__ __forceinline__ void cs_store(float* __restrict__ dst, const float* __restrict__ src, long long base, int n,
+                                         long long lo, long long hi, int lane) {
+  const int groups = (n + 3) >> 2;
+  for (int g = lane; g < groups; g += 32) {
+    const long long i = base + 4 * g;
+    if (i >= lo && i + 4 <= hi) {
+      *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + 4 * g);
+    } else {
+      for (int c = 0; c < 4; ++c)
+        if (i + c >= lo && i + c < hi) dst[i + c] = src[4 * g + c];
+    }
+  }
+}
+
+#define CS_BWD_FLOATS (6 * CS_CHUNK)     // alpha/d_alpha, T, rgb/d_rgb, step
+
+__global__ void __launch_bounds__(32 * CS_WARPS)
+composite_bwd_staged_kernel(const float* __restrict__ alpha, const float* __restrict__ rgb, const int* __restrict__ step_id,
+                            const int* __restrict__ ray_start, int R, float thres, float bg, const float* __restrict__ T_save,
+                            const int* __restrict__ n_used, const float* __restrict__ alphainv_last,
+                            const float* __restrict__ d_rgb_marched, const float* __restrict__ d_alphainv_last,
+                            const float* __restrict__ d_depth, float* __restrict__ d_alpha, float* __restrict__ d_rgb) {
+  extern __shared__ __align__(128) float cs_smem[];
+  __shared__ uint64_t bars[CS_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = (blockIdx.x * CS_WARPS + warp) * 32;
+  if (r0 >= R) return;
+  const int S = ray_start[r0], E = ray_start[min(r0 + 32, R)];
+  if (S == E) return;
+  float* sA = cs_smem + warp * CS_BWD_FLOATS;      // alpha in, d_alpha out (in place)
+  float* sT = sA + CS_CHUNK;                       // saved transmittance
+  float* sC = sT + CS_CHUNK;                       // rgb in, d_rgb out (in place)
+  float* sS = sC + 3 * CS_CHUNK;                   // step ids (int bits)
+  uint64_t* bar = &bars[warp];
+  const int r = r0 + lane;
+  const bool valid = r < R;
+  const int s = valid ? ray_start[r] : E, e = valid ? ray_start[r + 1] : E;
+  const int stop = valid ? s + n_used[r] : E;
+  const long long M = ray_start[R];
   CompGrad G;
-  G.gr = d_rgb_marched ? d_rgb_marched[3 * (size_t)r] : 0.f;
-  G.gg = d_rgb_marched ? d_rgb_marched[3 * (size_t)r + 1] : 0.f;
-  G.gb = d_rgb_marched ? d_rgb_marched[3 * (size_t)r + 2] : 0.f;
-  G.gd = d_depth ? d_depth[r] : 0.f;
-  float gl = d_alphainv_last ? d_alphainv_last[r] : 0.f;
+  G.gr = (valid && d_rgb_marched) ? d_rgb_marched[3 * (size_t)r] : 0.f;
+  G.gg = (valid && d_rgb_marched) ? d_rgb_marched[3 * (size_t)r + 1] : 0.f;
+  G.gb = (valid && d_rgb_marched) ? d_rgb_marched[3 * (size_t)r + 2] : 0.f;
+  G.gd = (valid && d_depth) ? d_depth[r] : 0.f;
+  float gl = (valid && d_alphainv_last) ? d_alphainv_last[r] : 0.f;
   gl += bg * (G.gr + G.gg + G.gb);
+  G.back = valid ? __fmul_rn(gl, alphainv_last[r]) : 0.f;
   const bool has_step = step_id != nullptr;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  {                                   // never visited: no gradient
-    int i = stop;
-    for (; i < e && (i & 3); ++i) {
-      d_alpha[i] = 0.f;
-      d_rgb[3 * (size_t)i] = 0.f; d_rgb[3 * (size_t)i + 1] = 0.f; d_rgb[3 * (size_t)i + 2] = 0.f;
-    }
-    for (; i + 4 <= e; i += 4) {
-      *reinterpret_cast<float4*>(d_alpha + i) = z4;
-      float4* o = reinterpret_cast<float4*>(d_rgb + 3 * (size_t)i);
-      o[0] = z4; o[1] = z4; o[2] = z4;
-    }
-    for (; i < e; ++i) {
-      d_alpha[i] = 0.f;
-      d_rgb[3 * (size_t)i] = 0.f; d_rgb[3 * (size_t)i + 1] = 0.f; d_rgb[3 * (size_t)i + 2] = 0.f;
-    }
+  if (lane == 0) {
+    tc05::mbar_init(bar, 1);
+    tc05::fence_barrier_init();
   }
-  G.back = __fmul_rn(gl, alphainv_last[r]);
-  auto scalar = [&](int i) {
-    float da, dr, dg, db;
-    comp_bwd_step(G, alpha[i], T_save[i], rgb[3 * (size_t)i], rgb[3 * (size_t)i + 1], rgb[3 * (size_t)i + 2],
-                  has_step ? (float)step_id[i] : 0.f, has_step, thres, da, dr, dg, db);
-    d_alpha[i] = da;
-    d_rgb[3 * (size_t)i] = dr; d_rgb[3 * (size_t)i + 1] = dg; d_rgb[3 * (size_t)i + 2] = db;
-  };
-  int i = stop - 1;
-  for (; i >= s && (i & 3) != 3; --i) scalar(i);                    // scalar head (top of the range)
-  for (; i - 3 >= s; i -= 4) {                                       // 16-byte body: samples i-3 .. i, consumed i first
-    const int j = i - 3;
-    const float4 a4 = __ldg(reinterpret_cast<const float4*>(alpha + j));
-    const float4 t4 = __ldg(reinterpret_cast<const float4*>(T_save + j));
-    const float4 c0 = __ldg(reinterpret_cast<const float4*>(rgb + 3 * (size_t)j));
-    const float4 c1 = __ldg(reinterpret_cast<const float4*>(rgb + 3 * (size_t)j) + 1);
-    const float4 c2 = __ldg(reinterpret_cast<const float4*>(rgb + 3 * (size_t)j) + 2);
-    int4 s4 = make_int4(0, 0, 0, 0);
-    if (has_step) s4 = __ldg(reinterpret_cast<const int4*>(step_id + j));
-    float4 da;
-    float4 o0, o1, o2;
-    comp_bwd_step(G, a4.w, t4.w, c2.y, c2.z, c2.w, (float)s4.w, has_step, thres, da.w, o2.y, o2.z, o2.w);
-    comp_bwd_step(G, a4.z, t4.z, c1.z, c1.w, c2.x, (float)s4.z, has_step, thres, da.z, o1.z, o1.w, o2.x);
-    comp_bwd_step(G, a4.y, t4.y, c0.w, c1.x, c1.y, (float)s4.y, has_step, thres, da.y, o0.w, o1.x, o1.y);
-    comp_bwd_step(G, a4.x, t4.x, c0.x, c0.y, c0.z, (float)s4.x, has_step, thres, da.x, o0.x, o0.y, o0.z);
-    *reinterpret_cast<float4*>(d_alpha + j) = da;
-    float4* o = reinterpret_cast<float4*>(d_rgb + 3 * (size_t)j);
-    o[0] = o0; o[1] = o1; o[2] = o2;
+  __syncwarp();
+  uint32_t phase = 0;
+  const int b0 = S & ~3;
+  const int n_chunks = (E - b0 + CS_CHUNK - 1) / CS_CHUNK;
+  for (int c = n_chunks - 1; c >= 0; --c) {
+    const int b = b0 + c * CS_CHUNK;
+    const int n = min(CS_CHUNK, E - b);
+    const int nb = cs_bulk_count(b, n, M);
+    if (lane == 0) {
+      tc05::fence_proxy_async_smem();
+      if (nb > 0) {
+        tc05::mbar_arrive_expect_tx(bar, (uint32_t)nb * (has_step ? 24u : 20u));
+        tc05::bulk_g2s(sA, alpha + b, (uint32_t)nb * 4u, bar);
+        tc05::bulk_g2s(sT, T_save + b, (uint32_t)nb * 4u, bar);
+        tc05::bulk_g2s(sC, rgb + 3LL * b, (uint32_t)nb * 12u, bar);
+        if (has_step) tc05::bulk_g2s(sS, step_id + b, (uint32_t)nb * 4u, bar);
+      }
+    }
+    cs_load_tail(sA, alpha, b, n, nb, M, lane);
+    cs_load_tail(sT, T_save, b, n, nb, M, lane);
+    if (has_step) cs_load_tail(sS, reinterpret_cast<const float*>(step_id), b, n, nb, M, lane);
+    for (int k = 3 * nb + lane; k < 3 * n; k += 32) sC[k] = (3LL * b + k < 3 * M) ? __ldg(rgb + 3LL * b + k) : 0.f;
+    if (nb > 0) {
+      tc05::mbar_wait(bar, phase);
+      phase ^= 1;
+    }
+    __syncwarp();
+    const int lo = max(s, b), hi = min(e, b + n);
+    for (int i = hi - 1; i >= lo; --i) {
+      const int k = i - b;
+      float da = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
+      if (i < stop)
+        comp_bwd_step(G, sA[k], sT[k], sC[3 * k], sC[3 * k + 1], sC[3 * k + 2], has_step ? (float)__float_as_int(sS[k]) : 0.f,
+                      has_step, thres, da, dr, dg, db);
+      sA[k] = da;
+      sC[3 * k] = dr; sC[3 * k + 1] = dg; sC[3 * k + 2] = db;
+    }
+    __syncwarp();
+    cs_store(d_alpha, sA, b, n, S, E, lane);
+    cs_store(d_rgb, sC, 3LL * b, 3 * n, 3LL * S, 3LL * E, lane);
+    __syncwarp();
   }
-  for (; i >= s; --i) scalar(i);                                     // scalar tail (bottom of the range)
+}
+
+static int composite_staged_attrs() {
+  static bool done = false;
+  if (!done) {
+    APN_CUDA(cudaFuncSetAttribute(composite_bwd_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(CS_WARPS * CS_BWD_FLOATS * sizeof(float))));
+    done = true;
+  }
+  return 0;
 }
 
 extern "C" int apn_composite_fwd(const float* alpha, const float* rgb, const int32_t* step_id, const float* extra,
@@ -217,9 +284,10 @@ extern "C" int apn_composite_bwd(const float* alpha, const float* rgb, const int
   cudaStream_t stream = (cudaStream_t)stream_;
   if (R <= 0) return 0;
   APN_CHECK_ARG(ray_start && n_used && alphainv_last, "null pointer");   // per-sample arrays are NULL when M == 0
-  composite_bwd_kernel<<<apn_div_up(R, 128), 128, 0, stream>>>(alpha, rgb, step_id, ray_start, R, thres, bg, T_save, n_used,
-                                                              alphainv_last, d_rgb_marched, d_alphainv_last, d_depth, d_alpha,
-                                                              d_rgb);
+  if (composite_staged_attrs()) return -2;
+  composite_bwd_staged_kernel<<<apn_div_up(R, 32 * CS_WARPS), 32 * CS_WARPS, CS_WARPS * CS_BWD_FLOATS * sizeof(float), stream>>>(
+      alpha, rgb, step_id, ray_start, R, thres, bg, T_save, n_used, alphainv_last, d_rgb_marched, d_alphainv_last, d_depth,
+      d_alpha, d_rgb);
   APN_LAUNCH_CHECK();
   return 0;
 }

@@ -75,10 +75,14 @@ __device__ __forceinline__ void softmax_row(float* row, int J, float theta, floa
 }
 
 // Forward: warp-centric, no block-wide barriers.  A warp owns 32 consecutive points per step:
-//   phase 1  lanes run over the bones of one point at a time: coalesced row read straight from global memory,
-//            softmax with two warp reductions, the weights go to the warp's shared-memory tile (odd row stride) and
-//            — when no merge rules apply — straight back to global memory, again coalesced;
-//   phase 2  lane = point: merge rules, blend of the bone 3x4s (broadcast reads), transform, closed-form inverse, bbox.
+//   phase 1  lanes run over the bones of one point at a time: coalesced row reads straight from global memory (four rows
+//            in flight, one batch ahead of their use) into the warp's shared-memory tile (odd row stride);
+//   phase 2  lane = point: softmax in three passes over its row (max; exp + sum; normalise), the last one fused with
+//            the blend of the bone 3x4s (shared-memory broadcasts, packed fp32x2 FMAs) unless merge rules apply;
+//            transform, closed-form inverse, bbox;
+//   phase 3  the (merged) weights go back to global memory row by row, coalesced.
+// The load/store pipe, not HBM, bounds this kernel (ncu: lsu 65 %, issue 65 % active, DRAM 33 % before the passes were
+// fused), so the passes keep shared-memory traffic to one load (+ one store where the value is needed later) per element.
 #define LBS_WARPS 4
 #define LBS_MAX_K (LBS_MAX_J / 32)
 
@@ -149,9 +153,60 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
     }
     __syncwarp();
     // ---------------------------------------------------------------- phase 2: lane = point
-    if (lane < n_valid) {
+    const bool active = lane < n_valid;   // every lane runs the algebra (keeps the bone loop warp-uniform); only stores are guarded
+    {
       float* row = sW + lane * JP;
-      if (theta_weight) softmax_row(row, J, theta, inv_theta);   // NULL: the caller passes final weights
+      float2 G2[6];                       // G[0..11] as six fp32x2 pairs: one FFMA2 updates two entries, same roundings
+#pragma unroll
+      for (int c = 0; c < 6; ++c) G2[c] = make_float2(0.f, 0.f);
+#define LBS_BLEND(w, j)                                                                                               \
+  do {                                                                                                                \
+    const float4* T = reinterpret_cast<const float4*>(sT + (j) * 12);                                                 \
+    const float4 t0 = T[0], t1 = T[1], t2 = T[2];                                                                     \
+    const float2 ww = make_float2(w, w);                                                                              \
+    G2[0] = __ffma2_rn(ww, make_float2(t0.x, t0.y), G2[0]); G2[1] = __ffma2_rn(ww, make_float2(t0.z, t0.w), G2[1]);   \
+    G2[2] = __ffma2_rn(ww, make_float2(t1.x, t1.y), G2[2]); G2[3] = __ffma2_rn(ww, make_float2(t1.z, t1.w), G2[3]);   \
+    G2[4] = __ffma2_rn(ww, make_float2(t2.x, t2.y), G2[4]); G2[5] = __ffma2_rn(ww, make_float2(t2.z, t2.w), G2[5]);   \
+  } while (0)
+      if (theta_weight) {
+        // x / theta as q = x * (1/theta) plus one residual correction (see softmax_row)
+        float mx = -INFINITY;
+#pragma unroll 4
+        for (int j = 0; j < J; ++j) {
+          const float x = row[j];
+          const float q = x * inv_theta;
+          mx = fmaxf(mx, fmaf(fmaf(-q, theta, x), inv_theta, q));
+        }
+        float sum = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < J; ++j) {
+          const float x = row[j];
+          const float q = x * inv_theta;
+          const float e = expf(fmaf(fmaf(-q, theta, x), inv_theta, q) - mx);
+          row[j] = e;
+          sum += e;
+        }
+        const float inv = 1.0f / sum;
+        if (!rules) {
+          if (w_out) {
+#pragma unroll 4
+            for (int j = 0; j < J; ++j) {
+              const float w = row[j] * inv;
+              row[j] = w;
+              LBS_BLEND(w, j);
+            }
+          } else {
+#pragma unroll 4
+            for (int j = 0; j < J; ++j) {
+              const float w = row[j] * inv;
+              LBS_BLEND(w, j);
+            }
+          }
+        } else {
+#pragma unroll 4
+          for (int j = 0; j < J; ++j) row[j] *= inv;
+        }
+      }
       if (rules) {
         for (int j = 0; j < J; ++j) {
           const int t = sR[j];
@@ -161,17 +216,16 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
           }
         }
       }
-      float G[12];
-#pragma unroll
-      for (int c = 0; c < 12; ++c) G[c] = 0.f;
-      for (int j = 0; j < J; ++j) {
-        const float w = row[j];
-        const float4* T = reinterpret_cast<const float4*>(sT + j * 12);
-        const float4 t0 = T[0], t1 = T[1], t2 = T[2];
-        G[0] = fmaf(w, t0.x, G[0]); G[1] = fmaf(w, t0.y, G[1]); G[2] = fmaf(w, t0.z, G[2]); G[3] = fmaf(w, t0.w, G[3]);
-        G[4] = fmaf(w, t1.x, G[4]); G[5] = fmaf(w, t1.y, G[5]); G[6] = fmaf(w, t1.z, G[6]); G[7] = fmaf(w, t1.w, G[7]);
-        G[8] = fmaf(w, t2.x, G[8]); G[9] = fmaf(w, t2.y, G[9]); G[10] = fmaf(w, t2.z, G[10]); G[11] = fmaf(w, t2.w, G[11]);
+      if (rules || !theta_weight) {
+#pragma unroll 4
+        for (int j = 0; j < J; ++j) {
+          const float w = row[j];
+          LBS_BLEND(w, j);
+        }
       }
+#undef LBS_BLEND
+      const float G[12] = {G2[0].x, G2[0].y, G2[1].x, G2[1].y, G2[2].x, G2[2].y, G2[3].x, G2[3].y, G2[4].x, G2[4].y, G2[5].x, G2[5].y};
+      if (active) {
       const size_t n = (size_t)base + lane;
       const float x = xyz[3 * n], y = xyz[3 * n + 1], z = xyz[3 * n + 2];
       const float ox = G[0] * x + G[1] * y + G[2] * z + G[3] + gx;
@@ -193,6 +247,7 @@ lbs_fwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
         go[1] = make_float4(G[4], G[5], G[6], G[7]);
         go[2] = make_float4(G[8], G[9], G[10], G[11]);
         go[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+      }
       }
     }
     __syncwarp();
