@@ -336,17 +336,29 @@ static int colsum(cudaStream_t st, const float* A, int lda, int rows, int N, flo
 // RGBNet backward (lib/tineuvox.py:77-88): d_rgb -> weight gradients of the three Linear layers and d_h (M,128) of
 // the rgb branch; shared by the fp32 and tensor-core backward paths
 int agg_rgbnet_bwd_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* sv,
-                          const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h) {
+                          const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h, ApnSide* side) {
   const int M = in->M;
   const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 8);
   const int KV = AGG_C + APN_PE_VIEW;   // 155
+  // The chain d_rgb -> d_v0 -> d_fv -> d_h is serial; the two weight gradients (+ bias column sums) only READ d_v0 /
+  // d_fv.  On small batches every one of these GEMMs fills less than half the GPU, so with side streams they run beside
+  // the chain instead of in it.
+  cudaStream_t s0 = side ? side->s[0] : st, s1 = side ? side->s[1] : st;
   agg_rgb_out_bwd_kernel<<<wblocks, 256, 0, st>>>(g->d_rgb, sv->rgb, sv->v0, w->rgb_v2_w, M, d_v0, g->d_rgb_v2_w, g->d_rgb_v2_b);
   APN_LAUNCH_CHECK();
-  APN_CHECK_ARG(gemm_wgrad(st, d_v0, AGG_V0, sv->fv, AGG_FV_LD, g->d_rgb_v0_w, KV, M, AGG_V0, KV) == 0, "wgrad v0");
-  APN_CHECK_ARG(colsum(st, d_v0, AGG_V0, M, AGG_V0, g->d_rgb_v0_b) == 0, "colsum v0");
+  if (side) {
+    APN_CUDA(cudaEventRecord(side->fork[0], st));
+    APN_CUDA(cudaStreamWaitEvent(s0, side->fork[0], 0));
+  }
+  APN_CHECK_ARG(gemm_wgrad(s0, d_v0, AGG_V0, sv->fv, AGG_FV_LD, g->d_rgb_v0_w, KV, M, AGG_V0, KV) == 0, "wgrad v0");
+  APN_CHECK_ARG(colsum(s0, d_v0, AGG_V0, M, AGG_V0, g->d_rgb_v0_b) == 0, "colsum v0");
   APN_CHECK_ARG(gemm_dgrad(st, d_v0, AGG_V0, w->rgb_v0_w, KV, d_fv, AGG_FV_LD, M, KV, AGG_V0, nullptr, 0, 1.f) == 0, "dgrad v0");
-  APN_CHECK_ARG(gemm_wgrad(st, d_fv, AGG_FV_LD, sv->h, AGG_C, g->d_rgb_feat_w, AGG_C, M, AGG_C, AGG_C) == 0, "wgrad rgb feat");
-  APN_CHECK_ARG(colsum(st, d_fv, AGG_FV_LD, M, AGG_C, g->d_rgb_feat_b) == 0, "colsum rgb feat");
+  if (side) {
+    APN_CUDA(cudaEventRecord(side->fork[1], st));
+    APN_CUDA(cudaStreamWaitEvent(s1, side->fork[1], 0));
+  }
+  APN_CHECK_ARG(gemm_wgrad(s1, d_fv, AGG_FV_LD, sv->h, AGG_C, g->d_rgb_feat_w, AGG_C, M, AGG_C, AGG_C) == 0, "wgrad rgb feat");
+  APN_CHECK_ARG(colsum(s1, d_fv, AGG_FV_LD, M, AGG_C, g->d_rgb_feat_b) == 0, "colsum rgb feat");
   APN_CHECK_ARG(gemm_dgrad(st, d_fv, AGG_FV_LD, w->rgb_feat_w, AGG_C, d_h, AGG_C, M, AGG_C, AGG_C, nullptr, 0, 1.f) == 0, "dgrad rgb feat");
   return 0;
 }

@@ -632,7 +632,11 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
                 "scratch too small or not 1 KiB aligned");
   const TcBwdScratch b = tc_bwd_layout((char*)scratch, M, N);
   // heads: RGBNet backward -> d_h, then densitynet / Raw2Alpha
-  if (agg_rgbnet_bwd_launch(st, in, w, sv, g, b.d_v0, b.d_fv, b.d_h)) return -1;
+  // small batches: the weight-gradient GEMMs of the heads and of the point table run on the library's side streams,
+  // beside the serial chain (each fills less than half the GPU); large batches fill it and stay on one stream
+  ApnSide* side = nullptr;
+  if (M <= 32768 && apn_side_streams(&side)) return -2;
+  if (agg_rgbnet_bwd_launch(st, in, w, sv, g, b.d_v0, b.d_fv, b.d_h, side)) return -1;
   const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 8);
   APN_CUDA(cudaMemsetAsync(b.d_ptable, 0, (size_t)N * APN_C * sizeof(float) + 1024, st));   // table + hmax
   tc_density_bwd_kernel<<<wblocks, 256, 0, st>>>(M, in->interval, sv->h, sv->exp_d, w->density_w, g->d_alpha, b.d_h,
@@ -658,6 +662,18 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
     tc_dgrad_kernel<<<grid, TC_THREADS, TcBwdSmem::TOTAL, st>>>(p);
     APN_LAUNCH_CHECK();
   }
+  cudaStream_t sw = st;
+  if (side) {                                   // the point-table GEMMs only need tc_dgrad's d_ptable
+    APN_CUDA(cudaEventRecord(side->fork[2], st));
+    APN_CUDA(cudaStreamWaitEvent(side->s[0], side->fork[2], 0));
+    sw = side->s[0];
+  }
+  // feature columns of layer 0 through the per-point table: d_feat = dP W0_feat, dW0_feat += dP^T feat
+  if (g->d_feat)
+    APN_CHECK_ARG(gemm_dgrad_accum(sw, b.d_ptable, APN_C, w->w[0] + APN_PE_POS, in->d_in, g->d_feat, APN_C, N, APN_C, APN_C) == 0,
+                  "dgrad point table");      // accumulates, like every other gradient of this entry point
+  APN_CHECK_ARG(gemm_wgrad(sw, b.d_ptable, APN_C, in->feat, APN_C, g->d_w[0] + APN_PE_POS, in->d_in, N, APN_C, APN_C) == 0,
+                "wgrad point table");
   {
     TcWgradParams p;
     p.tape = (const uint8_t*)tape;
@@ -673,11 +689,11 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
                                                                        g->d_b[3]);
     APN_LAUNCH_CHECK();
   }
-  // feature columns of layer 0 through the per-point table: d_feat = dP W0_feat, dW0_feat += dP^T feat
-  if (g->d_feat)
-    APN_CHECK_ARG(gemm_dgrad_accum(st, b.d_ptable, APN_C, w->w[0] + APN_PE_POS, in->d_in, g->d_feat, APN_C, N, APN_C, APN_C) == 0,
-                  "dgrad point table");      // accumulates, like every other gradient of this entry point
-  APN_CHECK_ARG(gemm_wgrad(st, b.d_ptable, APN_C, in->feat, APN_C, g->d_w[0] + APN_PE_POS, in->d_in, N, APN_C, APN_C) == 0,
-                "wgrad point table");
+  if (side) {                                   // join: everything this call launched is ordered before what follows on st
+    for (int i = 0; i < 2; ++i) {
+      APN_CUDA(cudaEventRecord(side->join[i], side->s[i]));
+      APN_CUDA(cudaStreamWaitEvent(st, side->join[i], 0));
+    }
+  }
   return 0;
 }

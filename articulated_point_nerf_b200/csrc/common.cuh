@@ -19,9 +19,16 @@ size_t heads_tc_weights_bytes();
 // exp_d / fv / v0: the tape of the fp32 heads backward (training), or NULL
 int agg_heads_tc_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const float* h, void* packed,
                         float* alpha, float* rgb, float* exp_d, float* fv, float* v0);
-// aggregate.cu: RGBNet backward: weight gradients + d_h (M,128) of the rgb branch
+// runtime.cu: library-owned side streams + events for fork/join inside one entry point
+struct ApnSide {
+  cudaStream_t s[2];
+  cudaEvent_t fork[3], join[2];
+};
+int apn_side_streams(ApnSide** out);
+// aggregate.cu: RGBNet backward: weight gradients + d_h (M,128) of the rgb branch.  With `side`, the weight-gradient
+// GEMMs run on the side streams (forked from `st`) and are NOT joined: the caller joins side->join[*] before it returns.
 int agg_rgbnet_bwd_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* sv,
-                          const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h);
+                          const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h, ApnSide* side = nullptr);
 
 #define APN_CHECK_ARG(cond, msg)                                   \
   do {                                                             \
