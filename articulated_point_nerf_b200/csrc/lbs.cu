@@ -509,6 +509,291 @@ lbs_bwd_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_
   for (int o = threadIdx.x; o < n_out + 4; o += blockDim.x) out[o] = sAcc[o];
 }
 
+// ---------------------------------------------------------------------------------------
+// backward on the tensor cores (no merge rules, J <= 80): the two contractions of the backward are small GEMMs,
+//   dm^T (J x 32) = T (J x 12) * dG^T (12 x 32 points)        "how much does the loss want bone j's weight at point p"
+//   dT   (J x 12) += w^T (J x 32 points) * dG (32 x 12)       accumulated over all points
+// and run as mma.sync m16n8k8 TF32 with the 3xTF32 split (x = hi + lo; lo*hi + hi*lo + hi*hi, fp32 accumulate:
+// fp32-class results).  A warp owns 32 points per step and holds the (bones x points) tile of raw / softmax weights
+// directly in the MMA accumulator layout (bone rows g, g+8 of each 16-row tile; points 2q, 2q+1 of each 8-point tile), so
+//   * the raw rows are read from and d_raw written to global memory in that layout (8 consecutive bones per quad: whole
+//     32-byte sectors) — no shared-memory tile, no transposition;
+//   * the softmax over bones is register arithmetic + three xor-shuffles over the lanes that share a point;
+//   * the same registers are the A fragments of the second GEMM (its contraction index — the point — may be permuted
+//     freely as long as dG's fragment uses the same permutation: k-slot q <-> point 2q, slot q+4 <-> point 2q+1).
+// Only dG (32 x 12 per warp) goes through shared memory, to change from lane = point (where it is computed from d_xyz,
+// d_ginv and the inverse frame) to fragment layout.  ~70 warp instructions per point instead of ~700.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = tf32_hi(x);
+  lo = tf32_hi(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// max / sum over the 8 lanes that share q = lane & 3 (all bones of one point)
+__device__ __forceinline__ float quad_col_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+}
+__device__ __forceinline__ float quad_col_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v + __shfl_xor_sync(0xffffffffu, v, 16);
+}
+
+#define LBS_MMA_WARPS 4
+#define LBS_DG_LD 13                     // row stride of the per-warp dG tile (odd: conflict-free lane = point stores)
+
+template <int MT>                        // MT = ceil(J / 16) bone tiles, J <= 16 * MT
+__global__ void __launch_bounds__(32 * LBS_MMA_WARPS)
+lbs_bwd_mma_kernel(const float* __restrict__ raw_w, const float* __restrict__ theta_weight, float eps,
+                   const float* __restrict__ bone_T, const float* __restrict__ xyz, int N, int J,
+                   const float* __restrict__ ginv, const float* __restrict__ d_xyz, const float* __restrict__ d_ginv,
+                   const float* __restrict__ d_w, float* __restrict__ d_raw, float* __restrict__ partial) {
+  extern __shared__ float smem[];
+  const int n_out = J * 12;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  // [T A-fragments hi | lo : MT*2*4*32 each] [block accumulators n_out + 4] [per warp dG 32 x LBS_DG_LD]
+  uint32_t* sTA_hi = reinterpret_cast<uint32_t*>(smem);
+  uint32_t* sTA_lo = sTA_hi + MT * 2 * 4 * 32;
+  float* sAcc = reinterpret_cast<float*>(sTA_lo + MT * 2 * 4 * 32);
+  float* sDG = sAcc + n_out + 4 + warp * 32 * LBS_DG_LD;
+  for (int i = threadIdx.x; i < MT * 2 * 4 * 32; i += blockDim.x) {     // [mt][kt][lane][reg]: one 16-byte load per fragment
+    const int reg = i & 3, l = (i >> 2) & 31, kt = (i >> 7) & 1, mt = i >> 8;
+    const int bone = 16 * mt + (l >> 2) + 8 * (reg & 1), c = 8 * kt + (l & 3) + 4 * (reg >> 1);
+    const float v = (bone < J && c < 12) ? bone_T[bone * 16 + c] : 0.f;
+    uint32_t hi, lo;
+    tf32_split(v, hi, lo);
+    sTA_hi[i] = hi;
+    sTA_lo[i] = lo;
+  }
+  for (int i = threadIdx.x; i < n_out + 4; i += blockDim.x) sAcc[i] = 0.f;
+  __syncthreads();
+  const float theta = fmaxf(eps, theta_weight[0]);
+  const float inv_theta = 1.0f / theta;
+  double acc_theta = 0.0;
+  float acc_g[3] = {0.f, 0.f, 0.f};
+  float accT[MT][2][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) accT[mt][ct][r] = 0.f;
+  const int n_chunks = (N + 31) / 32;
+  const int n_warps = gridDim.x * LBS_MMA_WARPS;
+  // raw values of one 8-point tile in accumulator layout: element r of bone tile mt = bone 16 mt + g + 8 (r >> 1),
+  // point base + 8 nt + 2 q + (r & 1); bones beyond J read as -inf (weight 0), points beyond N as 0 (their dG is 0)
+  // only the last bone tile can reach beyond J; a point is valid iff its index is below N
+#define LBS_BONE_OK(mt, r) ((mt) < MT - 1 || 16 * (mt) + g + 8 * ((r) >> 1) < J)
+  auto load_raw = [&](int base, int nt, float (&v)[MT][4]) {
+    const int p0 = base + 8 * nt + 2 * q;
+    const bool ok0 = p0 < N, ok1 = p0 + 1 < N;
+    const float* rp = raw_w + (size_t)p0 * J + g;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const bool bone_ok = LBS_BONE_OK(mt, r);
+        v[mt][r] = (bone_ok && ((r & 1) ? ok1 : ok0)) ? __ldg(rp + (r & 1) * J + 16 * mt + 8 * (r >> 1)) : (bone_ok ? 0.f : -INFINITY);
+      }
+  };
+  for (int chunk = blockIdx.x * LBS_MMA_WARPS + warp; chunk < n_chunks; chunk += n_warps) {
+    const int base = chunk * 32;
+    float nxt[MT][4];
+    load_raw(base, 0, nxt);               // issued first: longest latency
+    // ------------------------------------------------ lane = point: dG from d_xyz, d_ginv and the inverse frame
+    {
+      const int n = base + lane;
+      float g12[12];
+#pragma unroll
+      for (int c = 0; c < 12; ++c) g12[c] = 0.f;
+      if (n < N) {
+        float B[9], dB[9], dA[9], t1[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          B[c] = ginv[9 * (size_t)n + c];
+          dB[c] = d_ginv ? d_ginv[9 * (size_t)n + c] : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) t1[r * 3 + c] = B[0 * 3 + r] * dB[0 * 3 + c] + B[1 * 3 + r] * dB[1 * 3 + c] + B[2 * 3 + r] * dB[2 * 3 + c];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) dA[r * 3 + c] = -(t1[r * 3 + 0] * B[c * 3 + 0] + t1[r * 3 + 1] * B[c * 3 + 1] + t1[r * 3 + 2] * B[c * 3 + 2]);
+        const float x = xyz[3 * (size_t)n], y = xyz[3 * (size_t)n + 1], z = xyz[3 * (size_t)n + 2];
+        const float gx = d_xyz ? d_xyz[3 * (size_t)n] : 0.f, gy = d_xyz ? d_xyz[3 * (size_t)n + 1] : 0.f,
+                    gz = d_xyz ? d_xyz[3 * (size_t)n + 2] : 0.f;
+        acc_g[0] += gx; acc_g[1] += gy; acc_g[2] += gz;
+        g12[0] = dA[0] + gx * x; g12[1] = dA[1] + gx * y; g12[2] = dA[2] + gx * z; g12[3] = gx;
+        g12[4] = dA[3] + gy * x; g12[5] = dA[4] + gy * y; g12[6] = dA[5] + gy * z; g12[7] = gy;
+        g12[8] = dA[6] + gz * x; g12[9] = dA[7] + gz * y; g12[10] = dA[8] + gz * z; g12[11] = gz;
+      }
+      __syncwarp();                       // the previous step's fragment reads are done
+#pragma unroll
+      for (int c = 0; c < 12; ++c) sDG[lane * LBS_DG_LD + c] = g12[c];
+      __syncwarp();
+    }
+    float th = 0.f;
+#pragma unroll 1
+    for (int nt = 0; nt < 4; ++nt) {      // 8 points at a time: everything below lives in registers
+      float rawv[MT][4], w[MT][4];
+      const int p0 = base + 8 * nt + 2 * q;
+      const bool ok0 = p0 < N, ok1 = p0 + 1 < N;
+      const size_t at0 = (size_t)p0 * J + g;           // element (mt, r) of this lane: at0 + (r & 1) J + 16 mt + 8 (r >> 1)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rawv[mt][r] = nxt[mt][r];
+      if (nt < 3) load_raw(base, nt + 1, nxt);
+      // ---- softmax over bones for this lane's two points (h = 0, 1), shuffles over the lanes that share q
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = h + 2 * rr;
+            const float x = rawv[mt][r] * inv_theta;      // -inf (bones beyond J) stays -inf
+            w[mt][r] = x;
+            mx = fmaxf(mx, x);
+          }
+        mx = quad_col_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = h + 2 * rr;
+            const float e = __expf(w[mt][r] - mx);         // ex2.approx: ~2 ulp, far inside the gradient tolerance
+            w[mt][r] = e;
+            sum += e;
+          }
+        const float inv = 1.0f / quad_col_sum(sum);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) w[mt][h + 2 * rr] *= inv;
+      }
+      // ---- dm^T = T dG^T for these 8 points:  B fragment b0 = dG[8 nt + g][8 kt + q], b1: column + 4
+      uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = 8 * kt + q + 4 * h;
+          const float v = c < 12 ? sDG[(8 * nt + g) * LBS_DG_LD + c] : 0.f;
+          tf32_split(v, bh[kt][h], bl[kt][h]);
+        }
+      float acc[MT][4];
+      float dot0 = 0.f, dot1 = 0.f;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[mt][r] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          const uint4 ah = *reinterpret_cast<const uint4*>(sTA_hi + ((mt * 2 + kt) * 32 + lane) * 4);
+          const uint4 al = *reinterpret_cast<const uint4*>(sTA_lo + ((mt * 2 + kt) * 32 + lane) * 4);
+          mma_tf32(acc[mt], al.x, al.y, al.z, al.w, bh[kt][0], bh[kt][1]);
+          mma_tf32(acc[mt], ah.x, ah.y, ah.z, ah.w, bl[kt][0], bl[kt][1]);
+          mma_tf32(acc[mt], ah.x, ah.y, ah.z, ah.w, bh[kt][0], bh[kt][1]);
+        }
+        if (d_w) {                        // gradient arriving through the weights output (weight TV / sparsity losses)
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (LBS_BONE_OK(mt, r) && ((r & 1) ? ok1 : ok0)) acc[mt][r] += __ldg(d_w + at0 + (r & 1) * J + 16 * mt + 8 * (r >> 1));
+        }
+        dot0 = fmaf(w[mt][0], acc[mt][0], dot0); dot0 = fmaf(w[mt][2], acc[mt][2], dot0);
+        dot1 = fmaf(w[mt][1], acc[mt][1], dot1); dot1 = fmaf(w[mt][3], acc[mt][3], dot1);
+      }
+      dot0 = quad_col_sum(dot0);
+      dot1 = quad_col_sum(dot1);
+      // ---- dz = w (dm - dot) -> d_raw, theta gradient
+      float* dp = d_raw + at0;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (LBS_BONE_OK(mt, r) && ((r & 1) ? ok1 : ok0)) {
+            const float dz = w[mt][r] * (acc[mt][r] - ((r & 1) ? dot1 : dot0));
+            th = fmaf(-dz, rawv[mt][r], th);
+            dp[(r & 1) * J + 16 * mt + 8 * (r >> 1)] = dz * inv_theta;
+          }
+      // ---- dT += w^T dG:  A = (w r0, r2, r1, r3), B: b0 = dG[8 nt + 2 q][8 ct + g], b1: next point
+      uint32_t gh[2][2], gl[2][2];
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = 8 * ct + g;
+          const float v = c < 12 ? sDG[(8 * nt + 2 * q + h) * LBS_DG_LD + c] : 0.f;
+          tf32_split(v, gh[ct][h], gl[ct][h]);
+        }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        uint32_t ah[4], al[4];
+        tf32_split(w[mt][0], ah[0], al[0]);
+        tf32_split(w[mt][2], ah[1], al[1]);
+        tf32_split(w[mt][1], ah[2], al[2]);
+        tf32_split(w[mt][3], ah[3], al[3]);
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct) {
+          mma_tf32(accT[mt][ct], al[0], al[1], al[2], al[3], gh[ct][0], gh[ct][1]);
+          mma_tf32(accT[mt][ct], ah[0], ah[1], ah[2], ah[3], gl[ct][0], gl[ct][1]);
+          mma_tf32(accT[mt][ct], ah[0], ah[1], ah[2], ah[3], gh[ct][0], gh[ct][1]);
+        }
+      }
+    }
+    acc_theta += (double)th;
+  }
+  // block reduction (shared-memory atomics), then one partial slab per block as in lbs_bwd_kernel
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int bone = 16 * mt + g + 8 * (r >> 1), c = 8 * ct + 2 * q + (r & 1);
+        if (bone < J && c < 12) atomicAdd(&sAcc[bone * 12 + c], accT[mt][ct][r]);
+      }
+  {
+    double t = acc_theta;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    const float thf = (float)(t / ((double)theta * (double)theta));
+    const float a0 = warp_sum(acc_g[0]), a1 = warp_sum(acc_g[1]), a2 = warp_sum(acc_g[2]);
+    if (lane == 0) {
+      atomicAdd(&sAcc[n_out], thf);
+      atomicAdd(&sAcc[n_out + 1], a0);
+      atomicAdd(&sAcc[n_out + 2], a1);
+      atomicAdd(&sAcc[n_out + 3], a2);
+    }
+  }
+  __syncthreads();
+  float* out = partial + (size_t)blockIdx.x * (n_out + 4);
+  for (int o = threadIdx.x; o < n_out + 4; o += blockDim.x) out[o] = sAcc[o];
+}
+
+#undef LBS_BONE_OK
+static size_t lbs_bwd_mma_smem(int J, int MT) {
+  return sizeof(float) * ((size_t)2 * MT * 2 * 4 * 32 + J * 12 + 4 + (size_t)LBS_MMA_WARPS * 32 * LBS_DG_LD);
+}
+
 // fixed-order reduction of the per-block partials (deterministic): one warp per output, lanes stride over the blocks
 // and a fixed shuffle tree combines them
 __global__ void __launch_bounds__(128)
@@ -573,8 +858,16 @@ static int lbs_bwd_grid(int N, int J) {
   return blocks_needed < cap ? (blocks_needed > 0 ? blocks_needed : 1) : cap;
 }
 
+// tensor-core backward: persistent grid of up to 4 blocks per SM (the occupancy API gives the resident count per MT)
+static int lbs_bwd_mma_grid_cap(int N) {
+  const int blocks_needed = apn_div_up(apn_div_up(N, 32), LBS_MMA_WARPS);
+  const int cap = APN_SM_COUNT * 4;
+  return blocks_needed < cap ? (blocks_needed > 0 ? blocks_needed : 1) : cap;
+}
+
 extern "C" size_t apn_lbs_bwd_workspace_bytes(int N, int J) {
-  return sizeof(float) * (size_t)lbs_bwd_grid(N, J) * (J * 12 + 4);
+  const int g = lbs_bwd_grid(N, J), gm = lbs_bwd_mma_grid_cap(N);
+  return sizeof(float) * (size_t)(g > gm ? g : gm) * (J * 12 + 4);
 }
 
 extern "C" int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
@@ -587,9 +880,36 @@ extern "C" int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float 
   APN_CHECK_ARG(raw_w && bone_T && xyz && ginv && d_raw && d_bone_T && workspace, "null pointer");
   APN_CHECK_ARG(!theta_weight || d_theta, "d_theta is required when theta_weight is given");
   APN_CHECK_ARG(workspace_bytes >= apn_lbs_bwd_workspace_bytes(N, J), "workspace too small");
+  const int grid = lbs_bwd_grid(N, J);
+  if (theta_weight && !merge_rules && !d_g && J <= 80) {          // tensor-core path
+    const int MT = (J + 15) / 16;
+    const size_t sm = lbs_bwd_mma_smem(J, MT);
+    int g2 = lbs_bwd_mma_grid_cap(N);                               // never more slabs than the workspace holds
+#define LBS_BWD_MMA_LAUNCH(MM)                                                                                          \
+  do {                                                                                                                   \
+    APN_CUDA(cudaFuncSetAttribute(lbs_bwd_mma_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));        \
+    int per_sm = 0;                                                                                                      \
+    APN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbs_bwd_mma_kernel<MM>, 32 * LBS_MMA_WARPS, sm));    \
+    per_sm = per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm;                                                                   \
+    if (g2 > APN_SM_COUNT * per_sm) g2 = APN_SM_COUNT * per_sm;                                                          \
+    lbs_bwd_mma_kernel<MM><<<g2, 32 * LBS_MMA_WARPS, sm, stream>>>(raw_w, theta_weight, eps, bone_T, xyz, N, J, ginv,    \
+                                                                  d_xyz, d_ginv, d_w, d_raw, (float*)workspace);        \
+  } while (0)
+    if (MT == 1) LBS_BWD_MMA_LAUNCH(1);
+    else if (MT == 2) LBS_BWD_MMA_LAUNCH(2);
+    else if (MT == 3) LBS_BWD_MMA_LAUNCH(3);
+    else if (MT == 4) LBS_BWD_MMA_LAUNCH(4);
+    else LBS_BWD_MMA_LAUNCH(5);
+#undef LBS_BWD_MMA_LAUNCH
+    APN_LAUNCH_CHECK();
+    const int n = J * 12 + 4;
+    lbs_bwd_reduce_kernel<<<(n + 3) / 4, 128, 0, stream>>>((const float*)workspace, g2, J, theta_weight, eps, d_theta,
+                                                            d_bone_T, d_global_t);
+    APN_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = lbs_bwd_smem(J, merge_rules != nullptr);
   APN_CHECK_ARG(smem <= 227 * 1024, "J too large for the backward tile");
-  const int grid = lbs_bwd_grid(N, J);
 #define LBS_BWD_LAUNCH(KK)                                                                                               \
   do {                                                                                                                    \
     APN_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
