@@ -562,7 +562,8 @@ lbs_bwd_mma_kernel(const float* __restrict__ raw_w, const float* __restrict__ th
                    const float* __restrict__ d_w, float* __restrict__ d_raw, float* __restrict__ partial) {
   extern __shared__ float smem[];
   const int n_out = J * 12;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform: no divergence scaffolding around the MMAs
   const int g = lane >> 2, q = lane & 3;
   // [T A-fragments hi | lo : MT*2*4*32 each] [block accumulators n_out + 4] [per warp dG 32 x LBS_DG_LD]
   uint32_t* sTA_hi = reinterpret_cast<uint32_t*>(smem);
@@ -594,7 +595,8 @@ lbs_bwd_mma_kernel(const float* __restrict__ raw_w, const float* __restrict__ th
   const int n_chunks = (N + 31) / 32;
   const int n_warps = gridDim.x * LBS_MMA_WARPS;
   // raw values of one 8-point tile in accumulator layout: element r of bone tile mt = bone 16 mt + g + 8 (r >> 1),
-  // point base + 8 nt + 2 q + (r & 1); bones beyond J read as -inf (weight 0), points beyond N as 0 (their dG is 0)
+  // point base + 8 nt + 2 q + (r & 1); anything beyond J or N reads as 0 (bones beyond J are masked to -inf in the softmax,
+  // points beyond N have dG = 0: every product they enter is 0)
   // only the last bone tile can reach beyond J; a point is valid iff its index is below N
 #define LBS_BONE_OK(mt, r) ((mt) < MT - 1 || 16 * (mt) + g + 8 * ((r) >> 1) < J)
   auto load_raw = [&](int base, int nt, float (&v)[MT][4]) {
@@ -606,7 +608,7 @@ lbs_bwd_mma_kernel(const float* __restrict__ raw_w, const float* __restrict__ th
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const bool bone_ok = LBS_BONE_OK(mt, r);
-        v[mt][r] = (bone_ok && ((r & 1) ? ok1 : ok0)) ? __ldg(rp + (r & 1) * J + 16 * mt + 8 * (r >> 1)) : (bone_ok ? 0.f : -INFINITY);
+        v[mt][r] = (bone_ok && ((r & 1) ? ok1 : ok0)) ? __ldg(rp + (r & 1) * J + 16 * mt + 8 * (r >> 1)) : 0.f;
       }
   };
   for (int chunk = blockIdx.x * LBS_MMA_WARPS + warp; chunk < n_chunks; chunk += n_warps) {
@@ -647,7 +649,7 @@ lbs_bwd_mma_kernel(const float* __restrict__ raw_w, const float* __restrict__ th
       for (int c = 0; c < 12; ++c) sDG[lane * LBS_DG_LD + c] = g12[c];
       __syncwarp();
     }
-    float th = 0.f;
+    float th4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int nt = 0; nt < 4; ++nt) {      // 8 points at a time: everything below lives in registers
       float rawv[MT][4], w[MT][4];
@@ -662,28 +664,27 @@ lbs_bwd_mma_kernel(const float* __restrict__ raw_w, const float* __restrict__ th
       // ---- softmax over bones for this lane's two points (h = 0, 1), shuffles over the lanes that share q
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float mx = -INFINITY;
+        float mxa = -INFINITY, mxb = -INFINITY;            // two partial chains each (rows g and g + 8)
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+        for (int mt = 0; mt < MT; ++mt) {
+          const float xa = LBS_BONE_OK(mt, h) ? rawv[mt][h] * inv_theta : -INFINITY;
+          const float xb = LBS_BONE_OK(mt, h + 2) ? rawv[mt][h + 2] * inv_theta : -INFINITY;
+          w[mt][h] = xa;
+          w[mt][h + 2] = xb;
+          mxa = fmaxf(mxa, xa);
+          mxb = fmaxf(mxb, xb);
+        }
+        const float mx = quad_col_max(fmaxf(mxa, mxb));
+        float suma = 0.f, sumb = 0.f;
 #pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {
-            const int r = h + 2 * rr;
-            const float x = rawv[mt][r] * inv_theta;      // -inf (bones beyond J) stays -inf
-            w[mt][r] = x;
-            mx = fmaxf(mx, x);
-          }
-        mx = quad_col_max(mx);
-        float sum = 0.f;
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {
-            const int r = h + 2 * rr;
-            const float e = __expf(w[mt][r] - mx);         // ex2.approx: ~2 ulp, far inside the gradient tolerance
-            w[mt][r] = e;
-            sum += e;
-          }
-        const float inv = 1.0f / quad_col_sum(sum);
+        for (int mt = 0; mt < MT; ++mt) {
+          const float ea = __expf(w[mt][h] - mx), eb = __expf(w[mt][h + 2] - mx);   // ex2.approx: ~2 ulp
+          w[mt][h] = ea;
+          w[mt][h + 2] = eb;
+          suma += ea;
+          sumb += eb;
+        }
+        const float inv = 1.0f / quad_col_sum(suma + sumb);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -700,7 +701,7 @@ lbs_bwd_mma_kernel(const float* __restrict__ raw_w, const float* __restrict__ th
           tf32_split(v, bh[kt][h], bl[kt][h]);
         }
       float acc[MT][4];
-      float dot0 = 0.f, dot1 = 0.f;
+      float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f, dot3 = 0.f;    // per accumulator element: four independent chains
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -718,22 +719,22 @@ lbs_bwd_mma_kernel(const float* __restrict__ raw_w, const float* __restrict__ th
           for (int r = 0; r < 4; ++r)
             if (LBS_BONE_OK(mt, r) && ((r & 1) ? ok1 : ok0)) acc[mt][r] += __ldg(d_w + at0 + (r & 1) * J + 16 * mt + 8 * (r >> 1));
         }
-        dot0 = fmaf(w[mt][0], acc[mt][0], dot0); dot0 = fmaf(w[mt][2], acc[mt][2], dot0);
-        dot1 = fmaf(w[mt][1], acc[mt][1], dot1); dot1 = fmaf(w[mt][3], acc[mt][3], dot1);
+        dot0 = fmaf(w[mt][0], acc[mt][0], dot0); dot2 = fmaf(w[mt][2], acc[mt][2], dot2);
+        dot1 = fmaf(w[mt][1], acc[mt][1], dot1); dot3 = fmaf(w[mt][3], acc[mt][3], dot3);
       }
-      dot0 = quad_col_sum(dot0);
-      dot1 = quad_col_sum(dot1);
+      dot0 = quad_col_sum(dot0 + dot2);
+      dot1 = quad_col_sum(dot1 + dot3);
       // ---- dz = w (dm - dot) -> d_raw, theta gradient
       float* dp = d_raw + at0;
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          if (LBS_BONE_OK(mt, r) && ((r & 1) ? ok1 : ok0)) {
-            const float dz = w[mt][r] * (acc[mt][r] - ((r & 1) ? dot1 : dot0));
-            th = fmaf(-dz, rawv[mt][r], th);
-            dp[(r & 1) * J + 16 * mt + 8 * (r >> 1)] = dz * inv_theta;
-          }
+        {                                 // branch-free: w = 0 beyond J, dm = dot = 0 beyond N, so dz = 0 there
+          const float dz = w[mt][r] * (acc[mt][r] - ((r & 1) ? dot1 : dot0));
+          th4[r] = fmaf(-dz, rawv[mt][r], th4[r]);
+          if (LBS_BONE_OK(mt, r) && ((r & 1) ? ok1 : ok0)) dp[(r & 1) * J + 16 * mt + 8 * (r >> 1)] = dz * inv_theta;
+        }
       // ---- dT += w^T dG:  A = (w r0, r2, r1, r3), B: b0 = dG[8 nt + 2 q][8 ct + g], b1: next point
       uint32_t gh[2][2], gl[2][2];
 #pragma unroll
@@ -759,7 +760,7 @@ lbs_bwd_mma_kernel(const float* __restrict__ raw_w, const float* __restrict__ th
         }
       }
     }
-    acc_theta += (double)th;
+    acc_theta += (double)((th4[0] + th4[1]) + (th4[2] + th4[3]));
   }
   // block reduction (shared-memory atomics), then one partial slab per block as in lbs_bwd_kernel
 #pragma unroll
