@@ -74,7 +74,9 @@ int apn_lbs_fwd(const float* raw_w, const float* theta_weight, float eps, const 
 size_t apn_lbs_bwd_workspace_bytes(int N, int J);
 /* d_raw (N,J), d_theta (1), d_bone_T (J,4,4; last row 0), d_global_t (3) are overwritten.
  * d_w (N,J) is the extra gradient arriving on the merged weights (regularisers) or NULL;
- * d_g (N,4,4) the gradient arriving on g_out or NULL. */
+ * d_g (N,4,4) the gradient arriving on g_out or NULL.
+ * Without merge rules and d_g, and for J <= 80, the two contractions of the backward run on the tensor cores
+ * (mma.sync TF32 with the 3xTF32 split: fp32-class, within 1e-4 of the fp32 path); otherwise on the CUDA cores. */
 int apn_lbs_bwd(const float* raw_w, const float* theta_weight, float eps, const int32_t* merge_rules,
                 const float* bone_T, const float* xyz, int N, int J, const float* ginv,
                 const float* d_xyz, const float* d_ginv, const float* d_w, const float* d_g,

@@ -47,7 +47,9 @@ def _lbs_oracle(raw, theta, T, xyz, gt, rules, eps=1e-6):
     return out, ginv, w, G
 
 
-@pytest.mark.parametrize("N,J,merge", [(1, 2, False), (127, 21, False), (4099, 29, True), (20000, 65, False)])
+# J = 16 / 17 / 80 / 81: bone-tile boundaries of the tensor-core backward (J <= 80) and its CUDA-core fallback (81, merge rules)
+@pytest.mark.parametrize("N,J,merge", [(1, 2, False), (127, 21, False), (4099, 29, True), (20000, 65, False), (64, 16, False),
+                                       (40, 17, False), (33, 80, False), (1000, 81, False)])
 def test_lbs_forward_backward(N, J, merge):
     ops = _ops()
     raw, theta, T, xyz, gt, rules = _lbs_case(N, J, N + J, merge)
