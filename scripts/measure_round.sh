@@ -1,3 +1,5 @@
+# Measurement batch behind profiles/r01_*_final.* (run on the B200 box: gpurun -- bash scripts/measure_round.sh).
+# Every command that runs under ncu is first run without it, as the profiling recipe asks.
 set -x
 timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
 python bench.py > gpurun_out/f_c2.json 2> gpurun_out/f_c2.err
