@@ -77,6 +77,8 @@ SIGNATURES = {
     "apn_compact_samples": (I, [P, P, F, F, F, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P]),
     "apn_knn_points": (I, [P, I, P, I, P, P, P]),
     "apn_nn1_batched": (I, [P, P, I, I, I, I, P, P]),
+    "apn_time_embed": (I, [P, P, I, P, P]),
+    "apn_mse_loss_grad": (I, [P, P, I, F, P, P, P]),
     "apn_aggregate_scratch_bytes": (SZ, [I, I]),
     "apn_aggregate_fwd": (I, [P, P, P, P, SZ, P]),
     "apn_aggregate_bwd_scratch_bytes": (SZ, [I, I]),

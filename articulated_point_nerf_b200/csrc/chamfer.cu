@@ -1,3 +1,5 @@
+// Small helpers of the training step that would otherwise cost several framework launches each, and the batched NN-1.
+//
 // Batched exact nearest neighbour (K = 1) between two small point sets per batch item, 2-D or 3-D.
 // Replaces the KeOps reductions of the batch chamfer loss, lib/temporalpoints.py:783-787
 // (D_ij.argKmin(dim=2, K=1) and D_ij.argKmin(dim=1, K=1) over (B, N, M) squared distances; run.py:659-690 calls it
@@ -55,6 +57,63 @@ extern "C" int apn_nn1_batched(const float* query, const float* target, int n_ba
   const dim3 grid(apn_div_up(n_query, NN1_THREADS), n_batch);
   if (dim == 2) nn1_batched_kernel<2><<<grid, NN1_THREADS, 0, stream>>>(query, target, n_query, n_target, nn_idx);
   else nn1_batched_kernel<3><<<grid, NN1_THREADS, 0, stream>>>(query, target, n_query, n_target, nn_idx);
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Time embedding of the pose network input (lib/tineuvox.py:872-878 poc_fre on the scalar time, lib/temporalpoints.py:
+// 546-550): out = [t, sin(t f_0..f_{F-1}), cos(t f_0..f_{F-1})]  (1 + 2F floats); one launch instead of mul / sin / cos / cat.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void time_embed_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int n_freq, float* __restrict__ out) {
+  const int i = threadIdx.x;
+  const float tv = t[0];
+  if (i == 0) out[0] = tv;
+  if (i < n_freq) {
+    const float x = __fmul_rn(tv, freqs[i]);
+    out[1 + i] = sinf(x);
+    out[1 + n_freq + i] = cosf(x);
+  }
+}
+
+extern "C" int apn_time_embed(const float* t, const float* freqs, int n_freq, float* out, apn_stream_t stream_) {
+  APN_CHECK_ARG(t && freqs && out, "null pointer");
+  APN_CHECK_ARG(n_freq >= 0 && n_freq <= 1024, "0 <= n_freq <= 1024");
+  time_embed_kernel<<<1, n_freq < 32 ? 32 : ((n_freq + 31) & ~31), 0, (cudaStream_t)stream_>>>(t, freqs, n_freq, out);
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Render loss and its gradient (run.py:617-621: weight * mse(rgb_marched, target)):
+//   loss = weight * mean((pred - target)^2),  grad = (pred - target) * 2 weight / n
+// One block, fixed summation order (deterministic); n is a ray batch (8192 x 3), not a frame.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+mse_loss_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, int n, float weight,
+                     float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ float sred[32];
+  const float gscale = 2.0f * weight / (float)n;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = pred[i] - target[i];
+    acc = fmaf(d, d, acc);
+    grad[i] = d * gscale;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) loss[0] = weight * (v / (float)n);
+  }
+}
+
+extern "C" int apn_mse_loss_grad(const float* pred, const float* target, int n, float weight, float* loss, float* grad,
+                                 apn_stream_t stream_) {
+  APN_CHECK_ARG(n > 0 && pred && target && loss && grad, "need n > 0 and non-null pointers");
+  mse_loss_grad_kernel<<<1, 1024, 0, (cudaStream_t)stream_>>>(pred, target, n, weight, loss, grad);
   APN_LAUNCH_CHECK();
   return 0;
 }

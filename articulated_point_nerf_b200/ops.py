@@ -257,6 +257,28 @@ def nn1_batched(query: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     return idx.long()
 
 
+def time_embed(t: torch.Tensor, freqs: torch.Tensor) -> torch.Tensor:
+    """poc_fre of the scalar time (lib/tineuvox.py:872-878) in one launch: (1) -> (1 + 2 F)."""
+    lib = _lib.load()
+    t, freqs = _f32(t).reshape(-1), _f32(freqs)
+    assert t.numel() == 1
+    out = torch.empty(1 + 2 * freqs.numel(), device=t.device, dtype=torch.float32)
+    check(lib.apn_time_embed(ptr(t), ptr(freqs), freqs.numel(), ptr(out), stream()), "apn_time_embed")
+    return out
+
+
+def mse_loss_grad(pred: torch.Tensor, target: torch.Tensor, weight: float):
+    """-> (loss (0-dim) = weight * mse(pred, target), d loss / d pred); run.py:617-621 in one launch."""
+    lib = _lib.load()
+    pred, target = _f32(pred), _f32(target)
+    assert pred.shape == target.shape
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    grad = torch.empty_like(pred)
+    check(lib.apn_mse_loss_grad(ptr(pred), ptr(target), pred.numel(), float(weight), ptr(loss), ptr(grad), stream()),
+          "apn_mse_loss_grad")
+    return loss[0], grad
+
+
 def exclusive_scan(x: torch.Tensor) -> torch.Tensor:
     """int32 (n) -> int32 (n+1), out[n] = total."""
     lib = _lib.load()

@@ -127,7 +127,7 @@ class FusedTrainStep:
         dev = m.joints.device
         self.bucket.zero()
         # ---- forward
-        t_embed = poc_fre(t, m.time_poc)
+        t_embed = ops.time_embed(t, m.time_poc)
         wb = fw._mlp_params()
         cp = _Ctx((False, False, m.joints.requires_grad, *[w.requires_grad for w in wb]))
         bone_Ts, global_t, thetas = ops._Pose.forward(cp, fw._fused_tables(dev), t_embed, m.joints, *wb)
@@ -156,9 +156,7 @@ class FusedTrainStep:
         rgb_m, last, _, _ = ops._Composite.forward(cc, alpha, rgb, smp.step_id, None, smp.ray_start, R, m.fast_color_thres,
                                                    float(render_kwargs['bg']), False)
         # ---- loss (run.py:617-621: img2mse weighted by weight_render) and its gradient
-        diff = rgb_m - target
-        loss = WEIGHT_RENDER * (diff * diff).mean()
-        d_rgb_m = diff * (2.0 * WEIGHT_RENDER / diff.numel())
+        loss, d_rgb_m = ops.mse_loss_grad(rgb_m, target, WEIGHT_RENDER)
         # ---- backward, in autograd's order
         d_alpha, d_rgb = ops._Composite.backward(cc, d_rgb_m, None, None, None)[:2]
         ga = ops._AggregateTC.backward(ca, d_alpha, d_rgb)

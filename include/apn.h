@@ -131,6 +131,13 @@ int apn_knn_points(const float* query, int n_query, const void* grid, int k, int
  * target (B, n_target, dim) -> nn_idx (B, n_query), index into that batch item's targets; ties -> lowest index. */
 int apn_nn1_batched(const float* query, const float* target, int n_batch, int n_query, int n_target, int dim,
                     int32_t* nn_idx, apn_stream_t stream);
+/* time embedding of the pose-network input: poc_fre of the scalar time (lib/tineuvox.py:872-878; lib/temporalpoints.py:546-550):
+ * out (1 + 2 n_freq) = [t, sin(t f_i)..., cos(t f_i)...] */
+int apn_time_embed(const float* t, const float* freqs, int n_freq, float* out, apn_stream_t stream);
+/* render loss of the stage-2 loop and its gradient (run.py:617-621): loss (1) = weight * mean((pred - target)^2),
+ * grad (n) = (pred - target) * 2 weight / n; fixed summation order */
+int apn_mse_loss_grad(const float* pred, const float* target, int n, float weight, float* loss, float* grad,
+                      apn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3  Aggregation: gather + positional encoding + feature MLP + inverse-distance reduce + heads.

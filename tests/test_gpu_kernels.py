@@ -600,3 +600,23 @@ def test_composite_backward_staged_spans_stay_inside_their_arrays(tail):
     assert torch.equal(last.cpu(), o_last.detach())
     assert rel_err(buf_a[pad:pad + M], a.grad) < RTOL
     assert rel_err(buf_c[pad:pad + 3 * M].view(M, 3), c.grad) < RTOL
+
+
+def test_time_embed_and_render_loss_match_torch():
+    """One-launch helpers of the fused training step against the torch expressions they replace
+    (lib/tineuvox.py:872-878 on the scalar time; run.py:617-621)."""
+    ops = _ops()
+    from articulated_point_nerf_b200.heads import poc_fre
+    freqs = torch.tensor([2.0 ** i for i in range(8)], device="cuda")
+    for tv in (0.0, 0.37, 1.0):
+        t = torch.tensor([tv], device="cuda")
+        assert torch.equal(ops.time_embed(t, freqs), poc_fre(t, freqs))
+    g = torch.Generator().manual_seed(0)
+    for n in (1, 777, 8192):
+        pred = torch.rand(n, 3, generator=g).cuda().requires_grad_(True)
+        target = torch.rand(n, 3, generator=g).cuda()
+        ref = 200.0 * torch.nn.functional.mse_loss(pred, target)
+        ref.backward()
+        loss, grad = ops.mse_loss_grad(pred.detach(), target, 200.0)
+        assert abs(loss.item() - ref.item()) < 1e-5 * ref.item()
+        assert rel_err(grad, pred.grad) < 1e-6
