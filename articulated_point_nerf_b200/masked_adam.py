@@ -74,3 +74,6 @@ class MaskedAdam(torch.optim.Optimizer):
             self._plan_key = key
         for cls, ap in self._plan:
             ap.launch([e[5] for e in plan if e[0] == cls], *cls)
+        # the kernel wrote through raw pointers: tell autograd's version counters, which key every derived cache
+        # (packed tensor-core weights, per-point layer-0 table, ...) exactly as an in-place torch op would
+        torch.autograd.graph.increment_version([e[1] for e in plan])

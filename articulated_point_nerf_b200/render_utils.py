@@ -130,6 +130,7 @@ def _adam(mode):
         _chk(param, grad, exp_avg, exp_avg_sq)
         ss = ops.adam_step_size(step, beta1, beta2, lr)
         ops.adam_multi([(param, grad, exp_avg, exp_avg_sq, perlr, ss, mode)], beta1, beta2, eps)
+        torch.autograd.graph.increment_version([param, exp_avg, exp_avg_sq])     # in-place update through raw pointers
     return fn
 
 

@@ -365,3 +365,34 @@ def test_batch_chamfer_loss_matches_reference():
     with pytest.raises(Exception):
         from articulated_point_nerf_b200 import ops
         ops.nn1_batched(torch.rand(1, 4, 4).cuda(), torch.rand(1, 4, 4).cuda())
+
+
+def test_derived_decoder_state_follows_the_optimizer(golden_tiny):
+    """MaskedAdam updates the parameters through raw pointers; the packed tensor-core weights and the per-point layer-0
+    table are derived from them and must be rebuilt after every step (they are keyed on the tensors' version counters,
+    which the optimizer bumps).  After a training step with a large learning rate the tensor-core render has to agree
+    with the fp32 render of the UPDATED parameters."""
+    from articulated_point_nerf_b200.train import GradBucket, create_optimizer, train_step
+    g = golden_tiny
+    model, scene = model_from_golden(g, fused_pose=True)
+    model.decoder_train = "tc"
+    rk = _rk(scene, g)
+    t = g["train"]["t"].cuda()
+    opt = create_optimizer(model)
+    for grp in opt.param_groups:                                # move the decoder visibly, leave the geometry where it is
+        if grp["name"] in ("feat_net", "canonical_feat", "rgbnet", "densitynet"):
+            grp["lr"] = grp["lr"] * 30.0
+    bucket = GradBucket(opt)
+    with torch.no_grad():
+        model.decoder = "tc"
+        before = model(t, render_depth=True, render_kwargs=rk)["rgb_marched"].clone()
+    losses = [float(train_step(model, opt, bucket, t, rk, g["train"]["target"].cuda())) for _ in range(3)]
+    with torch.no_grad():
+        warped = model.warp(t)
+        model.decoder = "tc"
+        out_tc = model(t, render_depth=True, render_kwargs=rk, warped=warped)["rgb_marched"]
+        model.decoder = "fp32"
+        out_32 = model(t, render_depth=True, render_kwargs=rk, warped=warped)["rgb_marched"]
+    assert rel_err(out_tc, before) > 1e-3                      # the step really moved the image
+    assert rel_err(out_tc, out_32) < RTOL                      # ... and the tensor-core state moved with it
+    assert all(l == l and l > 0 for l in losses)
