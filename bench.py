@@ -91,14 +91,17 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx, self.proc, self.path = gpu_index, None, f"/tmp/apn_clocks_{os.getpid()}.csv"
+    def __init__(self, n_gpus):
+        """ONE sampler process for all GPUs of the job (rank 0 starts it): eight concurrent `nvidia-smi -lms` loops, one per
+        rank, contend for the driver and slowed every rank's host-bound step by ~45 % on the 8-GPU run."""
+        self.n, self.proc, self.path = n_gpus, None, f"/tmp/apn_clocks_{os.getpid()}.csv"
 
     def start(self):
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.idx)], stdout=self.fh, stderr=subprocess.DEVNULL)
+                                          "-i", ",".join(str(i) for i in range(self.n))],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -378,10 +381,11 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item()), launches
 
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks = ClockSampler(world) if rank == 0 else None
+    if clocks is not None:
+        clocks.start()
     total_ms, launches = timed_loop(e2e=False)
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks is not None else None
     stage_tot = _lib.STAGES.totals()
     _lib.STAGES.reset(False)
     timed_counts = list(counts)
