@@ -268,6 +268,8 @@ int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, con
  * weight > thres mask, torch_scatter.segment_coo sums for rgb / depth, + alphainv_last*bg.
  *   ray_start (R+1) offsets into the ray-major sample list
  *   T_save (M) and n_used (R) are written when non-NULL (needed by the backward)
+ *   the per-sample arrays (alpha, rgb, step_id, T_save, d_alpha, d_rgb) must be 16-byte aligned: the kernels move them with
+ *   16-byte vector accesses and, in the backward, with TMA bulk copies of each warp's 32-ray span
  * ------------------------------------------------------------------------------------- */
 int apn_composite_fwd(const float* alpha, const float* rgb, const int32_t* step_id, const float* extra, int n_extra,
                       const int32_t* ray_start, int R, float thres, float bg,
