@@ -228,6 +228,25 @@ class OraclePath:
         _, i2 = knn_bruteforce(joints.detach(), skeleton_pcd, 1)
         return ((joints[:, None, :] - skeleton_pcd[i2, :]) ** 2).sum(-1).sum()
 
+    @staticmethod
+    def batch_chamfer_loss(pcd1, pcd2):
+        """lib/temporalpoints.py:765-795 without the random sub-sampling: (B, N, D) vs (B, M, D), D = 2 or 3; nearest
+        neighbour per batch item by d2 = (dx*dx + dy*dy) [+ dz*dz], ties -> lowest index; gradients flow through the
+        gathered coordinates only."""
+        def nn1(a, b):                                            # (B, Na, D), (B, Nb, D) -> (B, Na) int64
+            diff = a.detach()[:, :, None, :] - b.detach()[:, None, :, :]
+            d2 = diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]
+            if a.shape[-1] == 3:
+                d2 = d2 + diff[..., 2] * diff[..., 2]
+            key = (d2.contiguous().view(torch.int32).to(torch.int64) << 32) | torch.arange(b.shape[1], dtype=torch.int64)
+            return key.min(-1).values & 0xFFFFFFFF
+        D = pcd1.shape[-1]
+        i12 = nn1(pcd1, pcd2)[..., None].expand(-1, -1, D)
+        i21 = nn1(pcd2, pcd1)[..., None].expand(-1, -1, D)
+        d1 = (pcd1 - torch.gather(pcd2, 1, i12)).pow(2)
+        d2 = (pcd2 - torch.gather(pcd1, 1, i21)).pow(2)
+        return d1.sum(-1).mean() + d2.sum(-1).mean()
+
     # -- sub-networks ---------------------------------------------------------------
     def transform_net(self, x):
         s = self.s

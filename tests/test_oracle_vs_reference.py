@@ -103,3 +103,17 @@ def test_regulariser_losses_match_reference(golden_tiny, oracle_tiny):
     for k, v in got.items():
         ref = float(g["losses"][k])
         assert abs(float(v) - ref) <= 1e-4 * max(abs(ref), 1e-3), (k, float(v), ref)
+
+
+def test_batch_chamfer_loss_matches_reference():
+    """lib/temporalpoints.py:765-795 (2-D / 3-D, integer pixel grids with exact ties) against the reference's own run."""
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle.path_oracle import OraclePath
+    sk = torch.load(os.path.join(GOLDEN_DIR, "ref_skeleton.pt"), weights_only=False)
+    for c in sk["batch_chamfer"]:
+        p1 = c["pcd1"].clone().requires_grad_(True)
+        loss = OraclePath.batch_chamfer_loss(p1, c["pcd2"])
+        loss.backward()
+        assert _rel(loss.detach(), c["loss"]) < 1e-6
+        assert _rel(p1.grad, c["grad1"]) < 1e-6
