@@ -9,7 +9,8 @@ from .pointwarper import PointWarper, TransformNet                     # noqa: F
 from .render_utils import (Alphas2Weights, Raw2Alpha, adam_upd_cuda,   # noqa: F401
                            render_utils_cuda)
 from .temporalpoints import NoPointsException, TemporalPoints          # noqa: F401
-from .render import (PoseCache, load_checkpoint, render_repose,        # noqa: F401
-                     render_viewpoints, save_checkpoint)
+from .render import (PoseCache, load_checkpoint, model_from_pcds,      # noqa: F401
+                     render_repose, render_viewpoints, save_checkpoint,
+                     save_pcds)
 
 __version__ = "0.1.0"

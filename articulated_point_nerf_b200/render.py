@@ -189,3 +189,41 @@ def load_checkpoint(path: str, tineuvox=None, device='cuda', strict: bool = Fals
     missing, unexpected = model.load_state_dict(ckpt['model_state_dict'], strict=strict)
     model = model.to(device)
     return model, ckpt
+
+
+# pcds/canonical.tar and pcds/skeleton.tar: what stage 1 hands to stage 2 (written by export_point_cloud, run.py:1090-1103,
+# 1229-1235; read by train_pcd, run.py:459-477).  export_point_cloud itself samples the stage-1 voxel model and runs the
+# skeletonizer (out of scope); the FORMATS are what lets existing exports flow into the B200 path.
+CANONICAL_KEYS = ('pcd', 'rgbs', 'feat', 'raw_feat', 'alphas', 't', 'xyz_min', 'xyz_max', 'voxel_size')
+SKELETON_KEYS = ('skeleton_pcd', 'joints', 'root', 'bones', 'pcd', 'weights', 'binary_volume')
+
+
+def save_pcds(folder: str, *, pcd, rgbs, feat, alphas, skeleton_pcd, joints, bones, xyz_min, xyz_max, voxel_size,
+              raw_feat=None, t: float = 0.0) -> None:
+    """Writes `canonical.tar` and `skeleton.tar` under `folder` in the reference's layout (run.py:1090-1103, 1214-1230)."""
+    import os
+    os.makedirs(folder, exist_ok=True)
+    torch.save({'pcd': pcd, 'rgbs': rgbs, 'feat': feat, 'raw_feat': raw_feat, 'alphas': alphas, 't': float(t),
+                'xyz_min': xyz_min, 'xyz_max': xyz_max, 'voxel_size': voxel_size}, os.path.join(folder, 'canonical.tar'))
+    joints_np = np.asarray(torch.as_tensor(joints).cpu())
+    torch.save({'skeleton_pcd': np.asarray(torch.as_tensor(skeleton_pcd).cpu()), 'joints': joints_np, 'root': joints_np[0],
+                'bones': [list(map(int, b)) for b in bones], 'pcd': None, 'weights': None, 'binary_volume': None},
+               os.path.join(folder, 'skeleton.tar'))
+
+
+def model_from_pcds(read_path: str, tineuvox, *, world_bound_scale: float = 1.05, **model_kwargs) -> TemporalPoints:
+    """run.py:457-503 (train_pcd): builds the stage-2 model from `<read_path>/pcds/canonical.tar` + `skeleton.tar`.
+    `tineuvox` supplies the frozen stage-1 heads; `model_kwargs` are the reference's `cfg.model_and_render` entries the
+    constructor understands (stepsize, fast_color_thres, timebase_pe, pose_embedding_dim, ...)."""
+    import os
+    can = torch.load(os.path.join(read_path, 'pcds', 'canonical.tar'), map_location='cpu', weights_only=False)
+    skel = torch.load(os.path.join(read_path, 'pcds', 'skeleton.tar'), map_location='cpu', weights_only=False)
+    missing = [k for k in ('pcd', 'feat', 'alphas', 'rgbs', 'xyz_min', 'xyz_max', 'voxel_size') if k not in can]
+    if missing:
+        raise KeyError(f"canonical.tar lacks {missing}")
+    model_kwargs.pop('world_bound_scale', None)
+    return TemporalPoints(
+        canonical_pcd=can['pcd'], canonical_feat=can['feat'], canonical_alpha=can['alphas'], canonical_rgbs=can['rgbs'],
+        skeleton_pcd=torch.as_tensor(skel['skeleton_pcd']), joints=torch.as_tensor(skel['joints']), bones=skel['bones'],
+        xyz_min=torch.as_tensor(can['xyz_min']) * world_bound_scale, xyz_max=torch.as_tensor(can['xyz_max']) * world_bound_scale,
+        voxel_size=can['voxel_size'], tineuvox=tineuvox, **model_kwargs)

@@ -244,3 +244,32 @@ def test_rotation_angle_of_relative_rotations():
     R, _ = rodrigues(torch.cat([axis, ang[:, None]], -1))
     # the 1e-5 inside the axis normalisation (lib/pointwarper.py:127) makes R slightly non-orthogonal: loose bound
     assert (TemporalPoints._rotation_angle(R) - ang).abs().max() < 1e-3
+
+
+def test_pcds_formats_round_trip_into_the_stage2_model(tmp_path):
+    """pcds/canonical.tar + pcds/skeleton.tar in the reference's layout (run.py:1090-1103, 1214-1230) and the stage-2
+    model construction from them (run.py:457-503)."""
+    import numpy as np
+    from articulated_point_nerf_b200 import model_from_pcds, save_pcds
+    from articulated_point_nerf_b200.heads import TiNeuVoxHeads
+    from articulated_point_nerf_b200.render import CANONICAL_KEYS, SKELETON_KEYS
+    from articulated_point_nerf_b200.scene import make_scene
+    scene = make_scene("tiny")
+    folder = os.path.join(tmp_path, "run", "pcds")
+    save_pcds(folder, pcd=scene.canonical_pcd, rgbs=scene.canonical_rgbs, feat=scene.canonical_feat,
+              alphas=scene.canonical_alpha, skeleton_pcd=scene.skeleton_pcd, joints=scene.joints, bones=scene.bones,
+              xyz_min=scene.xyz_min, xyz_max=scene.xyz_max, voxel_size=scene.voxel_size, t=0.0)
+    can = torch.load(os.path.join(folder, "canonical.tar"), weights_only=False)
+    skel = torch.load(os.path.join(folder, "skeleton.tar"), weights_only=False)
+    assert tuple(can.keys()) == CANONICAL_KEYS and tuple(skel.keys()) == SKELETON_KEYS     # the reference's dict layouts
+    assert isinstance(skel["joints"], np.ndarray) and np.array_equal(skel["root"], skel["joints"][0])
+    heads = TiNeuVoxHeads(scene.xyz_min.numpy(), scene.xyz_max.numpy(), num_voxels=scene.cfg.num_voxels,
+                          num_voxels_base=scene.cfg.num_voxels, alpha_init=1e-3, net_width=128, no_view_dir=False)
+    model = model_from_pcds(os.path.join(tmp_path, "run"), heads, world_bound_scale=1.05, stepsize=scene.cfg.stepsize,
+                            fast_color_thres=scene.cfg.fast_color_thres)
+    assert torch.equal(model.canonical_pcd, scene.canonical_pcd)
+    assert torch.equal(model.canonical_feat.detach(), scene.canonical_feat)
+    assert torch.equal(model.joints.detach(), scene.joints.float())
+    assert model.bones == [list(map(int, b)) for b in scene.bones]
+    assert torch.allclose(model.xyz_max, scene.xyz_max.float() * 1.05) and model.voxel_size == scene.voxel_size
+    assert model.weights.shape == (len(scene.canonical_pcd), len(scene.joints))          # initial skinning weights from the bones
