@@ -273,3 +273,21 @@ def test_pcds_formats_round_trip_into_the_stage2_model(tmp_path):
     assert model.bones == [list(map(int, b)) for b in scene.bones]
     assert torch.allclose(model.xyz_max, scene.xyz_max.float() * 1.05) and model.voxel_size == scene.voxel_size
     assert model.weights.shape == (len(scene.canonical_pcd), len(scene.joints))          # initial skinning weights from the bones
+
+
+def test_ctypes_arities_match_the_header_prototypes():
+    """Every prototype of include/apn.h has as many parameters as its ctypes signature (catches a binding that drifts
+    from the header when an entry point gains an argument)."""
+    from articulated_point_nerf_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "apn.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", " ", header)
+    protos = re.findall(r"\b(apn_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", header, flags=re.S)
+    seen = {}
+    for name, params in protos:
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        seen[name] = n
+    assert set(seen) == set(_lib.SIGNATURES)
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert len(argtypes) == seen[name], (name, len(argtypes), seen[name])
