@@ -291,3 +291,17 @@ def test_ctypes_arities_match_the_header_prototypes():
     assert set(seen) == set(_lib.SIGNATURES)
     for name, (_, argtypes) in _lib.SIGNATURES.items():
         assert len(argtypes) == seen[name], (name, len(argtypes), seen[name])
+    # ... and of the same kind, parameter by parameter: pointer / int / float / 64-bit size
+    def kind_c(decl):
+        decl = decl.strip()
+        if "*" in decl or decl.startswith("apn_stream_t"):
+            return "ptr"
+        base = decl.rsplit(" ", 1)[0].replace("const", "").strip()
+        return {"int": "int", "int32_t": "int", "float": "float", "size_t": "size", "long long": "ll",
+                "unsigned long long": "ll"}[base]
+    kinds_py = {_lib.I: "int", _lib.F: "float", _lib.P: "ptr", _lib.LL: "ll", _lib.SZ: "size"}
+    for name, params in protos:
+        params = " ".join(params.split())
+        decls = [] if params in ("", "void") else params.split(",")
+        for i, (d, a) in enumerate(zip(decls, _lib.SIGNATURES[name][1])):
+            assert kind_c(d) == kinds_py.get(a, "ptr"), (name, i, d.strip(), a)
