@@ -550,6 +550,34 @@ tc_wgrad_reduce_kernel(const float* __restrict__ partial, int n_slabs, const flo
   }
 }
 
+// Pose embedding (lib/temporalpoints.py:483-490,571-576: the same 64-vector e is appended to EVERY decoder input row).
+// The forward folds  W0[:, 191:] . e  into the layer-0 bias, so its backward needs no per-row work at all:
+//   d_e       = W0[:, 191:]^T . db0          db0 = sum over rows of dY0 = this launch's layer-0 bias gradient
+//   dW0[:, 191:] += db0 (x) e
+// One block; thread n owns output feature n.  db0 is re-summed from the per-CTA slabs (g->d_b[0] may already hold
+// gradient from an earlier accumulation).
+__global__ void __launch_bounds__(128)
+tc_pose_bwd_kernel(const float* __restrict__ partial, int n_slabs, const float* __restrict__ hmax, int d_in,
+                   const float* __restrict__ w0, const float* __restrict__ pose_emb, float* __restrict__ dw0,
+                   float* __restrict__ d_pose_emb) {
+  __shared__ float sDb[128];
+  const int n = threadIdx.x;
+  const int n_pose = d_in - (APN_PE_POS + APN_C);
+  float s = 0.f;
+  for (int b = 0; b < n_slabs; ++b) s += __ldg(partial + (size_t)b * TCW_SLAB + TCW_SLAB_BIAS + n);
+  s *= 1.f / tc_grad_scale(hmax);
+  sDb[n] = s;
+  float* dwr = dw0 + (size_t)n * d_in + APN_PE_POS + APN_C;
+  for (int j = 0; j < n_pose; ++j) dwr[j] += s * __ldg(pose_emb + j);
+  __syncthreads();
+  if (d_pose_emb)
+    for (int j = n; j < n_pose; j += 128) {
+      float a = 0.f;
+      for (int r = 0; r < 128; ++r) a = fmaf(__ldg(w0 + (size_t)r * d_in + APN_PE_POS + APN_C + j), sDb[r], a);
+      d_pose_emb[j] += a;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -620,7 +648,8 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
                                     size_t scratch_bytes, apn_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   APN_CHECK_ARG(in && w && packed_bwd && sv && tape && g, "null pointer");
-  APN_CHECK_ARG(in->d_in == APN_PE_POS + APN_C, "the tensor-core backward covers d_in = 191 (no pose embedding)");
+  APN_CHECK_ARG(in->d_in == APN_PE_POS + APN_C || (in->d_in > APN_PE_POS + APN_C && in->d_in <= 256 && in->pose_emb),
+                "d_in must be 191, or 192..256 with a pose embedding");
   const int M = in->M, N = in->N;
   if (M <= 0) return 0;
   APN_CHECK_ARG(sv->rgb && sv->idw && sv->h && sv->exp_d && sv->fv && sv->v0, "saved forward tensors missing");
@@ -688,6 +717,10 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
                                                                        g->d_w[2], g->d_w[3], g->d_b[0], g->d_b[1], g->d_b[2],
                                                                        g->d_b[3]);
     APN_LAUNCH_CHECK();
+    if (in->d_in > APN_PE_POS + APN_C) {
+      tc_pose_bwd_kernel<<<1, 128, 0, st>>>(b.partial, grid, b.hmax, in->d_in, w->w[0], in->pose_emb, g->d_w[0], g->d_pose_emb);
+      APN_LAUNCH_CHECK();
+    }
   }
   if (side) {                                   // join: everything this call launched is ordered before what follows on st
     for (int i = 0; i < 2; ++i) {

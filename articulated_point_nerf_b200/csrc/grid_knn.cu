@@ -322,7 +322,9 @@ __global__ void ray_candidates_kernel(const float* __restrict__ rays_o, const fl
       ++count;
     }
   }
-  if (!FILL) cand_count[r] = count;
+  // an overflowed grid (bbox too large for cell_capacity) is reported through the total the caller reads back anyway:
+  // ray 0 counts -1, every other ray 0  =>  sum = -1
+  if (!FILL) cand_count[r] = h->overflow ? (r == 0 ? -1 : 0) : count;
 }
 
 extern "C" int apn_ray_candidates(const float* rays_o, const float* rays_d, int R, float near, float far, float stepdist,

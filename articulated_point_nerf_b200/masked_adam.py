@@ -64,8 +64,10 @@ class MaskedAdam(torch.optim.Optimizer):
                 plan.append(((beta1, beta2, eps), param, grad, state, perlr, ss, mode))
         if not plan:
             return
-        key = tuple((cls, p.data_ptr(), g.data_ptr(), mode, None if pl is None else pl.data_ptr())
-                    for cls, p, g, _, pl, _, mode in plan)
+        # every pointer the descriptor table holds is part of the key: load_state_dict() replaces the moment tensors
+        # (the reference reads self.state[param] afresh every step, lib/masked_adam.py:52-60)
+        key = tuple((cls, p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(), mode,
+                     None if pl is None else pl.data_ptr()) for cls, p, g, st, pl, _, mode in plan)
         if getattr(self, '_plan_key', None) != key:
             batches = {}
             for cls, p, g, state, pl, ss, mode in plan:

@@ -202,6 +202,10 @@ def lbs(raw_w, theta_weight, bone_T, global_t, xyz, rules: Optional[torch.Tensor
 # --------------------------------------------------------------------------------------
 # K2: grid + ray samples + exact 8-NN
 # --------------------------------------------------------------------------------------
+class GridOverflow(_lib.ApnError):
+    """The padded bbox of the cloud holds more grid leaves than the grid's cell table."""
+
+
 class Grid:
     """Opaque multi-level uniform grid over a warped cloud (csrc/grid_knn.cu)."""
 
@@ -211,13 +215,34 @@ class Grid:
         self.xyz = _f32(xyz.detach())
         self.N = self.xyz.shape[0]
         if cell_capacity is None:
-            cell_capacity = int(min(max(8 * self.N, 1 << 18), 1 << 25))
+            cell_capacity = self.default_capacity(self.N)
         self.cell_capacity = cell_capacity
+        self._args = (query_radius, bbox_pad, cell_hint)
+        self._bbox = bbox
         self.bytes = lib.apn_grid_workspace_bytes(self.N, cell_capacity)
         self.blob = _empty((self.bytes,), self.xyz.device, torch.uint8)
         with stage("grid_build"):
             check(lib.apn_grid_build(ptr(self.xyz), ptr(_f32(bbox)), self.N, float(query_radius), float(bbox_pad),
                                      float(cell_hint), cell_capacity, ptr(self.blob), self.bytes, stream()), "apn_grid_build")
+
+    MAX_CAPACITY = 1 << 27
+
+    @staticmethod
+    def default_capacity(n_points: int) -> int:
+        # 2^20 leaves = 16384 top cells of edge 1.01*sqrt(r) = 17 units^3 of padded bbox at the reference's radius
+        return int(min(max(8 * n_points, 1 << 20), 1 << 25))
+
+    def grow(self) -> None:
+        """Rebuilds this grid IN PLACE with 8x the cell capacity (after an overflow: the padded bbox holds more leaves
+        than the table); callers that cache the grid per pose keep a valid object."""
+        if self.cell_capacity >= self.MAX_CAPACITY:
+            raise GridOverflow(f"the warped cloud's bbox needs more than {self.MAX_CAPACITY} grid leaves")
+        g = Grid(self.xyz, self._bbox, *self._args, cell_capacity=min(self.cell_capacity * 8, self.MAX_CAPACITY))
+        self.cell_capacity, self.bytes, self.blob = g.cell_capacity, g.bytes, g.blob
+
+    def overflowed(self) -> bool:
+        """Synchronising check of the header's overflow flag (set on the device by apn_grid_build)."""
+        return bool(self.describe()["overflow"])
 
     def describe(self) -> dict:
         """Synchronising debug helper: header fields of the grid."""
@@ -234,7 +259,7 @@ class Grid:
         return dict(origin=f[0:3], cell=f[3], inv_cell=f[4], top_cell=f[5], L=i[0], top_dim=i[1:4], n_top=i[4],
                     n_cells=i[5], r2=r2, bmin=bm[0:3], bmax=bm[3:6], n_points=n_points, overflow=overflow)
 
-    def knn(self, query: torch.Tensor, k: int = K_NEIGHBOURS):
+    def knn(self, query: torch.Tensor, k: int = K_NEIGHBOURS, check_overflow: bool = True):
         """Exact k-NN (k <= 8) of arbitrary points: indices (n,k) int32 ascending by (d2, index), d2 (n,k)."""
         lib = _lib.load()
         q = _f32(query.detach())
@@ -242,6 +267,9 @@ class Grid:
         idx = _empty((n, k), q.device, torch.int32)
         d2 = _empty((n, k), q.device)
         check(lib.apn_knn_points(ptr(q), n, ptr(self.blob), k, ptr(idx), ptr(d2), stream()), "apn_knn_points")
+        if check_overflow and self.overflowed():     # the kernel wrote index -1 everywhere: never hand that to a gather
+            self.grow()
+            return self.knn(query, k, check_overflow)
         return idx, d2
 
 
@@ -310,7 +338,11 @@ def sample_and_knn(grid: Grid, rays_o: torch.Tensor, rays_d: torch.Tensor, near:
                    return_d2: bool = False):
     """sample_ray + Kmin_argKmin + radius rule, fused (lib/temporalpoints.py:421-447)."""
     with stage("sample_ray+knn"):
-        return _sample_and_knn(grid, rays_o, rays_d, near, far, stepdist, return_d2)
+        while True:
+            try:
+                return _sample_and_knn(grid, rays_o, rays_d, near, far, stepdist, return_d2)
+            except GridOverflow:               # widely spread cloud: larger cell table (raises at the limit)
+                grid.grow()
 
 
 def _sample_and_knn(grid, rays_o, rays_d, near, far, stepdist, return_d2):
@@ -324,6 +356,8 @@ def _sample_and_knn(grid, rays_o, rays_d, near, far, stepdist, return_d2):
                                  None, None, st), "apn_ray_candidates(count)")
     base = exclusive_scan(count)
     n_cand = int(base[R].item())
+    if n_cand < 0:                     # grid overflow, reported through the count (csrc/grid_knn.cu ray_candidates_kernel)
+        raise GridOverflow("grid cell table too small for the warped cloud's bbox")
     cand_ray = _empty((n_cand,), dev, torch.int32)
     cand_step = _empty((n_cand,), dev, torch.int32)
     nn_c = _empty((n_cand, K_NEIGHBOURS), dev, torch.int32)
@@ -590,16 +624,18 @@ def _aligned_bytes(n: int, device, align: int = 1024) -> torch.Tensor:
 
 class _AggregateTC(torch.autograd.Function):
     """Training aggregation on the tcgen05 tensor cores: split-fp16 forward that records a tape, tensor-core dgrad
-    + wgrad backward (csrc/aggregate_tc.cu, csrc/aggregate_tc_bwd.cu).  Same contract as _Aggregate; d_in = 191."""
+    + wgrad backward (csrc/aggregate_tc.cu, csrc/aggregate_tc_bwd.cu).  Same contract as _Aggregate, including the
+    pose embedding of the ZJU configs (d_in = 255, lib/temporalpoints.py:483-490)."""
 
     @staticmethod
-    def forward(ctx, c: AggConst, packed: PackedDecoder, xyz, ginv, feat, *ws):
+    def forward(ctx, c: AggConst, packed: PackedDecoder, xyz, ginv, feat, pose_emb, *ws):
         lib = _lib.load()
         xyz, ginv, feat = _f32(xyz), _f32(ginv), _f32(feat)
+        pose_emb = None if pose_emb is None else _f32(pose_emb).reshape(-1)
         ws = [_f32(w) for w in ws]
         M = c.pts.shape[0]
         dev = xyz.device
-        d_in = PE_POS + FEAT_DIM
+        d_in = PE_POS + FEAT_DIM + (0 if pose_emb is None else pose_emb.numel())
         alpha, rgb = _empty((M,), dev), _empty((M, 3), dev)
         alpha_d = _empty((M,), dev) if c.direct else None
         rgb_d = _empty((M, 3), dev) if c.direct else None
@@ -612,14 +648,15 @@ class _AggregateTC(torch.autograd.Function):
             out = AggOutputs()
             out.alpha, out.rgb, out.alpha_direct, out.rgb_direct, out.idw = ptr(alpha), ptr(rgb), ptr(alpha_d), ptr(rgb_d), ptr(idw)
             out.h, out.exp_d, out.fv, out.v0 = ptr(h), ptr(exp_d), ptr(fv), ptr(v0)
-            a = _agg_inputs(c, xyz, ginv, feat, None, M, d_in)
+            a = _agg_inputs(c, xyz, ginv, feat, pose_emb, M, d_in)
             w = _mlp_struct(ws)
             pk, table = packed.get(ws, d_in, feat)
             with stage("feat_net"):
                 check(lib.apn_aggregate_fwd_tc(C.byref(a), C.byref(w), ptr(pk), ptr(table), C.byref(out), 1, ptr(tape),
                                                tape_bytes, None, 0, stream()), "apn_aggregate_fwd_tc(train)")
-        ctx.c, ctx.packed, ctx.d_in = c, packed, d_in
-        ctx.save_for_backward(xyz, ginv, feat, *ws, alpha, rgb, idw, h, exp_d, fv, v0, tape)
+        ctx.c, ctx.packed, ctx.d_in, ctx.has_pose = c, packed, d_in, pose_emb is not None
+        ctx.save_for_backward(xyz, ginv, feat, pose_emb if pose_emb is not None else xyz.new_empty(0), *ws, alpha, rgb, idw, h,
+                              exp_d, fv, v0, tape)
         ctx.mark_non_differentiable(idw)
         if c.direct:
             ctx.mark_non_differentiable(alpha_d, rgb_d)
@@ -630,23 +667,29 @@ class _AggregateTC(torch.autograd.Function):
         lib = _lib.load()
         c = ctx.c
         sv = ctx.saved_tensors
-        xyz, ginv, feat = sv[0:3]
-        ws = list(sv[3:19])
-        alpha, rgb, idw, h, exp_d, fv, v0, tape = sv[19:27]
+        xyz, ginv, feat, pose_emb = sv[0:4]
+        if not ctx.has_pose:
+            pose_emb = None
+        ws = list(sv[4:20])
+        alpha, rgb, idw, h, exp_d, fv, v0, tape = sv[20:28]
         M = c.pts.shape[0]
         dev = xyz.device
-        need = ctx.needs_input_grad      # (c, packed, xyz, ginv, feat, *ws)
+        need = ctx.needs_input_grad      # (c, packed, xyz, ginv, feat, pose_emb, *ws)
         # The backward kernels ACCUMULATE into caller-provided buffers.  With DIRECT_GRAD_ACCUM (set by
-        # train.GradBucket) a leaf parameter whose .grad already exists (a slice of the flat gradient bucket) receives
-        # its gradient in place and autograd is handed None: no temporary, no memset, no AccumulateGrad add kernel.
+        # train.GradBucket.direct_accum) a leaf parameter whose .grad already exists (a slice of the flat gradient bucket)
+        # receives its gradient in place and autograd is handed None: no temporary, no memset, no AccumulateGrad add kernel.
         direct = [DIRECT_GRAD_ACCUM and n and t.is_leaf and t.grad is not None and t.grad.is_contiguous()
-                  and t.grad.dtype == torch.float32 for t, n in zip([feat] + list(ws), need[4:])]
+                  and t.grad.dtype == torch.float32 for t, n in zip([feat] + list(ws), [need[4]] + list(need[6:]))]
+        want_pose = pose_emb is not None and need[5]
         wanted = [t for t, n in ((xyz, need[2]), (ginv, need[3])) if n]
+        if want_pose:
+            wanted.append(pose_emb)
         wanted += [t for t, dr in zip([feat] + list(ws), direct) if not dr]
         zs = _zeros_like_many(wanted) if wanted else []
         zi = iter(zs)
         d_xyz = next(zi) if need[2] else None
         d_ginv = next(zi) if need[3] else None
+        d_pose = next(zi) if want_pose else None
         d_all = [t.grad if dr else next(zi) for t, dr in zip([feat] + list(ws), direct)]
         d_feat = d_all[0] if need[4] else None
         d_ws = d_all[1:]
@@ -658,13 +701,13 @@ class _AggregateTC(torch.autograd.Function):
             out.h, out.exp_d, out.fv, out.v0 = ptr(h), ptr(exp_d), ptr(fv), ptr(v0)
             g = AggGrads()
             g.d_alpha, g.d_rgb = ptr(d_alpha), ptr(d_rgb)
-            g.d_xyz, g.d_ginv, g.d_feat, g.d_pose_emb = ptr(d_xyz), ptr(d_ginv), ptr(d_feat), None
+            g.d_xyz, g.d_ginv, g.d_feat, g.d_pose_emb = ptr(d_xyz), ptr(d_ginv), ptr(d_feat), ptr(d_pose)
             for l in range(4):
                 g.d_w[l] = ptr(d_ws[2 * l])
                 g.d_b[l] = ptr(d_ws[2 * l + 1])
             (g.d_density_w, g.d_density_b, g.d_rgb_feat_w, g.d_rgb_feat_b, g.d_rgb_v0_w, g.d_rgb_v0_b, g.d_rgb_v2_w,
              g.d_rgb_v2_b) = [ptr(t) for t in d_ws[8:16]]
-            a = _agg_inputs(c, xyz, ginv, feat, None, M, ctx.d_in)
+            a = _agg_inputs(c, xyz, ginv, feat, pose_emb, M, ctx.d_in)
             w = _mlp_struct(ws)
             pk = ctx.packed.get_bwd(ws, ctx.d_in)
             sb = lib.apn_aggregate_tc_bwd_scratch_bytes(M, xyz.shape[0])
@@ -672,14 +715,17 @@ class _AggregateTC(torch.autograd.Function):
             with stage("feat_net_bwd"):
                 check(lib.apn_aggregate_bwd_tc(C.byref(a), C.byref(w), ptr(pk), C.byref(out), ptr(tape), C.byref(g),
                                                ptr(scratch), sb, stream()), "apn_aggregate_bwd_tc")
-        return (None, None, d_xyz, d_ginv, (None if direct[0] else d_feat),
-                *[dw if (need[5 + i] and not direct[1 + i]) else None for i, dw in enumerate(d_ws)])
+        return (None, None, d_xyz, d_ginv, (None if direct[0] else d_feat), d_pose,
+                *[dw if (need[6 + i] and not direct[1 + i]) else None for i, dw in enumerate(d_ws)])
 
 
-def aggregate_tc_train(c: AggConst, xyz, ginv, feat, weights: Sequence[torch.Tensor], packed: PackedDecoder):
-    """Differentiable aggregation on the tensor cores (d_in = 191). -> alpha, rgb, alpha_direct, rgb_direct, idw."""
+def aggregate_tc_train(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch.Tensor], packed: PackedDecoder):
+    """Differentiable aggregation on the tensor cores (d_in = 191, or 255 with a pose embedding).
+    -> alpha, rgb, alpha_direct, rgb_direct, idw."""
     assert len(weights) == 16
-    return _AggregateTC.apply(c, packed, xyz, ginv, feat, *weights)
+    if pose_emb is not None:
+        pose_emb = pose_emb.reshape(-1)          # (1, 64) -> (64): the gradient comes back in this shape through autograd
+    return _AggregateTC.apply(c, packed, xyz, ginv, feat, pose_emb, *weights)
 
 
 # --------------------------------------------------------------------------------------

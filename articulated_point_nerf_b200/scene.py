@@ -241,6 +241,9 @@ CONFIGS = {
     # BASELINE.json configs[0..4]
     "tiny": SceneConfig(name="tiny", n_points=1500, H=40, W=40, n_views=4),
     "small": SceneConfig(name="small", n_points=6000, H=64, W=64, n_views=4),
+    # c4 in miniature (configs/zju/default.py:72,112; lib/load_data.py:45-46): pose embedding, black background, OpenCV rays
+    "tiny_pose": SceneConfig(name="tiny_pose", n_points=1500, skeleton="random", n_joints=10, H=40, W=40, n_views=4,
+                             cam_radius=3.0, near=1.0, far=4.0, bg=0.0, inverse_y=True, pose_embedding_dim=64),
     "c1": SceneConfig(name="c1", n_points=30000, H=400, W=400, n_views=8),
     "c2": SceneConfig(name="c2", n_points=30000, H=400, W=400, n_views=8),
     "c3": SceneConfig(name="c3", n_points=30000, skeleton="random", n_joints=24, body_scale=2.5, H=1024, W=1024,
@@ -348,6 +351,9 @@ def build_model(scene: Scene, seed: int = 0, density_bias: float = 7.0, theta_st
         sel = torch.randint(0, len(scene.canonical_pcd), (512,), generator=gcal)
         rel = torch.randn(512, 3, generator=gcal) * (0.7 * float(scene.lattice_h))
         x = torch.cat([poc_fre(rel, model.pos_poc), model.canonical_feat[sel]], dim=-1)
+        if cfg.pose_embedding_dim > 0:      # rest pose: joint offsets 0 (lib/temporalpoints.py:571-574)
+            e = model.pose_embedding_net(poc_fre(torch.zeros_like(model.joints), model.pos_poc).view(1, -1))
+            x = torch.cat([x, e.expand(len(x), -1)], dim=-1)
         if x.shape[-1] == model.feat_net[0].in_features:
             z = model.densitynet(model.feat_net(x)).reshape(-1)
             gain = density_std / max(float(z.std()), 1e-6)

@@ -159,7 +159,7 @@ class TemporalPoints(torch.nn.Module):
         # decoder used when no gradient is needed: "tc" = tcgen05 split-fp16 (fp32-class), "tc_fast" = tcgen05 fp16
         # operands, "fp32" = CUDA-core exact path (always used when autograd is recording)
         self.decoder = "tc"
-        # decoder used while autograd records: "tc" = tensor-core forward + backward (split-fp16; d_in = 191 only),
+        # decoder used while autograd records: "tc" = tensor-core forward + backward (split-fp16; d_in = 191 or 255),
         # "fp32" = CUDA-core exact path
         self.decoder_train = "fp32"
         self._packed_decoder = ops.PackedDecoder()
@@ -247,6 +247,7 @@ class TemporalPoints(torch.nn.Module):
         # the point spacing inside the occupied volume is finer than the bbox average; refine once
         grid = ops.Grid(pcd, bbox, query_radius=0.01, bbox_pad=0.01, cell_hint=max(spacing * 0.5, 1e-4))
         idx, d2 = grid.knn(pcd, self.neighbours)
+        assert int(idx.min()) >= 0, "k-NN returned an invalid neighbour index"
         self.nn_i = idx.long()
         self.nn_distance = torch.sqrt(((pcd[:, None, :] - pcd[self.nn_i, :]) ** 2).sum(-1) + self.eps.to(pcd.device))
         self.mean_min_distance = self.nn_distance[:, 1].mean()
@@ -464,9 +465,9 @@ class TemporalPoints(torch.nn.Module):
             alpha, rgb, alpha_d, rgb_d, idw = ops.aggregate_tc(c, t_hat_pcd, warped['ginv'], self.canonical_feat, pose_embedding,
                                                                self._mlp_weights(), self._packed_decoder,
                                                                precision=1 if self.decoder == "tc" else 0)
-        elif self.decoder_train == "tc" and pose_embedding is None and torch.is_grad_enabled():
+        elif self.decoder_train == "tc" and torch.is_grad_enabled():
             alpha, rgb, alpha_d, rgb_d, idw = ops.aggregate_tc_train(c, t_hat_pcd, warped['ginv'], self.canonical_feat,
-                                                                     self._mlp_weights(), self._packed_decoder)
+                                                                     pose_embedding, self._mlp_weights(), self._packed_decoder)
         else:
             alpha, rgb, alpha_d, rgb_d, idw = ops.aggregate(c, t_hat_pcd, warped['ginv'], self.canonical_feat, pose_embedding,
                                                             self._mlp_weights())
@@ -526,7 +527,7 @@ class TemporalPoints(torch.nn.Module):
         vol = float((hi - lo).clamp_min(1e-4).prod())
         cell = max((vol / max(len(tgt), 1)) ** (1 / 3), 1e-4)
         g = ops.Grid(tgt, torch.cat([lo, hi]), query_radius=0.01, bbox_pad=0.01, cell_hint=cell)
-        idx, _ = g.knn(query.detach().contiguous(), 1)
+        idx, _ = g.knn(query.detach().contiguous(), 1)      # checks the grid's overflow flag, grows the table if needed
         return idx.long()
 
     def get_chamfer_loss(self, pcd1, pcd2, N=None, M=None, c=0.03, get_raw=False):

@@ -61,22 +61,53 @@ class GradBucket:
             total += (p.numel() + 63) // 64 * 64          # 256-byte aligned slices
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.params = params
-        for p, o in zip(params, offs):
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+        self.offsets = offs
+        self.attach()
         self.numel = sum(p.numel() for p in params)
-        # gradients of the decoder parameters are accumulated by the backward kernels directly into these slices
-        from . import ops
-        ops.DIRECT_GRAD_ACCUM = True
+
+    def attach(self):
+        """(Re-)installs the bucket slices as the parameters' .grad."""
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+
+    def attached(self) -> bool:
+        """False once something detached a gradient from the bucket, e.g. optimizer.zero_grad(set_to_none=True) (the
+        reference's default, run.py:575): an all-reduce of `flat` would then exchange zeros."""
+        base = self.flat.data_ptr()
+        return all(p.grad is not None and p.grad.data_ptr() == base + 4 * o for p, o in zip(self.params, self.offsets))
+
+    def direct_accum(self):
+        """Context manager: inside it the decoder's backward kernels accumulate straight into the bucket slices (no
+        temporaries, no AccumulateGrad adds).  Scoped to the training step: outside it autograd sees ordinary
+        gradients, so torch.autograd.grad / gradcheck / hooks on the same model keep working."""
+        return _DirectAccum()
 
     def zero(self):
+        if not self.attached():
+            self.attach()
         self.flat.zero_()
 
     def all_reduce_avg(self, group=None):
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if not self.attached():
+                raise RuntimeError("GradBucket: a parameter's .grad no longer aliases the flat bucket (zero_grad(set_to_none="
+                                   "True)?); call bucket.zero() instead of optimizer.zero_grad()")
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if self.flat.is_cuda else dist.ReduceOp.SUM, group=group)
             if not self.flat.is_cuda:                      # gloo has no AVG
                 self.flat.div_(dist.get_world_size(group))
+
+
+class _DirectAccum:
+    def __enter__(self):
+        from . import ops
+        self.prev = ops.DIRECT_GRAD_ACCUM
+        ops.DIRECT_GRAD_ACCUM = True
+
+    def __exit__(self, *exc):
+        from . import ops
+        ops.DIRECT_GRAD_ACCUM = self.prev
+        return False
 
 
 def shard_rays(n_rays: int, rank: int, world: int):
@@ -115,7 +146,7 @@ class FusedTrainStep:
     @staticmethod
     def eligible(model) -> bool:
         fw = model.forward_warp
-        return (model.decoder_train == "tc" and model.pose_embedding_dim == 0 and model.joints.is_cuda and fw.fused_pose
+        return (model.decoder_train == "tc" and model.joints.is_cuda and fw.fused_pose
                 and fw._fused_tables(model.joints.device) is not None)
 
     @torch.no_grad()
@@ -150,8 +181,19 @@ class FusedTrainStep:
                          mean_min_distance=m._mmd_float, eps=float(m.eps), act_shift=float(m.tineuvox.act_shift),
                          interval=float(render_kwargs['stepsize']) * float(m.tineuvox.voxel_size_ratio), direct=False)
         ws = m._mlp_weights()
-        ca = _Ctx((False, False, True, True, m.canonical_feat.requires_grad, *[x.requires_grad for x in ws]))
-        alpha, rgb, _, _, _ = ops._AggregateTC.forward(ca, c, m._packed_decoder, xyz, ginv, m.canonical_feat, *ws)
+        # pose embedding (lib/temporalpoints.py:571-576; ZJU configs): a (1, 64) vector from the DETACHED joint offsets, so
+        # gradients reach pose_embedding_net only — and only if the optimiser owns it (the reference's stage-2 configs
+        # have no lrate_pose_embedding_net: the net stays at its initialisation, configs/zju/default.py:79-91)
+        pose_emb, pose_graph = None, False
+        if m.pose_embedding_dim > 0:
+            jh = torch.cat([m.joints, torch.ones((len(m.joints), 1), device=dev)], dim=-1)
+            delta = m.joints - torch.bmm(bone_Ts, jh.unsqueeze(-1)).squeeze(-1)[:, :3]
+            pose_graph = any(p.grad is not None for p in m.pose_embedding_net.parameters())
+            with torch.set_grad_enabled(pose_graph):
+                pose_emb = m.pose_embedding_net(poc_fre(delta.detach(), m.pos_poc).view(1, -1)).reshape(-1)
+        ca = _Ctx((False, False, True, True, m.canonical_feat.requires_grad, pose_graph, *[x.requires_grad for x in ws]))
+        alpha, rgb, _, _, _ = ops._AggregateTC.forward(ca, c, m._packed_decoder, xyz, ginv, m.canonical_feat,
+                                                       None if pose_emb is None else pose_emb.detach(), *ws)
         cc = _Ctx((True, True, False, False, False, False, False, False, False))
         rgb_m, last, _, _ = ops._Composite.forward(cc, alpha, rgb, smp.step_id, None, smp.ray_start, R, m.fast_color_thres,
                                                    float(render_kwargs['bg']), False)
@@ -160,7 +202,11 @@ class FusedTrainStep:
         # ---- backward, in autograd's order
         d_alpha, d_rgb = ops._Composite.backward(cc, d_rgb_m, None, None, None)[:2]
         ga = ops._AggregateTC.backward(ca, d_alpha, d_rgb)
-        self._accumulate([m.canonical_feat] + list(ws), ga[4:])            # None where the kernels wrote into .grad directly
+        self._accumulate([m.canonical_feat], ga[4:5])                      # None where the kernels wrote into .grad directly
+        self._accumulate(list(ws), ga[6:])
+        if pose_graph:
+            with torch.enable_grad():
+                pose_emb.backward(ga[5])                                    # accumulates into the bucket slices
         if m.weights.grad is not None and m.theta_weight.grad is not None:
             cl.grad_out = dict(raw=m.weights.grad, theta=m.theta_weight.grad.reshape(1))
         gl = ops._LBS.backward(cl, ga[2], ga[3], None, None, None)
@@ -180,28 +226,37 @@ class FusedTrainStep:
                 p.grad.add_(g.reshape(p.grad.shape))
 
 
-def train_step(model, optimizer: MaskedAdam, bucket: GradBucket, t, render_kwargs, target, *, decay_factor: float = 1.0,
-               fused: bool = True):
-    """One stage-2 iteration on one rank's ray batch.  Returns the (device) loss tensor."""
-    if fused and FusedTrainStep.eligible(model):
-        fs = getattr(bucket, "_fused_step", None)
-        if fs is None or fs.model is not model:
-            fs = bucket._fused_step = FusedTrainStep(model, optimizer, bucket)
-        loss = fs.run(t, render_kwargs, target)
-        if loss is not None:
-            bucket.all_reduce_avg()
-            optimizer.step()
-            if decay_factor != 1.0:
-                for g in optimizer.param_groups:                  # run.py:718-721
-                    g['lr'] = g['lr'] * decay_factor
-            return loss
-    bucket.zero()
-    res = model(t, False, render_kwargs, render_pcd_direct=False)
-    loss = WEIGHT_RENDER * F.mse_loss(res['rgb_marched'], target)
-    loss.backward()
+def _finish_step(optimizer, bucket, decay_factor):
     bucket.all_reduce_avg()
     optimizer.step()
     if decay_factor != 1.0:
         for g in optimizer.param_groups:                  # run.py:718-721
             g['lr'] = g['lr'] * decay_factor
-    return loss
+
+
+def train_step(model, optimizer: MaskedAdam, bucket: GradBucket, t, render_kwargs, target, *, decay_factor: float = 1.0,
+               fused: bool = True):
+    """One stage-2 iteration on one rank's ray batch.  Returns the (device) loss tensor.
+
+    A batch that keeps no sample (every ray of this rank's shard misses the cloud: the reference's NoPointsException
+    path, lib/temporalpoints.py:598-609) has a constant render loss: its gradient is zero, so the bucket stays zeroed —
+    but the rank still takes part in the all-reduce and the optimiser step, otherwise the other ranks of a sharded
+    batch would wait in NCCL for ever."""
+    with bucket.direct_accum():
+        if fused and FusedTrainStep.eligible(model):
+            fs = getattr(bucket, "_fused_step", None)
+            if fs is None or fs.model is not model:
+                fs = bucket._fused_step = FusedTrainStep(model, optimizer, bucket)
+            loss = fs.run(t, render_kwargs, target)
+            if loss is None:
+                bg = float(render_kwargs['bg'])
+                loss = WEIGHT_RENDER * F.mse_loss(torch.full_like(target, bg), target)
+            _finish_step(optimizer, bucket, decay_factor)
+            return loss
+        bucket.zero()
+        res = model(t, False, render_kwargs, render_pcd_direct=False)
+        loss = WEIGHT_RENDER * F.mse_loss(res['rgb_marched'], target)
+        if loss.requires_grad:
+            loss.backward()
+        _finish_step(optimizer, bucket, decay_factor)
+        return loss

@@ -252,7 +252,9 @@ int apn_aggregate_fwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, con
 
 /* Tensor-core backward of the same op (replaces autograd through lib/temporalpoints.py:446-515): split-fp16 dgrad chain
  * + wgrad with accumulators in tensor memory; heads in fp32.  Same gradient contract as apn_aggregate_bwd (all
- * outgoing buffers accumulated into; caller zeroes).  Covers d_in = 191 (no pose embedding).
+ * outgoing buffers accumulated into; caller zeroes).  d_in = 191, or up to 256 with a pose embedding (lib/temporalpoints.py:
+ * 483-490,571-576): the embedding is the same vector for every row, so its weight columns act as a layer-0 bias in the
+ * forward and its gradients follow from the layer-0 bias gradient (d_e = W0[:,191:]^T db0, dW0[:,191:] += db0 (x) e).
  * packed_bwd: apn_aggregate_tc_bwd_weights_bytes() bytes filled by apn_aggregate_tc_pack_weights_bwd. */
 size_t apn_aggregate_tc_bwd_weights_bytes(void);
 int apn_aggregate_tc_pack_weights_bwd(const apn_mlp_weights* w, int d_in, void* packed_bwd, apn_stream_t stream);

@@ -389,11 +389,22 @@ class OraclePath:
 
     # -- full forward -------------------------------------------------------------------
     def forward(self, t=None, rot_params=None, *, rays_o, rays_d, viewdirs, near, far, stepsize, bg,
-                query_radius=0.01, render_weights=False):
+                query_radius=0.01, render_weights=False, cloud=None, ginv3=None):
+        """`cloud` (test hook, not in the reference): evaluate everything downstream of the warp on THIS warped cloud
+        (values replaced, autograd graph of the warp kept).  The reference's sampler is discontinuous in the last bit of
+        the cloud's bbox (lib/cuda/render_utils_kernel.cu:23-33), so two correct warps that differ by one ulp keep
+        slightly different sample sets; comparisons that are meant to pin the stages AFTER the warp pass the other
+        side's cloud (and inverse frames, `ginv3`) in."""
         assert (t is None) ^ (rot_params is None)
         s = self.s
         wp = self.warp(t, rot_params)
+        if cloud is not None:
+            wp['xyz'] = wp['xyz'] + (cloud.to(F32) - wp['xyz']).detach()
         Ginv = torch.inverse(wp['G'])
+        if ginv3 is not None:                     # same hook for the inverse frames (N,3,3)
+            pad = torch.zeros_like(Ginv)
+            pad[:, :3, :3] = ginv3.to(F32) - Ginv[:, :3, :3].detach()
+            Ginv = Ginv + pad
         pose_embedding = None
         if self.pose_dim > 0:
             delta = (s['joints'] - wp['joints_rel']).clone().detach()

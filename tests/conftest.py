@@ -35,9 +35,30 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
 
 
+_GOLDEN_CACHE = {}
+
+
+def load_golden(name):
+    if name not in _GOLDEN_CACHE:
+        _GOLDEN_CACHE[name] = torch.load(os.path.join(GOLDEN_DIR, f"ref_{name}.pt"), weights_only=False)
+    return _GOLDEN_CACHE[name]
+
+
 @pytest.fixture(scope="session")
 def golden_tiny():
-    return torch.load(os.path.join(GOLDEN_DIR, "ref_tiny.pt"), weights_only=False)
+    return load_golden("tiny")
+
+
+@pytest.fixture(scope="session")
+def golden_tiny_pose():
+    """c4 in miniature: pose_embedding_dim=64 (decoder D_in=255), bg=0, inverse_y rays (oracle/make_golden.py tiny_pose)."""
+    return load_golden("tiny_pose")
+
+
+@pytest.fixture(scope="session", params=["tiny", "tiny_pose"])
+def golden_any(request):
+    """Every reference-run golden file: the jumpingjacks-shaped scene and the ZJU-shaped one (pose embedding)."""
+    return load_golden(request.param)
 
 
 def oracle_from_golden(g):
@@ -54,6 +75,11 @@ def oracle_from_golden(g):
 @pytest.fixture(scope="session")
 def oracle_tiny(golden_tiny):
     return oracle_from_golden(golden_tiny)
+
+
+@pytest.fixture(scope="session")
+def oracle_any(golden_any):
+    return oracle_from_golden(golden_any)
 
 
 def model_from_golden(g, device="cuda", fused_pose=False):
@@ -75,9 +101,16 @@ def model_from_golden(g, device="cuda", fused_pose=False):
     return model.to(device), scene
 
 
-def oracle_render_on_cloud(orc, cfg, g, xyz, ginv3, render_weights_from=None):
+def oracle_render_on_cloud(orc, cfg, g, xyz, ginv3, render_weights_from=None, t=None, rot_params=None):
     """Oracle sampling + aggregation + compositing on a GIVEN warped cloud (CPU tensors): what the reference computes
-    downstream of the warp.  -> dict(rgb_marched, alphainv_last, depth, rgb_marched_direct, alphainv_last_direct, M)."""
+    downstream of the warp.  -> dict(rgb_marched, alphainv_last, depth, rgb_marched_direct, alphainv_last_direct, M).
+    Scenes with a pose embedding need the pose (`t` or `rot_params`): the embedding comes from the warped joints."""
+    if getattr(orc, "pose_dim", 0) > 0:
+        assert (t is None) ^ (rot_params is None), "pose-embedding scenes: pass the pose"
+        out = orc.forward(t, rot_params, rays_o=g["rays_o"], rays_d=g["rays_d"], viewdirs=g["viewdirs"], near=cfg.near,
+                          far=cfg.far, stepsize=cfg.stepsize, bg=cfg.bg, cloud=xyz, ginv3=ginv3)
+        out["M"] = len(orc.trace["pts"])
+        return out
     Ginv = torch.eye(4).repeat(len(xyz), 1, 1)
     Ginv[:, :3, :3] = ginv3
     smp = orc.sample_and_knn(xyz, g["rays_o"], g["rays_d"], cfg.near, cfg.far, cfg.stepsize, 0.01)

@@ -131,6 +131,37 @@ def test_sample_and_knn_bit_exact(config, search, monkeypatch):
     assert torch.equal(rs[1:] - rs[:-1], counts)
 
 
+def test_grid_overflow_is_surfaced_and_recovered():
+    """A cell table too small for the padded bbox must never be silent (background frames, index -1 in gathers):
+    sample_and_knn and Grid.knn notice the header's overflow flag, grow the table in place and return the same
+    results as a grid that was large enough from the start; at the capacity limit they raise."""
+    ops = _ops()
+    scene, ro, rd, vd = _cloud_and_rays("tiny")
+    cfg = scene.cfg
+    d = "cuda"
+    xyz_d = scene.canonical_pcd.to(d)
+    bbox = torch.cat([xyz_d.min(0)[0], xyz_d.max(0)[0]])
+    good = ops.Grid(xyz_d, bbox, 0.01, 0.01, 1.5 * scene.lattice_h)
+    small = ops.Grid(xyz_d, bbox, 0.01, 0.01, 1.5 * scene.lattice_h, cell_capacity=1024)
+    assert small.overflowed() and not good.overflowed()
+    a = ops.sample_and_knn(good, ro.to(d), rd.to(d), cfg.near, cfg.far, cfg.stepsize * scene.voxel_size)
+    b = ops.sample_and_knn(small, ro.to(d), rd.to(d), cfg.near, cfg.far, cfg.stepsize * scene.voxel_size)
+    assert small.cell_capacity > 1024 and not small.overflowed()
+    assert a.M == b.M > 0 and torch.equal(a.nn_idx, b.nn_idx) and torch.equal(a.pts, b.pts)
+    small2 = ops.Grid(xyz_d, bbox, 0.01, 0.01, 1.5 * scene.lattice_h, cell_capacity=1024)
+    i1, d1 = good.knn(xyz_d[:500], 8)
+    i2, d2 = small2.knn(xyz_d[:500], 8)
+    assert int(i2.min()) >= 0 and torch.equal(i1, i2) and torch.equal(d1, d2)
+    old_max = ops.Grid.MAX_CAPACITY
+    try:
+        ops.Grid.MAX_CAPACITY = 1024
+        small3 = ops.Grid(xyz_d, bbox, 0.01, 0.01, 1.5 * scene.lattice_h, cell_capacity=1024)
+        with pytest.raises(ops.GridOverflow):
+            ops.sample_and_knn(small3, ro.to(d), rd.to(d), cfg.near, cfg.far, cfg.stepsize * scene.voxel_size)
+    finally:
+        ops.Grid.MAX_CAPACITY = old_max
+
+
 def test_knn_points_matches_bruteforce_with_lattice_ties():
     """Self k-NN of the canonical lattice cloud (exact ties everywhere): lowest index wins."""
     ops = _ops()
@@ -316,6 +347,33 @@ def test_adam_matches_reference_optimizer_golden(golden_tiny):
         opt.step()
     assert torch.equal(p0.detach().cpu(), a["after"][0])
     assert torch.equal(p1.detach().cpu(), a["after"][1])
+
+
+def test_adam_follows_load_state_dict():
+    """The cached descriptor table must see moment tensors replaced by optimizer.load_state_dict() (resume inside a
+    live process): step, load a saved state, step -> same as an optimizer that never cached anything."""
+    from articulated_point_nerf_b200 import MaskedAdam
+    from oracle import dvgo_ops
+    gen = torch.Generator().manual_seed(11)
+    p0, g0 = torch.randn(515, generator=gen), torch.randn(515, generator=gen)
+    p = torch.nn.Parameter(p0.clone().cuda())
+    opt = MaskedAdam([{"params": [p], "lr": 1e-3, "skip_zero_grad": False}])
+    p.grad = g0.cuda()
+    opt.step()
+    saved = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in opt.state[p].items()}
+    sd = opt.state_dict()
+    sd = {"state": {0: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in sd["state"][0].items()}},
+          "param_groups": sd["param_groups"]}
+    p_after1 = p.detach().clone()
+    opt.step()                                    # moves the live moments away from the saved ones
+    with torch.no_grad():
+        p.copy_(p_after1)
+    opt.load_state_dict(sd)                       # replaces state[p]['exp_avg'/'exp_avg_sq'] by new tensors
+    opt.step()
+    rp, rm, rv = p_after1.cpu().clone(), saved["exp_avg"].cpu().clone(), saved["exp_avg_sq"].cpu().clone()
+    dvgo_ops.adam_upd(rp, g0, rm, rv, 2, 0.9, 0.99, 1e-3, 1e-8)
+    assert torch.equal(p.detach().cpu(), rp)
+    assert torch.equal(opt.state[p]["exp_avg"].cpu(), rm) and torch.equal(opt.state[p]["exp_avg_sq"].cpu(), rv)
 
 
 def test_adam_perlr_mode():

@@ -18,8 +18,8 @@ def _rk(scene, g=None, rays=None, device="cuda"):
     return rk
 
 
-def test_render_matches_reference_golden(golden_tiny):
-    g = golden_tiny
+def test_render_matches_reference_golden(golden_any):
+    g = golden_any
     model, scene = model_from_golden(g)
     rk = _rk(scene, g)
     with torch.no_grad():
@@ -38,16 +38,32 @@ def test_render_matches_reference_golden(golden_tiny):
     assert rel_err(model.mean_min_distance, g["mean_min_distance"]) < 1e-6
 
 
-def test_repose_matches_reference_golden(golden_tiny):
-    g = golden_tiny
+def test_repose_matches_reference_golden(golden_any):
+    from conftest import oracle_from_golden, oracle_render_on_cloud
+    g = golden_any
     model, scene = model_from_golden(g)
     rk = _rk(scene, g)
+    rp = g["repose"]["rot_params"]
     with torch.no_grad():
-        out = model(None, render_depth=True, render_kwargs=rk, render_weights=True, rot_params=g["repose"]["rot_params"].cuda(),
-                    calc_min_max=True, get_skeleton=True, poses=scene.poses[0][None].cuda(), Ks=scene.Ks[0][None].cuda())
+        warped = model.warp(None, rp.cuda())
+        out = model(None, render_depth=True, render_kwargs=rk, render_weights=True, rot_params=rp.cuda(),
+                    calc_min_max=True, get_skeleton=True, poses=scene.poses[0][None].cuda(), Ks=scene.Ks[0][None].cuda(),
+                    warped=warped)
     ref = g["repose"]["out"]
-    for k in ["t_hat_pcd", "rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "weights"]:
-        assert rel_err(out[k], ref[k]) < RTOL, k
+    assert rel_err(out["t_hat_pcd"], ref["t_hat_pcd"]) < 2e-6
+    if torch.equal(out["t_hat_pcd"].min(0)[0].cpu(), ref["t_hat_pcd"].min(0)[0]) and \
+            torch.equal(out["t_hat_pcd"].max(0)[0].cpu(), ref["t_hat_pcd"].max(0)[0]):
+        # same bbox bits => same sample set: compare with the reference's outputs directly
+        for k in ["rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "weights"]:
+            assert rel_err(out[k], ref[k]) < RTOL, k
+    # and always: the stages behind the warp against the (reference-pinned) oracle on the kernel's own cloud — the sampler
+    # is discontinuous in the last bit of the cloud bbox (conftest.model_from_golden)
+    orc, cfg = oracle_from_golden(g)
+    with torch.no_grad():
+        o = oracle_render_on_cloud(orc, cfg, g, warped["xyz"].cpu(), warped["ginv"].cpu().view(-1, 3, 3), rot_params=rp)
+    assert model.last_counts["M"] == o["M"]
+    for k in ["rgb_marched", "alphainv_last", "depth", "rgb_marched_direct"]:
+        assert rel_err(out[k], o[k]) < RTOL, k
 
 
 # Gradients that pass through the positional encoding of the canonical-frame offset inherit its 2^9 frequency
@@ -62,11 +78,11 @@ GOLDEN_LOOSE = 5e-2
 
 
 @pytest.mark.parametrize("decoder", ["tc", "tc_fast", "fp32"])
-def test_render_with_fused_pose_matches_oracle_on_the_same_cloud(golden_tiny, decoder):
+def test_render_with_fused_pose_matches_oracle_on_the_same_cloud(golden_any, decoder):
     """Default product configuration (one-launch pose kernel): everything downstream of the warp against the oracle on the
     kernel's own warped cloud; the warp itself against the golden file."""
     from conftest import oracle_from_golden, oracle_render_on_cloud
-    g = golden_tiny
+    g = golden_any
     model, scene = model_from_golden(g, fused_pose=True)
     model.decoder = decoder
     rk = _rk(scene, g)
@@ -77,18 +93,22 @@ def test_render_with_fused_pose_matches_oracle_on_the_same_cloud(golden_tiny, de
     assert rel_err(model.forward_warp.prev_thetas, g["render"]["prev_thetas"]) < 1e-5
     orc, cfg = oracle_from_golden(g)
     with torch.no_grad():
-        ref = oracle_render_on_cloud(orc, cfg, g, warped["xyz"].cpu(), warped["ginv"].cpu().view(-1, 3, 3))
+        ref = oracle_render_on_cloud(orc, cfg, g, warped["xyz"].cpu(), warped["ginv"].cpu().view(-1, 3, 3), t=g["render"]["t"])
     assert model.last_counts["M"] == ref["M"]
     tol = RTOL if decoder != "tc_fast" else 3e-2
     for k in ["rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "alphainv_last_direct"]:
         assert rel_err(out[k], ref[k]) < tol, k
 
 
+@pytest.mark.parametrize("decoder_train", ["fp32", "tc"])
 @pytest.mark.parametrize("fused_pose", [False, True])
-def test_train_step_gradients_match_reference_golden(golden_tiny, fused_pose):
+def test_train_step_gradients_match_reference_golden(golden_any, fused_pose, decoder_train):
+    """Both training decoders (CUDA-core fp32 and tcgen05 split-fp16), both pose chains, both goldens (191 / 255 decoder
+    inputs).  The gradient of pose_embedding_net is part of the check although the reference's optimiser never owns it."""
     from conftest import oracle_from_golden
-    g = golden_tiny
+    g = golden_any
     model, scene = model_from_golden(g, fused_pose=fused_pose)
+    model.decoder_train = decoder_train
     rk = _rk(scene, g)
     model.zero_grad(set_to_none=True)
     warped = model.warp(g["train"]["t"].cuda())
@@ -97,7 +117,9 @@ def test_train_step_gradients_match_reference_golden(golden_tiny, fused_pose):
     loss = F.mse_loss(res["rgb_marched"], g["train"]["target"].cuda()) * 200.0
     loss.backward()
     named = dict(model.named_parameters())
-    if not fused_pose:
+    same_bbox = (torch.equal(warped["xyz"].detach().min(0)[0].cpu(), g["render"]["out"]["t_hat_pcd"].min(0)[0]) and
+                 torch.equal(warped["xyz"].detach().max(0)[0].cpu(), g["render"]["out"]["t_hat_pcd"].max(0)[0]))
+    if not fused_pose and same_bbox:
         # (1) against the reference's golden file (bit-compatible pose path, see conftest.model_from_golden)
         assert abs(loss.item() - g["train"]["loss"].item()) < RTOL * g["train"]["loss"].item()
         assert rel_err(res["rgb_marched"], g["train"]["rgb_marched"]) < RTOL
@@ -110,22 +132,17 @@ def test_train_step_gradients_match_reference_golden(golden_tiny, fused_pose):
     orc, cfg = oracle_from_golden(g)
     for k in g["train"]["grads"]:
         orc.s[k].requires_grad_(True)
-    wp = orc.warp(g["train"]["t"])
-    Ginv = torch.inverse(wp["G"])
     xyz_k = warped["xyz"].detach().cpu()
     ginv_k = warped["ginv"].detach().cpu().view(-1, 3, 3)
-    assert rel_err(xyz_k, wp["xyz"]) < 1e-6 and rel_err(ginv_k, Ginv[:, :3, :3]) < 2e-6
-    xyz = wp["xyz"] + (xyz_k - wp["xyz"]).detach()
-    pad = torch.zeros_like(Ginv)
-    pad[:, :3, :3] = ginv_k - Ginv[:, :3, :3].detach()
-    Ginv = Ginv + pad
-    smp = orc.sample_and_knn(xyz, g["rays_o"], g["rays_d"], cfg.near, cfg.far, cfg.stepsize, 0.01)
-    rgb, alpha, *_ = orc.aggregate(xyz, Ginv, smp, g["viewdirs"], cfg.stepsize)
-    rgb_m, *_ = orc.composite(alpha, rgb, smp["ray_id"], smp["step_id"], len(g["rays_o"]), cfg.bg)
-    loss_o = F.mse_loss(rgb_m, g["train"]["target"]) * 200.0
+    o = orc.forward(g["train"]["t"], rays_o=g["rays_o"], rays_d=g["rays_d"], viewdirs=g["viewdirs"], near=cfg.near, far=cfg.far,
+                    stepsize=cfg.stepsize, bg=cfg.bg, cloud=xyz_k, ginv3=ginv_k)
+    with torch.no_grad():
+        wp = orc.warp(g["train"]["t"])
+        assert rel_err(xyz_k, wp["xyz"]) < 1e-6 and rel_err(ginv_k, torch.inverse(wp["G"])[:, :3, :3]) < 2e-6
+    loss_o = F.mse_loss(o["rgb_marched"], g["train"]["target"]) * 200.0
     loss_o.backward()
     assert abs(loss.item() - loss_o.item()) < RTOL * loss_o.item()
-    assert rel_err(res["rgb_marched"], rgb_m) < RTOL
+    assert rel_err(res["rgb_marched"], o["rgb_marched"]) < RTOL
     for k in g["train"]["grads"]:
         assert rel_err(named[k].grad, orc.s[k].grad) < RTOL, k
 
@@ -150,8 +167,9 @@ def test_bucketed_train_step_equals_plain_autograd(golden_tiny):
     model.zero_grad(set_to_none=True)
     backward_once()
     plain = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
-    try:
-        bucket = GradBucket(create_optimizer(model))
+    bucket = GradBucket(create_optimizer(model))
+    assert not ops.DIRECT_GRAD_ACCUM                      # scoped: only inside bucket.direct_accum()
+    with bucket.direct_accum():
         assert ops.DIRECT_GRAD_ACCUM
         bucket.zero()
         backward_once()
@@ -163,34 +181,35 @@ def test_bucketed_train_step_equals_plain_autograd(golden_tiny):
         for k, ref in plain.items():
             if named[k].requires_grad:
                 assert rel_err(named[k].grad, 2 * ref) < RTOL, k
-    finally:
-        ops.DIRECT_GRAD_ACCUM = False
+    assert not ops.DIRECT_GRAD_ACCUM
+    # a gradient detached from the bucket (zero_grad(set_to_none=True), the reference's default) is noticed and re-attached
+    model.zero_grad(set_to_none=True)
+    assert not bucket.attached()
+    bucket.zero()
+    assert bucket.attached()
 
 
-def test_fused_train_step_equals_autograd_step(golden_tiny):
+def test_fused_train_step_equals_autograd_step(golden_any):
     """train.FusedTrainStep (explicit kernel chain, gradients written straight into the bucket) against the same step
     through autograd: same loss, same gradients, same parameters after Adam."""
     import copy
     from articulated_point_nerf_b200 import ops
     from articulated_point_nerf_b200.train import FusedTrainStep, GradBucket, create_optimizer, train_step
-    g = golden_tiny
-    rk_base = None
+    g = golden_any
     results = []
-    try:
-        for fused in (False, True):
-            model, scene = model_from_golden(g, fused_pose=True)
-            model.decoder_train = "tc"
-            rk = _rk(scene, g)
-            opt = create_optimizer(model)
-            bucket = GradBucket(opt)
-            assert FusedTrainStep.eligible(model)
-            t, tgt = g["train"]["t"].cuda(), g["train"]["target"].cuda()
-            loss = train_step(model, opt, bucket, t, rk, tgt, fused=fused)
-            assert (getattr(bucket, "_fused_step", None) is not None) == fused
-            results.append((float(loss.detach()), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None},
-                            {k: p.detach().clone() for k, p in model.named_parameters()}))
-    finally:
-        ops.DIRECT_GRAD_ACCUM = False
+    for fused in (False, True):
+        model, scene = model_from_golden(g, fused_pose=True)
+        model.decoder_train = "tc"
+        rk = _rk(scene, g)
+        opt = create_optimizer(model)
+        bucket = GradBucket(opt)
+        assert FusedTrainStep.eligible(model)
+        t, tgt = g["train"]["t"].cuda(), g["train"]["target"].cuda()
+        loss = train_step(model, opt, bucket, t, rk, tgt, fused=fused)
+        assert not ops.DIRECT_GRAD_ACCUM
+        assert (getattr(bucket, "_fused_step", None) is not None) == fused
+        results.append((float(loss.detach()), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None},
+                        {k: p.detach().clone() for k, p in model.named_parameters()}))
     (l0, g0, p0), (l1, g1, p1) = results
     assert abs(l0 - l1) <= 1e-6 * abs(l0)
     assert set(g0) == set(g1)
@@ -198,6 +217,29 @@ def test_fused_train_step_equals_autograd_step(golden_tiny):
         assert rel_err(g1[k], g0[k]) < RTOL, k
     for k in p0:       # Adam's first step moves every element by ~lr * sign(g): elements with g ~ 0 may differ by one lr
         assert rel_err(p1[k], p0[k]) < 1e-3, k
+
+
+def test_train_step_on_a_batch_without_samples(golden_tiny):
+    """Every ray misses the cloud (a rank's shard of a sharded batch can): the step must neither raise nor skip the
+    collective / optimiser step; loss = the constant background loss, gradients zero, parameters unchanged by Adam's
+    zero-gradient update."""
+    from articulated_point_nerf_b200.train import GradBucket, create_optimizer, train_step
+    g = golden_tiny
+    for fused in (True, False):
+        model, scene = model_from_golden(g, fused_pose=True)
+        model.decoder_train = "tc"
+        rk = _rk(scene, rays=(g["rays_o"][:64], (-g["rays_d"][:64]).contiguous(), (-g["viewdirs"][:64]).contiguous()))
+        opt = create_optimizer(model)
+        bucket = GradBucket(opt)
+        tgt = torch.rand(64, 3, device="cuda")
+        before = {k: p.detach().clone() for k, p in model.named_parameters()}
+        loss = train_step(model, opt, bucket, g["train"]["t"].cuda(), rk, tgt, fused=fused)
+        ref = 200.0 * F.mse_loss(torch.full_like(tgt, scene.cfg.bg), tgt)
+        assert abs(float(loss) - float(ref)) <= 1e-6 * float(ref)
+        assert float(bucket.flat.abs().max()) == 0.0
+        for k, p in model.named_parameters():
+            assert torch.equal(p.detach(), before[k]), k
+        assert all(opt.state[p]["step"] == 1 for grp in opt.param_groups for p in grp["params"] if p.grad is not None)
 
 
 def test_regulariser_losses_match_reference_golden(golden_tiny):

@@ -1,4 +1,4 @@
-"""CPU: pins oracle/path_oracle.py + oracle/dvgo_ops.py against tests/golden/ref_tiny.pt, which
+"""CPU: pins oracle/path_oracle.py + oracle/dvgo_ops.py against tests/golden/ref_tiny.pt and ref_tiny_pose.pt, which
 oracle/make_golden.py produced by running the reference's own Python under shims."""
 import torch
 import torch.nn.functional as F
@@ -17,9 +17,9 @@ def _call(orc, cfg, g, t=None, rot_params=None, **kw):
                        far=cfg.far, stepsize=cfg.stepsize, bg=cfg.bg, **kw)
 
 
-def test_render_outputs_match_reference(golden_tiny, oracle_tiny):
-    orc, cfg = oracle_tiny
-    g = golden_tiny
+def test_render_outputs_match_reference(golden_any, oracle_any):
+    orc, cfg = oracle_any
+    g = golden_any
     with torch.no_grad():
         out = _call(orc, cfg, g, t=g["render"]["t"], render_weights=True)
     ref = g["render"]["out"]
@@ -36,19 +36,24 @@ def test_render_outputs_match_reference(golden_tiny, oracle_tiny):
     assert _rel(orc.trace["weights"], g["render"]["last_weights"]) < RTOL
 
 
-def test_repose_outputs_match_reference(golden_tiny, oracle_tiny):
-    orc, cfg = oracle_tiny
-    g = golden_tiny
+def test_repose_outputs_match_reference(golden_any, oracle_any):
+    orc, cfg = oracle_any
+    g = golden_any
+    ref = g["repose"]["out"]
     with torch.no_grad():
         out = _call(orc, cfg, g, rot_params=g["repose"]["rot_params"], render_weights=True)
-    ref = g["repose"]["out"]
-    for k in ["t_hat_pcd", "rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "weights"]:
+        # the warp itself: last-bit agreement (the oracle sums the blend in another order than the reference's bmm)
+        assert _rel(out["t_hat_pcd"], ref["t_hat_pcd"]) < 2e-6
+        # everything behind the warp on the reference's own cloud: the sampler is discontinuous in the last bit of
+        # the cloud bbox, so a 1-ulp difference of min/max(xyz') may move a handful of samples across the bbox faces
+        out = _call(orc, cfg, g, rot_params=g["repose"]["rot_params"], render_weights=True, cloud=ref["t_hat_pcd"])
+    for k in ["rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "weights"]:
         assert _rel(out[k], ref[k]) < RTOL, k
 
 
-def test_train_gradients_match_reference(golden_tiny):
+def test_train_gradients_match_reference(golden_any):
     from conftest import oracle_from_golden
-    g = golden_tiny
+    g = golden_any
     orc, cfg = oracle_from_golden(g)
     for v in orc.s.values():
         if v.is_floating_point():
@@ -76,9 +81,9 @@ def test_adam_restatement_matches_reference_optimizer(golden_tiny):
         assert torch.equal(v, a["exp_avg_sq"][i])
 
 
-def test_empty_ray_batch_falls_back_to_background(oracle_tiny, golden_tiny):
-    orc, cfg = oracle_tiny
-    g = golden_tiny
+def test_empty_ray_batch_falls_back_to_background(oracle_any, golden_any):
+    orc, cfg = oracle_any
+    g = golden_any
     ro = g["rays_o"][:7]
     rd = -g["rays_d"][:7]            # looking away from the cloud: no sample in the bbox survives
     with torch.no_grad():
@@ -88,10 +93,10 @@ def test_empty_ray_batch_falls_back_to_background(oracle_tiny, golden_tiny):
     assert torch.equal(out["rgb_marched"], torch.ones(7, 3) * cfg.bg)
 
 
-def test_regulariser_losses_match_reference(golden_tiny, oracle_tiny):
+def test_regulariser_losses_match_reference(golden_any, oracle_any):
     from articulated_point_nerf_b200.scene import make_scene
-    orc, cfg = oracle_tiny
-    g = golden_tiny
+    orc, cfg = oracle_any
+    g = golden_any
     scene = make_scene(g["config"])
     with torch.no_grad():
         out = _call(orc, cfg, g, t=g["train"]["t"])
