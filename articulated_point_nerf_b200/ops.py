@@ -142,7 +142,7 @@ class _LBS(torch.autograd.Function):
     lib/pointwarper.py:241-266).  theta_weight=None: `raw_w` already holds the final weights."""
 
     @staticmethod
-    def forward(ctx, raw_w, theta_weight, bone_T, global_t, xyz, rules, eps, want_frames):
+    def forward(ctx, raw_w, theta_weight, bone_T, global_t, xyz, rules, eps, want_frames, want_weights=True):
         lib = _lib.load()
         raw_w, bone_T, xyz = _f32(raw_w), _f32(bone_T), _f32(xyz)
         theta_weight = None if theta_weight is None else _f32(theta_weight)
@@ -151,7 +151,8 @@ class _LBS(torch.autograd.Function):
         dev = raw_w.device
         xyz_out = _empty((N, 3), dev)
         ginv = _empty((N, 9), dev)
-        w_out = _empty((N, J), dev)
+        # merged skinning weights: a second 4J bytes per point of store traffic, skipped when nobody reads them
+        w_out = _empty((N, J), dev) if want_weights else None
         g_out = _empty((N, 4, 4), dev) if want_frames else None
         bbox = _empty((6,), dev)
         with stage("forward_warp"):
@@ -162,7 +163,8 @@ class _LBS(torch.autograd.Function):
         ctx.has_gt = global_t is not None
         ctx.want_frames = want_frames
         ctx.mark_non_differentiable(bbox)
-        return xyz_out, ginv, w_out, bbox, (g_out if want_frames else torch.zeros(0, device=dev))
+        return (xyz_out, ginv, (w_out if want_weights else torch.zeros(0, device=dev)), bbox,
+                (g_out if want_frames else torch.zeros(0, device=dev)))
 
     @staticmethod
     def backward(ctx, d_xyz, d_ginv, d_w, _d_bbox, d_g):
@@ -186,16 +188,17 @@ class _LBS(torch.autograd.Function):
                                   ptr(d_xyz), ptr(d_ginv), ptr(d_w), ptr(d_g), ptr(d_raw), ptr(d_theta), ptr(d_bone), ptr(d_gt),
                                   ptr(ws), ws_bytes, stream()), "apn_lbs_bwd")
         return (d_raw, None if d_theta is None else d_theta.reshape(theta_weight.shape), d_bone,
-                (d_gt if ctx.has_gt else None), None, None, None, None)
+                (d_gt if ctx.has_gt else None), None, None, None, None, None)
 
 
 def lbs(raw_w, theta_weight, bone_T, global_t, xyz, rules: Optional[torch.Tensor] = None, eps: float = 1e-6,
-        want_frames: bool = False):
-    """-> warped xyz (N,3), inverse frames (N,9), merged skinning weights (N,J), bbox (6) [min, max],
-    blended frames (N,4,4) if want_frames."""
+        want_frames: bool = False, want_weights: bool = True):
+    """-> warped xyz (N,3), inverse frames (N,9), merged skinning weights (N,J) (None unless want_weights), bbox (6)
+    [min, max], blended frames (N,4,4) if want_frames."""
     if rules is not None:
         rules = rules.to(torch.int32).contiguous()
-    xyz_out, ginv, w, bbox, g = _LBS.apply(raw_w, theta_weight, bone_T, global_t, xyz, rules, eps, want_frames)
+    xyz_out, ginv, w, bbox, g = _LBS.apply(raw_w, theta_weight, bone_T, global_t, xyz, rules, eps, want_frames, want_weights)
+    w = w if want_weights else None
     return (xyz_out, ginv, w, bbox, g) if want_frames else (xyz_out, ginv, w, bbox)
 
 

@@ -206,7 +206,7 @@ class PointWarper(torch.nn.Module):
         xyz = self.canonical_pcd
         if xyz.device != joints.device:
             xyz = self.canonical_pcd = xyz.to(joints.device)
-        res = ops.lbs(weights, None, bone_Ts, global_t, xyz, want_frames=get_frames)
+        res = ops.lbs(weights, None, bone_Ts, global_t, xyz, want_frames=get_frames, want_weights=False)
         jointsh = torch.cat([joints, torch.ones((len(joints), 1), device=joints.device, dtype=joints.dtype)], dim=-1)
         joints_warped_rel = torch.bmm(bone_Ts, jointsh.unsqueeze(-1)).squeeze(-1)[:, :3]
         out = [res[0], joints_warped_rel]

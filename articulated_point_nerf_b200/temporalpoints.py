@@ -154,7 +154,7 @@ class TemporalPoints(torch.nn.Module):
                 torch.nn.Linear(d // 2, pose_embedding_dim), torch.nn.LeakyReLU(inplace=True))
         self.beta = torch.nn.Parameter(torch.tensor([0.5]), requires_grad=True)
         self.beta_min = torch.nn.Parameter(torch.tensor([0.0001]), requires_grad=False)
-        self._last_weights = None
+        self._last_weights_value = None
         self.last_counts = {}
         # decoder used when no gradient is needed: "tc" = tcgen05 split-fp16 (fp32-class), "tc_fast" = tcgen05 fp16
         # operands, "fp32" = CUDA-core exact path (always used when autograd is recording)
@@ -378,8 +378,25 @@ class TemporalPoints(torch.nn.Module):
             self._rules_key = key
         return self._rules_cache
 
-    def warp(self, t=None, rot_params=None):
-        """forward_warp stage: -> dict(xyz, ginv, weights, bbox, bone_Ts, global_t, joints_rel)."""
+    @property
+    def _last_weights(self):
+        """The merged skinning weights of the last forward (lib/temporalpoints.py:555-556).  A no-grad render does not
+        store them (the LBS kernel skips that (N,J) write unless something reads it): they are then evaluated on demand."""
+        if self._last_weights_value is None and self.weights.is_cuda:
+            with torch.no_grad():
+                self._last_weights_value = self.get_weights()
+        return self._last_weights_value
+
+    @_last_weights.setter
+    def _last_weights(self, w):
+        self._last_weights_value = w
+
+    def warp(self, t=None, rot_params=None, want_weights=None):
+        """forward_warp stage: -> dict(xyz, ginv, weights, bbox, bone_Ts, global_t, joints_rel).
+        want_weights (default: whenever autograd records, i.e. training, where the regularisers read `_last_weights`):
+        also return the merged skinning weights."""
+        if want_weights is None:
+            want_weights = torch.is_grad_enabled()
         self._ensure_neighbourhood()
         t_embed = poc_fre(t, self.time_poc) if rot_params is None else None
         joints_rel = None
@@ -392,8 +409,8 @@ class TemporalPoints(torch.nn.Module):
             bone_Ts, global_t = self.forward_warp.pose(self.joints, t=t_embed, rot_params=rot_params)
         rules = self._merge_rules_i32()
         xyz, ginv, w, bbox = ops.lbs(self.weights, self.theta_weight, bone_Ts, global_t, self.canonical_pcd, rules=rules,
-                                     eps=float(self.eps))
-        self._last_weights = w
+                                     eps=float(self.eps), want_weights=want_weights)
+        self._last_weights = w                      # None: evaluated lazily by the property if someone asks
         if joints_rel is None:
             jh = torch.cat([self.joints, torch.ones((len(self.joints), 1), device=self.joints.device)], dim=-1)
             joints_rel = torch.bmm(bone_Ts, jh.unsqueeze(-1)).squeeze(-1)[:, :3]
@@ -426,7 +443,7 @@ class TemporalPoints(torch.nn.Module):
         assert render_kwargs is not None
         assert calc_min_max, "the reference's callers always sample inside the warped-cloud bbox"
         if warped is None:
-            warped = self.warp(t, rot_params)
+            warped = self.warp(t, rot_params, want_weights=True if render_weights else None)
         t_hat_pcd = warped['xyz']
         joints, bones = None, None
         pose_embedding = None
@@ -474,7 +491,8 @@ class TemporalPoints(torch.nn.Module):
         extra = None
         if render_weights:
             # lib/temporalpoints.py:517-519,690-701: per-sample LBS weights -> one colour per active bone
-            lw = self._last_weights.detach()
+            lw = warped['weights'] if warped.get('weights') is not None else self.get_weights()
+            lw = lw.detach()
             mask = lw.sum(dim=0) > 0
             cols = torch.tensor(hls_palette(int(mask.sum())), dtype=torch.float32)
             gen = torch.Generator().manual_seed(0)

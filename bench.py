@@ -337,7 +337,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(e2e: bool):
+    def timed_loop(e2e: bool, stages: bool = False):
+        """value loop (e2e=False): resident inputs, NO stage timers.  e2e loop: pinned host inputs, H2D + D2H inside.
+        stages=True (a third, separate pass): resident inputs with the per-stage CUDA-event brackets on — it feeds
+        `stages_ms_per_step` and the roofline figures, never `value`."""
         dev_in = None if e2e else [(t.to(dev), b.to(dev)) for t, b in host]
         for i in range(args.warmup):
             t_d, b_d = (host[i][0].to(dev, non_blocking=True), host[i][1].to(dev, non_blocking=True)) if e2e else dev_in[i]
@@ -352,7 +355,7 @@ def main():
             spare = torch.empty(max(int(0.5 * torch.cuda.memory_reserved(dev)), 64 << 20), dtype=torch.uint8, device=dev)
             del spare
         barrier()
-        _lib.STAGES.reset(not e2e)
+        _lib.STAGES.reset(stages)
         evs = []
         n0 = _lib.launch_count()
         for i in range(args.warmup, n_steps):
@@ -375,21 +378,25 @@ def main():
                   f"device_free={st.get('num_device_free')} retries={st.get('num_alloc_retries')} "
                   f"reserved={st.get('reserved_bytes.all.current', 0) / 1e6:.0f} MB", file=sys.stderr)
         launches = _lib.launch_count() - n0
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        per_step = torch.tensor([a.elapsed_time(b) for a, b in evs], device=dev, dtype=torch.float64)
+        tt = per_step.sum().reshape(1)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item()), launches
+            dist.all_reduce(per_step, op=dist.ReduceOp.MAX)          # per step: the slowest rank
+        q = torch.quantile(per_step, torch.tensor([0.1, 0.5, 0.9], device=dev, dtype=torch.float64)).tolist()
+        return float(tt.item()), launches, {"p10": q[0], "median": q[1], "p90": q[2], "min": float(per_step.min()),
+                                            "max": float(per_step.max())}
 
     clocks = ClockSampler(world) if rank == 0 else None
     if clocks is not None:
         clocks.start()
-    total_ms, launches = timed_loop(e2e=False)
+    total_ms, launches, dist_ms = timed_loop(e2e=False)
     clk = clocks.stop() if clocks is not None else None
+    e2e_ms, _, e2e_dist = timed_loop(e2e=True)
+    _, _, _ = timed_loop(e2e=False, stages=True)            # separate pass: stage brackets cost ~22 event pairs per step
     stage_tot = _lib.STAGES.totals()
     _lib.STAGES.reset(False)
     timed_counts = list(counts)
-    e2e_ms, _ = timed_loop(e2e=True)
 
     rays_per_step = len(host[0][1])
     value = rays_per_step * world * args.steps / (total_ms * 1e-3)
@@ -430,7 +437,9 @@ def main():
     N_pts, J_b, R_st = len(scene.canonical_pcd), len(scene.joints), rays_per_step
     M_avg = M_sum / max(args.steps, 1)
     T_avg = sum(c.get("candidates", 0) for c in timed_counts[:args.steps]) / max(args.steps, 1)
-    alg = {"forward_warp": N_pts * (4 * J_b + 12 + 12 + 36 + 4 * J_b) + 64 * J_b,
+    # LBS forward: SURVEY §8(d) bytes N(4J+12+12+36)+64J; the merged weights (another 4J per point) are only written
+    # when a caller needs them (training: the regularisers read _last_weights; no-grad renders skip the store)
+    alg = {"forward_warp": N_pts * (4 * J_b + 12 + 12 + 36) + 64 * J_b,
            "forward_warp_bwd": N_pts * (8 * J_b + 12 + 12 + 36 + 36),
            "grid_build": N_pts * 32,
            "sample_ray+knn": R_st * 24 + T_avg + M_avg * (12 + 8 + 64) + 12 * N_pts,
@@ -467,8 +476,9 @@ def main():
             "metric": METRIC[mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg, "clocks": clk,
+            "ms_per_step_dist": dist_ms,
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps, "ms_per_step_dist": e2e_dist},
             "gpu_launches": launches, "roofline": roofline, "roofline_hbm_stages": hbm_stages, "cpu_baseline": cpu_baseline,
             "counts": {"kept_samples_per_step": M_sum / max(args.steps, 1),
                        "candidates_per_step": sum(c.get("candidates", 0) for c in timed_counts[:args.steps]) / max(args.steps, 1)},
