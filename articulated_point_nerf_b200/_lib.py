@@ -32,7 +32,7 @@ class AggInputs(C.Structure):
                 ("ray_id", c_void_p), ("xyz", c_void_p), ("ginv", c_void_p), ("feat", c_void_p), ("pose_emb", c_void_p),
                 ("viewdirs", c_void_p), ("canonical_alpha", c_void_p), ("canonical_rgbs", c_void_p),
                 ("direct_eps", c_void_p), ("mean_min_distance", C.c_float), ("eps", C.c_float),
-                ("act_shift", C.c_float), ("interval", C.c_float)]
+                ("act_shift", C.c_float), ("interval", C.c_float), ("m_dev", c_void_p)]
 
 
 class AggOutputs(C.Structure):
@@ -97,6 +97,9 @@ SIGNATURES = {
     "apn_composite_bwd": (I, [P, P, P, P, I, F, F, P, P, P, P, P, P, P, P, P]),
     "apn_adam_step_size": (F, [I, F, F, F]),
     "apn_adam_multi": (I, [P, I, F, F, F, P]),
+    "apn_adam_multi_dev": (I, [P, I, F, F, F, P, P, P]),
+    "apn_sample_knn_static_workspace_bytes": (SZ, [I, I]),
+    "apn_sample_knn_static": (I, [P, P, I, F, F, F, P, I, I, P, SZ, P, P, P, P, P, P, P]),
     "apn_infer_t_minmax": (I, [P, P, P, P, F, F, I, P, P, P]),
     "apn_infer_n_samples": (I, [P, P, F, I, P, P]),
     "apn_infer_ray_start_dir": (I, [P, P, P, I, P, P, P]),

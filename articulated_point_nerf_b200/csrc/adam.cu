@@ -17,6 +17,8 @@ struct AdamBatch {
   apn_adam_tensor t[ADAM_MAX_TENSORS];
   int chunk_start[ADAM_MAX_TENSORS + 1];   // prefix of ceil(numel/ADAM_CHUNK)
   int n;
+  const float* step_sizes;                 // device array (one per tensor of this batch) overriding t.step_size, or NULL
+  const int32_t* skip;                     // device word: a non-zero value turns the launch into a no-op, or NULL
 };
 
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float perlr, float ss, float b1, float b2,
@@ -31,11 +33,13 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const __grid_constant__ AdamBatch batch, float b1, float b2, float eps) {
   const float omb1 = __fsub_rn(1.f, b1), omb2 = __fsub_rn(1.f, b2);
+  if (batch.skip && *reinterpret_cast<const volatile int32_t*>(batch.skip) != 0) return;   // e.g. a truncated sample workspace
   const int total_chunks = batch.chunk_start[batch.n];
   for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
     int ti = 0;
     while (batch.chunk_start[ti + 1] <= c) ++ti;     // n <= 64: linear search in constant bank
     const apn_adam_tensor& t = batch.t[ti];
+    const float step_size = batch.step_sizes ? __ldg(batch.step_sizes + ti) : t.step_size;
     const long long base = (long long)(c - batch.chunk_start[ti]) * ADAM_CHUNK;
     const long long n = min((long long)ADAM_CHUNK, t.numel - base);
     float* p = t.param + base;
@@ -53,17 +57,17 @@ adam_multi_kernel(const __grid_constant__ AdamBatch batch, float b1, float b2, f
       float4 V = reinterpret_cast<float4*>(v)[i];
       float4 PL = make_float4(1.f, 1.f, 1.f, 1.f);
       if (pl) PL = __ldg(reinterpret_cast<const float4*>(pl) + i);
-      adam_elem(P.x, G.x, M.x, V.x, PL.x, t.step_size, b1, b2, omb1, omb2, eps, t.mode);
-      adam_elem(P.y, G.y, M.y, V.y, PL.y, t.step_size, b1, b2, omb1, omb2, eps, t.mode);
-      adam_elem(P.z, G.z, M.z, V.z, PL.z, t.step_size, b1, b2, omb1, omb2, eps, t.mode);
-      adam_elem(P.w, G.w, M.w, V.w, PL.w, t.step_size, b1, b2, omb1, omb2, eps, t.mode);
+      adam_elem(P.x, G.x, M.x, V.x, PL.x, step_size, b1, b2, omb1, omb2, eps, t.mode);
+      adam_elem(P.y, G.y, M.y, V.y, PL.y, step_size, b1, b2, omb1, omb2, eps, t.mode);
+      adam_elem(P.z, G.z, M.z, V.z, PL.z, step_size, b1, b2, omb1, omb2, eps, t.mode);
+      adam_elem(P.w, G.w, M.w, V.w, PL.w, step_size, b1, b2, omb1, omb2, eps, t.mode);
       reinterpret_cast<float4*>(p)[i] = P;
       reinterpret_cast<float4*>(m)[i] = M;
       reinterpret_cast<float4*>(v)[i] = V;
     }
     for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
       float P = p[i], M = m[i], V = v[i];
-      adam_elem(P, g[i], M, V, pl ? pl[i] : 1.f, t.step_size, b1, b2, omb1, omb2, eps, t.mode);
+      adam_elem(P, g[i], M, V, pl ? pl[i] : 1.f, step_size, b1, b2, omb1, omb2, eps, t.mode);
       p[i] = P; m[i] = M; v[i] = V;
     }
   }
@@ -75,14 +79,15 @@ extern "C" float apn_adam_step_size(int step, float beta1, float beta2, float lr
   return lr * sqrtf(1.f - powf(beta2, fs)) / (1.f - powf(beta1, fs));
 }
 
-extern "C" int apn_adam_multi(const apn_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
-                              apn_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int adam_multi_launch(const apn_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
+                             const float* step_sizes_dev, const int32_t* skip_dev, cudaStream_t stream) {
   APN_CHECK_ARG(n_tensors >= 0 && (n_tensors == 0 || tensors), "bad tensor list");
   for (int s = 0; s < n_tensors; s += ADAM_MAX_TENSORS) {
     AdamBatch b;
     memset(&b, 0, sizeof(b));
     b.n = (n_tensors - s < ADAM_MAX_TENSORS) ? n_tensors - s : ADAM_MAX_TENSORS;
+    b.step_sizes = step_sizes_dev ? step_sizes_dev + s : nullptr;
+    b.skip = skip_dev;
     long long chunks = 0;
     for (int i = 0; i < b.n; ++i) {
       const apn_adam_tensor& t = tensors[s + i];
@@ -100,4 +105,19 @@ extern "C" int apn_adam_multi(const apn_adam_tensor* tensors, int n_tensors, flo
     APN_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int apn_adam_multi(const apn_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
+                              apn_stream_t stream_) {
+  return adam_multi_launch(tensors, n_tensors, beta1, beta2, eps, nullptr, nullptr, (cudaStream_t)stream_);
+}
+
+// Same update with the per-tensor step sizes read from DEVICE memory (step_sizes_dev[n_tensors], refreshed by the host
+// before a captured CUDA graph is replayed: kernel arguments are frozen at capture, the bias-corrected step size changes
+// every iteration) and an optional device-side skip word (non-zero: no update — the step's sample workspace overflowed and
+// the step is re-run; apn_sample_knn_static counts[2]).
+extern "C" int apn_adam_multi_dev(const apn_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
+                                  const float* step_sizes_dev, const int32_t* skip_dev, apn_stream_t stream_) {
+  APN_CHECK_ARG(step_sizes_dev, "step_sizes_dev is required (use apn_adam_multi for host-side step sizes)");
+  return adam_multi_launch(tensors, n_tensors, beta1, beta2, eps, step_sizes_dev, skip_dev, (cudaStream_t)stream_);
 }

@@ -222,6 +222,7 @@ static int agg_check_inputs(const apn_agg_inputs* in, const apn_mlp_weights* w) 
   APN_CHECK_ARG(in && w, "null struct");
   APN_CHECK_ARG(in->d_in == APN_PE_POS + AGG_C || (in->d_in > APN_PE_POS + AGG_C && in->d_in <= 256 && in->pose_emb),
                 "d_in must be 191, or 192..256 with a pose embedding");
+  APN_CHECK_ARG(in->m_dev == nullptr, "the fp32 path takes an exact host-side sample count (m_dev is for the tensor-core entry points)");
   APN_CHECK_ARG(in->pts && in->nn_idx && in->ray_id && in->xyz && in->ginv && in->feat && in->viewdirs, "null input pointer");
   for (int l = 0; l < 4; ++l) APN_CHECK_ARG(w->w[l] && w->b[l], "null feat_net weight");
   APN_CHECK_ARG(w->density_w && w->density_b && w->rgb_feat_w && w->rgb_feat_b && w->rgb_v0_w && w->rgb_v0_b && w->rgb_v2_w &&
@@ -267,8 +268,9 @@ extern "C" int apn_aggregate_fwd(const apn_agg_inputs* in, const apn_mlp_weights
 // d_pre = d_rgb * rgb (1-rgb); dW2 += d_pre^T v0; db2 += sum d_pre; d_v0 = relu'(v0) * (d_pre W2)
 __global__ void __launch_bounds__(256)
 agg_rgb_out_bwd_kernel(const float* __restrict__ d_rgb, const float* __restrict__ rgb, const float* __restrict__ v0,
-                       const float* __restrict__ W2, int M, float* __restrict__ d_v0, float* __restrict__ dW2,
-                       float* __restrict__ db2) {
+                       const float* __restrict__ W2, int M_cap, const int32_t* __restrict__ m_dev, float* __restrict__ d_v0,
+                       float* __restrict__ dW2, float* __restrict__ db2) {
+  const int M = apn_rt_count(m_dev, M_cap);
   __shared__ float sW[3 * AGG_V0];
   __shared__ float sAcc[3 * AGG_V0 + 3];
   for (int i = threadIdx.x; i < 3 * AGG_V0; i += blockDim.x) sW[i] = W2[i];
@@ -308,8 +310,11 @@ agg_rgb_out_bwd_kernel(const float* __restrict__ d_rgb, const float* __restrict_
 
 // column sums: out[n] += sum_r A[r*lda + n]
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ A, int lda, int rows, int N, int rows_per_block, float* __restrict__ out) {
+colsum_kernel(const float* __restrict__ A, int lda, int rows_cap, const int32_t* __restrict__ rows_dev, int N, int rows_per_block,
+              float* __restrict__ out) {
   __shared__ float sRed[8][32];
+  const int rows = apn_rt_count(rows_dev, rows_cap);
+  if (blockIdx.x * rows_per_block >= rows) return;
   const int n = blockIdx.y * 32 + (threadIdx.x & 31);
   const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   float s = 0.f;
@@ -324,11 +329,11 @@ colsum_kernel(const float* __restrict__ A, int lda, int rows, int N, int rows_pe
     atomicAdd(out + n, t);
   }
 }
-static int colsum(cudaStream_t st, const float* A, int lda, int rows, int N, float* out) {
+static int colsum(cudaStream_t st, const float* A, int lda, int rows, int N, float* out, const int32_t* rows_dev = nullptr) {
   if (rows <= 0) return 0;
   const int rpb = 1024;
   dim3 grid(apn_div_up(rows, rpb), apn_div_up(N, 32));
-  colsum_kernel<<<grid, 256, 0, st>>>(A, lda, rows, N, rpb, out);
+  colsum_kernel<<<grid, 256, 0, st>>>(A, lda, rows, rows_dev, N, rpb, out);
   apn_count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -344,22 +349,23 @@ int agg_rgbnet_bwd_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_m
   // d_fv.  On small batches every one of these GEMMs fills less than half the GPU, so with side streams they run beside
   // the chain instead of in it.
   cudaStream_t s0 = side ? side->s[0] : st, s1 = side ? side->s[1] : st;
-  agg_rgb_out_bwd_kernel<<<wblocks, 256, 0, st>>>(g->d_rgb, sv->rgb, sv->v0, w->rgb_v2_w, M, d_v0, g->d_rgb_v2_w, g->d_rgb_v2_b);
+  const int32_t* md = in->m_dev;         // device-side sample count (or NULL): every row loop / GEMM extent below follows it
+  agg_rgb_out_bwd_kernel<<<wblocks, 256, 0, st>>>(g->d_rgb, sv->rgb, sv->v0, w->rgb_v2_w, M, md, d_v0, g->d_rgb_v2_w, g->d_rgb_v2_b);
   APN_LAUNCH_CHECK();
   if (side) {
     APN_CUDA(cudaEventRecord(side->fork[0], st));
     APN_CUDA(cudaStreamWaitEvent(s0, side->fork[0], 0));
   }
-  APN_CHECK_ARG(gemm_wgrad(s0, d_v0, AGG_V0, sv->fv, AGG_FV_LD, g->d_rgb_v0_w, KV, M, AGG_V0, KV) == 0, "wgrad v0");
-  APN_CHECK_ARG(colsum(s0, d_v0, AGG_V0, M, AGG_V0, g->d_rgb_v0_b) == 0, "colsum v0");
-  APN_CHECK_ARG(gemm_dgrad(st, d_v0, AGG_V0, w->rgb_v0_w, KV, d_fv, AGG_FV_LD, M, KV, AGG_V0, nullptr, 0, 1.f) == 0, "dgrad v0");
+  APN_CHECK_ARG(gemm_wgrad(s0, d_v0, AGG_V0, sv->fv, AGG_FV_LD, g->d_rgb_v0_w, KV, M, AGG_V0, KV, md) == 0, "wgrad v0");
+  APN_CHECK_ARG(colsum(s0, d_v0, AGG_V0, M, AGG_V0, g->d_rgb_v0_b, md) == 0, "colsum v0");
+  APN_CHECK_ARG(gemm_dgrad(st, d_v0, AGG_V0, w->rgb_v0_w, KV, d_fv, AGG_FV_LD, M, KV, AGG_V0, nullptr, 0, 1.f, md) == 0, "dgrad v0");
   if (side) {
     APN_CUDA(cudaEventRecord(side->fork[1], st));
     APN_CUDA(cudaStreamWaitEvent(s1, side->fork[1], 0));
   }
-  APN_CHECK_ARG(gemm_wgrad(s1, d_fv, AGG_FV_LD, sv->h, AGG_C, g->d_rgb_feat_w, AGG_C, M, AGG_C, AGG_C) == 0, "wgrad rgb feat");
-  APN_CHECK_ARG(colsum(s1, d_fv, AGG_FV_LD, M, AGG_C, g->d_rgb_feat_b) == 0, "colsum rgb feat");
-  APN_CHECK_ARG(gemm_dgrad(st, d_fv, AGG_FV_LD, w->rgb_feat_w, AGG_C, d_h, AGG_C, M, AGG_C, AGG_C, nullptr, 0, 1.f) == 0, "dgrad rgb feat");
+  APN_CHECK_ARG(gemm_wgrad(s1, d_fv, AGG_FV_LD, sv->h, AGG_C, g->d_rgb_feat_w, AGG_C, M, AGG_C, AGG_C, md) == 0, "wgrad rgb feat");
+  APN_CHECK_ARG(colsum(s1, d_fv, AGG_FV_LD, M, AGG_C, g->d_rgb_feat_b, md) == 0, "colsum rgb feat");
+  APN_CHECK_ARG(gemm_dgrad(st, d_fv, AGG_FV_LD, w->rgb_feat_w, AGG_C, d_h, AGG_C, M, AGG_C, AGG_C, nullptr, 0, 1.f, md) == 0, "dgrad rgb feat");
   return 0;
 }
 

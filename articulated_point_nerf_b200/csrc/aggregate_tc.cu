@@ -145,9 +145,9 @@ struct TcRowLoad {
   int idx;
   float px, py, pz;
 };
-__device__ __forceinline__ TcRowLoad tc_row_load(const apn_agg_inputs& in, int tile, int erow) {
+__device__ __forceinline__ TcRowLoad tc_row_load(const apn_agg_inputs& in, int M, int tile, int erow) {
   TcRowLoad l;
-  const int m = min(tile * TC_SAMPLES + (erow >> 3), in.M - 1);
+  const int m = min(tile * TC_SAMPLES + (erow >> 3), M - 1);
   l.idx = __ldg(in.nn_idx + (size_t)m * APN_K + (erow & 7));
   l.px = __ldg(in.pts + 3 * (size_t)m);
   l.py = __ldg(in.pts + 3 * (size_t)m + 1);
@@ -158,12 +158,12 @@ __device__ __forceinline__ TcRowLoad tc_row_load(const apn_agg_inputs& in, int t
 // stage 2: geometry, inverse-distance weights, direct branch and the 32 PE columns of this thread as packed
 // half2 (hi[16], lo[16]: four 16-byte units each)
 template <int NSPLIT>
-__device__ __forceinline__ TcRow tc_prologue(const TcParams& p, int tile, int erow, int half, const TcRowLoad& l,
+__device__ __forceinline__ TcRow tc_prologue(const TcParams& p, int M, int tile, int erow, int half, const TcRowLoad& l,
                                              uint32_t (&hi)[16], uint32_t (&lo)[16]) {
   const apn_agg_inputs& in = p.in;
   const int m0 = tile * TC_SAMPLES, s = erow >> 3;
-  const int m = min(m0 + s, in.M - 1);
-  const bool valid = (m0 + s) < in.M;
+  const int m = min(m0 + s, M - 1);
+  const bool valid = (m0 + s) < M;
   const int idx = l.idx;
   const float rx = l.px - __ldg(in.xyz + 3 * (size_t)idx), ry = l.py - __ldg(in.xyz + 3 * (size_t)idx + 1),
               rz = l.pz - __ldg(in.xyz + 3 * (size_t)idx + 2);
@@ -325,9 +325,12 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) agg_tc_fwd_kernel(const TcP
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const apn_agg_inputs& in = p.in;
   TRACE_DECL;
+  // sample count: exact (host) or read here from the device counter (p.n_tiles then only sized the grid)
+  const int Mrt = apn_rt_count(in.m_dev, in.M);
+  const int n_tiles = (Mrt + TC_SAMPLES - 1) / TC_SAMPLES;
   // contiguous tile range of this CTA; group g takes every second tile starting at t_begin + g
-  const int t_begin = (int)(((long long)p.n_tiles * blockIdx.x) / gridDim.x);
-  const int t_end = (int)(((long long)p.n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int t_begin = (int)(((long long)n_tiles * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((long long)n_tiles * (blockIdx.x + 1)) / gridDim.x);
 
   if (tid == 0) {
     for (int i = 0; i < NSLOT; ++i) {
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) agg_tc_fwd_kernel(const TcP
     int tile = t_begin + g;
     if (tile < t_end) {
       uint32_t hi[16], lo[16];
-      row = tc_prologue<NSPLIT>(p, tile, erow, half, tc_row_load(in, tile, erow), hi, lo);
+      row = tc_prologue<NSPLIT>(p, Mrt, tile, erow, half, tc_row_load(in, Mrt, tile, erow), hi, lo);
       tc_store_pe<NSPLIT>(act, erow, half, hi, lo);
       tc_stage_ptable<NSPLIT>(p.ptable, row.idx, scratch, tacc0, half, lane);
       fence_proxy_async_smem();
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) agg_tc_fwd_kernel(const TcP
 #pragma unroll
       for (int layer = 0; layer < 3; ++layer) {
         // stage 1 of the next tile's prologue (4 registers, in flight during the layer-1 and layer-2 epilogues)
-        if (layer == 1 && next < t_end) nl = tc_row_load(in, next, erow);
+        if (layer == 1 && next < t_end) nl = tc_row_load(in, Mrt, next, erow);
         if (layer & 1) {
           mbar_wait(my_acc + 1, ph_acc1);
           ph_acc1 ^= 1;
@@ -541,7 +544,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) agg_tc_fwd_kernel(const TcP
       // ---------------------------------------------------------------- next tile's prologue, in registers (under the layer-3 MMAs)
       uint32_t nhi[16], nlo[16];
       TcRow nrow{0, 0.f};
-      if (next < t_end) nrow = tc_prologue<NSPLIT>(p, next, erow, half, nl, nhi, nlo);
+      if (next < t_end) nrow = tc_prologue<NSPLIT>(p, Mrt, next, erow, half, nl, nhi, nlo);
       if (wg == 0 && lane == 0) TRACE(g, 300);
       // ---------------------------------------------------------------- layer 3 complete: the operand buffer is free
       mbar_wait(my_acc + 1, ph_acc1);
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) agg_tc_fwd_kernel(const TcP
           x4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
         }
         const int m = m0 + (erow >> 3);
-        if (m < in.M) {
+        if (m < Mrt) {
           const int col = c0 + (b4 ? 16 : 0) + (b2 ? 8 : 0) + (b1 ? 4 : 0);
           *reinterpret_cast<float4*>(p.h + (size_t)m * APN_C + col) = make_float4(x4[0], x4[1], x4[2], x4[3]);
         }

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
   uint32_t* sTmem = (uint32_t*)(smem + S::OFF_TMEM);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const apn_agg_inputs& in = p.in;
+  const int Mrt = apn_rt_count(in.m_dev, in.M);                     // sample count: host-exact or read from the device counter
+  const int n_tiles = (Mrt + TC_SAMPLES - 1) / TC_SAMPLES;
 
   if (tid == 0) {
     for (int i = 0; i < TCB_SLOTS; ++i) {
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
     // ================================================================= weight producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int c = 0; c < TCB_NCHUNKS; ++c, ++it) {
           const uint32_t slot = it % TCB_SLOTS;
           mbar_wait(w_free + slot, ((it / TCB_SLOTS) & 1) ^ 1);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
     if (lane == 0) {
       const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
       uint32_t it = 0, ph_a0 = 0, ph_a1 = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int g = 0; g < 4; ++g) {                   // g = 0..2: dX_{3-g}; g = 3: dPE (N = 64)
           const uint32_t idesc = umma_idesc_f16(128, g == 3 ? 64 : 128);
           const uint32_t acc = tmem_base + (uint32_t)((g & 1) * 128);
@@ -189,16 +191,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
     const int erow = q * 32 + lane;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const float gscale = tc_grad_scale(p.hmax), inv_gscale = 1.f / gscale;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = tile * TC_SAMPLES;
       const uint8_t* tp = p.tape + (size_t)tile * TC_TAPE_TILE_BYTES;
       const int ms = m0 + (erow >> 3);
-      const bool valid = ms < in.M;
-      const int mc = min(ms, in.M - 1);
+      const bool valid = ms < Mrt;
+      const int mc = min(ms, Mrt - 1);
       if (tid < 128) {
         sDot[tid] = 0.f;
         sDrc[3 * tid] = 0.f; sDrc[3 * tid + 1] = 0.f; sDrc[3 * tid + 2] = 0.f;
-        sIdx[tid] = __ldg(in.nn_idx + (size_t)min(m0 + (tid >> 3), in.M - 1) * APN_K + (tid & 7));
+        sIdx[tid] = __ldg(in.nn_idx + (size_t)min(m0 + (tid >> 3), Mrt - 1) * APN_K + (tid & 7));
       }
       compute_sync();
       // ---------------------------------------------------------------- dY3 = idw * d_h * LeakyReLU'(act3); dw_k = <d_h, act3_k>
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
       // ---------------------------------------------------------------- IDW backward + scatter (one thread per row)
       if (tid < 128) {
         const int r = tid, m = m0 + (r >> 3);
-        const int mm = min(m, in.M - 1);
+        const int mm = min(m, Mrt - 1);
         const int idx = sIdx[r];
         const float px = __ldg(in.pts + 3 * (size_t)mm), py = __ldg(in.pts + 3 * (size_t)mm + 1), pz = __ldg(in.pts + 3 * (size_t)mm + 2);
         const float rp[3] = {px - __ldg(in.xyz + 3 * (size_t)idx), py - __ldg(in.xyz + 3 * (size_t)idx + 1),
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_dgrad_kernel(const TcBwdPara
         dot += __shfl_xor_sync(0xffffffffu, dot, 4);
         // w_k = u_k / S:  d_u = (d_w - <d_w, w>) / S ;  d_d2 = -d_u u^2
         const float d_d2 = -((dwk - dot) / su) * u * u;
-        if (m < in.M) {
+        if (m < Mrt) {
           const float dc[3] = {sDrc[3 * r], sDrc[3 * r + 1], sDrc[3 * r + 2]};
           const float* G = in.ginv + 9 * (size_t)idx;
           if (p.d_ginv) {
@@ -384,7 +386,8 @@ struct TcWgradParams {
   const uint8_t* tape;
   const uint8_t* dy;
   float* partial;             // gridDim.x slabs of TCW_SLAB floats: per-CTA sums, reduced by tc_wgrad_reduce_kernel
-  int n_tiles;
+  int M;                      // sample count (capacity when m_dev is given)
+  const int32_t* m_dev;
 };
 
 // slab layout: dW1 | dW2 | dW3 (128 x 128 each) | dW0_pe (128 x 64) | db0..db3 (128 each)
@@ -420,6 +423,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_wgrad_kernel(const TcWgradP
   uint64_t* done = bars + 2 * TCW_STAGES;
   uint32_t* sTmem = (uint32_t*)(smem + S::OFF_TMEM);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (apn_rt_count(p.m_dev, p.M) + TC_SAMPLES - 1) / TC_SAMPLES;
+  if ((int)blockIdx.x >= n_tiles) return;      // no tile for this CTA (device-side count below the grid's capacity): its slab is not summed
   if (tid == 0) {
     for (int i = 0; i < TCW_STAGES; ++i) {
       mbar_init(full + i, 1);
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_wgrad_kernel(const TcWgradP
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint8_t* tp = p.tape + (size_t)tile * TC_TAPE_TILE_BYTES;
         const uint8_t* dyt = p.dy + (size_t)tile * TC_DY_TILE_BYTES;
         for (int layer = 0; layer < 4; ++layer)
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_wgrad_kernel(const TcWgradP
       uint32_t it = 0;
       const uint32_t ones = smem_u32(sOnes);
       bool first_tile = true;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, first_tile = false) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
         for (int layer = 0; layer < 4; ++layer) {
           // A = dY^T (M = 128 out features), B = X^T (N = in features); both MN-major over the [row][col] tiles
           const uint32_t idesc = umma_idesc_f16_major(128, layer == 0 ? 64 : 128, true, true);
@@ -529,10 +534,12 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_wgrad_kernel(const TcWgradP
 
 // sums the per-CTA slabs, removes the gradient scale and accumulates into the (caller-zeroed) gradient buffers
 __global__ void __launch_bounds__(256)
-tc_wgrad_reduce_kernel(const float* __restrict__ partial, int n_slabs, const float* __restrict__ hmax, int d_in,
-                       float* dw0, float* dw1, float* dw2, float* dw3, float* db0, float* db1, float* db2, float* db3) {
+tc_wgrad_reduce_kernel(const float* __restrict__ partial, int grid_slabs, int M_cap, const int32_t* __restrict__ m_dev,
+                       const float* __restrict__ hmax, int d_in, float* dw0, float* dw1, float* dw2, float* dw3, float* db0,
+                       float* db1, float* db2, float* db3) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= TCW_SLAB) return;
+  const int n_slabs = min(grid_slabs, (apn_rt_count(m_dev, M_cap) + TC_SAMPLES - 1) / TC_SAMPLES);   // CTAs that had a tile
   float s = 0.f;
   for (int b = 0; b < n_slabs; ++b) s += __ldg(partial + (size_t)b * TCW_SLAB + e);
   s *= 1.f / tc_grad_scale(hmax);
@@ -557,10 +564,11 @@ tc_wgrad_reduce_kernel(const float* __restrict__ partial, int n_slabs, const flo
 // One block; thread n owns output feature n.  db0 is re-summed from the per-CTA slabs (g->d_b[0] may already hold
 // gradient from an earlier accumulation).
 __global__ void __launch_bounds__(128)
-tc_pose_bwd_kernel(const float* __restrict__ partial, int n_slabs, const float* __restrict__ hmax, int d_in,
-                   const float* __restrict__ w0, const float* __restrict__ pose_emb, float* __restrict__ dw0,
-                   float* __restrict__ d_pose_emb) {
+tc_pose_bwd_kernel(const float* __restrict__ partial, int grid_slabs, int M_cap, const int32_t* __restrict__ m_dev,
+                   const float* __restrict__ hmax, int d_in, const float* __restrict__ w0, const float* __restrict__ pose_emb,
+                   float* __restrict__ dw0, float* __restrict__ d_pose_emb) {
   __shared__ float sDb[128];
+  const int n_slabs = min(grid_slabs, (apn_rt_count(m_dev, M_cap) + TC_SAMPLES - 1) / TC_SAMPLES);
   const int n = threadIdx.x;
   const int n_pose = d_in - (APN_PE_POS + APN_C);
   float s = 0.f;
@@ -583,10 +591,12 @@ tc_pose_bwd_kernel(const float* __restrict__ partial, int n_slabs, const float* 
 // ---------------------------------------------------------------------------------------
 // d density / Raw2Alpha backward on the reduced feature: d_h += dd * w_density (lib/cuda/render_utils_kernel.cu:396-406)
 __global__ void __launch_bounds__(256)
-tc_density_bwd_kernel(int M, float interval, const float* __restrict__ h, const float* __restrict__ exp_d,
-                      const float* __restrict__ density_w, const float* __restrict__ d_alpha, float* __restrict__ d_h,
-                      float* __restrict__ d_density_w, float* __restrict__ d_density_b, float* __restrict__ hmax) {
+tc_density_bwd_kernel(int M_cap, const int32_t* __restrict__ m_dev, float interval, const float* __restrict__ h,
+                      const float* __restrict__ exp_d, const float* __restrict__ density_w, const float* __restrict__ d_alpha,
+                      float* __restrict__ d_h, float* __restrict__ d_density_w, float* __restrict__ d_density_b,
+                      float* __restrict__ hmax) {
   __shared__ float sAcc[APN_C + 1];
+  const int M = apn_rt_count(m_dev, M_cap);
   for (int i = threadIdx.x; i < APN_C + 1; i += blockDim.x) sAcc[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -668,7 +678,7 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
   if (agg_rgbnet_bwd_launch(st, in, w, sv, g, b.d_v0, b.d_fv, b.d_h, side)) return -1;
   const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 8);
   APN_CUDA(cudaMemsetAsync(b.d_ptable, 0, (size_t)N * APN_C * sizeof(float) + 1024, st));   // table + hmax
-  tc_density_bwd_kernel<<<wblocks, 256, 0, st>>>(M, in->interval, sv->h, sv->exp_d, w->density_w, g->d_alpha, b.d_h,
+  tc_density_bwd_kernel<<<wblocks, 256, 0, st>>>(M, in->m_dev, in->interval, sv->h, sv->exp_d, w->density_w, g->d_alpha, b.d_h,
                                                  g->d_density_w, g->d_density_b, b.hmax);
   APN_LAUNCH_CHECK();
   const int n_tiles = apn_div_up(M, TC_SAMPLES);
@@ -708,17 +718,19 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
     p.tape = (const uint8_t*)tape;
     p.dy = b.dy;
     p.partial = b.partial;
-    p.n_tiles = n_tiles;
+    p.M = M;
+    p.m_dev = in->m_dev;
     static_assert(TcWSmem::TOTAL <= 227 * 1024, "shared memory budget");
     APN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcWSmem::TOTAL));
     tc_wgrad_kernel<<<grid, TCW_THREADS, TcWSmem::TOTAL, st>>>(p);
     APN_LAUNCH_CHECK();
-    tc_wgrad_reduce_kernel<<<apn_div_up(TCW_SLAB, 256), 256, 0, st>>>(b.partial, grid, b.hmax, in->d_in, g->d_w[0], g->d_w[1],
-                                                                       g->d_w[2], g->d_w[3], g->d_b[0], g->d_b[1], g->d_b[2],
-                                                                       g->d_b[3]);
+    tc_wgrad_reduce_kernel<<<apn_div_up(TCW_SLAB, 256), 256, 0, st>>>(b.partial, grid, M, in->m_dev, b.hmax, in->d_in, g->d_w[0],
+                                                                       g->d_w[1], g->d_w[2], g->d_w[3], g->d_b[0], g->d_b[1],
+                                                                       g->d_b[2], g->d_b[3]);
     APN_LAUNCH_CHECK();
     if (in->d_in > APN_PE_POS + APN_C) {
-      tc_pose_bwd_kernel<<<1, 128, 0, st>>>(b.partial, grid, b.hmax, in->d_in, w->w[0], in->pose_emb, g->d_w[0], g->d_pose_emb);
+      tc_pose_bwd_kernel<<<1, 128, 0, st>>>(b.partial, grid, M, in->m_dev, b.hmax, in->d_in, w->w[0], in->pose_emb, g->d_w[0],
+                                            g->d_pose_emb);
       APN_LAUNCH_CHECK();
     }
   }

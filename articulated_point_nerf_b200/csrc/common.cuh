@@ -59,6 +59,12 @@ static inline size_t apn_align(size_t x, size_t a = 256) { return (x + a - 1) / 
 // ----------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------
+// run-time element count of a capacity-sized array: min(*dev, cap), or cap when no device counter is given
+__device__ __forceinline__ int apn_rt_count(const int32_t* dev, int cap) {
+  if (!dev) return cap;
+  const int n = *reinterpret_cast<const volatile int32_t*>(dev);
+  return n < 0 ? 0 : (n < cap ? n : cap);
+}
 __device__ __forceinline__ float atomic_min_float(float* addr, float v) {
   return (v >= 0.f) ? __int_as_float(atomicMin((int*)addr, __float_as_int(v)))
                     : __uint_as_float(atomicMax((unsigned int*)addr, __float_as_uint(v)));

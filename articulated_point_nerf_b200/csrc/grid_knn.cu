@@ -295,7 +295,7 @@ template <bool FILL>
 __global__ void ray_candidates_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int R, float near,
                                       float far, float stepdist, const void* __restrict__ blob, int* __restrict__ cand_count,
                                       const int* __restrict__ cand_base, int* __restrict__ cand_ray,
-                                      int* __restrict__ cand_step) {
+                                      int* __restrict__ cand_step, int cand_cap) {
   const GridView g = grid_view(blob);
   const GridHeader* h = g.h;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,7 +315,7 @@ __global__ void ray_candidates_kernel(const float* __restrict__ rays_o, const fl
       point_cell(h, px, py, pz, ix, iy, iz);
       const int t = ((iz >> L) * ty + (iy >> L)) * tx + (ix >> L);
       if (g.top[t] < APN_K) continue;
-      if (FILL) {
+      if (FILL && base + count < cand_cap) {          // a full candidate list truncates (flagged by the caller's count check)
         cand_ray[base + count] = r;
         cand_step[base + count] = step;
       }
@@ -338,11 +338,11 @@ extern "C" int apn_ray_candidates(const float* rays_o, const float* rays_d, int 
   if (fill) {
     APN_CHECK_ARG(cand_base && cand_ray && cand_step, "fill pass needs cand_base/cand_ray/cand_step");
     ray_candidates_kernel<true><<<blocks, 128, 0, stream>>>(rays_o, rays_d, R, near, far, stepdist, grid, nullptr, cand_base,
-                                                             cand_ray, cand_step);
+                                                             cand_ray, cand_step, 0x7fffffff);
   } else {
     APN_CHECK_ARG(cand_count, "count pass needs cand_count");
     ray_candidates_kernel<false><<<blocks, 128, 0, stream>>>(rays_o, rays_d, R, near, far, stepdist, grid, cand_count,
-                                                              nullptr, nullptr, nullptr);
+                                                              nullptr, nullptr, nullptr, 0);
   }
   APN_LAUNCH_CHECK();
   return 0;
@@ -586,11 +586,14 @@ __device__ __forceinline__ void top8_insert(unsigned long long (&b)[APN_K], unsi
 
 __global__ void __launch_bounds__(128)
 knn_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
-                  const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand,
-                  int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep, bool force, int force_lvl) {
+                  const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand_cap,
+                  const int* __restrict__ n_cand_dev, int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep,
+                  bool force, int force_lvl) {
   const GridView g = grid_view(blob);
   const GridHeader* h = g.h;
-  if (!force && !(h->occupancy < KNN_SPARSE_OCCUPANCY)) return;   // dense leaves: knn_kernel (warp per query) handles this launch
+  const int n_cand = apn_rt_count(n_cand_dev, n_cand_cap);
+  // dense leaves or a small batch: knn_kernel (warp per query) handles this launch
+  if (!force && !(h->occupancy < KNN_SPARSE_OCCUPANCY && n_cand >= KNN_THREAD_MIN_QUERIES)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cand) return;
   const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
@@ -669,14 +672,19 @@ knn_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
 
 __global__ void __launch_bounds__(128)
 knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
-           const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand,
-           int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep, int group, bool both) {
+           const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step, int n_cand_cap,
+           const int* __restrict__ n_cand_dev, int* __restrict__ nn_idx, float* __restrict__ nn_d2, int* __restrict__ keep, bool both) {
   const GridView g = grid_view(blob);
   const GridHeader* h = g.h;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
-  if (both && h->occupancy < KNN_SPARSE_OCCUPANCY) return;   // sparse leaves: knn_thread_kernel handles this launch
+  const int n_cand = apn_rt_count(n_cand_dev, n_cand_cap);
+  // sparse leaves and a large batch: knn_thread_kernel handles this launch
+  if (both && h->occupancy < KNN_SPARSE_OCCUPANCY && n_cand >= KNN_THREAD_MIN_QUERIES) return;
+  // consecutive candidates per warp: 16 when there is enough work to fill the machine anyway, down to 2 for small batches
+  int group = n_cand / (APN_SM_COUNT * 16 * 4);
+  group = group < 2 ? 2 : group > KNN_GROUP_MAX ? KNN_GROUP_MAX : group;
   const int n_groups = (n_cand + group - 1) / group;
   for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
     int prev_ray = -1, prev_step = 0;
@@ -709,43 +717,62 @@ knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, f
   }
 }
 
+// launches the search(es) over a candidate list whose length is exact (n_cand_dev == NULL) or a capacity with the true
+// length in device memory
+static int knn_launch(cudaStream_t stream, const float* rays_o, const float* rays_d, float near, float far, float stepdist,
+                      const void* grid, const int32_t* cand_ray, const int32_t* cand_step, int n_cand, const int32_t* n_cand_dev,
+                      int32_t* nn_idx, float* nn_d2, int32_t* keep) {
+  // APN_KNN_FORCE=warp|thread|thread0|thread1 pins the search (and its walk level): tests exercise all on the same inputs
+  const char* forced = getenv("APN_KNN_FORCE");
+  const bool force_thread = forced && forced[0] == 't', force_warp = forced && forced[0] == 'w';
+  const int force_lvl = (force_thread && (forced[6] == '0' || forced[6] == '1')) ? forced[6] - '0' : -1;
+  const bool both = !force_warp && !force_thread && n_cand >= KNN_THREAD_MIN_QUERIES;   // n_cand: exact count or capacity
+  if (both || force_thread) {
+    knn_thread_kernel<<<apn_div_up(n_cand, 128), 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step,
+                                                                   n_cand, n_cand_dev, nn_idx, nn_d2, keep, force_thread, force_lvl);
+    APN_LAUNCH_CHECK();
+    if (force_thread) return 0;
+  }
+  const int blocks = min(apn_div_up(n_cand, 4 * 2), APN_SM_COUNT * 16);   // 4 warps per block, persistent grid-stride
+  knn_kernel<<<blocks, 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand, n_cand_dev, nn_idx,
+                                         nn_d2, keep, both);
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int apn_knn(const float* rays_o, const float* rays_d, float near, float far, float stepdist, const void* grid,
                        const int32_t* cand_ray, const int32_t* cand_step, int n_cand, int32_t* nn_idx, float* nn_d2,
                        int32_t* keep, apn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_cand <= 0) return 0;
   APN_CHECK_ARG(rays_o && rays_d && grid && cand_ray && cand_step && nn_idx && keep, "null pointer");
-  // APN_KNN_FORCE=warp|thread|thread0|thread1 pins the search (and its walk level): tests exercise all on the same inputs
-  const char* forced = getenv("APN_KNN_FORCE");
-  const bool force_thread = forced && forced[0] == 't', force_warp = forced && forced[0] == 'w';
-  const int force_lvl = (force_thread && (forced[6] == '0' || forced[6] == '1')) ? forced[6] - '0' : -1;
-  const bool both = !force_warp && !force_thread && n_cand >= KNN_THREAD_MIN_QUERIES;
-  if (both || force_thread) {
-    knn_thread_kernel<<<apn_div_up(n_cand, 128), 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step,
-                                                                   n_cand, nn_idx, nn_d2, keep, force_thread, force_lvl);
-    APN_LAUNCH_CHECK();
-    if (force_thread) return 0;
-  }
-  const int resident_warps = APN_SM_COUNT * 16 * 4;
-  int group = n_cand / resident_warps;
-  group = group < 2 ? 2 : group > KNN_GROUP_MAX ? KNN_GROUP_MAX : group;
-  const int blocks = min(apn_div_up(n_cand, 4 * group), APN_SM_COUNT * 16);   // 4 warps per block, persistent grid-stride
-  knn_kernel<<<blocks, 128, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand, nn_idx, nn_d2,
-                                         keep, group, both);
-  APN_LAUNCH_CHECK();
-  return 0;
+  return knn_launch(stream, rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand, nullptr, nn_idx, nn_d2, keep);
 }
 
 __global__ void compact_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far,
                                float stepdist, const void* __restrict__ blob, const int* __restrict__ cand_ray,
                                const int* __restrict__ cand_step, const int* __restrict__ cand_base,
                                const int* __restrict__ keep, const int* __restrict__ kept_pos,
-                               const int* __restrict__ nn_idx_cand, int n_cand, int R, float* __restrict__ pts,
+                               const int* __restrict__ nn_idx_cand, int n_cand_cap, int R, float* __restrict__ pts,
                                int* __restrict__ ray_id, int* __restrict__ step_id, int* __restrict__ nn_idx,
-                               int* __restrict__ ray_start) {
+                               int* __restrict__ ray_start, const int* __restrict__ n_cand_dev, int m_cap,
+                               int* __restrict__ counts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= R) ray_start[i] = kept_pos[(i < R) ? cand_base[i] : n_cand];
-  if (i >= n_cand || !keep[i]) return;
+  // static mode (n_cand_dev != NULL): the candidate list and the sample arrays are capacity-sized; the true counts live on
+  // the device, truncation is flagged in counts[2] and the sample count clamps to m_cap
+  const int n_raw = n_cand_dev ? *n_cand_dev : n_cand_cap;
+  const int n_cand = n_cand_dev ? min(max(n_raw, 0), n_cand_cap) : n_cand_cap;
+  if (i <= R) ray_start[i] = min(kept_pos[(i < R) ? min(cand_base[i], n_cand) : n_cand], m_cap);
+  if (i == 0 && counts) {
+    const GridHeader* hh = (const GridHeader*)blob;
+    const int m_raw = kept_pos[n_cand];
+    counts[0] = n_cand;
+    counts[1] = min(m_raw, m_cap);
+    counts[2] = (hh->overflow ? 1 : 0) | (n_raw > n_cand_cap ? 2 : 0) | (m_raw > m_cap ? 4 : 0);
+    counts[3] = n_raw;
+    counts[4] = m_raw;
+  }
+  if (i >= n_cand || !keep[i] || kept_pos[i] >= m_cap) return;
   const GridHeader* h = (const GridHeader*)blob;
   const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
   const int r = cand_ray[i], st = cand_step[i];
@@ -771,7 +798,81 @@ extern "C" int apn_compact_samples(const float* rays_o, const float* rays_d, flo
   const int n = (n_cand > R + 1) ? n_cand : R + 1;
   compact_kernel<<<apn_div_up(n, 256), 256, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, cand_base,
                                                         keep, kept_pos, nn_idx_cand, n_cand, R, pts, ray_id, step_id, nn_idx,
-                                                        ray_start);
+                                                        ray_start, nullptr, 0x7fffffff, nullptr);
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Static (sync-free) sampling stage: count -> scan -> fill -> k-NN -> scan -> compact in ONE call, every length kept on
+// the device.  The reference reads its sample count back to the host (lib/cuda/render_utils_kernel.cu:205-206:
+// N_steps.sum().item()) and so did the two-call sequence above; here the candidate list and the sample arrays have fixed
+// CAPACITIES, the kernels read the true lengths from device memory, and `counts` reports them:
+//   counts[0] candidates used, [1] samples kept (the m_dev of apn_agg_inputs), [2] flags (1 grid overflow, 2 candidate
+//   list truncated, 4 sample arrays truncated), [3] candidates found, [4] samples found.
+// A truncated step is detected from counts[2] (the caller skips the optimiser update and re-runs with larger capacities).
+// Nothing here depends on the data, so the whole call can be captured in a CUDA graph.
+// ---------------------------------------------------------------------------------------
+struct SampleStaticLayout {
+  size_t cand_count, base, cand_ray, cand_step, nn_c, keep, kept_pos, scan, scan_bytes, total;
+};
+static SampleStaticLayout sample_static_layout(int R, int cand_cap) {
+  SampleStaticLayout l;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = apn_align(o + bytes); return at; };
+  l.cand_count = take(sizeof(int) * (size_t)R);
+  l.base = take(sizeof(int) * ((size_t)R + 1));
+  l.cand_ray = take(sizeof(int) * (size_t)cand_cap);
+  l.cand_step = take(sizeof(int) * (size_t)cand_cap);
+  l.nn_c = take(sizeof(int) * (size_t)cand_cap * APN_K);
+  l.keep = take(sizeof(int) * (size_t)cand_cap);
+  l.kept_pos = take(sizeof(int) * ((size_t)cand_cap + 1));
+  l.scan_bytes = scan_temp_bytes(cand_cap > R ? cand_cap : R);
+  l.scan = take(l.scan_bytes);
+  l.total = o;
+  return l;
+}
+extern "C" size_t apn_sample_knn_static_workspace_bytes(int R, int cand_cap) {
+  return (R > 0 && cand_cap > 0) ? sample_static_layout(R, cand_cap).total : 0;
+}
+
+extern "C" int apn_sample_knn_static(const float* rays_o, const float* rays_d, int R, float near, float far, float stepdist,
+                                     const void* grid, int cand_cap, int m_cap, void* workspace, size_t workspace_bytes,
+                                     float* pts, int32_t* ray_id, int32_t* step_id, int32_t* nn_idx, int32_t* ray_start,
+                                     int32_t* counts, apn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  APN_CHECK_ARG(rays_o && rays_d && grid && workspace && pts && ray_id && step_id && nn_idx && ray_start && counts, "null pointer");
+  APN_CHECK_ARG(R > 0 && cand_cap > 0 && m_cap > 0 && stepdist > 0.f, "bad sizes");
+  const SampleStaticLayout l = sample_static_layout(R, cand_cap);
+  APN_CHECK_ARG(workspace_bytes >= l.total, "workspace too small");
+  char* w = (char*)workspace;
+  int *cand_count = (int*)(w + l.cand_count), *base = (int*)(w + l.base), *cand_ray = (int*)(w + l.cand_ray),
+      *cand_step = (int*)(w + l.cand_step), *nn_c = (int*)(w + l.nn_c), *keep = (int*)(w + l.keep),
+      *kept_pos = (int*)(w + l.kept_pos);
+  const int rblocks = apn_div_up(R, 128);
+  ray_candidates_kernel<false><<<rblocks, 128, 0, stream>>>(rays_o, rays_d, R, near, far, stepdist, grid, cand_count, nullptr,
+                                                             nullptr, nullptr, 0);
+  APN_LAUNCH_CHECK();
+  size_t tb = l.scan_bytes;
+  APN_CUDA(cub::DeviceScan::ExclusiveSum(w + l.scan, tb, cand_count, base, R, stream));
+  apn_count_launch(2);
+  scan_tail_kernel<<<1, 1, 0, stream>>>(cand_count, base, R);        // base[R] = candidates found (-1: grid overflow)
+  APN_LAUNCH_CHECK();
+  ray_candidates_kernel<true><<<rblocks, 128, 0, stream>>>(rays_o, rays_d, R, near, far, stepdist, grid, nullptr, base, cand_ray,
+                                                            cand_step, cand_cap);
+  APN_LAUNCH_CHECK();
+  APN_CUDA(cudaMemsetAsync(keep, 0, sizeof(int) * (size_t)cand_cap, stream));      // entries behind the true length stay 0
+  if (knn_launch(stream, rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, cand_cap, base + R, nn_c, nullptr, keep))
+    return -2;
+  tb = l.scan_bytes;
+  APN_CUDA(cub::DeviceScan::ExclusiveSum(w + l.scan, tb, keep, kept_pos, cand_cap, stream));
+  apn_count_launch(2);
+  scan_tail_kernel<<<1, 1, 0, stream>>>(keep, kept_pos, cand_cap);
+  APN_LAUNCH_CHECK();
+  const int n = (cand_cap > R + 1) ? cand_cap : R + 1;
+  compact_kernel<<<apn_div_up(n, 256), 256, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, base, keep,
+                                                        kept_pos, nn_c, cand_cap, R, pts, ray_id, step_id, nn_idx, ray_start,
+                                                        base + R, m_cap, counts);
   APN_LAUNCH_CHECK();
   return 0;
 }

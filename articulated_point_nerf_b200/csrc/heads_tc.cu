@@ -64,7 +64,8 @@ struct HtParams {
   float* exp_d;                // (M)      exp(density + act_shift)
   float* fv;                   // (M,160)  [f (128) | view PE (27) | 0 (5)]
   float* v0;                   // (M,64)   ReLU(views_linears.0)
-  int M, n_tiles;
+  int M, n_tiles;              // capacity when m_dev is given
+  const int32_t* m_dev;        // device-side sample count or NULL
 };
 
 struct HtSmem {
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
   uint32_t* sTmem = (uint32_t*)(smem + S::OFF_TMEM);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sA = smem_u32(smem + S::OFF_A), sWf = smem_u32(smem + S::OFF_WF), sWv = smem_u32(smem + S::OFF_WV);
+  const int M = apn_rt_count(p.m_dev, p.M), n_tiles = (M + 127) >> 7;
 
   if (tid == 0) {
     mbar_init(bars, 1);
@@ -118,14 +120,14 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
   uint32_t ph = 0;
   bool w_ready = false;
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ph ^= 1) {
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ph ^= 1) {
     const int m0 = tile * 128;
     // ---------------------------------------------------------------- A: rows of h, one warp per row
     float my_dens = 0.f;
 #pragma unroll 4
     for (int rr = 0; rr < 32; ++rr) {
       const int r = warp * 32 + rr;
-      const int m = min(m0 + r, p.M - 1);
+      const int m = min(m0 + r, M - 1);
       const float4 x = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)m * APN_C) + lane);
       const float d = warp_sum(x.x * wd4.x + x.y * wd4.y + x.z * wd4.z + x.w * wd4.w);
       if (lane == rr) my_dens = d;
@@ -160,11 +162,11 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
     }
     // ---------------------------------------------------------------- (under G1) alpha + view PE -> operand chunk 2
     const int mrow = m0 + tid;
-    const int mc = min(mrow, p.M - 1);
+    const int mc = min(mrow, M - 1);
     {
       // lib/cuda/render_utils_kernel.cu:358-370 on this lane's row of the warp
       const float e = expf(my_dens + bd + p.act_shift);
-      if (mrow < p.M) {
+      if (mrow < M) {
         p.alpha[mrow] = 1.f - powf(1.f + e, -p.interval);
         if (p.exp_d) p.exp_d[mrow] = e;
       }
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
 #pragma unroll
         for (int i = 0; i < 4; ++i) sincosf(v * (float)(1 << i), &pe[3 + d * 4 + i], &pe[15 + d * 4 + i]);
       }
-      if (p.fv && mrow < p.M) {
+      if (p.fv && mrow < M) {
         float4* dst = reinterpret_cast<float4*>(p.fv + (size_t)mrow * 160 + APN_C);
 #pragma unroll
         for (int u = 0; u < 8; ++u) dst[u] = make_float4(pe[4 * u], pe[4 * u + 1], pe[4 * u + 2], pe[4 * u + 3]);
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
           fr[2 * e2 + 1] = __uint_as_float(v[u * 8 + 2 * e2 + 1]) + sBf[col + 1];
           split_half2(make_float2(fr[2 * e2], fr[2 * e2 + 1]), hi[e2], lo[e2]);
         }
-        if (p.fv && mrow < p.M) {
+        if (p.fv && mrow < M) {
           float4* dst = reinterpret_cast<float4*>(p.fv + (size_t)mrow * 160 + pc * 16 + u * 8);
           dst[0] = make_float4(fr[0], fr[1], fr[2], fr[3]);
           dst[1] = make_float4(fr[4], fr[5], fr[6], fr[7]);
@@ -267,13 +269,13 @@ __global__ void __launch_bounds__(HT_THREADS, 1) heads_tc_kernel(const HtParams 
         a1 = fmaf(x, sW2[64 + col], a1);
         a2 = fmaf(x, sW2[128 + col], a2);
       }
-      if (p.v0 && mrow < p.M) {
+      if (p.v0 && mrow < M) {
         float4* dst = reinterpret_cast<float4*>(p.v0 + (size_t)mrow * 64 + pc * 16);
 #pragma unroll
         for (int u = 0; u < 4; ++u) dst[u] = make_float4(xr[4 * u], xr[4 * u + 1], xr[4 * u + 2], xr[4 * u + 3]);
       }
     }
-    if (mrow < p.M) {
+    if (mrow < M) {
       p.rgb[3 * (size_t)mrow] = 1.f / (1.f + expf(-a0));
       p.rgb[3 * (size_t)mrow + 1] = 1.f / (1.f + expf(-a1));
       p.rgb[3 * (size_t)mrow + 2] = 1.f / (1.f + expf(-a2));
@@ -299,6 +301,7 @@ int agg_heads_tc_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp
   p.bf = w->rgb_feat_b; p.bv0 = w->rgb_v0_b; p.W2 = w->rgb_v2_w; p.b2 = w->rgb_v2_b; p.wd = w->density_w; p.bd = w->density_b;
   p.act_shift = in->act_shift; p.interval = in->interval;
   p.alpha = alpha; p.rgb = rgb; p.exp_d = exp_d; p.fv = fv; p.v0 = v0; p.M = M; p.n_tiles = apn_div_up(M, 128);
+  p.m_dev = in->m_dev;
   static_assert(HtSmem::TOTAL <= 227 * 1024, "shared memory budget");
   APN_CUDA(cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HtSmem::TOTAL));
   const int grid = p.n_tiles < APN_SM_COUNT ? p.n_tiles : APN_SM_COUNT;

@@ -24,6 +24,10 @@ struct GemmArgs {
   const float* mask;   // MASK: activation values whose sign selects the derivative (M x N, ld ldm) or NULL
   int ldm;
   int k_chunk;         // ATOMIC: k range per blockIdx.z
+  // optional device-side row count (see apn_agg_inputs::m_dev): the true extent of the SAMPLE dimension — M for the
+  // forward / dgrad shapes (rows_is_k = 0), K for the wgrad shape (rows_is_k = 1); the host value is then a capacity
+  const int32_t* rows_dev;
+  int rows_is_k;
 };
 
 #define GEMM_BM 128
@@ -105,10 +109,16 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
   __shared__ __align__(16) float As[GEMM_BK][GEMM_LDS];
   __shared__ __align__(16) float Bs[GEMM_BK][GEMM_LDS];
   const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * GEMM_BN;
-  int k_begin = 0, k_end = g.K;
+  int gM = g.M, gK = g.K;
+  if (g.rows_dev) {
+    if (g.rows_is_k) gK = apn_rt_count(g.rows_dev, g.K);
+    else gM = apn_rt_count(g.rows_dev, g.M);
+    if (m0 >= gM) return;                      // uniform over the block
+  }
+  int k_begin = 0, k_end = gK;
   if (EPI == GEMM_EPI_ATOMIC) {
     k_begin = blockIdx.z * g.k_chunk;
-    k_end = min(g.K, k_begin + g.k_chunk);
+    k_end = min(gK, k_begin + g.k_chunk);
     if (k_begin >= k_end) return;
   }
   const bool a_vec = ((g.lda & 3) == 0) && ((((uintptr_t)g.A) & 15) == 0) && (A_KCONTIG ? true : true);
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   float ra[8], rb[8];
-  gemm_load_slice<A_KCONTIG>(g.A, g.lda, m0, g.M, k_begin, k_end, a_vec, ra);
+  gemm_load_slice<A_KCONTIG>(g.A, g.lda, m0, gM, k_begin, k_end, a_vec, ra);
   gemm_load_slice<B_KCONTIG>(g.B, g.ldb, n0, g.N, k_begin, k_end, b_vec, rb);
   for (int k0 = k_begin; k0 < k_end; k0 += GEMM_BK) {
     __syncthreads();
@@ -128,7 +138,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
     gemm_store_slice<B_KCONTIG>(Bs, rb);
     __syncthreads();
     if (k0 + GEMM_BK < k_end) {
-      gemm_load_slice<A_KCONTIG>(g.A, g.lda, m0, g.M, k0 + GEMM_BK, k_end, a_vec, ra);
+      gemm_load_slice<A_KCONTIG>(g.A, g.lda, m0, gM, k0 + GEMM_BK, k_end, a_vec, ra);
       gemm_load_slice<B_KCONTIG>(g.B, g.ldb, n0, g.N, k0 + GEMM_BK, k_end, b_vec, rb);
     }
 #pragma unroll
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + ((i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-    if (m >= g.M) continue;
+    if (m >= gM) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int n = n0 + h * 64 + tx * 4;
@@ -192,9 +202,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 
 // Y = act(X W^T + b):  X (M x K, ld lda), W (N x K torch layout, ld ldw), Y (M x N, ld ldc)
 static inline int gemm_forward(cudaStream_t st, const float* X, int lda, const float* W, int ldw, const float* bias, float* Y,
-                               int ldc, int M, int N, int K, float slope) {
+                               int ldc, int M, int N, int K, float slope, const int32_t* rows_dev = nullptr) {
   if (M <= 0) return 0;
-  GemmArgs g = {X, lda, W, ldw, Y, ldc, M, N, K, bias, slope, nullptr, 0, 0};
+  GemmArgs g = {X, lda, W, ldw, Y, ldc, M, N, K, bias, slope, nullptr, 0, 0, rows_dev, 0};
   dim3 grid(apn_div_up(M, GEMM_BM), apn_div_up(N, GEMM_BN), 1);
   sgemm_kernel<true, true, GEMM_EPI_BIAS_ACT><<<grid, 256, 0, st>>>(g);
   apn_count_launch();
@@ -202,9 +212,9 @@ static inline int gemm_forward(cudaStream_t st, const float* X, int lda, const f
 }
 // dX = (dY W) * act'(mask):  dY (M x K), W (K x N torch layout: out=K, in=N), dX (M x N)
 static inline int gemm_dgrad(cudaStream_t st, const float* dY, int lda, const float* W, int ldw, float* dX, int ldc, int M, int N,
-                             int K, const float* mask, int ldm, float slope) {
+                             int K, const float* mask, int ldm, float slope, const int32_t* rows_dev = nullptr) {
   if (M <= 0) return 0;
-  GemmArgs g = {dY, lda, W, ldw, dX, ldc, M, N, K, nullptr, slope, mask, ldm, 0};
+  GemmArgs g = {dY, lda, W, ldw, dX, ldc, M, N, K, nullptr, slope, mask, ldm, 0, rows_dev, 0};
   dim3 grid(apn_div_up(M, GEMM_BM), apn_div_up(N, GEMM_BN), 1);
   sgemm_kernel<true, false, GEMM_EPI_MASK><<<grid, 256, 0, st>>>(g);
   apn_count_launch();
@@ -214,7 +224,7 @@ static inline int gemm_dgrad(cudaStream_t st, const float* dY, int lda, const fl
 static inline int gemm_dgrad_accum(cudaStream_t st, const float* dY, int lda, const float* W, int ldw, float* dX, int ldc, int M,
                                    int N, int K) {
   if (M <= 0) return 0;
-  GemmArgs g = {dY, lda, W, ldw, dX, ldc, M, N, K, nullptr, 1.f, nullptr, 0, 0};
+  GemmArgs g = {dY, lda, W, ldw, dX, ldc, M, N, K, nullptr, 1.f, nullptr, 0, 0, nullptr, 0};
   dim3 grid(apn_div_up(M, GEMM_BM), apn_div_up(N, GEMM_BN), 1);
   sgemm_kernel<true, false, GEMM_EPI_ACCUM><<<grid, 256, 0, st>>>(g);
   apn_count_launch();
@@ -222,7 +232,7 @@ static inline int gemm_dgrad_accum(cudaStream_t st, const float* dY, int lda, co
 }
 // dW (n_out x n_in, ld ldw) += dY^T X : dY (rows x n_out, ld ldy), X (rows x n_in, ld ldx)
 static inline int gemm_wgrad(cudaStream_t st, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, int rows,
-                             int n_out, int n_in) {
+                             int n_out, int n_in, const int32_t* rows_dev = nullptr) {
   if (rows <= 0) return 0;
   const int tiles = apn_div_up(n_out, GEMM_BM) * apn_div_up(n_in, GEMM_BN);
   int splits = (2 * APN_SM_COUNT + tiles - 1) / tiles;
@@ -230,7 +240,7 @@ static inline int gemm_wgrad(cudaStream_t st, const float* dY, int ldy, const fl
   k_chunk = ((k_chunk + GEMM_BK - 1) / GEMM_BK) * GEMM_BK;
   if (k_chunk < 64) k_chunk = 64;        // enough splits to fill the machine on the 8192-ray training batches (K ~ 1e4)
   splits = apn_div_up(rows, k_chunk);
-  GemmArgs g = {dY, ldy, X, ldx, dW, ldw, n_out, n_in, rows, nullptr, 1.f, nullptr, 0, k_chunk};
+  GemmArgs g = {dY, ldy, X, ldx, dW, ldw, n_out, n_in, rows, nullptr, 1.f, nullptr, 0, k_chunk, rows_dev, 1};
   dim3 grid(apn_div_up(n_out, GEMM_BM), apn_div_up(n_in, GEMM_BN), splits);
   sgemm_kernel<false, false, GEMM_EPI_ATOMIC><<<grid, 256, 0, st>>>(g);
   apn_count_launch();

@@ -31,9 +31,11 @@ class MaskedAdam(torch.optim.Optimizer):
         self.per_lr = (count.float() / count.max()).contiguous()
 
     @torch.no_grad()
-    def step(self):
-        """One multi-tensor launch per (betas, eps) class.  The descriptor table (device pointers of param / grad /
-        moments) is cached and rebuilt only when a pointer changes; per step only the step sizes are refreshed."""
+    def prepare_step(self):
+        """Host half of a step (no launch): advances the step counters, (re)builds the cached descriptor tables and returns
+        [(class (beta1, beta2, eps), AdamPlan, [step size per tensor]), ...] plus the parameters that will be updated.
+        `step()` launches them right away; train.GraphedTrainStep writes the step sizes to device memory and replays a
+        captured graph that holds the launches."""
         plan = []
         for group in self.param_groups:
             lr = group['lr']
@@ -63,7 +65,7 @@ class MaskedAdam(torch.optim.Optimizer):
                     ss = ss_cache[st] = ops.adam_step_size(st, beta1, beta2, lr)
                 plan.append(((beta1, beta2, eps), param, grad, state, perlr, ss, mode))
         if not plan:
-            return
+            return [], []
         # every pointer the descriptor table holds is part of the key: load_state_dict() replaces the moment tensors
         # (the reference reads self.state[param] afresh every step, lib/masked_adam.py:52-60)
         key = tuple((cls, p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(), mode,
@@ -74,8 +76,24 @@ class MaskedAdam(torch.optim.Optimizer):
                 batches.setdefault(cls, []).append((p.data, g, state['exp_avg'], state['exp_avg_sq'], pl, ss, mode))
             self._plan = [(cls, ops.AdamPlan(entries)) for cls, entries in batches.items()]
             self._plan_key = key
-        for cls, ap in self._plan:
-            ap.launch([e[5] for e in plan if e[0] == cls], *cls)
+        return ([(cls, ap, [e[5] for e in plan if e[0] == cls]) for cls, ap in self._plan], [e[1] for e in plan])
+
+    def undo_step_count(self):
+        """Takes back the step counters of the last prepare_step() (a step whose device-side update was skipped)."""
+        for group in self.param_groups:
+            for param in group['params']:
+                st = self.state.get(param)
+                if st and st.get('step', 0) > 0 and param.grad is not None:
+                    st['step'] -= 1
+
+    @torch.no_grad()
+    def step(self):
+        """One multi-tensor launch per (betas, eps) class.  The descriptor table (device pointers of param / grad /
+        moments) is cached and rebuilt only when a pointer changes; per step only the step sizes are refreshed."""
+        launches, params = self.prepare_step()
+        for cls, ap, sizes in launches:
+            ap.launch(sizes, *cls)
         # the kernel wrote through raw pointers: tell autograd's version counters, which key every derived cache
         # (packed tensor-core weights, per-point layer-0 table, ...) exactly as an in-place torch op would
-        torch.autograd.graph.increment_version([e[1] for e in plan])
+        if params:
+            torch.autograd.graph.increment_version(params)

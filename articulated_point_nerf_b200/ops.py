@@ -331,6 +331,9 @@ class Samples:
     ray_start: torch.Tensor  # (R+1) int32
     n_rays: int
     n_candidates: int
+    # static (sync-free) mode: the arrays above are CAPACITY-sized and the true sample count lives on the device
+    m_dev: Optional[torch.Tensor] = None     # (1) int32 view of counts[1]
+    counts: Optional[torch.Tensor] = None    # (5) int32: candidates used, samples kept, flags, candidates found, samples found
 
     @property
     def M(self) -> int:
@@ -387,6 +390,35 @@ def _sample_and_knn(grid, rays_o, rays_d, near, far, stepdist, return_d2):
     return smp
 
 
+class StaticSampler:
+    """Fixed-capacity workspace + output arrays of the sync-free sampling stage (apn_sample_knn_static): nothing is sized
+    from data, no count is read back, so the stage (and the training step around it) can be enqueued ahead of the GPU and
+    captured in a CUDA graph.  Flags in counts[2] (1 grid overflow | 2 candidate list truncated | 4 samples truncated)."""
+
+    def __init__(self, n_rays: int, cand_cap: int, m_cap: int, device):
+        lib = _lib.load()
+        self.R, self.cand_cap, self.m_cap = int(n_rays), int(cand_cap), int(m_cap)
+        self.ws_bytes = lib.apn_sample_knn_static_workspace_bytes(self.R, self.cand_cap)
+        self.ws = torch.empty(self.ws_bytes, device=device, dtype=torch.uint8)
+        self.pts = torch.empty(self.m_cap, 3, device=device)
+        self.ray_id = torch.empty(self.m_cap, device=device, dtype=torch.int32)
+        self.step_id = torch.empty(self.m_cap, device=device, dtype=torch.int32)
+        self.nn_idx = torch.empty(self.m_cap, K_NEIGHBOURS, device=device, dtype=torch.int32)
+        self.ray_start = torch.empty(self.R + 1, device=device, dtype=torch.int32)
+        self.counts = torch.zeros(8, device=device, dtype=torch.int32)
+
+    def run(self, grid: "Grid", rays_o, rays_d, near: float, far: float, stepdist: float) -> "Samples":
+        rays_o, rays_d = _f32(rays_o), _f32(rays_d)
+        assert rays_o.shape[0] == self.R
+        with stage("sample_ray+knn"):
+            check(_lib.load().apn_sample_knn_static(ptr(rays_o), ptr(rays_d), self.R, near, far, stepdist, ptr(grid.blob),
+                                                    self.cand_cap, self.m_cap, ptr(self.ws), self.ws_bytes, ptr(self.pts),
+                                                    ptr(self.ray_id), ptr(self.step_id), ptr(self.nn_idx), ptr(self.ray_start),
+                                                    ptr(self.counts), stream()), "apn_sample_knn_static")
+        return Samples(self.pts, self.ray_id, self.step_id, self.nn_idx, self.ray_start, self.R, self.cand_cap,
+                       m_dev=self.counts[1:2], counts=self.counts)
+
+
 # --------------------------------------------------------------------------------------
 # K3: aggregation (exact fp32 path, differentiable)
 # --------------------------------------------------------------------------------------
@@ -419,6 +451,8 @@ class AggConst:
     act_shift: float
     interval: float
     direct: bool = True
+    # static mode: pts / nn_idx / ray_id are capacity-sized, the true sample count is this (1) int32 device tensor
+    m_dev: Optional[torch.Tensor] = None
 
 
 def _agg_inputs(c: AggConst, xyz, ginv, feat, pose_emb, M, d_in) -> AggInputs:
@@ -429,6 +463,7 @@ def _agg_inputs(c: AggConst, xyz, ginv, feat, pose_emb, M, d_in) -> AggInputs:
     a.viewdirs = ptr(c.viewdirs)
     a.canonical_alpha, a.canonical_rgbs, a.direct_eps = ptr(c.canonical_alpha), ptr(c.canonical_rgbs), ptr(c.direct_eps)
     a.mean_min_distance, a.eps, a.act_shift, a.interval = c.mean_min_distance, c.eps, c.act_shift, c.interval
+    a.m_dev = ptr(c.m_dev)
     return a
 
 
@@ -556,11 +591,15 @@ class PackedDecoder:
         self.buf = self.table = self.buf_bwd = None
         self.key = self.table_key = self.key_bwd = None
 
+    # set while a CUDA graph is being captured: the packing launches must be part of the graph whatever the caches say
+    # (the optimiser changes the weights between replays)
+    force = False
+
     def get_bwd(self, ws: Sequence[torch.Tensor], d_in: int) -> torch.Tensor:
         """Transposed weight tiles of the dgrad kernel."""
         lib = _lib.load()
         key = tuple((w.data_ptr(), w._version) for w in ws[:8:2]) + (d_in,)
-        if self.key_bwd != key:
+        if self.key_bwd != key or self.force:
             if self.buf_bwd is None:
                 self.buf_bwd = _empty((lib.apn_aggregate_tc_bwd_weights_bytes(),), ws[0].device, torch.uint8)
             w = _mlp_struct(ws)
@@ -572,14 +611,14 @@ class PackedDecoder:
     def get(self, ws: Sequence[torch.Tensor], d_in: int, feat: torch.Tensor):
         lib = _lib.load()
         key = tuple((w.data_ptr(), w._version) for w in ws[:8:2]) + (d_in,)
-        if self.key != key:
+        if self.key != key or self.force:
             if self.buf is None:
                 self.buf = _empty((lib.apn_aggregate_tc_weights_bytes(d_in),), ws[0].device, torch.uint8)
             w = _mlp_struct(ws)
             check(lib.apn_aggregate_tc_pack_weights(C.byref(w), d_in, ptr(self.buf), stream()), "apn_aggregate_tc_pack_weights")
             self.key = key
         tkey = (feat.data_ptr(), feat._version, feat.shape[0], ws[0].data_ptr(), ws[0]._version, d_in)
-        if self.table_key != tkey:
+        if self.table_key != tkey or self.force:
             if self.table is None or self.table.shape[0] != feat.shape[0]:
                 self.table = _empty((feat.shape[0], FEAT_DIM), feat.device)
             check(lib.apn_aggregate_tc_point_table(ptr(feat), ptr(ws[0]), d_in, feat.shape[0], ptr(self.table), stream()),
@@ -817,6 +856,13 @@ class AdamPlan:
             self.arr[i].step_size = ss
         with stage("adam"):
             check(_lib.load().apn_adam_multi(self.cptr, self.n, beta1, beta2, eps, stream()), "apn_adam_multi")
+
+    def launch_dev(self, step_sizes_dev: torch.Tensor, skip_dev: Optional[torch.Tensor], beta1, beta2, eps):
+        """Step sizes from device memory (n floats) and an optional device skip word: the launch a CUDA graph can replay."""
+        assert step_sizes_dev.numel() >= self.n and step_sizes_dev.dtype == torch.float32
+        with stage("adam"):
+            check(_lib.load().apn_adam_multi_dev(self.cptr, self.n, beta1, beta2, eps, ptr(step_sizes_dev), ptr(skip_dev), stream()),
+                  "apn_adam_multi_dev")
 
 
 def adam_multi(entries, beta1: float, beta2: float, eps: float) -> None:

@@ -188,6 +188,8 @@ class TemporalPoints(torch.nn.Module):
         # plain-tensor attributes the reference leaves to the default CUDA tensor type (run.py:1248-1249)
         self.canonical_pcd = fn(self.canonical_pcd)
         self.forward_warp.canonical_pcd = self.canonical_pcd
+        # aliases of the heads' frequency buffers (lib/temporalpoints.py:150-151): follow the moved buffers
+        self.view_poc, self.pos_poc = self.tineuvox.view_poc, self.tineuvox.pos_poc
         if torch.is_tensor(self.skeleton_pcd):
             self.skeleton_pcd = fn(self.skeleton_pcd)
         for name in ('nn_i', 'nn_distance', 'mean_min_distance'):

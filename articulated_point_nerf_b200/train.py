@@ -137,7 +137,11 @@ class FusedTrainStep:
     AccumulateGrad, every gradient written by its kernel straight into the flat bucket).  Same arithmetic as
     `loss.backward()` through TemporalPoints.forward: it calls the very same forward/backward bodies (ops._Pose, _LBS,
     _AggregateTC, _Composite) in the order autograd would.  Covers the configuration the stage-2 loop runs in
-    (time input, fused pose kernel, tensor-core decoder, no pose embedding); `eligible()` says whether it applies."""
+    (time input, fused pose kernel, tensor-core decoder, with or without the pose embedding); `eligible()` says whether
+    it applies.
+
+    `sampler` (ops.StaticSampler): the sync-free variant — fixed-capacity sample arrays, every count stays on the device,
+    no host read-back anywhere in the step (GraphedTrainStep captures exactly this body in CUDA graphs)."""
 
     def __init__(self, model, optimizer: MaskedAdam, bucket: GradBucket):
         self.model, self.opt, self.bucket = model, optimizer, bucket
@@ -150,14 +154,21 @@ class FusedTrainStep:
                 and fw._fused_tables(model.joints.device) is not None)
 
     @torch.no_grad()
-    def run(self, t, render_kwargs, target):
-        """-> loss (device scalar), or None when the batch keeps no sample (the caller falls back to autograd)."""
+    def run(self, t, render_kwargs, target, sampler=None):
+        """-> loss (device scalar), or None when the batch keeps no sample (dynamic mode only; the static mode never
+        looks at the count: an empty batch simply produces zero gradients and the constant background loss)."""
+        st = self.forward_sampling(t, render_kwargs, sampler)
+        if st is None:
+            return None
+        return self.decode_and_backward(st, render_kwargs, target)
+
+    # ---- stage A: pose -> LBS -> grid -> ray samples + exact 8-NN
+    @torch.no_grad()
+    def forward_sampling(self, t, render_kwargs, sampler=None):
         from . import ops
-        from .heads import poc_fre
         m, fw = self.model, self.model.forward_warp
         dev = m.joints.device
         self.bucket.zero()
-        # ---- forward
         t_embed = ops.time_embed(t, m.time_poc)
         wb = fw._mlp_params()
         cp = _Ctx((False, False, m.joints.requires_grad, *[w.requires_grad for w in wb]))
@@ -169,17 +180,33 @@ class FusedTrainStep:
         m._last_weights = w
         warped = dict(xyz=xyz, ginv=ginv, weights=w, bbox=bbox, bone_Ts=bone_Ts, global_t=global_t, joints_rel=None)
         grid = m.build_grid(warped, 0.01)
-        rays_o, rays_d, viewdirs = render_kwargs['rays_o'], render_kwargs['rays_d'], render_kwargs['viewdirs']
+        rays_o, rays_d = render_kwargs['rays_o'], render_kwargs['rays_d']
         R = len(rays_o)
         stepdist = float(render_kwargs['stepsize']) * float(m.voxel_size)
-        smp = ops.sample_and_knn(grid, rays_o, rays_d, float(render_kwargs['near']), float(render_kwargs['far']), stepdist)
-        m.last_counts = dict(R=R, candidates=smp.n_candidates, M=smp.M, N=len(xyz))
-        if smp.M == 0:
-            return None
+        near, far = float(render_kwargs['near']), float(render_kwargs['far'])
+        if sampler is None:
+            smp = ops.sample_and_knn(grid, rays_o, rays_d, near, far, stepdist)
+            m.last_counts = dict(R=R, candidates=smp.n_candidates, M=smp.M, N=len(xyz))
+            if smp.M == 0:
+                return None
+        else:
+            smp = sampler.run(grid, rays_o, rays_d, near, far, stepdist)
+        return dict(cp=cp, cl=cl, wb=wb, xyz=xyz, ginv=ginv, bone_Ts=bone_Ts, smp=smp, R=R)
+
+    # ---- stage B: decoder -> compositing -> loss -> backward of everything (gradients land in the bucket)
+    @torch.no_grad()
+    def decode_and_backward(self, st, render_kwargs, target):
+        from . import ops
+        from .heads import poc_fre
+        m = self.model
+        dev = m.joints.device
+        cp, cl, wb, xyz, ginv, bone_Ts, smp, R = (st[k] for k in ("cp", "cl", "wb", "xyz", "ginv", "bone_Ts", "smp", "R"))
+        viewdirs = render_kwargs['viewdirs']
         c = ops.AggConst(pts=smp.pts, nn_idx=smp.nn_idx, ray_id=smp.ray_id, viewdirs=ops._f32(viewdirs),
                          canonical_alpha=m.canonical_alpha, canonical_rgbs=m.canonical_rgbs, direct_eps=m.direct_eps,
                          mean_min_distance=m._mmd_float, eps=float(m.eps), act_shift=float(m.tineuvox.act_shift),
-                         interval=float(render_kwargs['stepsize']) * float(m.tineuvox.voxel_size_ratio), direct=False)
+                         interval=float(render_kwargs['stepsize']) * float(m.tineuvox.voxel_size_ratio), direct=False,
+                         m_dev=smp.m_dev)
         ws = m._mlp_weights()
         # pose embedding (lib/temporalpoints.py:571-576; ZJU configs): a (1, 64) vector from the DETACHED joint offsets, so
         # gradients reach pose_embedding_net only — and only if the optimiser owns it (the reference's stage-2 configs
@@ -224,6 +251,239 @@ class FusedTrainStep:
         for p, g in zip(params, grads):
             if g is not None and p.requires_grad and p.grad is not None:
                 p.grad.add_(g.reshape(p.grad.shape))
+
+
+class WorkspaceOverflow(RuntimeError):
+    """A graph-captured step found more candidates / kept samples than its fixed workspace holds.  The step was skipped on
+    the device (no optimiser update on any rank), the workspace has been enlarged; feed the batch again."""
+
+
+class GraphedTrainStep:
+    """The stage-2 iteration with NO host synchronisation, replayed from CUDA graphs.
+
+    The reference reads its sample count back to the host in every forward (lib/cuda/render_utils_kernel.cu:205-206) and
+    so did the dynamic path (two `.item()` per step): the host cannot run ahead of the GPU, and every step pays ~80 launch
+    latencies.  Here the sample arrays have fixed capacities (ops.StaticSampler), every kernel reads its counts from
+    device memory (apn_agg_inputs.m_dev), Adam takes its step sizes from device memory (apn_adam_multi_dev), and the whole
+    chain is captured once:
+        graph A   zero bucket, pose, LBS, grid, samples + 8-NN, decoder, compositing, loss, full backward
+        (eager)   the one NCCL all-reduce of the flat bucket — only with more than one rank
+        graph B   Adam
+    Per step the host copies the inputs into the static buffers, writes ~30 step sizes, and launches two graphs.
+
+    Overflow: if a batch yields more samples than the workspace holds, the kernels truncate, raise a flag that travels with
+    the bucket through the all-reduce (so every rank sees it) and Adam skips the update on the device.  The host notices
+    on a later call (it polls, it never waits), enlarges the workspace, re-captures and raises WorkspaceOverflow; `flush()`
+    waits for the steps still in flight."""
+
+    RING = 8
+
+    def __init__(self, model, optimizer: MaskedAdam, bucket: GradBucket, n_rays: int, render_kwargs, *, cand_cap=None,
+                 m_cap=None, calibrate=None, use_graph: bool = True, packed_inputs: bool = False):
+        from . import ops
+        assert FusedTrainStep.eligible(model), "GraphedTrainStep needs the fused pose kernel and the tensor-core decoder"
+        self.model, self.opt, self.bucket = model, optimizer, bucket
+        self.fused = FusedTrainStep(model, optimizer, bucket)
+        dev = model.joints.device
+        self.dev, self.R, self.use_graph = dev, int(n_rays), use_graph
+        self.rk = {k: render_kwargs[k] for k in ("near", "far", "bg", "stepsize", "inverse_y", "flip_x", "flip_y") if k in render_kwargs}
+        # static inputs
+        self.t = torch.zeros(1, device=dev)
+        self.rays_o, self.rays_d, self.viewdirs, self.target = (torch.zeros(self.R, 3, device=dev) for _ in range(4))
+        self.rk.update(rays_o=self.rays_o, rays_d=self.rays_d, viewdirs=self.viewdirs)
+        self.loss = torch.zeros(1, device=dev)
+        # optional packed input: one (R, 12) buffer [rays_o | rays_d | viewdirs | target] that arrives with ONE host->device
+        # copy; the split into the four static tensors is then part of the captured graph
+        self.packed = torch.zeros(self.R, 12, device=dev) if packed_inputs else None
+        self.history = []                 # (candidates, kept samples) of every finished step, filled by _poll
+        self.launches_per_step = 0
+        # capacities: candidates = every step of every ray between near and far (cannot overflow), unless that is absurdly
+        # large; kept samples = 4x what a calibration batch keeps
+        stepdist = float(self.rk['stepsize']) * float(model.voxel_size)
+        worst = self.R * (int((float(self.rk['far']) - float(self.rk['near'])) / stepdist) + 3)
+        if calibrate is not None and (cand_cap is None or m_cap is None):
+            n_cand, n_kept = self._calibrate(calibrate)
+            cand_cap = cand_cap or min(worst, max(4 * n_cand, 1 << 16))
+            m_cap = m_cap or max(4 * n_kept, 1 << 15)
+        self.cand_cap = int(cand_cap or min(worst, 1 << 24))
+        self.m_cap = int(m_cap or max(self.cand_cap // 8, 1 << 15))
+        self.m_cap = (self.m_cap + 127) // 128 * 128
+        self.sampler = None
+        self.graphs = None
+        self._plan_key = None
+        self._pending = []          # (event, pinned status, step index)
+        self._ring = 0
+        self._steps = 0
+        self.world = 1
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            self.world = dist.get_world_size()
+        # status slot: the last 64 floats of a private extension of the bucket would change the bucket layout; instead a
+        # separate 64-float tensor is all-reduced together with the bucket (one extra tiny collective only when world > 1)
+        self.status = torch.zeros(64, device=dev)
+        self.skip_word = self.status[:1]          # non-zero (on any rank, after the all-reduce) => Adam skips
+        self._pinned = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(self.RING)]
+        self._pinned_ss = None
+        self.step_sizes = None
+
+    # ------------------------------------------------------------------------------------------
+    def _calibrate(self, batch):
+        """One dynamic (synchronising) sampling pass on a representative batch: -> (candidates, kept samples)."""
+        from . import ops
+        t, ro, rd = batch[0], batch[1], batch[2]
+        m = self.model
+        with torch.no_grad():
+            warped = m.warp(t)
+            grid = m.build_grid(warped, 0.01)
+            smp = ops.sample_and_knn(grid, ro, rd, float(self.rk['near']), float(self.rk['far']),
+                                     float(self.rk['stepsize']) * float(m.voxel_size))
+        return smp.n_candidates, smp.M
+
+    def _body_a(self):
+        if self.packed is not None:
+            for i, dst in enumerate((self.rays_o, self.rays_d, self.viewdirs, self.target)):
+                dst.copy_(self.packed[:, 3 * i:3 * i + 3])
+        st = self.fused.forward_sampling(self.t, self.rk, self.sampler)
+        loss = self.fused.decode_and_backward(st, self.rk, self.target)
+        self.loss.copy_(loss.reshape(1))
+        self.status[:1].copy_(self.sampler.counts[2:3])            # int flags -> float status word (0.0 = clean)
+        self.status[1:6].copy_(self.sampler.counts[0:5])           # counts, for the host's bookkeeping
+
+    def _body_b(self, launches, skip=None):
+        off = 0
+        for cls, ap, sizes in launches:
+            ap.launch_dev(self.step_sizes[off:off + len(sizes)], self.skip_word if skip is None else skip, *cls)
+            off += len(sizes)
+
+    def _capture(self, launches):
+        from . import ops
+        dev = self.dev
+        self.sampler = ops.StaticSampler(self.R, self.cand_cap, self.m_cap, dev)
+        n = sum(len(sz) for _, _, sz in launches)
+        self.step_sizes = torch.zeros(max(n, 1), device=dev)
+        self._pinned_ss = [torch.zeros(max(n, 1), dtype=torch.float32).pin_memory() for _ in range(self.RING)]
+        self._ss_events = [None] * self.RING
+        packed = self.model._packed_decoder
+        self.graphs = None
+        if not self.use_graph:
+            return
+        # warm-up on a side stream (allocator + lazy module state), then capture
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s), self.bucket.direct_accum():
+            packed.force = True
+            warm_skip = torch.ones(1, device=dev)     # Adam skips during warm-up: parameters and moments stay untouched
+            from . import _lib
+            for _ in range(2):
+                n0 = _lib.launch_count()
+                self._body_a()
+                self._body_b(launches, skip=warm_skip)
+                self.launches_per_step = _lib.launch_count() - n0     # our kernels in one replayed step
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with self.bucket.direct_accum():
+            with torch.cuda.graph(ga):
+                self._body_a()
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._body_b(launches)
+        packed.force = False
+        self.graphs = (ga, gb)
+
+    # ------------------------------------------------------------------------------------------
+    def _poll(self, wait: bool = False):
+        """Looks at the status of finished steps (never waits unless `wait`)."""
+        overflow = None
+        keep = []
+        for ev, pin, idx in self._pending:
+            if wait:
+                ev.synchronize()
+            if wait or ev.query():
+                flags = pin[0].item()
+                self.last_counts = dict(R=self.R, candidates=int(pin[1].item() / self.world), M=int(pin[2].item() / self.world),
+                                        N=len(self.model.canonical_pcd))
+                self.model.last_counts = self.last_counts
+                self.history.append((self.last_counts["candidates"], self.last_counts["M"]))
+                if flags != 0.0 and overflow is None:
+                    overflow = (idx, int(pin[4].item()), int(pin[5].item()))
+            else:
+                keep.append((ev, pin, idx))
+        self._pending = keep
+        if overflow is not None:
+            idx, n_cand, n_kept = overflow
+            self.flush_no_raise()
+            self.cand_cap = max(self.cand_cap, 2 * n_cand)
+            self.m_cap = (max(self.m_cap, 2 * n_kept) + 127) // 128 * 128
+            self.graphs, self.sampler = None, None
+            self.opt.undo_step_count()
+            raise WorkspaceOverflow(f"step {idx}: {n_cand} candidates / {n_kept} kept samples exceeded the workspace; the step was "
+                                    f"skipped on the device, capacities are now {self.cand_cap} / {self.m_cap}")
+
+    def flush_no_raise(self):
+        torch.cuda.synchronize(self.dev)
+        self._pending = []
+
+    def flush(self):
+        """Waits for the steps in flight and raises WorkspaceOverflow if one of them was skipped."""
+        self._poll(wait=True)
+
+    @torch.no_grad()
+    def step_packed(self, t, packed, decay_factor: float = 1.0):
+        """One iteration from a packed (R, 12) [rays_o | rays_d | viewdirs | target] buffer (host-pinned or device)."""
+        assert self.packed is not None, "construct with packed_inputs=True"
+        self.packed.copy_(packed, non_blocking=True)
+        return self.step(t, self.rays_o, self.rays_d, self.viewdirs, self.target, decay_factor)
+
+    @torch.no_grad()
+    def step(self, t, rays_o, rays_d, viewdirs, target, decay_factor: float = 1.0):
+        """One iteration.  -> loss (a (1,) device tensor that the NEXT call overwrites)."""
+        self._poll()
+        for dst, src in ((self.t, t), (self.rays_o, rays_o), (self.rays_d, rays_d), (self.viewdirs, viewdirs), (self.target, target)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src.reshape(dst.shape), non_blocking=True)
+        launches, params = self.opt.prepare_step()
+        if self.sampler is None or self._plan_key != self.opt._plan_key:
+            self._capture(launches)
+            self._plan_key = self.opt._plan_key
+        slot = self._ring
+        self._ring = (self._ring + 1) % self.RING
+        if self._ss_events[slot] is not None:
+            self._ss_events[slot].synchronize()                 # the copy that last used this pinned slot has run
+        ss = self._pinned_ss[slot]
+        off = 0
+        for _, _, sizes in launches:
+            for v in sizes:
+                ss[off] = v
+                off += 1
+        self.step_sizes.copy_(ss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ss_events[slot] = ev
+        with self.bucket.direct_accum():
+            if self.graphs is not None:
+                self.graphs[0].replay()
+            else:
+                self._body_a()
+            if self.world > 1:
+                import torch.distributed as dist
+                self.bucket.all_reduce_avg()
+                dist.all_reduce(self.status, op=dist.ReduceOp.SUM)
+            if self.graphs is not None:
+                self.graphs[1].replay()
+            else:
+                self._body_b(launches)
+        pin = self._pinned[slot]
+        pin[:8].copy_(self.status[:8], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        self._pending.append((done, pin, self._steps))
+        self._steps += 1
+        if params:
+            torch.autograd.graph.increment_version(params)
+        if decay_factor != 1.0:
+            for g in self.opt.param_groups:                  # run.py:718-721
+                g['lr'] = g['lr'] * decay_factor
+        return self.loss
 
 
 def _finish_step(optimizer, bucket, decay_factor):

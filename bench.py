@@ -239,6 +239,9 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print the per-stage CUDA-event breakdown to stderr")
+    ap.add_argument("--train-path", default="graph", choices=["graph", "static", "dynamic"],
+                    help="training step: CUDA graphs over the sync-free step (default), the same step launched eagerly, "
+                         "or the dynamic step with its two host read-backs")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
 
@@ -256,7 +259,8 @@ def main():
     n_steps = args.steps + args.warmup
     base_cfg = {"workload": f"{args.workload}: {mode}, N={len(scene.canonical_pcd)} points, J={len(scene.joints)}, "
                             f"{'%d-ray batch of one %dx%d view' % (N_RAND, scene.cfg.H, scene.cfg.W) if mode == 'train' else 'one %dx%d frame' % (scene.cfg.H, scene.cfg.W)} per step per GPU",
-                "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"rays sharded, dp{args.gpus}"}
+                "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"rays sharded, dp{args.gpus}",
+                "train_path": args.train_path if mode == "train" else None}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -296,7 +300,7 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     from articulated_point_nerf_b200 import _lib
-    from articulated_point_nerf_b200.train import GradBucket, create_optimizer, train_step
+    from articulated_point_nerf_b200.train import GradBucket, GraphedTrainStep, create_optimizer, train_step
 
     model = build_model(scene, seed=0)
     oracle_state = model_state_for_oracle(model) if (rank == 0 and not args.no_cpu_baseline and world == 1) else None
@@ -317,8 +321,16 @@ def main():
         bucket = GradBucket(opt)
     decay = 0.1 ** (1.0 / (160 * 1000))
     counts = []
+    gs = gs_stages = None
+    if mode == "train" and args.train_path != "dynamic":
+        t0, b0 = host[0][0].to(dev), host[0][1].to(dev)
+        cal = (t0, b0[:, 0:3].contiguous(), b0[:, 3:6].contiguous())
+        gs = GraphedTrainStep(model, opt, bucket, len(b0), rk, calibrate=cal, use_graph=args.train_path == "graph",
+                              packed_inputs=True)
 
-    def run_step(t_dev, buf_dev):
+    def run_step(t_dev, buf_dev, stepper=None):
+        if mode == "train" and (stepper or gs) is not None:
+            return (stepper or gs).step_packed(t_dev, buf_dev, decay)       # counts arrive later (gs.history)
         t, ro, rd, vd, tgt = unpack_dev(t_dev, buf_dev)
         kw = dict(rk, rays_o=ro, rays_d=rd, viewdirs=vd)
         if mode == "train":
@@ -342,11 +354,26 @@ def main():
         stages=True (a third, separate pass): resident inputs with the per-stage CUDA-event brackets on — it feeds
         `stages_ms_per_step` and the roofline figures, never `value`."""
         dev_in = None if e2e else [(t.to(dev), b.to(dev)) for t, b in host]
+        stepper = None
+        if stages and gs is not None:          # stage brackets are CUDA events: they cannot live inside a captured graph
+            nonlocal gs_stages
+            if gs_stages is None:
+                gs_stages = GraphedTrainStep(model, opt, bucket, gs.R, rk, cand_cap=gs.cand_cap, m_cap=gs.m_cap, use_graph=False,
+                                             packed_inputs=True)
+            stepper = gs_stages
+        on_host = e2e and (gs is not None)     # the graphed step takes the pinned host buffers directly (one H2D copy each)
         for i in range(args.warmup):
-            t_d, b_d = (host[i][0].to(dev, non_blocking=True), host[i][1].to(dev, non_blocking=True)) if e2e else dev_in[i]
-            o = run_step(t_d, b_d)
+            if on_host:
+                t_d, b_d = host[i]
+            else:
+                t_d, b_d = (host[i][0].to(dev, non_blocking=True), host[i][1].to(dev, non_blocking=True)) if e2e else dev_in[i]
+            o = run_step(t_d, b_d, stepper)
             if e2e:
                 (o.item() if mode == "train" else o.cpu())
+        for st_ in (gs, gs_stages):
+            if st_ is not None:
+                st_.flush()
+                st_.history.clear()
         counts.clear()
         if not e2e:
             # workspace headroom: sample counts differ from view to view, so later steps can need somewhat larger
@@ -362,22 +389,31 @@ def main():
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            if e2e:
+            if on_host:
+                t_d, b_d = host[i]
+            elif e2e:
                 t_d, b_d = host[i][0].to(dev, non_blocking=True), host[i][1].to(dev, non_blocking=True)
             else:
                 t_d, b_d = dev_in[i]
-            o = run_step(t_d, b_d)
+            o = run_step(t_d, b_d, stepper)
             if e2e:
                 (o.item() if mode == "train" else o.cpu())
             b.record()
             evs.append((a, b))
         barrier()
+        active = stepper or gs
+        if active is not None:
+            active.flush()
+            counts.extend(dict(R=active.R, candidates=c_, M=m_) for c_, m_ in active.history)
+            active.history.clear()
         if os.environ.get("APN_ALLOC_STATS") and rank == 0:
             st = torch.cuda.memory_stats()
             print(f"  alloc stats ({'e2e' if e2e else 'value'}): device_alloc={st.get('num_device_alloc')} "
                   f"device_free={st.get('num_device_free')} retries={st.get('num_alloc_retries')} "
                   f"reserved={st.get('reserved_bytes.all.current', 0) / 1e6:.0f} MB", file=sys.stderr)
         launches = _lib.launch_count() - n0
+        if gs is not None and gs.graphs is not None and not stages:
+            launches += (n_steps - args.warmup) * gs.launches_per_step       # kernels replayed from the graphs
         per_step = torch.tensor([a.elapsed_time(b) for a, b in evs], device=dev, dtype=torch.float64)
         tt = per_step.sum().reshape(1)
         if world > 1:

@@ -122,6 +122,17 @@ int apn_compact_samples(const float* rays_o, const float* rays_d, float near, fl
                         const int32_t* keep, const int32_t* kept_pos, const int32_t* nn_idx_cand, int n_cand, int R,
                         float* pts, int32_t* ray_id, int32_t* step_id, int32_t* nn_idx, int32_t* ray_start,
                         apn_stream_t stream);
+/* Sync-free sampling stage: count -> scan -> fill -> exact 8-NN -> scan -> compact in one call with every length kept on
+ * the device (the reference reads its sample count back, lib/cuda/render_utils_kernel.cu:205-206: N_steps.sum().item()).
+ * The candidate list (cand_cap) and the sample arrays (m_cap rows of pts / ray_id / step_id / nn_idx) have fixed capacities;
+ * counts (5 x int32, device): [0] candidates used, [1] samples kept = the m_dev of apn_agg_inputs, [2] flags (1 grid
+ * overflow | 2 candidate list truncated | 4 sample arrays truncated), [3] candidates found, [4] samples found.
+ * Same results as apn_ray_candidates + apn_knn + apn_compact_samples whenever counts[2] == 0; capturable in a CUDA graph. */
+size_t apn_sample_knn_static_workspace_bytes(int R, int cand_cap);
+int apn_sample_knn_static(const float* rays_o, const float* rays_d, int R, float near, float far, float stepdist,
+                          const void* grid, int cand_cap, int m_cap, void* workspace, size_t workspace_bytes,
+                          float* pts, int32_t* ray_id, int32_t* step_id, int32_t* nn_idx, int32_t* ray_start,
+                          int32_t* counts, apn_stream_t stream);
 /* brute-force-free k-NN of arbitrary query points against the grid (init self-k-NN,
  * lib/temporalpoints.py:104-111; chamfer K=1, :747-751). max_d2 <= 0: unbounded. */
 int apn_knn_points(const float* query, int n_query, const void* grid, int k, int32_t* nn_idx, float* nn_d2,
@@ -180,6 +191,12 @@ typedef struct apn_agg_inputs {
   float eps;                   /* 1e-6 */
   float act_shift;
   float interval;              /* stepsize * voxel_size_ratio */
+  /* Optional device-side sample count (NULL: M is exact).  When given, M is the CAPACITY of the per-sample arrays and
+   * the kernels read the true count min(*m_dev, M) on the device: the host never reads a count back, so a whole
+   * training step can be enqueued ahead of the GPU and captured as a CUDA graph (the reference synchronises on its
+   * sample count, lib/cuda/render_utils_kernel.cu:205-206).  Honoured by the tensor-core entry points
+   * (apn_aggregate_fwd_tc, apn_aggregate_bwd_tc); rows >= *m_dev of every per-sample output are left untouched. */
+  const int32_t* m_dev;
 } apn_agg_inputs;
 
 typedef struct apn_agg_outputs {
@@ -302,6 +319,12 @@ float apn_adam_step_size(int step, float beta1, float beta2, float lr);
 /* `tensors` is a HOST array of n_tensors descriptors (copied into kernel parameters in chunks). */
 int apn_adam_multi(const apn_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
                    apn_stream_t stream);
+/* The same update with the per-tensor step sizes in DEVICE memory (step_sizes_dev[n_tensors]; the host refreshes them
+ * before a captured CUDA graph is replayed — kernel arguments are frozen at capture, lib/masked_adam.py:62 changes the
+ * bias-corrected step size every iteration) and an optional device-side skip word: *skip_dev != 0 makes the launch a
+ * no-op (the step's sample workspace overflowed, apn_sample_knn_static counts[2], and the step is re-run). */
+int apn_adam_multi_dev(const apn_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
+                       const float* step_sizes_dev, const int32_t* skip_dev, apn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Reference-compatible single ops (the pybind surface of lib/cuda/render_utils.cpp:144-155).

@@ -31,7 +31,7 @@ def test_ctypes_struct_layout_matches_header_sizes():
     from articulated_point_nerf_b200 import _lib
     P = ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.MlpWeights) == 16 * P
-    assert ctypes.sizeof(_lib.AggInputs) == 4 * 4 + 11 * P + 4 * 4     # 3 ints (+pad), 11 pointers, 4 floats
+    assert ctypes.sizeof(_lib.AggInputs) == 4 * 4 + 11 * P + 4 * 4 + P     # 3 ints (+pad), 11 pointers, 4 floats, m_dev
     assert ctypes.sizeof(_lib.AggOutputs) == 14 * P
     assert ctypes.sizeof(_lib.AggGrads) == 22 * P
     assert ctypes.sizeof(_lib.AdamTensor) == 5 * P + 8 + 4 + 4

@@ -512,7 +512,7 @@ def test_aggregate_tensor_core_backward(golden_tiny):
     kx = xyz.detach().cuda().requires_grad_(True)
     kg = gi.detach()[:, :3, :3].reshape(-1, 9).contiguous().cuda().requires_grad_(True)
     model.zero_grad()
-    k_alpha, k_rgb, *_ = ops.aggregate_tc_train(c, kx, kg, model.canonical_feat, model._mlp_weights(), ops.PackedDecoder())
+    k_alpha, k_rgb, *_ = ops.aggregate_tc_train(c, kx, kg, model.canonical_feat, None, model._mlp_weights(), ops.PackedDecoder())
     assert rel_err(k_alpha, alpha) < RTOL and rel_err(k_rgb, rgb) < RTOL
     ((k_alpha * ca.cuda()).sum() + (k_rgb * cr.cuda()).sum()).backward()
     errs = {"d_xyz": rel_err(kx.grad, xyz.grad), "d_ginv": rel_err(kg.grad.view(-1, 3, 3), gi.grad[:, :3, :3])}
@@ -560,7 +560,7 @@ def test_aggregate_tensor_core_backward_matches_fp32_kernels_on_ragged_sizes(M):
         for l in lin:
             ws += [l.weight.detach().to(d).requires_grad_(True), l.bias.detach().to(d).requires_grad_(True)]
         if tc:
-            out = ops.aggregate_tc_train(c, *leaves, ws, ops.PackedDecoder())
+            out = ops.aggregate_tc_train(c, *leaves, None, ws, ops.PackedDecoder())
         else:
             out = ops.aggregate(c, *leaves, None, ws)
         ((out[0] * ca).sum() + (out[1] * cr).sum()).backward()

@@ -438,3 +438,114 @@ def test_derived_decoder_state_follows_the_optimizer(golden_tiny):
     assert rel_err(out_tc, before) > 1e-3                      # the step really moved the image
     assert rel_err(out_tc, out_32) < RTOL                      # ... and the tensor-core state moved with it
     assert all(l == l and l > 0 for l in losses)
+
+
+# ----------------------------------------------------------------------------------------
+# sync-free training step (device-side counts, CUDA graphs)
+# ----------------------------------------------------------------------------------------
+def test_static_sampler_equals_dynamic_sampler(golden_tiny):
+    """apn_sample_knn_static (fixed capacities, counts on the device, no read-back) against the two-read-back sequence:
+    identical samples, neighbours, CSR; counts reported on the device; truncation flagged."""
+    from articulated_point_nerf_b200 import ops
+    g = golden_tiny
+    model, scene = model_from_golden(g, fused_pose=True)
+    rk = _rk(scene, g)
+    with torch.no_grad():
+        warped = model.warp(g["train"]["t"].cuda())
+        grid = model.build_grid(warped)
+        stepdist = scene.cfg.stepsize * scene.voxel_size
+        dyn = ops.sample_and_knn(grid, rk["rays_o"], rk["rays_d"], scene.cfg.near, scene.cfg.far, stepdist)
+        R = len(rk["rays_o"])
+        ss = ops.StaticSampler(R, cand_cap=4 * dyn.n_candidates + 100, m_cap=2 * dyn.M + 64, device="cuda")
+        st = ss.run(grid, rk["rays_o"], rk["rays_d"], scene.cfg.near, scene.cfg.far, stepdist)
+        counts = st.counts.cpu().tolist()
+        assert counts[0] == dyn.n_candidates and counts[1] == dyn.M and counts[2] == 0
+        assert counts[3] == dyn.n_candidates and counts[4] == dyn.M
+        M = dyn.M
+        assert torch.equal(st.pts[:M], dyn.pts) and torch.equal(st.nn_idx[:M], dyn.nn_idx)
+        assert torch.equal(st.ray_id[:M], dyn.ray_id) and torch.equal(st.step_id[:M], dyn.step_id)
+        assert torch.equal(st.ray_start, dyn.ray_start)
+        # sample arrays too small: flagged, clamped, nothing written out of bounds
+        small = ops.StaticSampler(R, cand_cap=4 * dyn.n_candidates, m_cap=M // 2, device="cuda")
+        guard = small.pts.clone()
+        sm = small.run(grid, rk["rays_o"], rk["rays_d"], scene.cfg.near, scene.cfg.far, stepdist)
+        c2 = sm.counts.cpu().tolist()
+        assert c2[2] == 4 and c2[1] == M // 2 and c2[4] == M
+        assert torch.equal(sm.pts[:M // 2], dyn.pts[:M // 2]) and int(sm.ray_start.max()) == M // 2
+        # candidate list too small: flagged
+        small2 = ops.StaticSampler(R, cand_cap=dyn.n_candidates // 2, m_cap=2 * M, device="cuda")
+        c3 = small2.run(grid, rk["rays_o"], rk["rays_d"], scene.cfg.near, scene.cfg.far, stepdist).counts.cpu().tolist()
+        assert c3[2] & 2 and c3[0] == dyn.n_candidates // 2 and c3[3] == dyn.n_candidates
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_graphed_train_step_equals_fused_step(golden_any, use_graph):
+    """train.GraphedTrainStep (no host read-back; CUDA graphs) against the dynamic fused step over three iterations with
+    changing inputs: same losses, same parameters, same Adam moments."""
+    from articulated_point_nerf_b200.train import GradBucket, GraphedTrainStep, create_optimizer, train_step
+    g = golden_any
+    gen = torch.Generator().manual_seed(5)
+    R = len(g["rays_o"])
+    batches = []
+    for i in range(3):
+        sel = torch.randperm(R, generator=gen)
+        batches.append((torch.tensor([0.2 + 0.3 * i]).cuda(), g["rays_o"][sel].cuda(), g["rays_d"][sel].cuda(),
+                        g["viewdirs"][sel].cuda(), torch.rand(R, 3, generator=gen).cuda()))
+    decay = 0.1 ** (1.0 / 1000)
+    results = []
+    for mode in ("dynamic", "graphed"):
+        model, scene = model_from_golden(g, fused_pose=True)
+        model.decoder_train = "tc"
+        opt = create_optimizer(model)
+        bucket = GradBucket(opt)
+        rk0 = scene.render_kwargs()
+        losses = []
+        if mode == "dynamic":
+            for t, ro, rd, vd, tgt in batches:
+                rk = dict(rk0, rays_o=ro, rays_d=rd, viewdirs=vd)
+                losses.append(float(train_step(model, opt, bucket, t, rk, tgt, decay_factor=decay)))
+        else:
+            gs = GraphedTrainStep(model, opt, bucket, R, rk0, calibrate=batches[0], use_graph=use_graph)
+            for t, ro, rd, vd, tgt in batches:
+                losses.append(float(gs.step(t, ro, rd, vd, tgt, decay_factor=decay)))
+            gs.flush()
+            assert gs.last_counts["M"] > 0
+        results.append((losses, {k: p.detach().clone() for k, p in model.named_parameters()},
+                        {k: opt.state[p]["exp_avg"].clone() for k, p in model.named_parameters() if p in opt.state},
+                        [grp["lr"] for grp in opt.param_groups]))
+    (l0, p0, m0, lr0), (l1, p1, m1, lr1) = results
+    assert lr0 == lr1
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * abs(a), (l0, l1)
+    assert set(m0) == set(m1)
+    for k in m0:       # float atomics: run-to-run noise ~1e-6 of the tensor's scale
+        assert rel_err(m1[k], m0[k]) < RTOL, k
+    for k in p0:
+        assert rel_err(p1[k], p0[k]) < 1e-3, k
+
+
+def test_graphed_train_step_overflow_is_skipped_and_reported(golden_tiny):
+    """A workspace that is too small: the step is skipped ON THE DEVICE (parameters, moments untouched), the host learns
+    about it without ever having waited, the workspace grows, and the re-fed batch then trains normally."""
+    from articulated_point_nerf_b200.train import GradBucket, GraphedTrainStep, WorkspaceOverflow, create_optimizer
+    g = golden_tiny
+    model, scene = model_from_golden(g, fused_pose=True)
+    model.decoder_train = "tc"
+    opt = create_optimizer(model)
+    bucket = GradBucket(opt)
+    R = len(g["rays_o"])
+    batch = (g["train"]["t"].cuda(), g["rays_o"].cuda(), g["rays_d"].cuda(), g["viewdirs"].cuda(), g["train"]["target"].cuda())
+    gs = GraphedTrainStep(model, opt, bucket, R, scene.render_kwargs(), cand_cap=1 << 16, m_cap=256)
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    gs.step(*batch)
+    with pytest.raises(WorkspaceOverflow):
+        gs.flush()
+    for k, p in model.named_parameters():
+        assert torch.equal(p.detach(), before[k]), k
+    assert all(st["step"] == 0 for st in opt.state.values())
+    assert gs.m_cap >= 2 * 1332 // 1
+    loss = gs.step(*batch)
+    gs.flush()
+    assert torch.isfinite(loss).all() and gs.last_counts["M"] == len(g["render"]["agg"]["ray_id"]) or gs.last_counts["M"] > 256
+    assert any(not torch.equal(p.detach(), before[k]) for k, p in model.named_parameters())
+    assert all(st["step"] == 1 for st in opt.state.values())
