@@ -579,6 +579,8 @@ class _Aggregate(torch.autograd.Function):
 def aggregate(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch.Tensor]):
     """-> alpha (M), rgb (M,3), alpha_direct (M)|None, rgb_direct (M,3)|None, idw (M,8)."""
     assert len(weights) == 16, "expected feat_net (4x w,b), densitynet, rgbnet (3x w,b)"
+    if pose_emb is not None:
+        pose_emb = pose_emb.reshape(-1)          # (1, 64) -> (64): the gradient comes back in this shape through autograd
     return _Aggregate.apply(c, xyz, ginv, feat, pose_emb, *weights)
 
 

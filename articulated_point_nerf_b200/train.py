@@ -304,9 +304,9 @@ class GraphedTrainStep:
         if calibrate is not None and (cand_cap is None or m_cap is None):
             n_cand, n_kept = self._calibrate(calibrate)
             cand_cap = cand_cap or min(worst, max(4 * n_cand, 1 << 16))
-            m_cap = m_cap or max(4 * n_kept, 1 << 15)
+            m_cap = m_cap or max(2 * n_kept, 1 << 14)       # grids and split-K factors of the backward are sized by this
         self.cand_cap = int(cand_cap or min(worst, 1 << 24))
-        self.m_cap = int(m_cap or max(self.cand_cap // 8, 1 << 15))
+        self.m_cap = int(m_cap or max(self.cand_cap // 8, 1 << 14))
         self.m_cap = (self.m_cap + 127) // 128 * 128
         self.sampler = None
         self.graphs = None
@@ -322,7 +322,7 @@ class GraphedTrainStep:
         # separate 64-float tensor is all-reduced together with the bucket (one extra tiny collective only when world > 1)
         self.status = torch.zeros(64, device=dev)
         self.skip_word = self.status[:1]          # non-zero (on any rank, after the all-reduce) => Adam skips
-        self._pinned = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(self.RING)]
+        self._pinned = [torch.zeros(9, dtype=torch.float32).pin_memory() for _ in range(self.RING)]   # status[0:8] | loss
         self._pinned_ss = None
         self.step_sizes = None
 
@@ -381,12 +381,18 @@ class GraphedTrainStep:
                 self.launches_per_step = _lib.launch_count() - n0     # our kernels in one replayed step
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        ga, gb = torch.cuda.CUDAGraph(), None
         with self.bucket.direct_accum():
-            with torch.cuda.graph(ga):
-                self._body_a()
-            with torch.cuda.graph(gb, pool=ga.pool()):
-                self._body_b(launches)
+            if self.world == 1:                      # no collective between the backward and Adam: ONE graph per step
+                with torch.cuda.graph(ga):
+                    self._body_a()
+                    self._body_b(launches)
+            else:
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    self._body_a()
+                with torch.cuda.graph(gb, pool=ga.pool()):
+                    self._body_b(launches)
         packed.force = False
         self.graphs = (ga, gb)
 
@@ -418,6 +424,17 @@ class GraphedTrainStep:
             self.opt.undo_step_count()
             raise WorkspaceOverflow(f"step {idx}: {n_cand} candidates / {n_kept} kept samples exceeded the workspace; the step was "
                                     f"skipped on the device, capacities are now {self.cand_cap} / {self.m_cap}")
+
+    def loss_reader(self):
+        """-> a callable that returns THIS step's loss as a Python float: it waits for the step's own completion event and
+        reads the value from pinned host memory (the copy was enqueued with the step).  Calling it one step late (after the
+        next step has been enqueued) reads every step's loss without ever draining the GPU."""
+        done, pin = self._last_done
+
+        def read():
+            done.synchronize()
+            return float(pin[8])
+        return read
 
     def flush_no_raise(self):
         torch.cuda.synchronize(self.dev)
@@ -468,15 +485,17 @@ class GraphedTrainStep:
                 import torch.distributed as dist
                 self.bucket.all_reduce_avg()
                 dist.all_reduce(self.status, op=dist.ReduceOp.SUM)
-            if self.graphs is not None:
-                self.graphs[1].replay()
-            else:
+            if self.graphs is None:
                 self._body_b(launches)
+            elif self.graphs[1] is not None:
+                self.graphs[1].replay()
         pin = self._pinned[slot]
         pin[:8].copy_(self.status[:8], non_blocking=True)
+        pin[8:9].copy_(self.loss, non_blocking=True)
         done = torch.cuda.Event()
         done.record()
         self._pending.append((done, pin, self._steps))
+        self._last_done = (done, pin)
         self._steps += 1
         if params:
             torch.autograd.graph.increment_version(params)
