@@ -74,6 +74,8 @@ SIGNATURES = {
     "apn_exclusive_scan_i32": (I, [P, P, I, P, SZ, P]),
     "apn_ray_candidates": (I, [P, P, I, F, F, F, P, I, P, P, P, P, P]),
     "apn_knn": (I, [P, P, F, F, F, P, P, P, I, P, P, P, P]),
+    "apn_knn_sorted_workspace_bytes": (SZ, [I]),
+    "apn_knn_sorted": (I, [P, P, F, F, F, P, P, P, I, P, P, P, P, SZ, P]),
     "apn_compact_samples": (I, [P, P, F, F, F, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P]),
     "apn_knn_points": (I, [P, I, P, I, P, P, P]),
     "apn_nn1_batched": (I, [P, P, I, I, I, I, P, P]),

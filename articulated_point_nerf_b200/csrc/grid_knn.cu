@@ -21,6 +21,7 @@
 // level whose cell edge covers the 8th distance found so far.
 #include <stdlib.h>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -717,6 +718,271 @@ knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, f
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// k-NN of the ray samples, CELL-SORTED and LANE-PARALLEL over shared-memory staged points (apn_knn_sorted).
+//
+// Both searches above spend their instructions on traversal: the warp search ~1800 warp instructions per query (one query
+// per warp, cross-lane top-8), the thread search ~29 000 thread instructions per query on c3 (every lane box-tests up to
+// 9^3 mostly empty leaves on its own).  Here the candidates are first sorted by the grid leaf that contains them (one
+// radix sort of (leaf key, candidate index)), so the 32 queries of a warp sit in the same or neighbouring leaves and
+// share ONE neighbourhood:
+//   * the warp takes a group of lanes whose queries lie in the same leaf (within one leaf when that gives < 8 lanes),
+//   * enumerates the leaves of the group's bounding box grown by a radius rho — lane = leaf, pruned against the group's
+//     current worst bound — and copies their points (contiguous float4 runs of `sorted`) into the warp's shared-memory
+//     stage with coalesced loads,
+//   * every lane then scans the staged points against ITS query with a register top-8 of 64-bit (d2, index) keys:
+//     one broadcast LDS.128 + 8 FP32 operations + one compare per point and warp, for 32 queries at once;
+//   * a lane is finished when its 8th distance is certified by the scanned box (every unscanned point is farther than
+//     the distance from the query to the box faces) or the box covers the query radius; otherwise rho grows to the
+//     largest outstanding bound (doubling for lanes that have not found 8 points yet) and only the new shell is scanned.
+// Exactness: the result is the top-8 by (d2, index) over a superset of the ball that contains it — identical bits to the
+// other searches and to the brute-force oracle (same d2 arithmetic: (dx*dx + dy*dy) + dz*dz without FMA).
+// ---------------------------------------------------------------------------------------
+#define KS_WARPS 8
+#define KS_CHUNK 256          // staged points per warp (4 KiB)
+
+__global__ void knn_key_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far,
+                               float stepdist, const void* __restrict__ blob, const int* __restrict__ cand_ray,
+                               const int* __restrict__ cand_step, int n_cand_cap, const int* __restrict__ n_cand_dev,
+                               int* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand_cap) return;
+  const GridHeader* h = (const GridHeader*)blob;
+  const int n_cand = apn_rt_count(n_cand_dev, n_cand_cap);
+  int key = 0x7fffffff;                                 // entries behind the true length sort to the end
+  if (i < n_cand && !h->overflow) {
+    const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
+    const RaySetup rs = ray_setup(rays_o, rays_d, __ldg(cand_ray + i), bmin, bmax, near, far, stepdist);
+    float qx, qy, qz;
+    ray_point(rs, __ldg(cand_step + i), stepdist, qx, qy, qz);
+    int ix, iy, iz;
+    point_cell(h, qx, qy, qz, ix, iy, iz);
+    key = cell_key(ix, iy, iz, h->L, h->top_dim[0], h->top_dim[1]);
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+
+__global__ void __launch_bounds__(32 * KS_WARPS)
+knn_sorted_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
+                  const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step,
+                  const int* __restrict__ order, int n_cand_cap, const int* __restrict__ n_cand_dev, int* __restrict__ nn_idx,
+                  float* __restrict__ nn_d2, int* __restrict__ keep) {
+  __shared__ float4 sP[KS_WARPS][KS_CHUNK];
+  const GridView g = grid_view(blob);
+  const GridHeader* h = g.h;
+  if (h->overflow) return;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n_cand = apn_rt_count(n_cand_dev, n_cand_cap);
+  const int n_warps = gridDim.x * KS_WARPS;
+  const float bmin[3] = {h->bmin[0], h->bmin[1], h->bmin[2]}, bmax[3] = {h->bmax[0], h->bmax[1], h->bmax[2]};
+  const float cell = h->cell, inv_cell = h->inv_cell, ox = h->origin[0], oy = h->origin[1], oz = h->origin[2];
+  const int L = h->L, tx = h->top_dim[0], ty = h->top_dim[1];
+  const int nx = tx << L, ny = ty << L, nz = h->top_dim[2] << L;
+  const float r2 = h->r2, rmax = sqrtf(r2);
+  const float eps = 1e-4f * cell + 1e-6f;
+  // first radius: the ball expected to hold ~32 points (4 x K) at the cloud's density, between 0.35 and 2 leaf edges
+  const float rho0 = cell * fminf(fmaxf(cbrtf(7.64f / fmaxf(h->occupancy, 1e-3f)), 0.35f), 2.0f);
+  float4* stage = sP[wib];
+
+  for (int base = (blockIdx.x * KS_WARPS + wib) * 32; base < n_cand; base += n_warps * 32) {
+    const int j = base + lane;
+    const bool valid = j < n_cand;
+    const int i = valid ? __ldg(order + j) : 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    int cx = 0, cy = 0, cz = 0;
+    if (valid) {
+      const RaySetup rs = ray_setup(rays_o, rays_d, __ldg(cand_ray + i), bmin, bmax, near, far, stepdist);
+      ray_point(rs, __ldg(cand_step + i), stepdist, qx, qy, qz);
+      point_cell(h, qx, qy, qz, cx, cy, cz);
+    }
+    unsigned long long best[APN_K];
+#pragma unroll
+    for (int k = 0; k < APN_K; ++k) best[k] = KEY_INF;
+    unsigned long long thr = bound_key(r2);
+    unsigned int rem = __ballot_sync(FULL_MASK, valid);
+    while (rem) {
+      // ---- group: the lanes in the leader's leaf when they are at least half a warp (dense query sets); otherwise every
+      // remaining lane whose leaf is within 2 leaves of the leader's (the sort keeps a warp's queries in Morton-adjacent
+      // leaves: one shared neighbourhood, all lanes busy, a handful of groups per warp at worst)
+      const int leader = __ffs(rem) - 1;
+      const int lx = __shfl_sync(FULL_MASK, cx, leader), ly = __shfl_sync(FULL_MASK, cy, leader), lz = __shfl_sync(FULL_MASK, cz, leader);
+      const bool open = (rem >> lane) & 1u;
+      unsigned int gm = __ballot_sync(FULL_MASK, open && cx == lx && cy == ly && cz == lz);
+      if (__popc(gm) < 16) gm = __ballot_sync(FULL_MASK, open && abs(cx - lx) <= 2 && abs(cy - ly) <= 2 && abs(cz - lz) <= 2);
+      const bool mine = (gm >> lane) & 1u;
+      rem &= ~gm;
+      const float qlx = warp_min(mine ? qx : INFINITY), qly = warp_min(mine ? qy : INFINITY), qlz = warp_min(mine ? qz : INFINITY);
+      const float qhx = warp_max(mine ? qx : -INFINITY), qhy = warp_max(mine ? qy : -INFINITY), qhz = warp_max(mine ? qz : -INFINITY);
+      bool fin = !mine;
+      float rho = rho0;
+      int px0 = 1, px1 = 0, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;       // box scanned so far (empty)
+      for (;;) {
+        const bool last_round = rho >= rmax + 8.f * eps;      // this box covers the query radius of every lane of the group
+        const int x0 = min(max((int)floorf((qlx - rho - ox) * inv_cell), 0), nx - 1), x1 = min(max((int)floorf((qhx + rho - ox) * inv_cell), 0), nx - 1);
+        const int y0 = min(max((int)floorf((qly - rho - oy) * inv_cell), 0), ny - 1), y1 = min(max((int)floorf((qhy + rho - oy) * inv_cell), 0), ny - 1);
+        const int z0 = min(max((int)floorf((qlz - rho - oz) * inv_cell), 0), nz - 1), z1 = min(max((int)floorf((qhz + rho - oz) * inv_cell), 0), nz - 1);
+        const int Lx = x1 - x0 + 1, Ly = y1 - y0 + 1, n_leaves = Lx * Ly * (z1 - z0 + 1);
+        float bmax2 = warp_max(fin ? 0.f : key_d2(thr));       // no unfinished lane can use a point beyond this
+        const bool act = mine && !fin;
+        for (int e0 = 0; e0 < n_leaves; e0 += 32) {
+          const int e = e0 + lane;
+          int s = 0, n = 0;
+          if (e < n_leaves) {
+            const int ex = e % Lx, t = e / Lx, ey = t % Ly, ez = t / Ly;
+            const int ix = x0 + ex, iy = y0 + ey, iz = z0 + ez;
+            const bool old = ix >= px0 && ix <= px1 && iy >= py0 && iy <= py1 && iz >= pz0 && iz <= pz1;
+            if (!old) {
+              const float bx = ox + ix * cell, by = oy + iy * cell, bz = oz + iz * cell;
+              const float dx = fmaxf(fmaxf(bx - eps - qhx, qlx - (bx + cell + eps)), 0.f);
+              const float dy = fmaxf(fmaxf(by - eps - qhy, qly - (by + cell + eps)), 0.f);
+              const float dz = fmaxf(fmaxf(bz - eps - qhz, qlz - (bz + cell + eps)), 0.f);
+              if (dx * dx + dy * dy + dz * dz <= bmax2) {
+                const int key = cell_key(ix, iy, iz, L, tx, ty);
+                s = __ldg(g.cell_start + key);
+                n = __ldg(g.cell_start + key + 1) - s;
+              }
+            }
+          }
+          int incl = n;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += v;
+          }
+          const int total = __shfl_sync(FULL_MASK, incl, 31);
+          for (int c0 = 0; c0 < total; c0 += KS_CHUNK) {
+            const int cn = min(KS_CHUNK, total - c0);
+            // ---- stage: flattened index -> (range, offset) by a binary search over the inclusive counts
+            for (int j0 = 0; j0 < cn; j0 += 32) {
+              const int f = c0 + j0 + lane;
+              int c = 0;
+#pragma unroll
+              for (int st = 16; st > 0; st >>= 1) {
+                const int v = __shfl_sync(FULL_MASK, incl, c + st - 1);
+                if (f >= v) c += st;
+              }
+              c = min(c, 31);
+              const int cs = __shfl_sync(FULL_MASK, s, c), ci = __shfl_sync(FULL_MASK, incl, c), cnn = __shfl_sync(FULL_MASK, n, c);
+              if (j0 + lane < cn) stage[j0 + lane] = __ldg(g.sorted + cs + (f - (ci - cnn)));
+            }
+            __syncwarp();
+            // ---- scan: every lane against its own query
+            if (act) {
+#pragma unroll 4
+              for (int jj = 0; jj < cn; ++jj) {
+                const float4 P = stage[jj];
+                const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
+                if (d2 <= key_d2(thr)) {
+                  const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
+                  if (k < thr) {
+                    top8_insert(best, k);
+                    thr = best[APN_K - 1] < thr ? best[APN_K - 1] : thr;
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
+          bmax2 = warp_max(fin ? 0.f : key_d2(thr));
+        }
+        // ---- certification: every unscanned point lies outside the box [x0..x1] x [y0..y1] x [z0..z1]
+        float bnd = INFINITY;
+        if (x0 > 0) bnd = fminf(bnd, qx - (ox + x0 * cell));
+        if (x1 < nx - 1) bnd = fminf(bnd, (ox + (x1 + 1) * cell) - qx);
+        if (y0 > 0) bnd = fminf(bnd, qy - (oy + y0 * cell));
+        if (y1 < ny - 1) bnd = fminf(bnd, (oy + (y1 + 1) * cell) - qy);
+        if (z0 > 0) bnd = fminf(bnd, qz - (oz + z0 * cell));
+        if (z1 < nz - 1) bnd = fminf(bnd, (oz + (z1 + 1) * cell) - qz);
+        const float reach = fmaxf(bnd - 3.f * eps, 0.f);
+        const float reach2 = reach * reach;
+        const bool have8 = best[APN_K - 1] != KEY_INF;
+        if (!fin) {
+          if (have8 && key_d2(best[APN_K - 1]) < reach2) fin = true;       // certified
+          else if (reach2 > r2 || last_round) fin = true;                    // the box covers the query radius
+        }
+        if (__all_sync(FULL_MASK, fin)) break;
+        // next radius: the largest outstanding bound; lanes without 8 points yet grow by ONE leaf edge: shells stay thin, so
+        // the shell in which a far query first meets the surface yields a bound close to its true 8th distance, and the
+        // points scanned stay close to those inside that ball (a doubling radius scans the whole 0.1-ball of dense clouds)
+        const float need = fin ? 0.f : (have8 ? fminf(sqrtf(key_d2(best[APN_K - 1])), rmax) : fminf(rho + cell, rmax));
+        rho = fminf(fmaxf(warp_max(need) + 4.f * eps, rho + 0.25f * cell), rmax + 8.f * eps);
+        px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
+      }
+    }
+    if (valid) {
+      const bool ok = best[APN_K - 1] != KEY_INF && key_d2(best[APN_K - 1]) <= r2;
+      keep[i] = ok ? 1 : 0;
+      if (ok) {
+        int4 a = make_int4((int)(unsigned int)best[0], (int)(unsigned int)best[1], (int)(unsigned int)best[2], (int)(unsigned int)best[3]);
+        int4 b = make_int4((int)(unsigned int)best[4], (int)(unsigned int)best[5], (int)(unsigned int)best[6], (int)(unsigned int)best[7]);
+        reinterpret_cast<int4*>(nn_idx)[2 * (size_t)i] = a;
+        reinterpret_cast<int4*>(nn_idx)[2 * (size_t)i + 1] = b;
+        if (nn_d2) {
+#pragma unroll
+          for (int k = 0; k < APN_K; ++k) nn_d2[(size_t)i * APN_K + k] = key_d2(best[k]);
+        }
+      }
+    }
+  }
+}
+
+struct KnnSortedLayout {
+  size_t keys_in, keys_out, vals_in, vals_out, temp, temp_bytes, total;
+};
+static KnnSortedLayout knn_sorted_layout(int n) {
+  KnnSortedLayout l;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = apn_align(o + bytes); return at; };
+  l.keys_in = take(sizeof(int) * (size_t)n);
+  l.keys_out = take(sizeof(int) * (size_t)n);
+  l.vals_in = take(sizeof(int) * (size_t)n);
+  l.vals_out = take(sizeof(int) * (size_t)n);
+  l.temp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, l.temp_bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, n, 0, 31);
+  l.temp = take(l.temp_bytes);
+  l.total = o;
+  return l;
+}
+extern "C" size_t apn_knn_sorted_workspace_bytes(int n_cand) { return n_cand > 0 ? knn_sorted_layout(n_cand).total : 0; }
+
+static int knn_sorted_launch(cudaStream_t stream, const float* rays_o, const float* rays_d, float near, float far, float stepdist,
+                             const void* grid, const int32_t* cand_ray, const int32_t* cand_step, int n_cand,
+                             const int32_t* n_cand_dev, int32_t* nn_idx, float* nn_d2, int32_t* keep, void* workspace) {
+  const KnnSortedLayout l = knn_sorted_layout(n_cand);
+  char* w = (char*)workspace;
+  int *keys_in = (int*)(w + l.keys_in), *keys_out = (int*)(w + l.keys_out), *vals_in = (int*)(w + l.vals_in),
+      *vals_out = (int*)(w + l.vals_out);
+  knn_key_kernel<<<apn_div_up(n_cand, 256), 256, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand,
+                                                             n_cand_dev, keys_in, vals_in);
+  APN_LAUNCH_CHECK();
+  size_t tb = l.temp_bytes;
+  APN_CUDA(cub::DeviceRadixSort::SortPairs(w + l.temp, tb, keys_in, keys_out, vals_in, vals_out, n_cand, 0, 31, stream));
+  apn_count_launch(4);
+  const int blocks = min(apn_div_up(n_cand, 32 * KS_WARPS), APN_SM_COUNT * 6);
+  knn_sorted_kernel<<<blocks, 32 * KS_WARPS, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, vals_out,
+                                                          n_cand, n_cand_dev, nn_idx, nn_d2, keep);
+  APN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int apn_knn_sorted(const float* rays_o, const float* rays_d, float near, float far, float stepdist, const void* grid,
+                              const int32_t* cand_ray, const int32_t* cand_step, int n_cand, int32_t* nn_idx, float* nn_d2,
+                              int32_t* keep, void* workspace, size_t workspace_bytes, apn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_cand <= 0) return 0;
+  APN_CHECK_ARG(rays_o && rays_d && grid && cand_ray && cand_step && nn_idx && keep && workspace, "null pointer");
+  APN_CHECK_ARG(workspace_bytes >= apn_knn_sorted_workspace_bytes(n_cand), "workspace too small");
+  return knn_sorted_launch(stream, rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand, nullptr, nn_idx, nn_d2, keep,
+                           workspace);
+}
+
 // launches the search(es) over a candidate list whose length is exact (n_cand_dev == NULL) or a capacity with the true
 // length in device memory
 static int knn_launch(cudaStream_t stream, const float* rays_o, const float* rays_d, float near, float far, float stepdist,
@@ -814,8 +1080,15 @@ extern "C" int apn_compact_samples(const float* rays_o, const float* rays_d, flo
 // Nothing here depends on the data, so the whole call can be captured in a CUDA graph.
 // ---------------------------------------------------------------------------------------
 struct SampleStaticLayout {
-  size_t cand_count, base, cand_ray, cand_step, nn_c, keep, kept_pos, scan, scan_bytes, total;
+  size_t cand_count, base, cand_ray, cand_step, nn_c, keep, kept_pos, scan, scan_bytes, sort, total;
 };
+// APN_KNN_STATIC=legacy pins the warp / thread searches in the static stage (default: the cell-sorted search)
+static bool static_uses_sorted(int cand_cap) {
+  const char* e = getenv("APN_KNN_STATIC");
+  if (e && e[0] == 'l') return false;
+  if (e && e[0] == 's') return true;
+  return cand_cap >= (1 << 20);      // training batches (8192 rays, ~4e4 candidates): the warp search has the lower latency
+}
 static SampleStaticLayout sample_static_layout(int R, int cand_cap) {
   SampleStaticLayout l;
   size_t o = 0;
@@ -829,6 +1102,7 @@ static SampleStaticLayout sample_static_layout(int R, int cand_cap) {
   l.kept_pos = take(sizeof(int) * ((size_t)cand_cap + 1));
   l.scan_bytes = scan_temp_bytes(cand_cap > R ? cand_cap : R);
   l.scan = take(l.scan_bytes);
+  l.sort = take(knn_sorted_layout(cand_cap).total);
   l.total = o;
   return l;
 }
@@ -862,8 +1136,14 @@ extern "C" int apn_sample_knn_static(const float* rays_o, const float* rays_d, i
                                                             cand_step, cand_cap);
   APN_LAUNCH_CHECK();
   APN_CUDA(cudaMemsetAsync(keep, 0, sizeof(int) * (size_t)cand_cap, stream));      // entries behind the true length stay 0
-  if (knn_launch(stream, rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, cand_cap, base + R, nn_c, nullptr, keep))
+  if (static_uses_sorted(cand_cap)) {
+    if (knn_sorted_launch(stream, rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, cand_cap, base + R, nn_c, nullptr, keep,
+                          w + l.sort))
+      return -2;
+  } else if (knn_launch(stream, rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, cand_cap, base + R, nn_c, nullptr,
+                        keep)) {
     return -2;
+  }
   tb = l.scan_bytes;
   APN_CUDA(cub::DeviceScan::ExclusiveSum(w + l.scan, tb, keep, kept_pos, cand_cap, stream));
   apn_count_launch(2);

@@ -9,6 +9,7 @@ Alphas2Weights / post-mask / segment_coo.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -23,6 +24,7 @@ PE_POS = 63
 PE_VIEW = 27
 FV_LD = 160
 V0_DIM = 64
+KNN_SORTED_MIN = 16384          # candidates from which the cell-sorted k-NN search is used (below: warp / thread searches)
 
 
 # set by train.GradBucket: backward kernels that accumulate may write straight into an existing leaf .grad
@@ -372,8 +374,17 @@ def _sample_and_knn(grid, rays_o, rays_d, near, far, stepdist, return_d2):
     if n_cand > 0:
         check(lib.apn_ray_candidates(ptr(rays_o), ptr(rays_d), R, near, far, stepdist, ptr(grid.blob), 1, None, ptr(base),
                                      ptr(cand_ray), ptr(cand_step), st), "apn_ray_candidates(fill)")
-        check(lib.apn_knn(ptr(rays_o), ptr(rays_d), near, far, stepdist, ptr(grid.blob), ptr(cand_ray), ptr(cand_step),
-                          n_cand, ptr(nn_c), ptr(d2_c), ptr(keep), st), "apn_knn")
+        # search: the cell-sorted, shared-memory staged kernel for batches large enough to amortise its sort; the warp /
+        # thread searches below that (APN_KNN_FORCE=sorted|warp|thread|thread0|thread1 pins one: the tests run them all)
+        forced = os.environ.get("APN_KNN_FORCE", "")
+        if forced.startswith("s") or (not forced and n_cand >= KNN_SORTED_MIN):
+            wsb = lib.apn_knn_sorted_workspace_bytes(n_cand)
+            ws = _empty((wsb,), dev, torch.uint8)
+            check(lib.apn_knn_sorted(ptr(rays_o), ptr(rays_d), near, far, stepdist, ptr(grid.blob), ptr(cand_ray), ptr(cand_step),
+                                     n_cand, ptr(nn_c), ptr(d2_c), ptr(keep), ptr(ws), wsb, st), "apn_knn_sorted")
+        else:
+            check(lib.apn_knn(ptr(rays_o), ptr(rays_d), near, far, stepdist, ptr(grid.blob), ptr(cand_ray), ptr(cand_step),
+                              n_cand, ptr(nn_c), ptr(d2_c), ptr(keep), st), "apn_knn")
     kept_pos = exclusive_scan(keep)
     M = int(kept_pos[n_cand].item())
     pts = _empty((M, 3), dev)

@@ -48,18 +48,32 @@ def create_optimizer(model, lrates: Optional[Dict[str, float]] = None, global_st
 
 class GradBucket:
     """All gradients of the optimiser's parameters as views of ONE flat fp32 buffer: zeroing is one memset and the
-    data-parallel exchange is one all-reduce ([canonical_feat | weights | joints | theta_weight |
-    transform_net | feat_net | rgbnet | densitynet])."""
+    data-parallel exchange is an all-reduce over it.
 
-    def __init__(self, optimizer: torch.optim.Optimizer):
+    Layout: [early | late | status].  `early` holds the parameters named by `early` (GraphedTrainStep passes the
+    decoder's: canonical_feat, feat_net, rgbnet, densitynet — 90 % of the bytes — whose gradients are complete as soon as
+    the decoder backward has run), `late` the rest (skinning weights, joints, pose network: complete after the LBS and
+    pose backward).  The two parts can be reduced separately, the first one overlapping the LBS / pose backward.
+    `status` (64 floats) is a side channel that travels with the `late` all-reduce (a device-side flag every rank has to
+    agree on, e.g. "a rank's sample workspace overflowed: skip this update")."""
+
+    STATUS = 64
+
+    def __init__(self, optimizer: torch.optim.Optimizer, early=()):
         params = [p for g in optimizer.param_groups for p in g['params'] if p.requires_grad]
         assert params, "no trainable parameters"
+        early_ids = {id(p) for p in early}
+        params = [p for p in params if id(p) in early_ids] + [p for p in params if id(p) not in early_ids]
         dev = params[0].device
-        offs, total = [], 0
+        offs, total, split = [], 0, 0
         for p in params:
             offs.append(total)
             total += (p.numel() + 63) // 64 * 64          # 256-byte aligned slices
-        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+            if id(p) in early_ids:
+                split = total
+        self.split, self.total = split, total
+        self.flat = torch.zeros(total + self.STATUS, device=dev, dtype=torch.float32)
+        self.status = self.flat[total:total + self.STATUS]
         self.params = params
         self.offsets = offs
         self.attach()
@@ -87,15 +101,20 @@ class GradBucket:
             self.attach()
         self.flat.zero_()
 
-    def all_reduce_avg(self, group=None):
+    def all_reduce_avg(self, group=None, part=None):
+        """part None: the whole bucket (+ status); 0: the early slice; 1: the late slice + status."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             if not self.attached():
                 raise RuntimeError("GradBucket: a parameter's .grad no longer aliases the flat bucket (zero_grad(set_to_none="
                                    "True)?); call bucket.zero() instead of optimizer.zero_grad()")
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if self.flat.is_cuda else dist.ReduceOp.SUM, group=group)
-            if not self.flat.is_cuda:                      # gloo has no AVG
-                self.flat.div_(dist.get_world_size(group))
+            buf = self.flat if part is None else (self.flat[:self.split] if part == 0 else self.flat[self.split:])
+            if buf.numel() == 0:
+                return
+            avg = dist.get_backend(group) == "nccl"        # gloo has no AVG
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=group)
+            if not avg:
+                buf.div_(dist.get_world_size(group))
 
 
 class _DirectAccum:
@@ -108,6 +127,19 @@ class _DirectAccum:
         from . import ops
         ops.DIRECT_GRAD_ACCUM = self.prev
         return False
+
+
+def decoder_parameters(model):
+    """The parameters whose gradients the decoder backward completes (before the LBS / pose backward run)."""
+    ps = [model.canonical_feat]
+    for mod in (model.feat_net, model.rgbnet, model.densitynet):
+        ps += list(mod.parameters())
+    return ps
+
+
+def make_bucket(model, optimizer) -> "GradBucket":
+    """The flat gradient bucket with the decoder's parameters in the early slice (see GradBucket)."""
+    return GradBucket(optimizer, early=decoder_parameters(model))
 
 
 def shard_rays(n_rays: int, rank: int, world: int):
@@ -195,7 +227,9 @@ class FusedTrainStep:
 
     # ---- stage B: decoder -> compositing -> loss -> backward of everything (gradients land in the bucket)
     @torch.no_grad()
-    def decode_and_backward(self, st, render_kwargs, target):
+    def decode_and_backward(self, st, render_kwargs, target, warp_backward: bool = True):
+        """warp_backward=False stops after the decoder backward (every decoder gradient is then final in the bucket: a
+        data-parallel caller can start reducing them) and leaves the rest to `warp_backward(st)`."""
         from . import ops
         from .heads import poc_fre
         m = self.model
@@ -234,6 +268,17 @@ class FusedTrainStep:
         if pose_graph:
             with torch.enable_grad():
                 pose_emb.backward(ga[5])                                    # accumulates into the bucket slices
+        st["ga"] = ga
+        if warp_backward:
+            self.warp_backward(st)
+        return loss
+
+    # ---- stage C: LBS backward + pose backward (skinning weights, joints, pose network)
+    @torch.no_grad()
+    def warp_backward(self, st):
+        from . import ops
+        m = self.model
+        cp, cl, wb, ga = st["cp"], st["cl"], st["wb"], st["ga"]
         if m.weights.grad is not None and m.theta_weight.grad is not None:
             cl.grad_out = dict(raw=m.weights.grad, theta=m.theta_weight.grad.reshape(1))
         gl = ops._LBS.backward(cl, ga[2], ga[3], None, None, None)
@@ -244,13 +289,17 @@ class FusedTrainStep:
         gp = ops._Pose.backward(cp, gl[2], gl[3], None)
         if not hasattr(cp, "grad_out"):
             self._accumulate([m.joints] + list(wb), gp[2:])
-        return loss
 
     @staticmethod
     def _accumulate(params, grads):
         for p, g in zip(params, grads):
             if g is not None and p.requires_grad and p.grad is not None:
                 p.grad.add_(g.reshape(p.grad.shape))
+
+
+def _lib_stage(name):
+    from . import _lib
+    return _lib.stage(name)
 
 
 class WorkspaceOverflow(RuntimeError):
@@ -318,10 +367,10 @@ class GraphedTrainStep:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             self.world = dist.get_world_size()
-        # status slot: the last 64 floats of a private extension of the bucket would change the bucket layout; instead a
-        # separate 64-float tensor is all-reduced together with the bucket (one extra tiny collective only when world > 1)
-        self.status = torch.zeros(64, device=dev)
+        # the status words live behind the gradients in the bucket and travel with its (late) all-reduce
+        self.status = bucket.status
         self.skip_word = self.status[:1]          # non-zero (on any rank, after the all-reduce) => Adam skips
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._pinned = [torch.zeros(9, dtype=torch.float32).pin_memory() for _ in range(self.RING)]   # status[0:8] | loss
         self._pinned_ss = None
         self.step_sizes = None
@@ -339,13 +388,23 @@ class GraphedTrainStep:
                                      float(self.rk['stepsize']) * float(m.voxel_size))
         return smp.n_candidates, smp.M
 
-    def _body_a(self):
+    def _body_a(self, split: bool = False):
+        """forward + decoder backward [+ LBS / pose backward unless `split`]."""
         if self.packed is not None:
             for i, dst in enumerate((self.rays_o, self.rays_d, self.viewdirs, self.target)):
                 dst.copy_(self.packed[:, 3 * i:3 * i + 3])
         st = self.fused.forward_sampling(self.t, self.rk, self.sampler)
-        loss = self.fused.decode_and_backward(st, self.rk, self.target)
+        loss = self.fused.decode_and_backward(st, self.rk, self.target, warp_backward=not split)
         self.loss.copy_(loss.reshape(1))
+        self._st = st
+        if not split:
+            self._body_status()
+
+    def _body_a2(self):
+        self.fused.warp_backward(self._st)
+        self._body_status()
+
+    def _body_status(self):
         self.status[:1].copy_(self.sampler.counts[2:3])            # int flags -> float status word (0.0 = clean)
         self.status[1:6].copy_(self.sampler.counts[0:5])           # counts, for the host's bookkeeping
 
@@ -381,20 +440,27 @@ class GraphedTrainStep:
                 self.launches_per_step = _lib.launch_count() - n0     # our kernels in one replayed step
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        ga, gb = torch.cuda.CUDAGraph(), None
+        ga, ga2, gb = torch.cuda.CUDAGraph(), None, None
         with self.bucket.direct_accum():
             if self.world == 1:                      # no collective between the backward and Adam: ONE graph per step
                 with torch.cuda.graph(ga):
                     self._body_a()
                     self._body_b(launches)
             else:
+                # three graphs around the two all-reduces: [forward + decoder backward] | early slice reduces on the
+                # communication stream while [LBS + pose backward] runs | late slice + status reduce | [Adam]
+                split = self.bucket.split > 0
                 gb = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga):
-                    self._body_a()
+                    self._body_a(split=split)
+                if split:
+                    ga2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(ga2, pool=ga.pool()):
+                        self._body_a2()
                 with torch.cuda.graph(gb, pool=ga.pool()):
                     self._body_b(launches)
         packed.force = False
-        self.graphs = (ga, gb)
+        self.graphs = (ga, ga2, gb)
 
     # ------------------------------------------------------------------------------------------
     def _poll(self, wait: bool = False):
@@ -406,20 +472,21 @@ class GraphedTrainStep:
                 ev.synchronize()
             if wait or ev.query():
                 flags = pin[0].item()
-                self.last_counts = dict(R=self.R, candidates=int(pin[1].item() / self.world), M=int(pin[2].item() / self.world),
+                self.last_counts = dict(R=self.R, candidates=int(pin[1].item()), M=int(pin[2].item()),     # mean over ranks
                                         N=len(self.model.canonical_pcd))
                 self.model.last_counts = self.last_counts
                 self.history.append((self.last_counts["candidates"], self.last_counts["M"]))
                 if flags != 0.0 and overflow is None:
-                    overflow = (idx, int(pin[4].item()), int(pin[5].item()))
+                    overflow = (idx, int(pin[4].item()) + 1, int(pin[5].item()) + 1)       # (rank-averaged) counts found
             else:
                 keep.append((ev, pin, idx))
         self._pending = keep
         if overflow is not None:
             idx, n_cand, n_kept = overflow
             self.flush_no_raise()
-            self.cand_cap = max(self.cand_cap, 2 * n_cand)
-            self.m_cap = (max(self.m_cap, 2 * n_kept) + 127) // 128 * 128
+            # the averaged counts under-estimate the worst rank: at least double what there was
+            self.cand_cap = max(2 * self.cand_cap if n_cand > self.cand_cap // 2 else self.cand_cap, 2 * n_cand)
+            self.m_cap = (max(2 * self.m_cap if n_kept > self.m_cap // 2 else self.m_cap, 2 * n_kept) + 127) // 128 * 128
             self.graphs, self.sampler = None, None
             self.opt.undo_step_count()
             raise WorkspaceOverflow(f"step {idx}: {n_cand} candidates / {n_kept} kept samples exceeded the workspace; the step was "
@@ -477,18 +544,33 @@ class GraphedTrainStep:
         ev.record()
         self._ss_events[slot] = ev
         with self.bucket.direct_accum():
+            split = self.world > 1 and self.bucket.split > 0
             if self.graphs is not None:
                 self.graphs[0].replay()
             else:
-                self._body_a()
+                self._body_a(split=split)
             if self.world > 1:
-                import torch.distributed as dist
-                self.bucket.all_reduce_avg()
-                dist.all_reduce(self.status, op=dist.ReduceOp.SUM)
+                cur = torch.cuda.current_stream(self.dev)
+                if split:
+                    # the decoder's gradients (90 % of the bucket) are final: reduce them on the communication stream
+                    # while the LBS / pose backward runs here
+                    self.comm_stream.wait_stream(cur)
+                    with torch.cuda.stream(self.comm_stream), _lib_stage("allreduce_early"):
+                        self.bucket.all_reduce_avg(part=0)
+                    if self.graphs is not None:
+                        self.graphs[1].replay()
+                    else:
+                        self._body_a2()
+                    with _lib_stage("allreduce_late"):
+                        self.bucket.all_reduce_avg(part=1)
+                    cur.wait_stream(self.comm_stream)
+                else:
+                    with _lib_stage("allreduce"):
+                        self.bucket.all_reduce_avg()
             if self.graphs is None:
                 self._body_b(launches)
-            elif self.graphs[1] is not None:
-                self.graphs[1].replay()
+            elif self.graphs[2] is not None:
+                self.graphs[2].replay()
         pin = self._pinned[slot]
         pin[:8].copy_(self.status[:8], non_blocking=True)
         pin[8:9].copy_(self.loss, non_blocking=True)

@@ -115,6 +115,14 @@ int apn_ray_candidates(const float* rays_o, const float* rays_d, int R, float ne
 int apn_knn(const float* rays_o, const float* rays_d, float near, float far, float stepdist, const void* grid,
             const int32_t* cand_ray, const int32_t* cand_step, int n_cand,
             int32_t* nn_idx, float* nn_d2, int32_t* keep, apn_stream_t stream);
+/* The same contract as apn_knn, served by the cell-sorted search: the candidates are radix-sorted by the grid leaf that holds
+ * them, a warp's 32 queries share one neighbourhood whose points are staged in shared memory, and every lane scans the
+ * stage against its own query with a register top-8 (csrc/grid_knn.cu, knn_sorted_kernel).  Bit-identical results.
+ * workspace: apn_knn_sorted_workspace_bytes(n_cand) bytes (sort keys / values + radix-sort temporaries). */
+size_t apn_knn_sorted_workspace_bytes(int n_cand);
+int apn_knn_sorted(const float* rays_o, const float* rays_d, float near, float far, float stepdist, const void* grid,
+                   const int32_t* cand_ray, const int32_t* cand_step, int n_cand,
+                   int32_t* nn_idx, float* nn_d2, int32_t* keep, void* workspace, size_t workspace_bytes, apn_stream_t stream);
 /* order-preserving compaction of the kept candidates (kept_pos = exclusive scan of keep).
  * ray_start (R+1): first kept sample of each ray. */
 int apn_compact_samples(const float* rays_o, const float* rays_d, float near, float far, float stepdist,

@@ -18,6 +18,18 @@ with torch.no_grad():
     smp, dbg = ops.sample_and_knn(grid, ro, rd, scene.cfg.near, scene.cfg.far, stepdist, return_d2=True)
 keep = dbg["keep"].bool()
 print("candidates", len(keep), "kept", int(keep.sum()))
+if len(sys.argv) > 2 and sys.argv[2] == "time":       # end-to-end sample_and_knn with the search the environment selects
+    if os.environ.get("APN_KNN_LEGACY"):
+        ops.KNN_SORTED_MIN = 1 << 60
+    for _ in range(2):
+        ops.sample_and_knn(grid, ro, rd, scene.cfg.near, scene.cfg.far, stepdist)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        s2 = ops.sample_and_knn(grid, ro, rd, scene.cfg.near, scene.cfg.far, stepdist)
+    b.record(); torch.cuda.synchronize()
+    print(f"sample_and_knn {wl} FORCE={os.environ.get('APN_KNN_FORCE')} LEGACY={os.environ.get('APN_KNN_LEGACY')}: {a.elapsed_time(b) / 5:.3f} ms per frame, M={s2.M}")
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == "short":      # under ncu: the one sample_and_knn call above is all that is profiled
     torch.cuda.synchronize()
     sys.exit(0)

@@ -96,7 +96,7 @@ def _cloud_and_rays(config="tiny", view=0):
     return scene, ro, rd, vd
 
 
-@pytest.mark.parametrize("search", ["warp", "thread0", "thread1"])
+@pytest.mark.parametrize("search", ["warp", "thread0", "thread1", "sorted"])
 @pytest.mark.parametrize("config", ["tiny", "small"])
 def test_sample_and_knn_bit_exact(config, search, monkeypatch):
     """pts / ray_id / step_id / neighbour indices identical to the oracle's brute force (ties -> lower index)."""

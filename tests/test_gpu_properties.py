@@ -29,10 +29,13 @@ def c1_model():
     return scene, model
 
 
-@pytest.mark.parametrize("search", ["auto", "thread0", "thread1"])
+_FULL_SIZE_RESULTS = {}
+
+
+@pytest.mark.parametrize("search", ["auto", "sorted", "warp", "thread0", "thread1"])
 def test_knn_at_full_size_sorted_within_radius_and_exact_on_a_subset(c1_model, search, monkeypatch):
     if search != "auto":
-        monkeypatch.setenv("APN_KNN_FORCE", search)       # the per-thread search too (auto picks the warp search on c1)
+        monkeypatch.setenv("APN_KNN_FORCE", search)       # every search on the same frame (auto picks the cell-sorted one on c1)
     ops = _ops()
     scene, model = c1_model
     ro, rd, vd = [x.reshape(-1, 3).contiguous().cuda() for x in scene.rays(2)]
@@ -71,6 +74,10 @@ def test_knn_at_full_size_sorted_within_radius_and_exact_on_a_subset(c1_model, s
     key = (full.view(torch.int32).long() << 32) | torch.arange(N, device="cuda")[None, :]     # (d2 bits, index): lexicographic
     ref = torch.topk(key, 8, dim=1, largest=False, sorted=True).indices
     assert torch.equal(ref, idx[sel])
+    # all searches agree on EVERY sample of the frame (M, neighbour lists, CSR): bit-identical outputs
+    first = _FULL_SIZE_RESULTS.setdefault("first", (search, M, smp.nn_idx.clone(), smp.ray_start.clone(), dbg["keep"].clone()))
+    assert first[1] == M and torch.equal(first[2], smp.nn_idx) and torch.equal(first[3], smp.ray_start), (first[0], search)
+    assert torch.equal(first[4], dbg["keep"])
 
 
 def test_lbs_invariants_at_one_million_points():
