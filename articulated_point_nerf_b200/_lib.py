@@ -61,6 +61,8 @@ SIGNATURES = {
     "apn_version": (I, []),
     "apn_last_error": (C.c_char_p, []),
     "apn_launch_count": (C.c_ulonglong, []),
+    "apn_range_push": (I, [C.c_char_p]),
+    "apn_range_pop": (I, []),
     "apn_pose_saved_bytes": (SZ, [I]),
     "apn_pose_fwd": (I, [P, I, P, P, P, P, P, P, P, I, P, P, P, P, P]),
     "apn_pose_bwd": (I, [P, I, P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P]),
@@ -79,6 +81,9 @@ SIGNATURES = {
     "apn_compact_samples": (I, [P, P, F, F, F, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P]),
     "apn_knn_points": (I, [P, I, P, I, P, P, P]),
     "apn_nn1_batched": (I, [P, P, I, I, I, I, P, P]),
+    "apn_rays_of_a_view": (I, [P, P, I, I, I, I, I, I, P, LL, I, P, P, P, P]),
+    "apn_point_regularisers": (I, [P, P, P, P, I, I, I, F, F, F, F, P, P, P, P]),
+    "apn_pose_regularisers": (I, [P, P, P, P, I, I, F, F, P, P, P, P, P]),
     "apn_time_embed": (I, [P, P, I, P, P]),
     "apn_mse_loss_grad": (I, [P, P, I, F, P, P, P]),
     "apn_aggregate_scratch_bytes": (SZ, [I, I]),
@@ -186,6 +191,25 @@ class _StageTimer:
 
 STAGES = _StageTimer()
 
+# NVTX ranges around the same call groups (apn_range_push / apn_range_pop): on with APN_NVTX=1 or nvtx(True).  Each name is the
+# reference's torch.profiler.record_function name where the group is one reference range, and the reference names joined
+# with '+' where one launch group covers several (lib/temporalpoints.py:421-653, lib/pointwarper.py:217-241):
+NVTX_NAMES = {
+    "transform_net": b"poc_fre+transform_net+calc_rec_abs_T",      # pose chain (one fused cluster kernel)
+    "forward_warp": b"forward_warp+weighted_G_tw",                  # skinning-weight softmax/merge + LBS
+    "grid_build": b"grid_build",                                    # no reference range (KeOps has no build step)
+    "sample_ray+knn": b"sample_ray+knn+knn-post",
+    "feat_net": b"feat_net+densitynet+rgbnet",
+    "Alphas2Weights": b"pre-mask+Alphas2Weights+post-mask+segment_coo",
+}
+_nvtx_on = bool(os.environ.get("APN_NVTX"))
+
+
+def nvtx(enabled: bool) -> None:
+    global _nvtx_on
+    _nvtx_on = bool(enabled)
+
+
 
 class stage:
     """with stage("aggregate_fwd"): ...   (names follow the reference's profiler ranges where one exists)"""
@@ -195,12 +219,16 @@ class stage:
         self.name = name
 
     def __enter__(self):
+        if _nvtx_on:
+            load().apn_range_push(NVTX_NAMES.get(self.name) or self.name.encode())
         if STAGES.enabled:
             self.a = torch.cuda.Event(enable_timing=True)
             self.a.record()
         return self
 
     def __exit__(self, *exc):
+        if _nvtx_on:
+            load().apn_range_pop()
         if STAGES.enabled:
             b = torch.cuda.Event(enable_timing=True)
             b.record()

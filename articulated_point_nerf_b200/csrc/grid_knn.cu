@@ -773,7 +773,7 @@ __global__ void __launch_bounds__(32 * KS_WARPS)
 knn_sorted_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
                   const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step,
                   const int* __restrict__ order, int n_cand_cap, const int* __restrict__ n_cand_dev, int* __restrict__ nn_idx,
-                  float* __restrict__ nn_d2, int* __restrict__ keep) {
+                  float* __restrict__ nn_d2, int* __restrict__ keep, float grow_mul, float grow_add) {
   __shared__ float4 sP[KS_WARPS][KS_CHUNK];
   const GridView g = grid_view(blob);
   const GridHeader* h = g.h;
@@ -911,7 +911,7 @@ knn_sorted_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
         // next radius: the largest outstanding bound; lanes without 8 points yet grow by ONE leaf edge: shells stay thin, so
         // the shell in which a far query first meets the surface yields a bound close to its true 8th distance, and the
         // points scanned stay close to those inside that ball (a doubling radius scans the whole 0.1-ball of dense clouds)
-        const float need = fin ? 0.f : (have8 ? fminf(sqrtf(key_d2(best[APN_K - 1])), rmax) : fminf(rho + cell, rmax));
+        const float need = fin ? 0.f : (have8 ? fminf(sqrtf(key_d2(best[APN_K - 1])), rmax) : fminf(grow_mul * rho + grow_add * cell, rmax));
         rho = fminf(fmaxf(warp_max(need) + 4.f * eps, rho + 0.25f * cell), rmax + 8.f * eps);
         px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
       }
@@ -966,8 +966,11 @@ static int knn_sorted_launch(cudaStream_t stream, const float* rays_o, const flo
   APN_CUDA(cub::DeviceRadixSort::SortPairs(w + l.temp, tb, keys_in, keys_out, vals_in, vals_out, n_cand, 0, 31, stream));
   apn_count_launch(4);
   const int blocks = min(apn_div_up(n_cand, 32 * KS_WARPS), APN_SM_COUNT * 6);
+  // radius growth of lanes that have not found 8 points yet: rho <- mul * rho + add * leaf edge (APN_KS_GROWTH="mul,add")
+  float grow_mul = 1.f, grow_add = 1.f;
+  if (const char* e = getenv("APN_KS_GROWTH")) sscanf(e, "%f,%f", &grow_mul, &grow_add);
   knn_sorted_kernel<<<blocks, 32 * KS_WARPS, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, vals_out,
-                                                          n_cand, n_cand_dev, nn_idx, nn_d2, keep);
+                                                          n_cand, n_cand_dev, nn_idx, nn_d2, keep, grow_mul, grow_add);
   APN_LAUNCH_CHECK();
   return 0;
 }

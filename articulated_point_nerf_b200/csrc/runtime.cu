@@ -3,6 +3,8 @@
 
 #include <atomic>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -38,3 +40,9 @@ int apn_side_streams(ApnSide** out) {
   *out = &g_side;
   return 0;
 }
+
+// NVTX ranges around the C-ABI call groups, named after the reference's profiler ranges (torch.profiler.record_function at
+// lib/temporalpoints.py:421-653, lib/pointwarper.py:217-241) so that a timeline of this path reads like one of the reference.
+// nvtx3 is header-only: without an attached tool the calls are a branch on a null function table.
+extern "C" int apn_range_push(const char* name) { return nvtxRangePushA(name ? name : ""); }
+extern "C" int apn_range_pop(void) { return nvtxRangePop(); }

@@ -290,6 +290,26 @@ def nn1_batched(query: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     return idx.long()
 
 
+def rays_of_a_view(H: int, W: int, K, c2w, device, inverse_y=False, flip_x=False, flip_y=False, pixel_ids=None,
+                   first_pixel: int = 0, n: Optional[int] = None):
+    """get_rays_of_a_view (lib/tineuvox.py:675-738) on the device, from the camera alone: -> rays_o, rays_d, viewdirs (n,3).
+    `pixel_ids` (int32 device tensor) selects pixels (row-major indices); otherwise n pixels from first_pixel (default all)."""
+    lib = _lib.load()
+    Kh = torch.as_tensor(K, dtype=torch.float32).detach().cpu().contiguous().reshape(-1)
+    ch = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu().contiguous()
+    assert Kh.numel() == 9 and ch.dim() == 2 and ch.shape[1] == 4 and ch.shape[0] in (3, 4)
+    if pixel_ids is not None:
+        pixel_ids = pixel_ids.to(device=device, dtype=torch.int32).contiguous()
+        n = pixel_ids.numel()
+    elif n is None:
+        n = H * W - first_pixel
+    ro, rd, vd = (_empty((n, 3), device) for _ in range(3))
+    check(lib.apn_rays_of_a_view(Kh.data_ptr(), ch.data_ptr(), ch.shape[0], int(H), int(W), int(bool(inverse_y)), int(bool(flip_x)),
+                                 int(bool(flip_y)), ptr(pixel_ids), int(first_pixel), int(n), ptr(ro), ptr(rd), ptr(vd), stream()),
+          "apn_rays_of_a_view")
+    return ro, rd, vd
+
+
 def time_embed(t: torch.Tensor, freqs: torch.Tensor) -> torch.Tensor:
     """poc_fre of the scalar time (lib/tineuvox.py:872-878) in one launch: (1) -> (1 + 2 F)."""
     lib = _lib.load()
@@ -310,6 +330,45 @@ def mse_loss_grad(pred: torch.Tensor, target: torch.Tensor, weight: float):
     check(lib.apn_mse_loss_grad(ptr(pred), ptr(target), pred.numel(), float(weight), ptr(loss), ptr(grad), stream()),
           "apn_mse_loss_grad")
     return loss[0], grad
+
+
+def point_regularisers(xyz, w, nn_i32, nn_dist, eps: float, weight_arap: float, weight_tv: float, weight_sparsity: float,
+                       d_xyz: torch.Tensor, d_w: Optional[torch.Tensor] = None, losses: Optional[torch.Tensor] = None):
+    """ARAP + neighbour weight TV + weight sparsity (lib/temporalpoints.py:714-725, weighted as run.py:633-648 does) with
+    their gradients in one launch: d_xyz (N,3) is accumulated into, d_w (N,J) overwritten.  -> (losses (3), d_w)."""
+    lib = _lib.load()
+    N, K = nn_i32.shape
+    assert nn_i32.dtype == torch.int32 and nn_i32.is_contiguous() and d_xyz.is_contiguous()
+    need_w = weight_tv != 0.0 or weight_sparsity != 0.0
+    J = w.shape[1] if w is not None else 1
+    if need_w and d_w is None:
+        d_w = _empty((N, J), xyz.device)
+    if losses is None:
+        losses = _empty((3,), xyz.device)
+    check(lib.apn_point_regularisers(ptr(_f32(xyz)), ptr(_f32(w)) if need_w else None, ptr(nn_i32), ptr(_f32(nn_dist)), N, K, J,
+                                     float(eps), float(weight_arap), float(weight_tv), float(weight_sparsity), ptr(d_xyz),
+                                     ptr(d_w) if need_w else None, ptr(losses), stream()), "apn_point_regularisers")
+    return losses, (d_w if need_w else None)
+
+
+def pose_regularisers(thetas, global_t, joints, skeleton, weight_transformation_reg: float, weight_joint_chamfer: float,
+                      losses: Optional[torch.Tensor] = None):
+    """Transformation regulariser + joint chamfer loss (lib/temporalpoints.py:797-800, 731-733) with gradients in one launch.
+    -> (losses (2), d_thetas (J) or None, d_global_t (3) or None, d_joints (J,3) or None)."""
+    lib = _lib.load()
+    J = joints.shape[0]
+    dev = joints.device
+    d_thetas = _empty((J,), dev) if weight_transformation_reg != 0.0 else None
+    d_global_t = _empty((3,), dev) if weight_transformation_reg != 0.0 else None
+    d_joints = _empty((J, 3), dev) if weight_joint_chamfer != 0.0 else None
+    if losses is None:
+        losses = _empty((2,), dev)
+    skeleton = None if skeleton is None else _f32(skeleton)
+    check(lib.apn_pose_regularisers(ptr(_f32(thetas)), ptr(_f32(global_t)), ptr(_f32(joints)), ptr(skeleton), J,
+                                    0 if skeleton is None else skeleton.shape[0], float(weight_transformation_reg),
+                                    float(weight_joint_chamfer), ptr(d_thetas), ptr(d_global_t), ptr(d_joints), ptr(losses), stream()),
+          "apn_pose_regularisers")
+    return losses, d_thetas, d_global_t, d_joints
 
 
 def exclusive_scan(x: torch.Tensor) -> torch.Tensor:

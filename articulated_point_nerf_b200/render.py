@@ -20,8 +20,18 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
-from .scene import get_rays_of_a_view
+from . import ops
 from .temporalpoints import TemporalPoints
+
+
+def tile_pixels(H: int, W: int, rank: int, world: int, tile: int = 16) -> torch.Tensor:
+    """Row-major pixel indices of the `tile` x `tile` image tiles that rank `rank` of `world` owns (tiles dealt round-robin
+    in raster order: only ~10-40 % of the rays of a frame hit the cloud, contiguous bands would be badly balanced;
+    SURVEY.md §8(e)).  CPU int32 tensor, sorted."""
+    ty, tx = (H + tile - 1) // tile, (W + tile - 1) // tile
+    owner = (torch.arange(ty * tx) % world).reshape(ty, tx)
+    mask = owner.repeat_interleave(tile, 0).repeat_interleave(tile, 1)[:H, :W] == rank
+    return torch.nonzero(mask.reshape(-1)).reshape(-1).to(torch.int32)
 
 
 class PoseCache:
@@ -60,14 +70,17 @@ def _scale_cameras(HW, Ks, render_factor):
 
 
 def _render_frame(model, cache, H, W, K, c2w, render_kwargs, *, t=None, rot_params=None, render_pcd_direct=False,
-                  fixed_viewdirs=None, chunk_rays=None, inverse_y=False, flip_x=False, flip_y=False, Ks_i=None):
+                  fixed_viewdirs=None, chunk_rays=None, inverse_y=False, flip_x=False, flip_y=False, Ks_i=None, pixel_ids=None):
+    """One frame (or, with `pixel_ids`, this rank's pixels of it) -> dict of (H, W, C) device tensors (unowned pixels 0).
+    The rays are produced ON THE DEVICE from (K, c2w) (ops.rays_of_a_view: lib/tineuvox.py:675-738 in one launch): a frame
+    costs ~100 bytes of host->device traffic instead of 36 bytes per pixel."""
     dev = model.device
-    rays_o, rays_d, viewdirs = get_rays_of_a_view(H, W, K.to(torch.float32), c2w, inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y)
+    rays_o, rays_d, viewdirs = ops.rays_of_a_view(H, W, K.to(torch.float32), c2w, dev, inverse_y=inverse_y, flip_x=flip_x,
+                                                  flip_y=flip_y, pixel_ids=pixel_ids)
     if fixed_viewdirs is not None:
-        viewdirs = fixed_viewdirs
-    rays_o = rays_o.reshape(-1, 3).to(dev).contiguous()
-    rays_d = rays_d.reshape(-1, 3).to(dev).contiguous()
-    viewdirs = viewdirs.reshape(-1, 3).to(dev).contiguous()
+        viewdirs = torch.as_tensor(fixed_viewdirs).reshape(-1, 3).to(dev).contiguous()
+        if pixel_ids is not None:
+            viewdirs = viewdirs[pixel_ids.to(dev).long()].contiguous()
     warped, grid = cache.get(t=t, rot_params=rot_params)
     R = rays_o.shape[0]
     step = R if not chunk_rays else int(chunk_rays)
@@ -80,8 +93,13 @@ def _render_frame(model, cache, H, W, K, c2w, render_kwargs, *, t=None, rot_para
         if render_pcd_direct:
             out['rgb_marched'] = out['rgb_marched_direct']
         outs.append(out)
-    cat = {k: (outs[0][k] if len(outs) == 1 else torch.cat([o[k] for o in outs])).reshape(H, W, -1)
+    cat = {k: (outs[0][k] if len(outs) == 1 else torch.cat([o[k] for o in outs])).reshape(R, -1)
            for k in ('rgb_marched', 'depth', 'weights')}
+    if pixel_ids is None:
+        cat = {k: v.reshape(H, W, -1) for k, v in cat.items()}
+    else:                                  # scatter this rank's pixels into a full (zero) frame
+        ids = pixel_ids.to(dev).long()
+        cat = {k: torch.zeros(H * W, v.shape[-1], device=dev).index_copy_(0, ids, v).reshape(H, W, -1) for k, v in cat.items()}
     return cat, outs[0]['joints'], outs[0]['bones']
 
 
@@ -102,30 +120,56 @@ def _finish(rgbs, depths, weights, joints, gt_imgs, render_factor, eval_psnr, ot
 def render_viewpoints(model, render_poses, HW, Ks, ndc, render_kwargs, gt_imgs=None, savedir=None, test_times=None,
                       render_factor=0, eval_psnr=False, eval_ssim=False, eval_lpips_alex=False, eval_lpips_vgg=False,
                       inverse_y=False, flip_x=False, flip_y=False, batch_size=None, verbose=True, render_pcd_direct=False,
-                      render_flow=False, fixed_viewdirs=None, return_joints=False):
+                      render_flow=False, fixed_viewdirs=None, return_joints=False, rank: int = 0, world: int = 1,
+                      shard: str = "views", gather: bool = True):
     """run.py:82-260.  -> rgbs (V,H,W,3), depths (V,H,W,1), weights (V,H,W,3), flows (empty) as numpy arrays.
-    `batch_size=None` renders each frame in one pass; an integer reproduces the reference's ray chunking (same result)."""
+    `batch_size=None` renders each frame in one pass; an integer reproduces the reference's ray chunking (same result).
+
+    Multi-GPU (not in the reference): with `world` > 1 this rank renders its share — whole frames
+    (`shard="views"`: frame i belongs to rank i % world, e.g. one 1024^2 view per GPU) or its 16x16 tiles of every frame
+    (`shard="tiles"`, round-robin: one large frame split over the GPUs).  Rays are independent given the warped cloud,
+    every rank warps the full cloud itself, so the render needs NO collective; `gather=True` (default) finally sums the
+    disjoint shares with one all-reduce so that every rank returns complete frames (skipped when torch.distributed is
+    not initialised: the caller then holds this rank's share, unowned pixels / frames zero)."""
     assert len(render_poses) == len(HW) and len(HW) == len(Ks)
     assert isinstance(model, TemporalPoints), "this entry point drives the point-cloud model"
     assert not ndc, "the PCD path never uses NDC rays (configs keep ndc=False)"
     assert not render_flow, "scene flow is not part of the PCD hot path"
     HW, Ks = _scale_cameras(HW, Ks, render_factor)
+    assert shard in ("views", "tiles") and 0 <= rank < max(world, 1)
     cache = PoseCache(model)
     rgbs, depths, weights, joints = [], [], [], {}
     bones = None
+    tiles = {}
+    frames_dev = []
     for i, c2w in enumerate(render_poses):
         H, W = int(HW[i][0]), int(HW[i][1])
+        if world > 1 and shard == "views" and i % world != rank:
+            frames_dev.append(torch.zeros(H, W, 7, device=model.device))
+            continue
+        pix = None
+        if world > 1 and shard == "tiles":
+            if (H, W) not in tiles:
+                tiles[(H, W)] = tile_pixels(H, W, rank, world).to(model.device)
+            pix = tiles[(H, W)]
         t = torch.as_tensor(test_times[i], dtype=torch.float32, device=model.device).reshape(1)
         frame, jt, bn = _render_frame(model, cache, H, W, torch.as_tensor(Ks[i]), torch.as_tensor(c2w), render_kwargs, t=t,
                                       render_pcd_direct=render_pcd_direct, fixed_viewdirs=fixed_viewdirs, chunk_rays=batch_size,
-                                      inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y)
+                                      inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y, pixel_ids=pix)
         if jt is not None and i not in joints:
             jt = jt.clone()
             if not render_kwargs['inverse_y']:
                 jt[:, :, 0] = (int(HW[0][0]) - 1) - jt[:, :, 0]
             joints[i] = jt[0].cpu().numpy()
             bones = bn
-        host = torch.cat([frame['rgb_marched'], frame['depth'], frame['weights']], dim=-1).cpu().numpy()   # one D2H per frame
+        frames_dev.append(torch.cat([frame['rgb_marched'], frame['depth'], frame['weights']], dim=-1))
+    if world > 1 and gather:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            for f in frames_dev:               # disjoint shares: the sum IS the assembled frame
+                dist.all_reduce(f, op=dist.ReduceOp.SUM)
+    for f in frames_dev:
+        host = f.cpu().numpy()                                                                  # one D2H per frame
         rgbs.append(host[..., 0:3])
         depths.append(host[..., 3:4])
         weights.append(host[..., 4:7])

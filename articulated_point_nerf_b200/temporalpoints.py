@@ -163,9 +163,11 @@ class TemporalPoints(torch.nn.Module):
         # "fp32" = CUDA-core exact path
         self.decoder_train = "fp32"
         self._packed_decoder = ops.PackedDecoder()
-        # replay the PyTorch pose chain (fwd + bwd) as CUDA graphs while training; only used when the fused pose
-        # kernel (forward_warp.fused_pose) does not cover the tree / MLP shape
-        self.graph_pose = True
+        # replay the PyTorch pose chain (fwd + bwd) as CUDA graphs while training; only relevant when the fused pose
+        # kernel (forward_warp.fused_pose) does not cover the tree / MLP shape.  Opt-in: torch.cuda.make_graphed_callables
+        # returns its gradients in static buffers, and a SECOND backward through one forward (retain_graph=True; e.g. separate
+        # autograd.grad calls per loss term) silently yields wrong joint gradients (found with the full stage-2 loss test)
+        self.graph_pose = False
         object.__setattr__(self, '_pose_graph', None)
         object.__setattr__(self, '_pose_graph_key', None)
 

@@ -8,7 +8,8 @@ flat fp32 gradient bucket per step.  torch.distributed is plu
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, Optional
+from dataclasses import dataclass
+from typing import Callable, Dict, Iterable, Optional
 
 import torch
 import torch.nn.functional as F
@@ -20,6 +21,58 @@ STAGE2_LRATES = dict(rgbnet=1e-4, densitynet=1e-4, featurenet=1e-4, canonical_fe
                      theta_weight=1e-4, forward_warp=1e-4, joints=1e-5, theta=1e-5, feat_net=1e-3)
 WEIGHT_RENDER = 2e2          # configs/nerf/default.py:95
 LRATE_DECAY = 160            # N_iters // 1000 (configs/nerf/default.py:76)
+
+
+@dataclass(frozen=True)
+class Regularisers:
+    """Weights of the stage-2 regulariser losses that run.py:633-657 adds to the render loss in every iteration
+    (defaults: configs/nerf/default.py:96-103 = configs/zju/default.py:95-102).  A zero weight switches a term off.
+    `sparsity` only applies from `weight_start_iter` on (run.py:645): pass 0 before that iteration.
+    The 2-D chamfer term (weight_chamfer2D, run.py:659-690) needs data (mask pixels, cameras): it enters through the
+    `extra_loss` hook of FusedTrainStep (see Chamfer2D)."""
+    arap: float = 5e-3
+    tv: float = 1e1
+    sparsity: float = 2e-1
+    transformation_reg: float = 1e-1
+    joint_chamfer: float = 1.0
+
+    def any_point(self) -> bool:
+        return self.arap != 0 or self.tv != 0 or self.sparsity != 0
+
+    def any_pose(self) -> bool:
+        return self.transformation_reg != 0 or self.joint_chamfer != 0
+
+
+class Chamfer2D:
+    """The 2-D chamfer term of run.py:659-690 as an `extra_loss` for FusedTrainStep / GraphedTrainStep: projects the warped
+    cloud into B views and compares it with M mask pixels per view (get_batch_chamfer_loss, lib/temporalpoints.py:765-795;
+    nearest neighbours by apn_nn1_batched).  `poses` (B,4,4), `Ks` (B,3,3) and `mask_pcd` (B,M,2) [(row, col) pixel
+    coordinates] are STATIC device buffers: the caller refreshes their contents per step (`update`), so the term can live
+    inside a captured graph.  `image_height` mirrors the y flip of run.py:677-678 (None = render_kwargs['inverse_y'])."""
+
+    def __init__(self, model, poses, Ks, mask_pcd, weight: float = 5e-3, n_points: Optional[int] = 3000, image_height=None):
+        self.model, self.weight, self.image_height = model, float(weight), image_height
+        self.n_points = None if n_points is None else int(n_points)
+        dev = mask_pcd.device
+        # world->camera matrices: the reference inverts the poses inside project_point_to_image_plane (lib/utils.py:444) in
+        # every iteration; torch.inverse reads an error flag back to the host, so the inversion happens here, on the host
+        # copy of the (B,4,4) poses, and only the product with the points is part of the (capturable) step
+        self.w2c = torch.linalg.inv(poses.detach().double().cpu()).float().to(dev)
+        self.Ks, self.mask_pcd = Ks.detach().clone().float().to(dev), mask_pcd.detach().clone().float()
+
+    def update(self, poses, Ks, mask_pcd):
+        self.w2c.copy_(torch.linalg.inv(poses.detach().double().cpu()).float(), non_blocking=True)
+        self.Ks.copy_(Ks, non_blocking=True)
+        self.mask_pcd.copy_(mask_pcd, non_blocking=True)
+
+    def __call__(self, xyz):
+        pts = torch.matmul(xyz, self.w2c[:, :3, :3].transpose(1, 2)) + self.w2c[:, None, :3, 3]       # (B, N, 3) camera frame
+        pts = torch.matmul(pts, self.Ks.transpose(1, 2))
+        proj = pts[:, :, :2] / pts[:, :, 2:]                                                         # lib/utils.py:446-448
+        if self.image_height is not None:
+            proj = torch.cat([(self.image_height - 1) - proj[:, :, :1], proj[:, :, 1:]], dim=-1)
+        proj = proj.flip(-1)
+        return self.weight * self.model.get_batch_chamfer_loss(proj, self.mask_pcd, N=self.n_points, M=None)
 
 
 def create_optimizer(model, lrates: Optional[Dict[str, float]] = None, global_step: int = 0,
@@ -175,9 +228,20 @@ class FusedTrainStep:
     `sampler` (ops.StaticSampler): the sync-free variant — fixed-capacity sample arrays, every count stays on the device,
     no host read-back anywhere in the step (GraphedTrainStep captures exactly this body in CUDA graphs)."""
 
-    def __init__(self, model, optimizer: MaskedAdam, bucket: GradBucket):
+    def __init__(self, model, optimizer: MaskedAdam, bucket: GradBucket, regularisers: Optional[Regularisers] = None,
+                 extra_loss: Optional[Callable] = None):
+        """`regularisers`: the stage-2 regulariser terms (run.py:633-657), evaluated with their gradients by two kernels
+        (apn_point_regularisers, apn_pose_regularisers) that add into the LBS / pose backward's incoming gradients.
+        `extra_loss(xyz) -> scalar`: any further differentiable (torch) term on the warped cloud, e.g. Chamfer2D; its
+        gradient w.r.t. xyz joins d_xyz before the LBS backward."""
         self.model, self.opt, self.bucket = model, optimizer, bucket
+        self.reg, self.extra_loss = regularisers, extra_loss
         model._ensure_neighbourhood()
+        dev = model.joints.device
+        # [arap, tv, sparsity, transformation_reg, joint_chamfer, extra, render, total]
+        self.loss_terms = torch.zeros(8, device=dev)
+        self._nn_i32 = model.nn_i.to(torch.int32).contiguous() if regularisers is not None and regularisers.any_point() else None
+        self._d_w = None
 
     @staticmethod
     def eligible(model) -> bool:
@@ -193,6 +257,9 @@ class FusedTrainStep:
         if st is None:
             return None
         return self.decode_and_backward(st, render_kwargs, target)
+
+    def has_extra_terms(self) -> bool:
+        return self.reg is not None or self.extra_loss is not None
 
     # ---- stage A: pose -> LBS -> grid -> ray samples + exact 8-NN
     @torch.no_grad()
@@ -219,7 +286,7 @@ class FusedTrainStep:
         if sampler is None:
             smp = ops.sample_and_knn(grid, rays_o, rays_d, near, far, stepdist)
             m.last_counts = dict(R=R, candidates=smp.n_candidates, M=smp.M, N=len(xyz))
-            if smp.M == 0:
+            if smp.M == 0 and not self.has_extra_terms():
                 return None
         else:
             smp = sampler.run(grid, rays_o, rays_d, near, far, stepdist)
@@ -269,9 +336,41 @@ class FusedTrainStep:
             with torch.enable_grad():
                 pose_emb.backward(ga[5])                                    # accumulates into the bucket slices
         st["ga"] = ga
+        if self.has_extra_terms():
+            loss = self._regularise(st, ga[2], loss)
         if warp_backward:
             self.warp_backward(st)
         return loss
+
+    def _regularise(self, st, d_xyz, render_loss):
+        """Regulariser losses + gradients (run.py:633-694): d_xyz (N,3) receives the ARAP / extra-loss gradients, st gets d_w
+        (merged skinning weights), d_thetas / d_global_t / d_joints for the LBS and pose backward.  -> total loss."""
+        from . import ops
+        m, fw, reg, lt = self.model, self.model.forward_warp, self.reg, self.loss_terms
+        xyz = st["xyz"]
+        lt.zero_()
+        with _lib_stage("regularisers"):
+            if reg is not None and reg.any_point():
+                N, J = m._last_weights.shape
+                if self._d_w is None or self._d_w.shape != (N, J):
+                    self._d_w = torch.empty(N, J, device=xyz.device)
+                _, st["d_w"] = ops.point_regularisers(xyz, m._last_weights, self._nn_i32, m.nn_distance, float(m.eps), reg.arap,
+                                                      reg.tv, reg.sparsity, d_xyz, self._d_w, lt[0:3])
+            if reg is not None and reg.any_pose():
+                _, st["d_thetas"], st["d_gt_reg"], st["d_joints_reg"] = ops.pose_regularisers(
+                    fw.prev_thetas, fw.prev_global_t, m.joints, m.skeleton_pcd if reg.joint_chamfer != 0 else None,
+                    reg.transformation_reg, reg.joint_chamfer, lt[3:5])
+        if self.extra_loss is not None:
+            with _lib_stage("extra_loss"):
+                with torch.enable_grad():
+                    leaf = xyz.detach().requires_grad_(True)
+                    extra = self.extra_loss(leaf)
+                    (g,) = torch.autograd.grad(extra, leaf)
+                d_xyz.add_(g)
+                lt[5:6].copy_(extra.detach().reshape(1))
+        lt[6:7].copy_(render_loss.reshape(1))
+        torch.sum(lt[0:7], dim=0, keepdim=True, out=lt[7:8])
+        return lt[7]
 
     # ---- stage C: LBS backward + pose backward (skinning weights, joints, pose network)
     @torch.no_grad()
@@ -281,14 +380,19 @@ class FusedTrainStep:
         cp, cl, wb, ga = st["cp"], st["cl"], st["wb"], st["ga"]
         if m.weights.grad is not None and m.theta_weight.grad is not None:
             cl.grad_out = dict(raw=m.weights.grad, theta=m.theta_weight.grad.reshape(1))
-        gl = ops._LBS.backward(cl, ga[2], ga[3], None, None, None)
+        gl = ops._LBS.backward(cl, ga[2], ga[3], st.get("d_w"), None, None)
         if not hasattr(cl, "grad_out"):
             self._accumulate([m.weights, m.theta_weight], gl[0:2])
         if all(p.grad is not None for p in [m.joints] + list(wb)):
             cp.grad_out = dict(wb=[p.grad for p in wb], joints=m.joints.grad)
-        gp = ops._Pose.backward(cp, gl[2], gl[3], None)
+        d_gt = gl[3]
+        if st.get("d_gt_reg") is not None:          # transformation regulariser on the global translation
+            d_gt = st["d_gt_reg"] if d_gt is None else d_gt.add_(st["d_gt_reg"])
+        gp = ops._Pose.backward(cp, gl[2], d_gt, st.get("d_thetas"))
         if not hasattr(cp, "grad_out"):
             self._accumulate([m.joints] + list(wb), gp[2:])
+        if st.get("d_joints_reg") is not None:      # joint chamfer: the pose backward has overwritten d_joints, add on top
+            self._accumulate([m.joints], [st["d_joints_reg"]])
 
     @staticmethod
     def _accumulate(params, grads):
@@ -328,11 +432,12 @@ class GraphedTrainStep:
     RING = 8
 
     def __init__(self, model, optimizer: MaskedAdam, bucket: GradBucket, n_rays: int, render_kwargs, *, cand_cap=None,
-                 m_cap=None, calibrate=None, use_graph: bool = True, packed_inputs: bool = False):
+                 m_cap=None, calibrate=None, use_graph: bool = True, packed_inputs: bool = False,
+                 regularisers: Optional[Regularisers] = None, extra_loss: Optional[Callable] = None):
         from . import ops
         assert FusedTrainStep.eligible(model), "GraphedTrainStep needs the fused pose kernel and the tensor-core decoder"
         self.model, self.opt, self.bucket = model, optimizer, bucket
-        self.fused = FusedTrainStep(model, optimizer, bucket)
+        self.fused = FusedTrainStep(model, optimizer, bucket, regularisers, extra_loss)
         dev = model.joints.device
         self.dev, self.R, self.use_graph = dev, int(n_rays), use_graph
         self.rk = {k: render_kwargs[k] for k in ("near", "far", "bg", "stepsize", "inverse_y", "flip_x", "flip_y") if k in render_kwargs}
@@ -595,8 +700,26 @@ def _finish_step(optimizer, bucket, decay_factor):
             g['lr'] = g['lr'] * decay_factor
 
 
+def regulariser_losses(model, t_hat_pcd, reg: Regularisers):
+    """The regulariser terms of run.py:633-657 through the model's own loss getters (plain torch expressions + autograd):
+    what the kernels of FusedTrainStep._regularise replace, kept as the autograd fallback and as their test reference.
+    Call after a forward (reads model._last_weights and forward_warp.prev_thetas / prev_global_t)."""
+    loss = 0
+    if reg.arap != 0:
+        loss = loss + reg.arap * model.get_arap_loss(t_hat_pcd)
+    if reg.tv != 0:
+        loss = loss + reg.tv * model.get_neighbour_weight_tv_loss()
+    if reg.sparsity != 0:
+        loss = loss + reg.sparsity * model.get_weight_sparsity_loss()
+    if reg.transformation_reg != 0:
+        loss = loss + reg.transformation_reg * model.get_transformation_regularisation_loss()
+    if reg.joint_chamfer != 0:
+        loss = loss + reg.joint_chamfer * model.get_joint_chamfer_loss()
+    return loss
+
+
 def train_step(model, optimizer: MaskedAdam, bucket: GradBucket, t, render_kwargs, target, *, decay_factor: float = 1.0,
-               fused: bool = True):
+               fused: bool = True, regularisers: Optional[Regularisers] = None, extra_loss: Optional[Callable] = None):
     """One stage-2 iteration on one rank's ray batch.  Returns the (device) loss tensor.
 
     A batch that keeps no sample (every ray of this rank's shard misses the cloud: the reference's NoPointsException
@@ -606,8 +729,8 @@ def train_step(model, optimizer: MaskedAdam, bucket: GradBucket, t, render_kwarg
     with bucket.direct_accum():
         if fused and FusedTrainStep.eligible(model):
             fs = getattr(bucket, "_fused_step", None)
-            if fs is None or fs.model is not model:
-                fs = bucket._fused_step = FusedTrainStep(model, optimizer, bucket)
+            if fs is None or fs.model is not model or fs.reg != regularisers or fs.extra_loss is not extra_loss:
+                fs = bucket._fused_step = FusedTrainStep(model, optimizer, bucket, regularisers, extra_loss)
             loss = fs.run(t, render_kwargs, target)
             if loss is None:
                 bg = float(render_kwargs['bg'])
@@ -617,6 +740,10 @@ def train_step(model, optimizer: MaskedAdam, bucket: GradBucket, t, render_kwarg
         bucket.zero()
         res = model(t, False, render_kwargs, render_pcd_direct=False)
         loss = WEIGHT_RENDER * F.mse_loss(res['rgb_marched'], target)
+        if regularisers is not None:
+            loss = loss + regulariser_losses(model, res['t_hat_pcd'], regularisers)
+        if extra_loss is not None:
+            loss = loss + extra_loss(res['t_hat_pcd'])
         if loss.requires_grad:
             loss.backward()
         _finish_step(optimizer, bucket, decay_factor)

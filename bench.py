@@ -239,6 +239,10 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print the per-stage CUDA-event breakdown to stderr")
+    ap.add_argument("--full-loss", action="store_true",
+                    help="training workloads: the COMPLETE stage-2 iteration of run.py:615-694 — render loss + ARAP + weight TV + "
+                         "sparsity + transformation regulariser + joint chamfer (configs/nerf/default.py:96-103) + the 2-D chamfer "
+                         "term against synthetic mask pixels (5 views x 3000 pixels, 3000 random projected points)")
     ap.add_argument("--train-path", default="graph", choices=["graph", "static", "dynamic"],
                     help="training step: CUDA graphs over the sync-free step (default), the same step launched eagerly, "
                          "or the dynamic step with its two host read-backs")
@@ -322,11 +326,24 @@ def main():
     decay = 0.1 ** (1.0 / (160 * 1000))
     counts = []
     gs = gs_stages = None
+    reg = extra = None
+    if mode == "train" and args.full_loss:
+        from articulated_point_nerf_b200.train import Chamfer2D, Regularisers
+        reg = Regularisers()
+        gen = torch.Generator().manual_seed(123)
+        Bv = min(5, len(scene.poses))                     # run.py:663: at most 5 cameras of the time step
+        mask_pcd = torch.stack([torch.randint(0, scene.cfg.H, (Bv, 3000), generator=gen),
+                                torch.randint(0, scene.cfg.W, (Bv, 3000), generator=gen)], dim=-1).float()
+        extra = Chamfer2D(model, scene.poses[:Bv].float().to(dev), scene.Ks[:Bv].float().to(dev), mask_pcd.to(dev), weight=5e-3,
+                          n_points=3000, image_height=None if scene.cfg.inverse_y else scene.cfg.H)
+        base_cfg["loss"] = "render + arap + weight_tv + sparsity + transformation_reg + joint_chamfer + chamfer2D (run.py:615-694)"
+    elif mode == "train":
+        base_cfg["loss"] = "render loss only (run.py:615-631)"
     if mode == "train" and args.train_path != "dynamic":
         t0, b0 = host[0][0].to(dev), host[0][1].to(dev)
         cal = (t0, b0[:, 0:3].contiguous(), b0[:, 3:6].contiguous())
         gs = GraphedTrainStep(model, opt, bucket, len(b0), rk, calibrate=cal, use_graph=args.train_path == "graph",
-                              packed_inputs=True)
+                              packed_inputs=True, regularisers=reg, extra_loss=extra)
 
     def run_step(t_dev, buf_dev, stepper=None):
         if mode == "train" and (stepper or gs) is not None:
@@ -334,7 +351,7 @@ def main():
         t, ro, rd, vd, tgt = unpack_dev(t_dev, buf_dev)
         kw = dict(rk, rays_o=ro, rays_d=rd, viewdirs=vd)
         if mode == "train":
-            out = train_step(model, opt, bucket, t, kw, tgt, decay_factor=decay)
+            out = train_step(model, opt, bucket, t, kw, tgt, decay_factor=decay, regularisers=reg, extra_loss=extra)
         else:
             with torch.no_grad():
                 if t.dim() == 2:      # repose: rot_params instead of a time (run.py:287)
@@ -359,7 +376,7 @@ def main():
             nonlocal gs_stages
             if gs_stages is None:
                 gs_stages = GraphedTrainStep(model, opt, bucket, gs.R, rk, cand_cap=gs.cand_cap, m_cap=gs.m_cap, use_graph=False,
-                                             packed_inputs=True)
+                                             packed_inputs=True, regularisers=reg, extra_loss=extra)
             stepper = gs_stages
         on_host = e2e and (gs is not None)     # the graphed step takes the pinned host buffers directly (one H2D copy each)
         for i in range(args.warmup):

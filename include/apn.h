@@ -33,6 +33,11 @@ int apn_version(void);
 const char* apn_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long apn_launch_count(void);
+/* NVTX range push / pop (nvtx3) for the host-side call groups; names follow the reference's torch.profiler.record_function
+ * ranges (lib/temporalpoints.py:421,433,439,452,496,503,546,552,611,629,634,653; lib/pointwarper.py:217,230,241).
+ * Return the nesting level NVTX reports (negative without a tool attached). */
+int apn_range_push(const char* name);
+int apn_range_pop(void);
 
 /* ---------------------------------------------------------------------------------------
  * K0  Pose chain.  Replaces lib/pointwarper.py:217-236: TransformNet (lib/pointwarper.py:5-37; 256-wide, 4 hidden
@@ -150,6 +155,32 @@ int apn_knn_points(const float* query, int n_query, const void* grid, int k, int
  * target (B, n_target, dim) -> nn_idx (B, n_query), index into that batch item's targets; ties -> lowest index. */
 int apn_nn1_batched(const float* query, const float* target, int n_batch, int n_query, int n_target, int dim,
                     int32_t* nn_idx, apn_stream_t stream);
+/* Camera rays on the device: get_rays_of_a_view (lib/tineuvox.py:675-738, mode='center', ndc=False) in one launch from the
+ * camera (K 3x3 and c2w (3|4)x4, HOST pointers, passed to the kernel by value) — for n consecutive pixels starting at
+ * first_pixel (row-major), or for the pixels listed in pixel_ids (device, n entries: a rank's tiles, a training batch).
+ * rays_o / rays_d / viewdirs (n,3); viewdirs may be NULL. */
+int apn_rays_of_a_view(const float* K_host9, const float* c2w_host, int c2w_rows, int H, int W, int inverse_y, int flip_x,
+                       int flip_y, const int32_t* pixel_ids, long long first_pixel, int n,
+                       float* rays_o, float* rays_d, float* viewdirs, apn_stream_t stream);
+/* Stage-2 regulariser losses with their gradients (run.py:633-657; lib/temporalpoints.py:714-725), one launch over the
+ * canonical points and their static neighbourhood nn_i (N,K) (lib/temporalpoints.py:104-110):
+ *   losses3[0] = weight_arap * sum_ik |nn_dist_ik - sqrt(|xyz_i - xyz_n|^2 + eps)|               (get_arap_loss)
+ *   losses3[1] = weight_tv * mean_ikj |w_ij - w_nj|                                              (get_neighbour_weight_tv_loss)
+ *   losses3[2] = weight_sparsity * -mean_ij [w log(w+eps) + (1-w) log(1-w+eps)]                  (get_weight_sparsity_loss)
+ * xyz (N,3) warped cloud, w (N,J) merged skinning weights.  d_xyz (N,3) is ACCUMULATED into (it already holds the
+ * render-loss gradient), d_w (N,J) is OVERWRITTEN (zeroed first); both feed apn_lbs_bwd.  A zero weight skips its term
+ * (and its pointers may then be NULL). */
+int apn_point_regularisers(const float* xyz, const float* w, const int32_t* nn_i, const float* nn_dist, int N, int K, int J,
+                           float eps, float weight_arap, float weight_tv, float weight_sparsity, float* d_xyz, float* d_w,
+                           float* losses3, apn_stream_t stream);
+/* Pose-side regularisers in one launch:
+ *   losses2[0] = weight_transformation_reg * (sum|global_t| + sum|thetas|) / J     (get_transformation_regularisation_loss,
+ *                lib/temporalpoints.py:797-800) -> d_thetas (J), d_global_t (3) OVERWRITTEN; skipped if d_thetas NULL
+ *   losses2[1] = weight_joint_chamfer * sum_j min_s |joints_j - skeleton_s|^2       (get_joint_chamfer_loss, :731-733; nearest
+ *                by the k-NN contract, ties -> lowest index) -> d_joints (J,3) OVERWRITTEN; skipped if d_joints NULL */
+int apn_pose_regularisers(const float* thetas, const float* global_t, const float* joints, const float* skeleton, int J, int S,
+                          float weight_transformation_reg, float weight_joint_chamfer, float* d_thetas, float* d_global_t,
+                          float* d_joints, float* losses2, apn_stream_t stream);
 /* time embedding of the pose-network input: poc_fre of the scalar time (lib/tineuvox.py:872-878; lib/temporalpoints.py:546-550):
  * out (1 + 2 n_freq) = [t, sin(t f_i)..., cos(t f_i)...] */
 int apn_time_embed(const float* t, const float* freqs, int n_freq, float* out, apn_stream_t stream);

@@ -678,3 +678,49 @@ def test_time_embed_and_render_loss_match_torch():
         loss, grad = ops.mse_loss_grad(pred.detach(), target, 200.0)
         assert abs(loss.item() - ref.item()) < 1e-5 * ref.item()
         assert rel_err(grad, pred.grad) < 1e-6
+
+
+@pytest.mark.parametrize("N,K,J", [(700, 8, 21), (1500, 8, 65), (257, 5, 3)])
+def test_regulariser_kernels_match_torch_autograd(N, K, J):
+    """apn_point_regularisers / apn_pose_regularisers: losses and gradients against the torch expressions of
+    lib/temporalpoints.py:714-733,797-800 differentiated by autograd (J > 32 exercises the column loop)."""
+    from articulated_point_nerf_b200 import ops
+    gen = torch.Generator().manual_seed(N + J)
+    xyz0 = torch.rand(N, 3, generator=gen).cuda()
+    nn_i = torch.randint(0, N, (N, K), generator=gen).cuda()
+    nn_i[:, 0] = torch.arange(N).cuda()                                   # a point is its own first neighbour
+    eps = 1e-6
+    nn_dist = torch.sqrt(((xyz0[:, None] - xyz0[nn_i]) ** 2).sum(-1) + eps)
+    xyz = (xyz0 + 0.02 * torch.randn(N, 3, generator=gen).cuda()).requires_grad_(True)
+    w = torch.softmax(3 * torch.randn(N, J, generator=gen).cuda(), dim=-1).requires_grad_(True)
+    wa, wt, ws = 5e-3, 10.0, 0.2
+    arap = wa * (nn_dist - torch.sqrt((xyz[:, None] - xyz[nn_i]).pow(2).sum(-1) + eps)).abs().sum()
+    tv = wt * (w[:, None, :] - w[nn_i, :]).abs().mean()
+    sp = ws * -(w * torch.log(w + eps) + (1 - w) * torch.log(1 - w + eps)).mean()
+    (arap + tv + sp).backward()
+    d_xyz = torch.full((N, 3), 0.5, device="cuda")                        # accumulated into
+    losses, d_w = ops.point_regularisers(xyz.detach(), w.detach(), nn_i.int().contiguous(), nn_dist, eps, wa, wt, ws, d_xyz)
+    for got, ref in zip(losses.tolist(), (arap, tv, sp)):
+        assert abs(got - float(ref)) < 1e-4 * abs(float(ref))
+    assert rel_err(d_xyz - 0.5, xyz.grad) < 1e-4
+    assert rel_err(d_w, w.grad) < 1e-4
+    # single terms: a zero weight switches a term off
+    d2 = torch.zeros(N, 3, device="cuda")
+    l2, dw2 = ops.point_regularisers(xyz.detach(), w.detach(), nn_i.int().contiguous(), nn_dist, eps, wa, 0.0, 0.0, d2)
+    assert dw2 is None and l2[1] == 0 and l2[2] == 0 and rel_err(d2, xyz.grad) < 1e-4
+    # pose side
+    S = 300
+    skel = torch.rand(S, 3, generator=gen).cuda()
+    joints = torch.rand(J, 3, generator=gen).cuda().requires_grad_(True)
+    thetas = torch.randn(J, generator=gen).cuda().requires_grad_(True)
+    thetas.data[0] = 0.0
+    gt = torch.randn(3, generator=gen).cuda().requires_grad_(True)
+    treg = 0.1 * (gt.abs().sum() + thetas.abs().sum()) / J
+    d = ((joints[:, None] - skel[None]) ** 2).sum(-1)
+    jc = 1.5 * d.min(dim=1)[0].sum()
+    (treg + jc).backward()
+    lp, d_th, d_gt, d_j = ops.pose_regularisers(thetas.detach(), gt.detach(), joints.detach(), skel, 0.1, 1.5)
+    assert abs(float(lp[0]) - float(treg)) < 1e-5 * float(treg) and abs(float(lp[1]) - float(jc)) < 1e-5 * float(jc)
+    assert rel_err(d_th, thetas.grad) < 1e-6 and rel_err(d_gt, gt.grad) < 1e-6 and rel_err(d_j, joints.grad) < 1e-5
+    lp, d_th, d_gt, d_j = ops.pose_regularisers(thetas.detach(), gt.detach(), joints.detach(), None, 0.1, 0.0)
+    assert d_j is None and float(lp[1]) == 0.0 and rel_err(d_th, thetas.grad) < 1e-6

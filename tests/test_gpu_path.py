@@ -143,7 +143,7 @@ def test_train_step_gradients_match_reference_golden(golden_any, fused_pose, dec
         assert rel_err(res["rgb_marched"], g["train"]["rgb_marched"]) < RTOL
         for k, ref in g["train"]["grads"].items():
             assert named[k].grad is not None, k
-            tol = GOLDEN_LOOSE if k.startswith(PE_AMPLIFIED) else RTOL
+            tol = GOLDEN_LOOSE if k.startswith(PE_AMPLIFIED) else (TC_TOL if decoder_train == "tc" else RTOL)
             assert rel_err(named[k].grad, ref) < tol, k
     # (2) every gradient at 1e-4 against the oracle run on the kernel's own warped cloud: the oracle's warp keeps
     # its autograd graph, its VALUES are replaced by the kernel's (straight-through)
@@ -603,3 +603,184 @@ def test_graphed_train_step_overflow_is_skipped_and_reported(golden_tiny):
     assert torch.isfinite(loss).all() and gs.last_counts["M"] == len(g["render"]["agg"]["ray_id"]) or gs.last_counts["M"] > 256
     assert any(not torch.equal(p.detach(), before[k]) for k, p in model.named_parameters())
     assert all(st["step"] == 1 for st in opt.state.values())
+
+
+@pytest.mark.parametrize("inverse_y,flip_x,flip_y", [(False, False, False), (True, False, False), (False, True, True)])
+def test_device_rays_equal_host_rays(inverse_y, flip_x, flip_y):
+    """apn_rays_of_a_view (rays from the camera in one launch) against get_rays_of_a_view (lib/tineuvox.py:675-738) evaluated by
+    torch on the host: origins and directions bit-equal, unit directions to the last bit of the norm; pixel lists and ranges."""
+    from articulated_point_nerf_b200 import ops
+    from articulated_point_nerf_b200.scene import get_rays_of_a_view
+    H, W = 37, 53
+    gen = torch.Generator().manual_seed(3)
+    K = torch.tensor([[61.3, 0., W / 2 + 0.2], [0., 60.1, H / 2 - 0.4], [0., 0., 1.]])
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=gen))
+    c2w = torch.eye(4)
+    c2w[:3, :3] = q
+    c2w[:3, 3] = torch.randn(3, generator=gen)
+    ro_h, rd_h, vd_h = [x.reshape(-1, 3) for x in get_rays_of_a_view(H, W, K, c2w, inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y)]
+    ro, rd, vd = ops.rays_of_a_view(H, W, K, c2w, "cuda", inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y)
+    assert torch.equal(ro.cpu(), ro_h)
+    assert torch.equal(rd.cpu(), rd_h)
+    assert (vd.cpu() - vd_h).abs().max() < 2e-7
+    ids = torch.randperm(H * W, generator=gen)[:301].to(torch.int32)
+    ro2, rd2, vd2 = ops.rays_of_a_view(H, W, K, c2w[:3], "cuda", inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y, pixel_ids=ids)
+    assert torch.equal(rd2.cpu(), rd_h[ids.long()]) and torch.equal(vd2, vd[ids.long().cuda()])
+    ro3, rd3, _ = ops.rays_of_a_view(H, W, K, c2w, "cuda", inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y, first_pixel=100, n=64)
+    assert torch.equal(rd3.cpu(), rd_h[100:164]) and torch.equal(ro3.cpu(), ro_h[100:164])
+
+
+def test_render_viewpoints_rank_shares_assemble_the_frame(golden_tiny):
+    """Multi-GPU render entry point: the tile shares of 3 ranks (16x16 tiles, round-robin) are disjoint and sum
+    to the single-rank frame bit for bit; view sharding leaves the other ranks' frames zero."""
+    from articulated_point_nerf_b200 import render_viewpoints
+    from articulated_point_nerf_b200.render import tile_pixels
+    g = golden_tiny
+    model, scene = model_from_golden(g)
+    rk = scene.render_kwargs()
+    V = 2
+    times = [0.25] * V
+    args = (model, scene.poses[:V], scene.HW[:V], scene.Ks[:V], False)
+    full = render_viewpoints(*args, dict(rk), test_times=times, inverse_y=scene.cfg.inverse_y, verbose=False)
+    world = 3
+    H, W = int(scene.HW[0][0]), int(scene.HW[0][1])
+    owned = torch.zeros(H * W, dtype=torch.int32)
+    acc = [0 * x for x in full[:3]]
+    for r in range(world):
+        owned[tile_pixels(H, W, r, world).long()] += 1
+        part = render_viewpoints(*args, dict(rk), test_times=times, inverse_y=scene.cfg.inverse_y, verbose=False, rank=r, world=world,
+                                 shard="tiles", gather=False)
+        acc = [a + p for a, p in zip(acc, part[:3])]
+    assert bool((owned == 1).all())
+    for a, f in zip(acc, full[:3]):
+        assert (a == f).all()
+    by_view = render_viewpoints(*args, dict(rk), test_times=times, inverse_y=scene.cfg.inverse_y, verbose=False, rank=1, world=2,
+                                shard="views", gather=False)
+    assert (by_view[0][1] == full[0][1]).all() and not by_view[0][0].any()
+
+
+def _fullstep_extras(model, scene, gf, n_points=None):
+    """Regulariser weights + the 2-D chamfer term with the inputs stored in ref_tiny_fullstep.pt."""
+    from articulated_point_nerf_b200.train import Chamfer2D, Regularisers
+    w = gf["weights"]
+    reg = Regularisers(arap=w["arap"], tv=w["tv"], sparsity=w["sparsity"], transformation_reg=w["transformation_reg"],
+                       joint_chamfer=w["joint_chamfer"])
+    B = gf["n_views"]
+    ch = Chamfer2D(model, scene.poses[:B].float().cuda(), scene.Ks[:B].float().cuda(), gf["mask_pcd"].cuda(), weight=w["chamfer2D"],
+                   n_points=n_points, image_height=None if scene.cfg.inverse_y else scene.cfg.H)
+    return reg, ch
+
+
+@pytest.mark.parametrize("decoder_train", ["fp32", "tc"])
+def test_full_stage2_loss_matches_reference_golden(golden_tiny, decoder_train):
+    """The COMPLETE stage-2 iteration loss of run.py:615-694 (render + ARAP + weight TV + sparsity + transformation regulariser +
+    joint chamfer + 2-D chamfer) against the reference's own run (tests/golden/ref_tiny_fullstep.pt, oracle/make_golden_fullstep.py):
+    every loss term and the gradient of every parameter.  PyTorch pose chain (bit-compatible cloud, see model_from_golden)."""
+    from conftest import load_golden
+    from articulated_point_nerf_b200.train import regulariser_losses
+    g, gf = golden_tiny, load_golden("tiny_fullstep")
+    assert torch.equal(gf["target"], g["train"]["target"])
+    model, scene = model_from_golden(g)
+    model.decoder_train = decoder_train
+    reg, ch = _fullstep_extras(model, scene, gf)
+    rk = _rk(scene, g)
+    model.zero_grad(set_to_none=True)
+    res = model(gf["t"].cuda(), False, rk, render_pcd_direct=False)
+    render = 200.0 * F.mse_loss(res["rgb_marched"], gf["target"].cuda())
+    regs = regulariser_losses(model, res["t_hat_pcd"], reg)
+    c2d = ch(res["t_hat_pcd"])
+    ref_regs = sum(float(gf["terms"][k]) for k in ("arap", "tv", "sparsity", "transformation_reg", "joint_chamfer"))
+    assert abs(float(render) - float(gf["terms"]["render"])) < RTOL * float(gf["terms"]["render"])
+    assert abs(float(regs) - ref_regs) < RTOL * ref_regs
+    assert abs(float(c2d) - float(gf["terms"]["chamfer2D"])) < RTOL * float(gf["terms"]["chamfer2D"])
+    # (1) the regulariser part alone (without ARAP) at 1e-4 for EVERY parameter: it does not pass through the positional encoding
+    from dataclasses import replace
+    params = [(k, p) for k, p in model.named_parameters() if k in gf["grads_reg"]]
+    got = torch.autograd.grad(regulariser_losses(model, res["t_hat_pcd"], replace(reg, arap=0.0)) + c2d, [p for _, p in params],
+                              retain_graph=True)
+    for (k, _), gr in zip(params, got):
+        assert rel_err(gr, gf["grads_reg"][k]) < RTOL, k
+    # ARAP: |D0 - d| has its kink exactly where a neighbourhood moves rigidly (d == D0 up to rounding), so its gradient there is
+    # the sign of rounding noise; loosely here, exactly on non-degenerate data in test_regulariser_kernels_match_torch_autograd
+    got = torch.autograd.grad(reg.arap * model.get_arap_loss(res["t_hat_pcd"]), [p for _, p in params], retain_graph=True,
+                              allow_unused=True)
+    for (k, _), gr in zip(params, got):
+        if k in gf["grads_arap"]:
+            assert rel_err(gr, gf["grads_arap"][k]) < 0.25, k
+    # (2) the full gradient; the parameters upstream of the positional encoding carry the render gradient's ill-conditioning
+    # (see PE_AMPLIFIED above): loose there, and covered by (1) + the render-only test by linearity
+    (render + regs + c2d).backward()
+    named = dict(model.named_parameters())
+    for k, ref in gf["grads"].items():
+        assert named[k].grad is not None, k
+        tol = 2 * GOLDEN_LOOSE if k.startswith(PE_AMPLIFIED) else (TC_TOL if decoder_train == "tc" else RTOL)
+        assert rel_err(named[k].grad, ref) < tol, k
+
+
+def test_fused_step_with_regularisers_equals_autograd_step(golden_any):
+    """The regulariser kernels inside the fused step (apn_point_regularisers, apn_pose_regularisers, the extra-loss hook) against
+    the same full loss through autograd and the model's torch loss getters (pinned to the reference by the test above): loss
+    terms, gradients, parameters after Adam.  Joints are perturbed so that the joint chamfer term has a gradient."""
+    from conftest import load_golden
+    from articulated_point_nerf_b200.train import FusedTrainStep, GradBucket, create_optimizer, train_step
+    g, gf = golden_any, load_golden("tiny_fullstep")
+    results = []
+    for fused in (False, True):
+        model, scene = model_from_golden(g, fused_pose=True)
+        model.decoder_train = "tc"
+        gen = torch.Generator().manual_seed(11)
+        with torch.no_grad():
+            model.joints.add_(0.01 * torch.randn(model.joints.shape, generator=gen).cuda())
+        reg, ch = _fullstep_extras(model, scene, gf)
+        rk = _rk(scene, g)
+        opt = create_optimizer(model)
+        bucket = GradBucket(opt)
+        t, tgt = g["train"]["t"].cuda(), g["train"]["target"].cuda()
+        loss = train_step(model, opt, bucket, t, rk, tgt, fused=fused, regularisers=reg, extra_loss=ch)
+        terms = bucket._fused_step.loss_terms.cpu() if fused else None
+        results.append((float(loss.detach()), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None},
+                        {k: p.detach().clone() for k, p in model.named_parameters()}, terms))
+    (l0, g0, p0, _), (l1, g1, p1, terms) = results
+    assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
+    assert float(terms[4]) > 0 and float(terms[0]) > 0 and float(terms[5]) > 0          # joint chamfer, ARAP, 2-D chamfer are live
+    assert abs(float(terms[:7].sum()) - l1) <= 1e-6 * l1
+    g0 = {k: v for k, v in g0.items() if not k.startswith("pose_embedding_net.")}
+    g1 = {k: v for k, v in g1.items() if not k.startswith("pose_embedding_net.")}
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert rel_err(g1[k], g0[k]) < RTOL, k
+    for k in p0:
+        assert rel_err(p1[k], p0[k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_graphed_step_with_regularisers_equals_fused_step(golden_tiny, use_graph):
+    """The full iteration (regularisers + 2-D chamfer with its RNG-free point set) captured in the CUDA graph replays the same
+    arithmetic as the eager fused step."""
+    from conftest import load_golden
+    from articulated_point_nerf_b200.train import GradBucket, GraphedTrainStep, create_optimizer, train_step
+    g, gf = golden_tiny, load_golden("tiny_fullstep")
+    t, tgt = g["train"]["t"].cuda(), g["train"]["target"].cuda()
+    ro, rd, vd = g["rays_o"].cuda(), g["rays_d"].cuda(), g["viewdirs"].cuda()
+    out = []
+    for graphed in (False, True):
+        model, scene = model_from_golden(g, fused_pose=True)
+        model.decoder_train = "tc"
+        reg, ch = _fullstep_extras(model, scene, gf)
+        opt = create_optimizer(model)
+        bucket = GradBucket(opt)
+        rk0 = scene.render_kwargs()
+        if graphed:
+            gs = GraphedTrainStep(model, opt, bucket, len(ro), rk0, calibrate=(t, ro, rd), use_graph=use_graph, regularisers=reg,
+                                  extra_loss=ch)
+            loss = float(gs.step(t, ro, rd, vd, tgt))
+            gs.flush()
+        else:
+            loss = float(train_step(model, opt, bucket, t, dict(rk0, rays_o=ro, rays_d=rd, viewdirs=vd), tgt, regularisers=reg,
+                                    extra_loss=ch))
+        out.append((loss, {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = out
+    assert abs(l0 - l1) <= 1e-5 * abs(l0)
+    for k in g0:
+        tol = 1e-2 if k == "theta_weight" else 3 * RTOL
+        assert rel_err(g1[k], g0[k]) < tol, k
