@@ -19,7 +19,7 @@ OBJ_DIR = os.path.join(ROOT, "build", "obj")
 LIB_PATH = os.path.join(PKG, "libapn_sm100.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr"]
+              "--expt-relaxed-constexpr"] + os.environ.get("APN_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DKS_STATS
 
 
 def _nvcc() -> str:

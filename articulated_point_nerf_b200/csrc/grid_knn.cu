@@ -723,28 +723,46 @@ knn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, f
 //
 // Both searches above spend their instructions on traversal: the warp search ~1800 warp instructions per query (one query
 // per warp, cross-lane top-8), the thread search ~29 000 thread instructions per query on c3 (every lane box-tests up to
-// 9^3 mostly empty leaves on its own).  Here the candidates are first sorted by the grid leaf that contains them (one
-// radix sort of (leaf key, candidate index)), so the 32 queries of a warp sit in the same or neighbouring leaves and
-// share ONE neighbourhood:
-//   * the warp takes a group of lanes whose queries lie in the same leaf (within one leaf when that gives < 8 lanes),
-//   * enumerates the leaves of the group's bounding box grown by a radius rho — lane = leaf, pruned against the group's
-//     current worst bound — and copies their points (contiguous float4 runs of `sorted`) into the warp's shared-memory
-//     stage with coalesced loads,
+// 9^3 mostly empty leaves on its own).  Here the candidates are first sorted by the grid leaf that contains them and by
+// their position inside it (one radix sort of (leaf key << 6 | 2-bit-per-axis Morton offset, candidate index)), so the 32
+// queries of a warp are neighbours in space — a fraction of a leaf on dense query sets — and share ONE neighbourhood:
+//   * the warp takes a group of lanes whose queries lie in the same leaf (within two leaves when that gives < 16 lanes),
+//   * enumerates the cells overlapping the group's bounding box grown by a radius rho — lane = cell: leaves in the first
+//     round, 2x2x2 leaf blocks (contiguous ranges of the Morton-ordered table) afterwards; only cells that are not
+//     entirely inside the previous round's box (six slabs), pruned against the group's current worst bound,
+//   * copies their points (contiguous float4 runs of `sorted`, coalesced loads) into the warp's shared-memory stage,
+//     keeping only the points INSIDE this round's float box, outside the previous one and within the worst bound of
+//     the group's bounding box (ballot compaction): a round scans exactly its shell, not whole leaves,
 //   * every lane then scans the staged points against ITS query with a register top-8 of 64-bit (d2, index) keys:
 //     one broadcast LDS.128 + 8 FP32 operations + one compare per point and warp, for 32 queries at once;
-//   * a lane is finished when its 8th distance is certified by the scanned box (every unscanned point is farther than
-//     the distance from the query to the box faces) or the box covers the query radius; otherwise rho grows to the
-//     largest outstanding bound (doubling for lanes that have not found 8 points yet) and only the new shell is scanned.
+//   * a lane is finished when its 8th distance is certified by the scanned box (every untested point lies outside the
+//     box, i.e. farther than the distance from the query to the box faces) or the box covers the query radius; otherwise
+//     rho grows to the largest outstanding bound (1.5 rho + one leaf for lanes that have not found 8 points yet).
+// Measured work per query (scripts/knn_profile.py stats, -DKS_STATS): c3 31 distance evaluations, 7 cell slots, 7 points
+// loaded; c5 68 / 7 / 27; c1 272 / 14 / 64 (sparse query set: a warp's 32 queries span several leaves).
 // Exactness: the result is the top-8 by (d2, index) over a superset of the ball that contains it — identical bits to the
 // other searches and to the brute-force oracle (same d2 arithmetic: (dx*dx + dy*dy) + dz*dz without FMA).
 // ---------------------------------------------------------------------------------------
 #define KS_WARPS 8
 #define KS_CHUNK 256          // staged points per warp (4 KiB)
 
+#ifdef KS_STATS      // debugging build (-DKS_STATS): work counters of the sorted search, read with apn_knn_sorted_stats
+__device__ unsigned long long ks_stats[8];
+#define KS_COUNT(i, v) do { const unsigned long long v__ = (unsigned long long)(v); if (lane == 0) atomicAdd(&ks_stats[i], v__); } while (0)
+extern "C" int apn_knn_sorted_stats(unsigned long long* out8) {
+  cudaMemcpyFromSymbol(out8, ks_stats, sizeof(ks_stats));
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(ks_stats, z, sizeof(z));
+  return 0;
+}
+#else
+#define KS_COUNT(i, v) do { } while (0)
+#endif
+
 __global__ void knn_key_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far,
                                float stepdist, const void* __restrict__ blob, const int* __restrict__ cand_ray,
                                const int* __restrict__ cand_step, int n_cand_cap, const int* __restrict__ n_cand_dev,
-                               int* __restrict__ keys, int* __restrict__ vals) {
+                               int* __restrict__ keys, int* __restrict__ vals, int sub_bits) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cand_cap) return;
   const GridHeader* h = (const GridHeader*)blob;
@@ -758,6 +776,17 @@ __global__ void knn_key_kernel(const float* __restrict__ rays_o, const float* __
     int ix, iy, iz;
     point_cell(h, qx, qy, qz, ix, iy, iz);
     key = cell_key(ix, iy, iz, h->L, h->top_dim[0], h->top_dim[1]);
+    sub_bits = min(sub_bits, (31 - (32 - __clz(max(h->n_cells, 1)))) / 3 * 3);      // the key stays a positive int32
+    if (sub_bits > 0) {
+      // position inside the leaf, Morton-interleaved (sub_bits / 3 bits per axis): consecutive queries of the sorted list
+      // are then neighbours INSIDE the leaf, so the bounding box of a warp's 32 queries is a fraction of the leaf
+      const int sb = sub_bits / 3, m = (1 << sb) - 1;
+      const float fx = (qx - h->origin[0]) * h->inv_cell - (float)ix, fy = (qy - h->origin[1]) * h->inv_cell - (float)iy,
+                  fz = (qz - h->origin[2]) * h->inv_cell - (float)iz;
+      const int sx = min(max((int)(fx * (float)(m + 1)), 0), m), sy = min(max((int)(fy * (float)(m + 1)), 0), m),
+                sz = min(max((int)(fz * (float)(m + 1)), 0), m);
+      key = (key << sub_bits) | (int)(part1by2(sx) | (part1by2(sy) << 1) | (part1by2(sz) << 2));
+    }
   }
   keys[i] = key;
   vals[i] = i;
@@ -773,7 +802,8 @@ __global__ void __launch_bounds__(32 * KS_WARPS)
 knn_sorted_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float near, float far, float stepdist,
                   const void* __restrict__ blob, const int* __restrict__ cand_ray, const int* __restrict__ cand_step,
                   const int* __restrict__ order, int n_cand_cap, const int* __restrict__ n_cand_dev, int* __restrict__ nn_idx,
-                  float* __restrict__ nn_d2, int* __restrict__ keep, float grow_mul, float grow_add) {
+                  float* __restrict__ nn_d2, int* __restrict__ keep, float grow_mul, float grow_add, float rho0_scale, float lv1_at,
+                  float lv2_at) {
   __shared__ float4 sP[KS_WARPS][KS_CHUNK];
   const GridView g = grid_view(blob);
   const GridHeader* h = g.h;
@@ -788,7 +818,7 @@ knn_sorted_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
   const float r2 = h->r2, rmax = sqrtf(r2);
   const float eps = 1e-4f * cell + 1e-6f;
   // first radius: the ball expected to hold ~32 points (4 x K) at the cloud's density, between 0.35 and 2 leaf edges
-  const float rho0 = cell * fminf(fmaxf(cbrtf(7.64f / fmaxf(h->occupancy, 1e-3f)), 0.35f), 2.0f);
+  const float rho0 = rho0_scale * cell * fminf(fmaxf(cbrtf(7.64f / fmaxf(h->occupancy, 1e-3f)), 0.35f), 2.0f);
   float4* stage = sP[wib];
 
   for (int base = (blockIdx.x * KS_WARPS + wib) * 32; base < n_cand; base += n_warps * 32) {
@@ -822,32 +852,106 @@ knn_sorted_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
       const float qhx = warp_max(mine ? qx : -INFINITY), qhy = warp_max(mine ? qy : -INFINITY), qhz = warp_max(mine ? qz : -INFINITY);
       bool fin = !mine;
       float rho = rho0;
-      int px0 = 1, px1 = 0, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;       // box scanned so far (empty)
+      KS_COUNT(0, 1);                    // groups
+      KS_COUNT(7, __popc(gm));           // queries in groups
+      // box scanned so far: float bounds (empty at first) and the leaves that lie entirely inside it
+      float olx = 1.f, oly = 1.f, olz = 1.f, ohx = 0.f, ohy = 0.f, ohz = 0.f;
+      int ox0 = 1, ox1 = 0, oy0 = 1, oy1 = 0, oz0 = 1, oz1 = 0;       // leaf ranges of the previous box (empty)
       for (;;) {
         const bool last_round = rho >= rmax + 8.f * eps;      // this box covers the query radius of every lane of the group
-        const int x0 = min(max((int)floorf((qlx - rho - ox) * inv_cell), 0), nx - 1), x1 = min(max((int)floorf((qhx + rho - ox) * inv_cell), 0), nx - 1);
-        const int y0 = min(max((int)floorf((qly - rho - oy) * inv_cell), 0), ny - 1), y1 = min(max((int)floorf((qhy + rho - oy) * inv_cell), 0), ny - 1);
-        const int z0 = min(max((int)floorf((qlz - rho - oz) * inv_cell), 0), nz - 1), z1 = min(max((int)floorf((qhz + rho - oz) * inv_cell), 0), nz - 1);
-        const int Lx = x1 - x0 + 1, Ly = y1 - y0 + 1, n_leaves = Lx * Ly * (z1 - z0 + 1);
+        // enumeration level of this round: leaves for the first (small) boxes, 2x2x2 or 4x4x4 leaf blocks (contiguous ranges of
+        // the Morton-ordered cell table) once the box spans many leaves — far queries walk mostly EMPTY space, where a block
+        // costs one lane instead of 8 / 64; the exact point filter below makes the coarser granularity harmless
+        const int lv = rho >= lv2_at * cell ? min(2, L) : (rho >= lv1_at * cell ? min(1, L) : 0);
+        const float lcell = cell * (float)(1 << lv);
+        // the box of this round: the group's bounding box grown by rho.  Points are tested against these FLOAT bounds when
+        // they are staged, so a round scans exactly the points inside its box and outside the previous one — not whole
+        // leaves — and the certification bound is the distance to the box faces
+        const float nlx = qlx - rho, nly = qly - rho, nlz = qlz - rho, nhx = qhx + rho, nhy = qhy + rho, nhz = qhz + rho;
+        const int fx0 = min(max((int)floorf((nlx - ox) * inv_cell), 0), nx - 1), fx1 = min(max((int)floorf((nhx - ox) * inv_cell), 0), nx - 1);
+        const int fy0 = min(max((int)floorf((nly - oy) * inv_cell), 0), ny - 1), fy1 = min(max((int)floorf((nhy - oy) * inv_cell), 0), ny - 1);
+        const int fz0 = min(max((int)floorf((nlz - oz) * inv_cell), 0), nz - 1), fz1 = min(max((int)floorf((nhz - oz) * inv_cell), 0), nz - 1);
+        // in units of this round's cells; cells strictly between the first and last cell of the PREVIOUS box lie entirely
+        // inside it (points and box faces are binned by the same monotone expression)
+        const int x0 = fx0 >> lv, x1 = fx1 >> lv, y0 = fy0 >> lv, y1 = fy1 >> lv, z0 = fz0 >> lv, z1 = fz1 >> lv;
+        const bool had = ox1 >= ox0;
+        const int px0 = had ? (ox0 >> lv) + 1 : 1, px1 = had ? (ox1 >> lv) - 1 : 0, py0 = had ? (oy0 >> lv) + 1 : 1,
+                  py1 = had ? (oy1 >> lv) - 1 : 0, pz0 = had ? (oz0 >> lv) + 1 : 1, pz1 = had ? (oz1 >> lv) - 1 : 0;
+        // ---- the cells of this box that do not lie entirely inside the previous box, as up to six slabs (z below / above
+        // the old interior over the full xy extent, then y below / above inside the old z range, then x below / above inside
+        // the old yz range): only those leaves cost a lane, and the index arithmetic is one float reciprocal per slab
+        int sx0[6], sy0[6], sz0[6], sLx[6], sLy[6], send[6];
+        {
+          const bool none = px1 < px0 || py1 < py0 || pz1 < pz0;      // no interior yet: everything is new (one slab)
+          const int a0 = none ? z1 + 1 : pz0, a1 = none ? z1 : pz1;
+          const int b0 = none ? y1 + 1 : py0, b1 = none ? y1 : py1;
+          const int c0 = none ? x1 + 1 : px0, c1 = none ? x1 : px1;
+          const int FX = x1 - x0 + 1, FY = y1 - y0 + 1;
+          int acc = 0;
+          // slab 0: z in [z0, a0-1]           slab 1: z in [a1+1, z1]
+          sx0[0] = x0; sy0[0] = y0; sz0[0] = z0;     sLx[0] = FX; sLy[0] = FY; acc += FX * FY * max(a0 - z0, 0); send[0] = acc;
+          sx0[1] = x0; sy0[1] = y0; sz0[1] = a1 + 1; sLx[1] = FX; sLy[1] = FY; acc += FX * FY * max(z1 - a1, 0); send[1] = acc;
+          const int ZR = max(a1 - a0 + 1, 0);
+          // slab 2: y in [y0, b0-1]           slab 3: y in [b1+1, y1]           (z in the old range)
+          sx0[2] = x0; sy0[2] = y0;     sz0[2] = a0; sLx[2] = FX; sLy[2] = max(b0 - y0, 0); acc += FX * sLy[2] * ZR; send[2] = acc;
+          sx0[3] = x0; sy0[3] = b1 + 1; sz0[3] = a0; sLx[3] = FX; sLy[3] = max(y1 - b1, 0); acc += FX * sLy[3] * ZR; send[3] = acc;
+          const int YR = max(b1 - b0 + 1, 0);
+          // slab 4: x in [x0, c0-1]           slab 5: x in [c1+1, x1]           (y, z in the old range)
+          sx0[4] = x0;     sy0[4] = b0; sz0[4] = a0; sLx[4] = max(c0 - x0, 0); sLy[4] = YR; acc += sLx[4] * YR * ZR; send[4] = acc;
+          sx0[5] = c1 + 1; sy0[5] = b0; sz0[5] = a0; sLx[5] = max(x1 - c1, 0); sLy[5] = YR; acc += sLx[5] * YR * ZR; send[5] = acc;
+        }
+        const int n_leaves = send[5];
+        KS_COUNT(1, 1);                    // rounds
+        KS_COUNT(2, n_leaves);             // leaves enumerated
         float bmax2 = warp_max(fin ? 0.f : key_d2(thr));       // no unfinished lane can use a point beyond this
         const bool act = mine && !fin;
+        int fill = 0;                                          // staged points waiting for a scan (warp-uniform)
+        // scan of the staged points: every lane against its own query
+#define KS_FLUSH()                                                                                                     \
+  do {                                                                                                                 \
+    __syncwarp();                                                                                                      \
+    KS_COUNT(6, (unsigned long long)fill * __popc(__ballot_sync(FULL_MASK, act)));   /* distance evaluations */         \
+    if (act) {                                                                                                         \
+      _Pragma("unroll 4") for (int jj = 0; jj < fill; ++jj) {                                                          \
+        const float4 P = stage[jj];                                                                                    \
+        const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);                                                    \
+        if (d2 <= key_d2(thr)) {                                                                                       \
+          const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w); \
+          if (k < thr) {                                                                                               \
+            top8_insert(best, k);                                                                                      \
+            thr = best[APN_K - 1] < thr ? best[APN_K - 1] : thr;                                                       \
+          }                                                                                                            \
+        }                                                                                                              \
+      }                                                                                                                \
+    }                                                                                                                  \
+    __syncwarp();                                                                                                      \
+    fill = 0;                                                                                                          \
+    bmax2 = warp_max(fin ? 0.f : key_d2(thr));                                                                         \
+  } while (0)
         for (int e0 = 0; e0 < n_leaves; e0 += 32) {
           const int e = e0 + lane;
           int s = 0, n = 0;
           if (e < n_leaves) {
-            const int ex = e % Lx, t = e / Lx, ey = t % Ly, ez = t / Ly;
-            const int ix = x0 + ex, iy = y0 + ey, iz = z0 + ez;
-            const bool old = ix >= px0 && ix <= px1 && iy >= py0 && iy <= py1 && iz >= pz0 && iz <= pz1;
-            if (!old) {
-              const float bx = ox + ix * cell, by = oy + iy * cell, bz = oz + iz * cell;
-              const float dx = fmaxf(fmaxf(bx - eps - qhx, qlx - (bx + cell + eps)), 0.f);
-              const float dy = fmaxf(fmaxf(by - eps - qhy, qly - (by + cell + eps)), 0.f);
-              const float dz = fmaxf(fmaxf(bz - eps - qhz, qlz - (bz + cell + eps)), 0.f);
-              if (dx * dx + dy * dy + dz * dz <= bmax2) {
-                const int key = cell_key(ix, iy, iz, L, tx, ty);
-                s = __ldg(g.cell_start + key);
-                n = __ldg(g.cell_start + key + 1) - s;
-              }
+            int q = 0;
+#pragma unroll
+            for (int u = 0; u < 5; ++u) q += (e >= send[u]) ? 1 : 0;
+            int bx0 = sx0[0], by0 = sy0[0], bz0 = sz0[0], lx_ = sLx[0], ly_ = sLy[0], st_ = 0;
+#pragma unroll
+            for (int u = 1; u < 6; ++u)
+              if (q == u) { bx0 = sx0[u]; by0 = sy0[u]; bz0 = sz0[u]; lx_ = sLx[u]; ly_ = sLy[u]; st_ = send[u - 1]; }
+            const int el = e - st_;
+            // el < 2^20: the float quotient with a half-unit bias is exact
+            const int t = (int)(((float)el + 0.5f) * (1.0f / (float)lx_)), ex = el - t * lx_;
+            const int ez = (int)(((float)t + 0.5f) * (1.0f / (float)ly_)), ey = t - ez * ly_;
+            const int ix = bx0 + ex, iy = by0 + ey, iz = bz0 + ez;
+            const float bx = ox + ix * lcell, by = oy + iy * lcell, bz = oz + iz * lcell;
+            const float dx = fmaxf(fmaxf(bx - eps - qhx, qlx - (bx + lcell + eps)), 0.f);
+            const float dy = fmaxf(fmaxf(by - eps - qhy, qly - (by + lcell + eps)), 0.f);
+            const float dz = fmaxf(fmaxf(bz - eps - qhz, qlz - (bz + lcell + eps)), 0.f);
+            if (dx * dx + dy * dy + dz * dz <= bmax2) {
+              const int key = cell_key(ix << lv, iy << lv, iz << lv, L, tx, ty);      // first leaf of the block
+              s = __ldg(g.cell_start + key);
+              n = __ldg(g.cell_start + key + (1 << (3 * lv))) - s;
             }
           }
           int incl = n;
@@ -857,49 +961,43 @@ knn_sorted_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
             if (lane >= o) incl += v;
           }
           const int total = __shfl_sync(FULL_MASK, incl, 31);
-          for (int c0 = 0; c0 < total; c0 += KS_CHUNK) {
-            const int cn = min(KS_CHUNK, total - c0);
-            // ---- stage: flattened index -> (range, offset) by a binary search over the inclusive counts
-            for (int j0 = 0; j0 < cn; j0 += 32) {
-              const int f = c0 + j0 + lane;
-              int c = 0;
+          KS_COUNT(3, __popc(__ballot_sync(FULL_MASK, n > 0)));   // non-empty leaves that passed the box test
+          KS_COUNT(4, total);                                       // points loaded
+          const float bm = bmax2 * 1.00001f + 1e-12f;
+          // ---- stage: flattened index -> (range, offset) by a binary search over the inclusive counts; a point is kept if it
+          // lies inside this round's box, was not inside the previous one, and is within the largest outstanding bound of
+          // the group's bounding box
+          for (int f0 = 0; f0 < total; f0 += 32) {
+            const int f = f0 + lane;
+            int c = 0;
 #pragma unroll
-              for (int st = 16; st > 0; st >>= 1) {
-                const int v = __shfl_sync(FULL_MASK, incl, c + st - 1);
-                if (f >= v) c += st;
-              }
-              c = min(c, 31);
-              const int cs = __shfl_sync(FULL_MASK, s, c), ci = __shfl_sync(FULL_MASK, incl, c), cnn = __shfl_sync(FULL_MASK, n, c);
-              if (j0 + lane < cn) stage[j0 + lane] = __ldg(g.sorted + cs + (f - (ci - cnn)));
+            for (int st = 16; st > 0; st >>= 1) {
+              const int v = __shfl_sync(FULL_MASK, incl, c + st - 1);
+              if (f >= v) c += st;
             }
-            __syncwarp();
-            // ---- scan: every lane against its own query
-            if (act) {
-#pragma unroll 4
-              for (int jj = 0; jj < cn; ++jj) {
-                const float4 P = stage[jj];
-                const float d2 = dist2_contract(qx, qy, qz, P.x, P.y, P.z);
-                if (d2 <= key_d2(thr)) {
-                  const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(P.w);
-                  if (k < thr) {
-                    top8_insert(best, k);
-                    thr = best[APN_K - 1] < thr ? best[APN_K - 1] : thr;
-                  }
-                }
-              }
+            c = min(c, 31);
+            const int cs = __shfl_sync(FULL_MASK, s, c), ci = __shfl_sync(FULL_MASK, incl, c), cnn = __shfl_sync(FULL_MASK, n, c);
+            bool pass = false;
+            float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < total) {
+              P = __ldg(g.sorted + cs + (f - (ci - cnn)));
+              const bool in_new = P.x >= nlx && P.x <= nhx && P.y >= nly && P.y <= nhy && P.z >= nlz && P.z <= nhz;
+              const bool in_old = P.x >= olx && P.x <= ohx && P.y >= oly && P.y <= ohy && P.z >= olz && P.z <= ohz;
+              const float dx = fmaxf(fmaxf(qlx - P.x, P.x - qhx), 0.f), dy = fmaxf(fmaxf(qly - P.y, P.y - qhy), 0.f),
+                          dz = fmaxf(fmaxf(qlz - P.z, P.z - qhz), 0.f);
+              pass = in_new && !in_old && dx * dx + dy * dy + dz * dz <= bm;
             }
-            __syncwarp();
+            const unsigned int pm = __ballot_sync(FULL_MASK, pass);
+            if (pass) stage[fill + __popc(pm & ((1u << lane) - 1u))] = P;
+            fill += __popc(pm);
+            KS_COUNT(5, __popc(pm));                                // points staged
+            if (fill > KS_CHUNK - 32) KS_FLUSH();
           }
-          bmax2 = warp_max(fin ? 0.f : key_d2(thr));
         }
-        // ---- certification: every unscanned point lies outside the box [x0..x1] x [y0..y1] x [z0..z1]
-        float bnd = INFINITY;
-        if (x0 > 0) bnd = fminf(bnd, qx - (ox + x0 * cell));
-        if (x1 < nx - 1) bnd = fminf(bnd, (ox + (x1 + 1) * cell) - qx);
-        if (y0 > 0) bnd = fminf(bnd, qy - (oy + y0 * cell));
-        if (y1 < ny - 1) bnd = fminf(bnd, (oy + (y1 + 1) * cell) - qy);
-        if (z0 > 0) bnd = fminf(bnd, qz - (oz + z0 * cell));
-        if (z1 < nz - 1) bnd = fminf(bnd, (oz + (z1 + 1) * cell) - qz);
+        if (fill) KS_FLUSH();
+#undef KS_FLUSH
+        // ---- certification: every point not tested so far lies outside this round's box
+        const float bnd = fminf(fminf(fminf(qx - nlx, nhx - qx), fminf(qy - nly, nhy - qy)), fminf(qz - nlz, nhz - qz));
         const float reach = fmaxf(bnd - 3.f * eps, 0.f);
         const float reach2 = reach * reach;
         const bool have8 = best[APN_K - 1] != KEY_INF;
@@ -908,12 +1006,13 @@ knn_sorted_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
           else if (reach2 > r2 || last_round) fin = true;                    // the box covers the query radius
         }
         if (__all_sync(FULL_MASK, fin)) break;
-        // next radius: the largest outstanding bound; lanes without 8 points yet grow by ONE leaf edge: shells stay thin, so
-        // the shell in which a far query first meets the surface yields a bound close to its true 8th distance, and the
-        // points scanned stay close to those inside that ball (a doubling radius scans the whole 0.1-ball of dense clouds)
+        // next radius: the largest outstanding bound; lanes without 8 points yet grow to 1.5 rho + one leaf edge: shells stay
+        // moderately thin, so the shell in which a far query first meets the surface yields a bound close to its true 8th
+        // distance (a doubling radius scans the whole 0.1-ball of dense clouds; +1 leaf per round costs rounds)
         const float need = fin ? 0.f : (have8 ? fminf(sqrtf(key_d2(best[APN_K - 1])), rmax) : fminf(grow_mul * rho + grow_add * cell, rmax));
         rho = fminf(fmaxf(warp_max(need) + 4.f * eps, rho + 0.25f * cell), rmax + 8.f * eps);
-        px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
+        olx = nlx; oly = nly; olz = nlz; ohx = nhx; ohy = nhy; ohz = nhz;
+        ox0 = fx0; ox1 = fx1; oy0 = fy0; oy1 = fy1; oz0 = fz0; oz1 = fz1;
       }
     }
     if (valid) {
@@ -959,18 +1058,25 @@ static int knn_sorted_launch(cudaStream_t stream, const float* rays_o, const flo
   char* w = (char*)workspace;
   int *keys_in = (int*)(w + l.keys_in), *keys_out = (int*)(w + l.keys_out), *vals_in = (int*)(w + l.vals_in),
       *vals_out = (int*)(w + l.vals_out);
+  // sort key = leaf key (<= 25 bits: the cell table holds at most 2^25 leaves) + 6 bits of position inside the leaf
+  int sub_bits = 6;
+  if (const char* e = getenv("APN_KS_SUBBITS")) sub_bits = atoi(e) / 3 * 3;
+  if (sub_bits < 0 || sub_bits > 6) sub_bits = 6;
   knn_key_kernel<<<apn_div_up(n_cand, 256), 256, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, n_cand,
-                                                             n_cand_dev, keys_in, vals_in);
+                                                             n_cand_dev, keys_in, vals_in, sub_bits);
   APN_LAUNCH_CHECK();
   size_t tb = l.temp_bytes;
   APN_CUDA(cub::DeviceRadixSort::SortPairs(w + l.temp, tb, keys_in, keys_out, vals_in, vals_out, n_cand, 0, 31, stream));
   apn_count_launch(4);
   const int blocks = min(apn_div_up(n_cand, 32 * KS_WARPS), APN_SM_COUNT * 6);
   // radius growth of lanes that have not found 8 points yet: rho <- mul * rho + add * leaf edge (APN_KS_GROWTH="mul,add")
-  float grow_mul = 1.f, grow_add = 1.f;
+  float grow_mul = 1.5f, grow_add = 1.f, rho0_scale = 0.6f;    // measured optimum on c1 / c3 / c5 (gpurun_out/r2g_*, r2i_* sweeps)
   if (const char* e = getenv("APN_KS_GROWTH")) sscanf(e, "%f,%f", &grow_mul, &grow_add);
+  if (const char* e = getenv("APN_KS_RHO0")) sscanf(e, "%f", &rho0_scale);
+  float lv1_at = 1.0f, lv2_at = 1e9f;          // box growth (in leaf edges) from which a round enumerates 2^3 / 4^3 leaf blocks
+  if (const char* e = getenv("APN_KS_LEVELS")) sscanf(e, "%f,%f", &lv1_at, &lv2_at);
   knn_sorted_kernel<<<blocks, 32 * KS_WARPS, 0, stream>>>(rays_o, rays_d, near, far, stepdist, grid, cand_ray, cand_step, vals_out,
-                                                          n_cand, n_cand_dev, nn_idx, nn_d2, keep, grow_mul, grow_add);
+                                                          n_cand, n_cand_dev, nn_idx, nn_d2, keep, grow_mul, grow_add, rho0_scale, lv1_at, lv2_at);
   APN_LAUNCH_CHECK();
   return 0;
 }

@@ -21,14 +21,31 @@ print("candidates", len(keep), "kept", int(keep.sum()))
 if len(sys.argv) > 2 and sys.argv[2] == "time":       # end-to-end sample_and_knn with the search the environment selects
     if os.environ.get("APN_KNN_LEGACY"):
         ops.KNN_SORTED_MIN = 1 << 60
-    for _ in range(2):
+    for _ in range(3):
         ops.sample_and_knn(grid, ro, rd, scene.cfg.near, scene.cfg.far, stepdist)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(5):
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(12):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         s2 = ops.sample_and_knn(grid, ro, rd, scene.cfg.near, scene.cfg.far, stepdist)
-    b.record(); torch.cuda.synchronize()
-    print(f"sample_and_knn {wl} FORCE={os.environ.get('APN_KNN_FORCE')} LEGACY={os.environ.get('APN_KNN_LEGACY')}: {a.elapsed_time(b) / 5:.3f} ms per frame, M={s2.M}")
+        b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    print(f"sample_and_knn {wl} FORCE={os.environ.get('APN_KNN_FORCE')} LEGACY={os.environ.get('APN_KNN_LEGACY')}: median {ts[len(ts) // 2]:.3f} ms, "
+          f"min {ts[0]:.3f} ms, max {ts[-1]:.3f} ms per frame, M={s2.M}")
+    sys.exit(0)
+if len(sys.argv) > 2 and sys.argv[2] == "stats":       # needs a build with APN_EXTRA_NVCC_FLAGS=-DKS_STATS
+    import ctypes
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    buf = (ctypes.c_ulonglong * 8)()
+    torch.cuda.synchronize(); raw.apn_knn_sorted_stats(buf)
+    ops.sample_and_knn(grid, ro, rd, scene.cfg.near, scene.cfg.far, stepdist)
+    torch.cuda.synchronize(); raw.apn_knn_sorted_stats(buf)
+    v = list(buf)
+    q = max(v[7], 1)
+    print(f"stats {wl}: queries {v[7]}, groups {v[0]} ({v[7] / max(v[0], 1):.1f} q/group), rounds/group {v[1] / max(v[0], 1):.2f}, per QUERY: "
+          f"leaf slots {v[2] / q:.1f}, leaves read {v[3] / q:.1f}, points loaded {v[4] / q:.1f}, staged {v[5] / q:.1f}, distance evals {v[6] / q:.1f}")
     sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == "short":      # under ncu: the one sample_and_knn call above is all that is profiled
     torch.cuda.synchronize()
