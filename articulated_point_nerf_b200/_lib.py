@@ -100,6 +100,7 @@ SIGNATURES = {
     "apn_aggregate_tc_pack_weights_bwd": (I, [P, I, P, P]),
     "apn_aggregate_tc_bwd_scratch_bytes": (SZ, [I, I]),
     "apn_aggregate_bwd_tc": (I, [P, P, P, P, P, P, P, SZ, P]),
+    "apn_aggregate_bwd_tc_phase": (I, [P, P, P, P, P, P, P, SZ, I, P]),
     "apn_composite_fwd": (I, [P, P, P, P, I, P, I, F, F, P, P, P, P, P, P, P]),
     "apn_composite_bwd": (I, [P, P, P, P, I, F, F, P, P, P, P, P, P, P, P, P]),
     "apn_adam_step_size": (F, [I, F, F, F]),

@@ -653,10 +653,16 @@ static TcBwdScratch tc_bwd_layout(char* base, int M, int N) {
 }
 extern "C" size_t apn_aggregate_tc_bwd_scratch_bytes(int M, int N) { return (M > 0 && N > 0) ? tc_bwd_layout(nullptr, M, N).total : 0; }
 
-extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_bwd,
-                                    const apn_agg_outputs* sv, const void* tape, const apn_agg_grads* g, void* scratch,
-                                    size_t scratch_bytes, apn_stream_t stream_) {
+// phase 0: the whole backward.  phase 1: everything up to the gradient of the point features (heads, density, dgrad chain,
+// d_feat = dP W0_feat) — canonical_feat.grad, the bulk of a data-parallel gradient exchange, is final when it returns.
+// phase 2: the rest (weight gradients of feat_net, the point-table weight gradient, the pose-embedding gradient) from the
+// SAME scratch buffer.  1 followed by 2 == 0.
+static int aggregate_bwd_tc_impl(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_bwd,
+                                 const apn_agg_outputs* sv, const void* tape, const apn_agg_grads* g, void* scratch,
+                                 size_t scratch_bytes, int phase, apn_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  APN_CHECK_ARG(phase >= 0 && phase <= 2, "phase must be 0, 1 or 2");
+  const bool do1 = phase != 2, do2 = phase != 1;
   APN_CHECK_ARG(in && w && packed_bwd && sv && tape && g, "null pointer");
   APN_CHECK_ARG(in->d_in == APN_PE_POS + APN_C || (in->d_in > APN_PE_POS + APN_C && in->d_in <= 256 && in->pose_emb),
                 "d_in must be 191, or 192..256 with a pose embedding");
@@ -675,15 +681,15 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
   // beside the serial chain (each fills less than half the GPU); large batches fill it and stay on one stream
   ApnSide* side = nullptr;
   if (M <= 32768 && apn_side_streams(&side)) return -2;
-  if (agg_rgbnet_bwd_launch(st, in, w, sv, g, b.d_v0, b.d_fv, b.d_h, side)) return -1;
-  const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 8);
-  APN_CUDA(cudaMemsetAsync(b.d_ptable, 0, (size_t)N * APN_C * sizeof(float) + 1024, st));   // table + hmax
-  tc_density_bwd_kernel<<<wblocks, 256, 0, st>>>(M, in->m_dev, in->interval, sv->h, sv->exp_d, w->density_w, g->d_alpha, b.d_h,
-                                                 g->d_density_w, g->d_density_b, b.hmax);
-  APN_LAUNCH_CHECK();
   const int n_tiles = apn_div_up(M, TC_SAMPLES);
   const int grid = n_tiles < APN_SM_COUNT ? n_tiles : APN_SM_COUNT;
-  {
+  if (do1) {
+    if (agg_rgbnet_bwd_launch(st, in, w, sv, g, b.d_v0, b.d_fv, b.d_h, side)) return -1;
+    const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 8);
+    APN_CUDA(cudaMemsetAsync(b.d_ptable, 0, (size_t)N * APN_C * sizeof(float) + 1024, st));   // table + hmax
+    tc_density_bwd_kernel<<<wblocks, 256, 0, st>>>(M, in->m_dev, in->interval, sv->h, sv->exp_d, w->density_w, g->d_alpha, b.d_h,
+                                                   g->d_density_w, g->d_density_b, b.hmax);
+    APN_LAUNCH_CHECK();
     TcBwdParams p;
     p.in = *in;
     p.d_h = b.d_h;
@@ -702,18 +708,23 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
     APN_LAUNCH_CHECK();
   }
   cudaStream_t sw = st;
-  if (side) {                                   // the point-table GEMMs only need tc_dgrad's d_ptable
+  if (side && phase == 0) {                     // the point-table GEMMs only need tc_dgrad's d_ptable
     APN_CUDA(cudaEventRecord(side->fork[2], st));
     APN_CUDA(cudaStreamWaitEvent(side->s[0], side->fork[2], 0));
     sw = side->s[0];
   }
   // feature columns of layer 0 through the per-point table: d_feat = dP W0_feat, dW0_feat += dP^T feat
-  if (g->d_feat)
+  if (do1 && g->d_feat)                         // phase 1 keeps it on the caller's stream: it is what the caller waits for
     APN_CHECK_ARG(gemm_dgrad_accum(sw, b.d_ptable, APN_C, w->w[0] + APN_PE_POS, in->d_in, g->d_feat, APN_C, N, APN_C, APN_C) == 0,
                   "dgrad point table");      // accumulates, like every other gradient of this entry point
-  APN_CHECK_ARG(gemm_wgrad(sw, b.d_ptable, APN_C, in->feat, APN_C, g->d_w[0] + APN_PE_POS, in->d_in, N, APN_C, APN_C) == 0,
-                "wgrad point table");
-  {
+  if (do2) {
+    if (side && phase == 2) {
+      APN_CUDA(cudaEventRecord(side->fork[2], st));
+      APN_CUDA(cudaStreamWaitEvent(side->s[0], side->fork[2], 0));
+      sw = side->s[0];
+    }
+    APN_CHECK_ARG(gemm_wgrad(sw, b.d_ptable, APN_C, in->feat, APN_C, g->d_w[0] + APN_PE_POS, in->d_in, N, APN_C, APN_C) == 0,
+                  "wgrad point table");
     TcWgradParams p;
     p.tape = (const uint8_t*)tape;
     p.dy = b.dy;
@@ -735,10 +746,24 @@ extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weig
     }
   }
   if (side) {                                   // join: everything this call launched is ordered before what follows on st
-    for (int i = 0; i < 2; ++i) {
+    // only the side streams THIS call forked (under stream capture a wait on an event of a stream that is not part of the
+    // capture is an error): phase 1 / 0 fork both in the heads backward, phase 2 only the point-table stream
+    for (int i = 0; i < (do1 ? 2 : 1); ++i) {
       APN_CUDA(cudaEventRecord(side->join[i], side->s[i]));
       APN_CUDA(cudaStreamWaitEvent(st, side->join[i], 0));
     }
   }
   return 0;
+}
+
+extern "C" int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_bwd,
+                                    const apn_agg_outputs* sv, const void* tape, const apn_agg_grads* g, void* scratch,
+                                    size_t scratch_bytes, apn_stream_t stream_) {
+  return aggregate_bwd_tc_impl(in, w, packed_bwd, sv, tape, g, scratch, scratch_bytes, 0, stream_);
+}
+
+extern "C" int apn_aggregate_bwd_tc_phase(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_bwd,
+                                          const apn_agg_outputs* sv, const void* tape, const apn_agg_grads* g, void* scratch,
+                                          size_t scratch_bytes, int phase, apn_stream_t stream_) {
+  return aggregate_bwd_tc_impl(in, w, packed_bwd, sv, tape, g, scratch, scratch_bytes, phase, stream_);
 }

@@ -778,6 +778,15 @@ class _AggregateTC(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_alpha, d_rgb, *_):
+        state = _AggregateTC.backward_prepare(ctx, d_alpha, d_rgb)
+        _AggregateTC.backward_launch(state, 0)
+        return state["result"]
+
+    @staticmethod
+    def backward_prepare(ctx, d_alpha, d_rgb):
+        """Allocates / binds every gradient buffer and builds the argument structs; `backward_launch(state, phase)` runs the
+        kernels: phase 0 = all, or 1 (through canonical_feat.grad) then 2 (the rest) for a data-parallel step that starts
+        exchanging the point-feature gradient while the weight gradients are still being computed (apn_aggregate_bwd_tc_phase)."""
         lib = _lib.load()
         c = ctx.c
         sv = ctx.saved_tensors
@@ -807,6 +816,7 @@ class _AggregateTC(torch.autograd.Function):
         d_all = [t.grad if dr else next(zi) for t, dr in zip([feat] + list(ws), direct)]
         d_feat = d_all[0] if need[4] else None
         d_ws = d_all[1:]
+        state = dict(M=M, keep=[])
         if M > 0:
             d_alpha = torch.zeros_like(alpha) if d_alpha is None else _f32(d_alpha)
             d_rgb = torch.zeros_like(rgb) if d_rgb is None else _f32(d_rgb)
@@ -826,11 +836,28 @@ class _AggregateTC(torch.autograd.Function):
             pk = ctx.packed.get_bwd(ws, ctx.d_in)
             sb = lib.apn_aggregate_tc_bwd_scratch_bytes(M, xyz.shape[0])
             scratch = _aligned_bytes(sb, dev)
-            with stage("feat_net_bwd"):
-                check(lib.apn_aggregate_bwd_tc(C.byref(a), C.byref(w), ptr(pk), C.byref(out), ptr(tape), C.byref(g),
-                                               ptr(scratch), sb, stream()), "apn_aggregate_bwd_tc")
-        return (None, None, d_xyz, d_ginv, (None if direct[0] else d_feat), d_pose,
-                *[dw if (need[6 + i] and not direct[1 + i]) else None for i, dw in enumerate(d_ws)])
+            state.update(a=a, w=w, pk=pk, out=out, g=g, tape=tape, scratch=scratch, sb=sb)
+            state["keep"] = [d_alpha, d_rgb, scratch, pk, tape, xyz, ginv, feat, pose_emb, ws, alpha, rgb, idw, h, exp_d, fv, v0,
+                             d_xyz, d_ginv, d_pose, d_all]
+        state["result"] = (None, None, d_xyz, d_ginv, (None if direct[0] else d_feat), d_pose,
+                           *[dw if (need[6 + i] and not direct[1 + i]) else None for i, dw in enumerate(d_ws)])
+        return state
+
+    @staticmethod
+    def backward_launch(state, phase: int):
+        if state["M"] <= 0:
+            return
+        lib = _lib.load()
+        with stage("feat_net_bwd"):
+            if phase == 0:
+                check(lib.apn_aggregate_bwd_tc(C.byref(state["a"]), C.byref(state["w"]), ptr(state["pk"]), C.byref(state["out"]),
+                                               ptr(state["tape"]), C.byref(state["g"]), ptr(state["scratch"]), state["sb"],
+                                               stream()), "apn_aggregate_bwd_tc")
+            else:
+                check(lib.apn_aggregate_bwd_tc_phase(C.byref(state["a"]), C.byref(state["w"]), ptr(state["pk"]),
+                                                     C.byref(state["out"]), ptr(state["tape"]), C.byref(state["g"]),
+                                                     ptr(state["scratch"]), state["sb"], int(phase), stream()),
+                      "apn_aggregate_bwd_tc_phase")
 
 
 def aggregate_tc_train(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence[torch.Tensor], packed: PackedDecoder):

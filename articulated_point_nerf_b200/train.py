@@ -112,19 +112,26 @@ class GradBucket:
 
     STATUS = 64
 
-    def __init__(self, optimizer: torch.optim.Optimizer, early=()):
+    def __init__(self, optimizer: torch.optim.Optimizer, early=(), first=()):
+        """`first` (a subset of `early`) goes to the very front: [first | rest of early | late | status]; `first_split` /
+        `split` are the two boundaries.  GraphedTrainStep puts canonical_feat there: its gradient is final before the
+        decoder's weight gradients are (apn_aggregate_bwd_tc_phase) and is ~90 % of the bytes."""
         params = [p for g in optimizer.param_groups for p in g['params'] if p.requires_grad]
         assert params, "no trainable parameters"
         early_ids = {id(p) for p in early}
-        params = [p for p in params if id(p) in early_ids] + [p for p in params if id(p) not in early_ids]
+        first_ids = {id(p) for p in first} & early_ids
+        params = ([p for p in params if id(p) in first_ids] + [p for p in params if id(p) in early_ids and id(p) not in first_ids]
+                  + [p for p in params if id(p) not in early_ids])
         dev = params[0].device
-        offs, total, split = [], 0, 0
+        offs, total, split, first_split = [], 0, 0, 0
         for p in params:
             offs.append(total)
             total += (p.numel() + 63) // 64 * 64          # 256-byte aligned slices
             if id(p) in early_ids:
                 split = total
-        self.split, self.total = split, total
+            if id(p) in first_ids:
+                first_split = total
+        self.split, self.total, self.first_split = split, total, first_split
         self.flat = torch.zeros(total + self.STATUS, device=dev, dtype=torch.float32)
         self.status = self.flat[total:total + self.STATUS]
         self.params = params
@@ -155,13 +162,19 @@ class GradBucket:
         self.flat.zero_()
 
     def all_reduce_avg(self, group=None, part=None):
-        """part None: the whole bucket (+ status); 0: the early slice; 1: the late slice + status."""
+        """part None: the whole bucket (+ status); 0: the early slice; 1: the late slice + status; "first": the front of the
+        early slice (canonical_feat); "early_rest": the remainder of the early slice."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             if not self.attached():
                 raise RuntimeError("GradBucket: a parameter's .grad no longer aliases the flat bucket (zero_grad(set_to_none="
                                    "True)?); call bucket.zero() instead of optimizer.zero_grad()")
-            buf = self.flat if part is None else (self.flat[:self.split] if part == 0 else self.flat[self.split:])
+            if part == "first":
+                buf = self.flat[:self.first_split]
+            elif part == "early_rest":
+                buf = self.flat[self.first_split:self.split]
+            else:
+                buf = self.flat if part is None else (self.flat[:self.split] if part == 0 else self.flat[self.split:])
             if buf.numel() == 0:
                 return
             avg = dist.get_backend(group) == "nccl"        # gloo has no AVG
@@ -190,9 +203,22 @@ def decoder_parameters(model):
     return ps
 
 
-def make_bucket(model, optimizer) -> "GradBucket":
-    """The flat gradient bucket with the decoder's parameters in the early slice (see GradBucket)."""
-    return GradBucket(optimizer, early=decoder_parameters(model))
+OVERLAP_MIN_FLOATS = 8 << 20       # 32 MiB of gradients
+
+
+def make_bucket(model, optimizer, overlap="auto") -> "GradBucket":
+    """The flat gradient bucket of a data-parallel run.  With `overlap` the decoder's parameters form the early slice with
+    canonical_feat at the front (see GradBucket): GraphedTrainStep then reduces them in three parts beside the backward.
+    "auto": only when the bucket is large (>= 32 MiB).  Measured on 8 x B200 (gpurun_out/r2l_*, r2m_*): at c4 (61 MB) the
+    overlapped exchange wins (2.30 vs 2.33 ms / step), at c2 (17.6 MB) one all-reduce after the backward does (1.01 vs 1.03 ms):
+    the persistent decoder kernels occupy every SM, so NCCL's blocks mostly wait for them anyway, and each extra graph
+    boundary costs ~10 us."""
+    if overlap == "auto":
+        n = sum(p.numel() for g in optimizer.param_groups for p in g['params'] if p.requires_grad)
+        overlap = n >= OVERLAP_MIN_FLOATS
+    if not overlap:
+        return GradBucket(optimizer)
+    return GradBucket(optimizer, early=decoder_parameters(model), first=[model.canonical_feat])
 
 
 def shard_rays(n_rays: int, rank: int, world: int):
@@ -294,9 +320,11 @@ class FusedTrainStep:
 
     # ---- stage B: decoder -> compositing -> loss -> backward of everything (gradients land in the bucket)
     @torch.no_grad()
-    def decode_and_backward(self, st, render_kwargs, target, warp_backward: bool = True):
+    def decode_and_backward(self, st, render_kwargs, target, warp_backward: bool = True, stop_after_feat: bool = False):
         """warp_backward=False stops after the decoder backward (every decoder gradient is then final in the bucket: a
-        data-parallel caller can start reducing them) and leaves the rest to `warp_backward(st)`."""
+        data-parallel caller can start reducing them) and leaves the rest to `warp_backward(st)`.
+        stop_after_feat=True stops even earlier, as soon as canonical_feat.grad is final (phase 1 of the decoder backward,
+        apn_aggregate_bwd_tc_phase); `decoder_backward_rest(st)` continues.  -> loss (the render loss in that case)."""
         from . import ops
         from .heads import poc_fre
         m = self.model
@@ -329,12 +357,29 @@ class FusedTrainStep:
         loss, d_rgb_m = ops.mse_loss_grad(rgb_m, target, WEIGHT_RENDER)
         # ---- backward, in autograd's order
         d_alpha, d_rgb = ops._Composite.backward(cc, d_rgb_m, None, None, None)[:2]
-        ga = ops._AggregateTC.backward(ca, d_alpha, d_rgb)
+        state = ops._AggregateTC.backward_prepare(ca, d_alpha, d_rgb)
+        st.update(agg_state=state, ws=ws, pose_emb=pose_emb, pose_graph=pose_graph, render_loss=loss)
+        if stop_after_feat:
+            ops._AggregateTC.backward_launch(state, 1)
+            return loss
+        ops._AggregateTC.backward_launch(state, 0)
+        return self._after_decoder(st, warp_backward)
+
+    @torch.no_grad()
+    def decoder_backward_rest(self, st, warp_backward: bool = True):
+        """Second part of a decoder backward that was stopped after canonical_feat.grad (stop_after_feat=True).  -> loss."""
+        from . import ops
+        ops._AggregateTC.backward_launch(st["agg_state"], 2)
+        return self._after_decoder(st, warp_backward)
+
+    def _after_decoder(self, st, warp_backward):
+        m = self.model
+        ga, ws, loss = st["agg_state"]["result"], st["ws"], st["render_loss"]
         self._accumulate([m.canonical_feat], ga[4:5])                      # None where the kernels wrote into .grad directly
         self._accumulate(list(ws), ga[6:])
-        if pose_graph:
+        if st["pose_graph"]:
             with torch.enable_grad():
-                pose_emb.backward(ga[5])                                    # accumulates into the bucket slices
+                st["pose_emb"].backward(ga[5])                              # accumulates into the bucket slices
         st["ga"] = ga
         if self.has_extra_terms():
             loss = self._regularise(st, ga[2], loss)
@@ -493,19 +538,38 @@ class GraphedTrainStep:
                                      float(self.rk['stepsize']) * float(m.voxel_size))
         return smp.n_candidates, smp.M
 
+    def reserve(self, batch):
+        """Grows the fixed workspace so that `batch` = (t, rays_o, rays_d, ...) fits (one synchronising sampling pass, like the
+        constructor's `calibrate`): call it for representative batches BEFORE training — e.g. the densest view — so that no
+        step overflows and gets skipped.  Capacities only grow; graphs are re-captured on the next step if they did."""
+        n_cand, n_kept = self._calibrate(batch)
+        stepdist = float(self.rk['stepsize']) * float(self.model.voxel_size)
+        worst = self.R * (int((float(self.rk['far']) - float(self.rk['near'])) / stepdist) + 3)
+        cand_cap = max(self.cand_cap, min(worst, max(4 * n_cand, 1 << 16)))
+        m_cap = max(self.m_cap, (max(2 * n_kept, 1 << 14) + 127) // 128 * 128)
+        if cand_cap != self.cand_cap or m_cap != self.m_cap:
+            self.flush_no_raise()
+            self.cand_cap, self.m_cap = cand_cap, m_cap
+            self.graphs, self.sampler = None, None
+
     def _body_a(self, split: bool = False):
-        """forward + decoder backward [+ LBS / pose backward unless `split`]."""
+        """forward + decoder backward [+ LBS / pose backward unless `split`: then only up to canonical_feat.grad]."""
         if self.packed is not None:
             for i, dst in enumerate((self.rays_o, self.rays_d, self.viewdirs, self.target)):
                 dst.copy_(self.packed[:, 3 * i:3 * i + 3])
         st = self.fused.forward_sampling(self.t, self.rk, self.sampler)
-        loss = self.fused.decode_and_backward(st, self.rk, self.target, warp_backward=not split)
-        self.loss.copy_(loss.reshape(1))
+        loss = self.fused.decode_and_backward(st, self.rk, self.target, warp_backward=not split, stop_after_feat=split)
         self._st = st
         if not split:
+            self.loss.copy_(loss.reshape(1))
             self._body_status()
 
     def _body_a2(self):
+        """rest of the decoder backward (weight gradients) + regularisers"""
+        loss = self.fused.decoder_backward_rest(self._st, warp_backward=False)
+        self.loss.copy_(loss.reshape(1))
+
+    def _body_a3(self):
         self.fused.warp_backward(self._st)
         self._body_status()
 
@@ -545,27 +609,31 @@ class GraphedTrainStep:
                 self.launches_per_step = _lib.launch_count() - n0     # our kernels in one replayed step
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        ga, ga2, gb = torch.cuda.CUDAGraph(), None, None
+        ga, ga2, ga3, gb = torch.cuda.CUDAGraph(), None, None, None
         with self.bucket.direct_accum():
             if self.world == 1:                      # no collective between the backward and Adam: ONE graph per step
                 with torch.cuda.graph(ga):
                     self._body_a()
                     self._body_b(launches)
             else:
-                # three graphs around the two all-reduces: [forward + decoder backward] | early slice reduces on the
-                # communication stream while [LBS + pose backward] runs | late slice + status reduce | [Adam]
+                # four graphs around the three all-reduces: [forward + decoder backward up to canonical_feat.grad] | that
+                # gradient (~90 % of the bytes) reduces on the communication stream while [decoder weight gradients +
+                # regularisers] run | the decoder's weight gradients reduce while [LBS + pose backward] runs | late slice +
+                # status reduce | [Adam]
                 split = self.bucket.split > 0
                 gb = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga):
                     self._body_a(split=split)
                 if split:
-                    ga2 = torch.cuda.CUDAGraph()
+                    ga2, ga3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                     with torch.cuda.graph(ga2, pool=ga.pool()):
                         self._body_a2()
+                    with torch.cuda.graph(ga3, pool=ga.pool()):
+                        self._body_a3()
                 with torch.cuda.graph(gb, pool=ga.pool()):
                     self._body_b(launches)
         packed.force = False
-        self.graphs = (ga, ga2, gb)
+        self.graphs = (ga, ga2, ga3, gb)
 
     # ------------------------------------------------------------------------------------------
     def _poll(self, wait: bool = False):
@@ -657,15 +725,22 @@ class GraphedTrainStep:
             if self.world > 1:
                 cur = torch.cuda.current_stream(self.dev)
                 if split:
-                    # the decoder's gradients (90 % of the bucket) are final: reduce them on the communication stream
-                    # while the LBS / pose backward runs here
+                    # canonical_feat.grad (90 % of the bucket) is final: reduce it on the communication stream while the
+                    # decoder's weight gradients are computed here; then those, beside the LBS / pose backward
                     self.comm_stream.wait_stream(cur)
-                    with torch.cuda.stream(self.comm_stream), _lib_stage("allreduce_early"):
-                        self.bucket.all_reduce_avg(part=0)
+                    with torch.cuda.stream(self.comm_stream), _lib_stage("allreduce_feat"):
+                        self.bucket.all_reduce_avg(part="first")
                     if self.graphs is not None:
                         self.graphs[1].replay()
                     else:
                         self._body_a2()
+                    self.comm_stream.wait_stream(cur)
+                    with torch.cuda.stream(self.comm_stream), _lib_stage("allreduce_early"):
+                        self.bucket.all_reduce_avg(part="early_rest")
+                    if self.graphs is not None:
+                        self.graphs[2].replay()
+                    else:
+                        self._body_a3()
                     with _lib_stage("allreduce_late"):
                         self.bucket.all_reduce_avg(part=1)
                     cur.wait_stream(self.comm_stream)
@@ -674,8 +749,8 @@ class GraphedTrainStep:
                         self.bucket.all_reduce_avg()
             if self.graphs is None:
                 self._body_b(launches)
-            elif self.graphs[2] is not None:
-                self.graphs[2].replay()
+            elif self.graphs[3] is not None:
+                self.graphs[3].replay()
         pin = self._pinned[slot]
         pin[:8].copy_(self.status[:8], non_blocking=True)
         pin[8:9].copy_(self.loss, non_blocking=True)

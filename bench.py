@@ -45,7 +45,9 @@ def make_batches(scene, mode, n_steps, rank, n_rand=N_RAND, repose=False):
     n_views = len(scene.HW)
     cache = {}
     for i in range(n_steps):
-        v = (i + 3 * rank) % n_views
+        # train: every rank draws ITS pixels from the SAME view / time step (one iteration of run.py:587-601 is one time step: the
+        # data-parallel batch is n_rand x ranks rays of it, sharded); render: a different view per rank (view-per-GPU)
+        v = (i % n_views) if mode == "train" else (i + 3 * rank) % n_views
         if v not in cache:
             cache[v] = [x.reshape(-1, 3).contiguous() for x in scene.rays(v)]
         ro, rd, vd = cache[v]
@@ -243,6 +245,7 @@ def main():
                     help="training workloads: the COMPLETE stage-2 iteration of run.py:615-694 — render loss + ARAP + weight TV + "
                          "sparsity + transformation regulariser + joint chamfer (configs/nerf/default.py:96-103) + the 2-D chamfer "
                          "term against synthetic mask pixels (5 views x 3000 pixels, 3000 random projected points)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one all-reduce of the whole bucket after the backward (A/B)")
     ap.add_argument("--train-path", default="graph", choices=["graph", "static", "dynamic"],
                     help="training step: CUDA graphs over the sync-free step (default), the same step launched eagerly, "
                          "or the dynamic step with its two host read-backs")
@@ -304,7 +307,7 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     from articulated_point_nerf_b200 import _lib
-    from articulated_point_nerf_b200.train import GradBucket, GraphedTrainStep, create_optimizer, train_step
+    from articulated_point_nerf_b200.train import GradBucket, GraphedTrainStep, create_optimizer, make_bucket, train_step
 
     model = build_model(scene, seed=0)
     oracle_state = model_state_for_oracle(model) if (rank == 0 and not args.no_cpu_baseline and world == 1) else None
@@ -322,7 +325,7 @@ def main():
     opt = bucket = None
     if mode == "train":
         opt = create_optimizer(model)
-        bucket = GradBucket(opt)
+        bucket = GradBucket(opt) if args.no_overlap else make_bucket(model, opt)          # large buckets: three slices reduced beside the backward
     decay = 0.1 ** (1.0 / (160 * 1000))
     counts = []
     gs = gs_stages = None
@@ -344,6 +347,13 @@ def main():
         cal = (t0, b0[:, 0:3].contiguous(), b0[:, 3:6].contiguous())
         gs = GraphedTrainStep(model, opt, bucket, len(b0), rk, calibrate=cal, use_graph=args.train_path == "graph",
                               packed_inputs=True, regularisers=reg, extra_loss=extra)
+        seen = set()
+        for t_h, b_h in host:                       # one sampling pass per distinct view: the workspace fits the densest one
+            key = float(t_h.reshape(-1)[0])
+            if key not in seen:
+                seen.add(key)
+                b_d = b_h.to(dev)
+                gs.reserve((t_h.to(dev), b_d[:, 0:3].contiguous(), b_d[:, 3:6].contiguous()))
 
     def run_step(t_dev, buf_dev, stepper=None):
         if mode == "train" and (stepper or gs) is not None:

@@ -318,6 +318,14 @@ size_t apn_aggregate_tc_bwd_scratch_bytes(int M, int N);
 int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_bwd,
                          const apn_agg_outputs* saved, const void* tape, const apn_agg_grads* g, void* scratch,
                          size_t scratch_bytes, apn_stream_t stream);
+/* The same backward in two parts for data-parallel training (not in the reference, which is single-GPU): phase 1 runs
+ * everything up to g->d_feat (heads, density, dgrad chain, d_xyz / d_ginv, d_feat = dP W0_feat) — the gradient of the point
+ * features, ~90 % of the bytes a rank exchanges, is final when it returns and its all-reduce can start; phase 2 adds the
+ * feat_net weight gradients, the point-table weight gradient and the pose-embedding gradient from the SAME scratch buffer
+ * (untouched in between).  phase 0 == apn_aggregate_bwd_tc.  Phase 1 followed by phase 2 gives the same results. */
+int apn_aggregate_bwd_tc_phase(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_bwd,
+                               const apn_agg_outputs* saved, const void* tape, const apn_agg_grads* g, void* scratch,
+                               size_t scratch_bytes, int phase, apn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4  Ray compositing.

@@ -20,7 +20,7 @@ def run(rank, world, port, mode, out_dir):
     model, scene = model_from_golden(g, fused_pose=True)
     model.decoder_train = "tc"
     opt = create_optimizer(model)
-    bucket = make_bucket(model, opt)
+    bucket = make_bucket(model, opt, overlap=True)
     R = len(g["rays_o"])
     a, b = shard_rays(R, rank, world)
     t = g["train"]["t"].cuda()

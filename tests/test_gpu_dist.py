@@ -32,7 +32,7 @@ def test_two_rank_gradient_equals_single_process_full_batch(golden_tiny, tmp_pat
     model, scene = model_from_golden(g, fused_pose=True)
     model.decoder_train = "tc"
     opt = create_optimizer(model)
-    bucket = make_bucket(model, opt)
+    bucket = make_bucket(model, opt, overlap=True)
     rk = dict(scene.render_kwargs(), rays_o=g["rays_o"].cuda(), rays_d=g["rays_d"].cuda(), viewdirs=g["viewdirs"].cuda())
     with bucket.direct_accum():
         loss = FusedTrainStep(model, opt, bucket).run(g["train"]["t"].cuda(), rk, g["train"]["target"].cuda())
