@@ -221,16 +221,55 @@ def save_checkpoint(path: str, model: TemporalPoints, optimizer=None, global_ste
                 'optimizer_state_dict': None if optimizer is None else optimizer.state_dict()}, path)
 
 
+class _ReferenceObject(torch.nn.Module):
+    """Stand-in for a reference class (module `lib.*`) met while unpickling a reference-written checkpoint when the
+    reference's code is not importable: pickle restores the instance state (an nn.Module's parameters, buffers, sub-modules
+    and plain attributes) without ever calling the class, so the tensors and attribute names survive."""
+
+    def forward(self, *a, **k):
+        raise RuntimeError("a reference object loaded without the reference's code cannot be called")
+
+
+def _reference_pickle_module():
+    """A pickle module whose Unpickler maps the reference's classes onto this package's: lib.tineuvox.TiNeuVox ->
+    heads.TiNeuVoxHeads (same attribute names for everything TemporalPoints reads: lib/temporalpoints.py:118-147,498-500),
+    lib.tineuvox.RGBNet -> heads.RGBNet, anything else under `lib.` -> _ReferenceObject.  Only used when the class cannot be
+    imported (a reader that has the reference on its path gets the real classes, as the reference's load_model does)."""
+    import importlib
+    import pickle
+    import types
+    from . import heads
+
+    class Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module == "lib" or module.startswith("lib."):
+                try:
+                    return getattr(importlib.import_module(module), name)
+                except Exception:
+                    if module == "lib.tineuvox" and name == "TiNeuVox":
+                        return heads.TiNeuVoxHeads
+                    if module == "lib.tineuvox" and name == "RGBNet":
+                        return heads.RGBNet
+                    return _ReferenceObject            # one module-level class: the loaded model stays picklable
+            return super().find_class(module, name)
+
+    return types.SimpleNamespace(Unpickler=Unpickler, load=lambda f, **kw: Unpickler(f, **kw).load(), __name__="pickle",
+                                 loads=pickle.loads, dumps=pickle.dumps, dump=pickle.dump, HIGHEST_PROTOCOL=pickle.HIGHEST_PROTOCOL)
+
+
 def load_checkpoint(path: str, tineuvox=None, device='cuda', strict: bool = False):
     """lib/utils.py:519-523 `load_model` for the point-cloud model: rebuilds `TemporalPoints(**model_kwargs)` and loads
-    the state dict (`strict=False`, as the reference does).  `tineuvox` supplies the frozen stage-1 heads the constructor
-    needs (the reference passes the loaded TiNeuVox; `heads.TiNeuVoxHeads` here).  -> (model, checkpoint dict)."""
-    ckpt = torch.load(path, map_location='cpu', weights_only=False)
+    the state dict (`strict=False`, as the reference does).  Reads checkpoints written by this package AND
+    `temporalpoints_last.tar` files written by the reference (run.py:813-819): their `model_kwargs['tineuvox']` is a pickled
+    lib.tineuvox.TiNeuVox, which is mapped onto heads.TiNeuVoxHeads when the reference's code is not importable.
+    `tineuvox` (optional) overrides the heads object.  -> (model, checkpoint dict)."""
+    ckpt = torch.load(path, map_location='cpu', weights_only=False, pickle_module=_reference_pickle_module())
     kw = dict(ckpt['model_kwargs'])
     if tineuvox is not None:            # default: the heads object pickled inside model_kwargs, as the reference does
         kw['tineuvox'] = tineuvox
     model = TemporalPoints(**kw)
     missing, unexpected = model.load_state_dict(ckpt['model_state_dict'], strict=strict)
+    ckpt['missing_keys'], ckpt['unexpected_keys'] = list(missing), list(unexpected)
     model = model.to(device)
     return model, ckpt
 

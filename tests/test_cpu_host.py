@@ -305,3 +305,99 @@ def test_ctypes_arities_match_the_header_prototypes():
         decls = [] if params in ("", "void") else params.split(",")
         for i, (d, a) in enumerate(zip(decls, _lib.SIGNATURES[name][1])):
             assert kind_c(d) == kinds_py.get(a, "ptr"), (name, i, d.strip(), a)
+
+
+def test_reference_written_checkpoint_loads_without_the_reference():
+    """`temporalpoints_last.tar` as run.py:813-819 writes it (oracle/make_golden_checkpoint.py ran the reference): model_kwargs
+    pickles a lib.tineuvox.TiNeuVox; here `lib` is not importable, the loader maps it onto heads.TiNeuVoxHeads.  Every
+    state-dict key of the reference model is present and loaded; save -> load round-trips; pcds/*.tar build a model."""
+    import sys
+    import tempfile
+    from articulated_point_nerf_b200 import heads
+    from articulated_point_nerf_b200.render import load_checkpoint, model_from_pcds, save_checkpoint
+    gd = os.path.join(ROOT, "tests", "golden")
+    model, ck = load_checkpoint(os.path.join(gd, "ref_mini_last.tar"), device="cpu")
+    ref = torch.load(os.path.join(gd, "ref_mini_render.pt"), weights_only=False)
+    assert ck["global_step"] == 1234 and not ck["missing_keys"] and not ck["unexpected_keys"]
+    assert isinstance(model.tineuvox, (heads.TiNeuVoxHeads,)) or type(model.tineuvox).__name__ == "TiNeuVox"
+    assert sorted(model.state_dict().keys()) == ref["state_keys"]
+    N = len(model.canonical_pcd)
+    assert 250 <= N <= 350 and model.weights.shape == (N, len(model.joints))
+    assert abs(float(model.tineuvox.act_shift) - float(torch.log(torch.tensor(1 / (1 - 1e-3) - 1)))) < 1e-6
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "temporalpoints_last.tar")
+        save_checkpoint(p, model, global_step=7)
+        m2, ck2 = load_checkpoint(p, device="cpu")
+        assert ck2["global_step"] == 7
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, m2.state_dict()[k]), k
+    m3 = model_from_pcds(os.path.join(gd, "ref_mini_pcds"), model.tineuvox, stepsize=0.5, fast_color_thres=1e-4)
+    assert torch.equal(m3.canonical_pcd, model.canonical_pcd) and torch.equal(m3.canonical_feat.detach(), torch.load(
+        os.path.join(gd, "ref_mini_pcds", "pcds", "canonical.tar"), weights_only=False)["feat"])
+
+
+class _CapsuleField:
+    """Analytic stand-in for the stage-1 voxel model behind export_point_cloud: density of a capsule around one segment, with
+    the two methods the reference calls on its TiNeuVox (lib/tineuvox.py:238-250, 253-372)."""
+    voxel_size = 0.05
+
+    def __init__(self):
+        self.xyz_min, self.xyz_max = torch.tensor([-1., -1., -1.]), torch.tensor([1., 1., 1.])
+        self.world_size = torch.tensor([24, 24, 24])
+        self.calls = 0
+
+    def get_grid_xyz(self, f):
+        ax = [torch.linspace(float(self.xyz_min[i]), float(self.xyz_max[i]), int(int(self.world_size[i]) * f)) for i in range(3)]
+        return torch.stack(torch.meshgrid(*ax, indexing="ij"), -1)
+
+    def _alpha(self, p):
+        a, b = torch.tensor([-0.5, 0., 0.]), torch.tensor([0.5, 0.1, 0.])
+        tt = ((p - a) @ (b - a) / (b - a).dot(b - a)).clamp(0, 1)
+        d = (p - (a + tt[:, None] * (b - a))).norm(dim=-1)
+        return torch.sigmoid((0.25 - d) * 40)
+
+    def get_grid_as_point_cloud(self, stepsize, time_sel, viewdir, threshold, sampling_freq, N_batch, alpha_xyz_only, grid_xyz=None):
+        self.calls += 1
+        g = self.get_grid_xyz(sampling_freq) if grid_xyz is None else grid_xyz
+        shape = g.shape[:-1]
+        alpha = self._alpha(g.reshape(-1, 3)).reshape(shape)
+        if alpha_xyz_only:
+            return None, None, None, None, None, None, g, alpha
+        pts = g.reshape(-1, 3)
+        return pts, alpha.reshape(-1), torch.rand(len(pts), 3), torch.rand(len(pts), 128), torch.rand(len(pts), 12), None, g, alpha
+
+
+def test_export_point_cloud_on_an_analytic_field(tmp_path):
+    """export.export_point_cloud (run.py:1081-1240): the frequency search ends near the requested point count, the volume clean-up
+    keeps one component without small holes, canonical.tar / skeleton.tar have the reference's keys and feed model_from_pcds."""
+    import numpy as np
+    from articulated_point_nerf_b200 import heads
+    from articulated_point_nerf_b200.export import export_point_cloud, preprocess_volume
+    from articulated_point_nerf_b200.render import CANONICAL_KEYS, SKELETON_KEYS, model_from_pcds
+    vol = np.zeros((20, 20, 20))
+    vol[2:12, 2:12, 2:12] = 1.0
+    vol[5:7, 5:7, 5:7] = 0.0                       # a small hole: filled
+    vol[15:18, 15:18, 15:18] = 1.0                 # a second, smaller component: dropped
+    m = preprocess_volume(vol, 0.5)
+    assert m[5, 5, 5] and not m[16, 16, 16] and m.sum() == 1000
+    field = _CapsuleField()
+
+    def skeleton(binary_volume, grid_xyz, bone_length):
+        pts = grid_xyz[binary_volume]
+        j = np.stack([pts[pts[:, 0].argmin()], pts.mean(0), pts[pts[:, 0].argmax()]]).astype(np.float32)
+        return {'skeleton_pcd': j, 'joints': j, 'root': j[0], 'bones': [[0, 1], [1, 2]], 'pcd': None, 'weights': None,
+                'binary_volume': binary_volume}
+
+    target = 3000
+    can = export_point_cloud(field, str(tmp_path), viewdir=[0., 0., -1.], stepsize=0.5, threshold=0.2, canonical_pcd_num=target,
+                             create_skeleton=skeleton)
+    assert set(CANONICAL_KEYS) <= set(can) and abs(len(can["pcd"]) - target) < 0.15 * target      # the lattice size is int(world_size * freq): counts move in steps
+    assert can['feat'].shape == (len(can['pcd']), 128) and can['alphas'].min() > 0.2
+    sk = torch.load(tmp_path / 'pcds' / 'skeleton.tar', weights_only=False)
+    assert set(SKELETON_KEYS) <= set(sk)
+    calls = field.calls
+    export_point_cloud(field, str(tmp_path), viewdir=[0., 0., -1.], stepsize=0.5, canonical_pcd_num=target, create_skeleton=skeleton)
+    assert field.calls == calls                    # existing exports are left alone (run.py:1087-1089)
+    tv = heads.TiNeuVoxHeads(can['xyz_min'].numpy(), can['xyz_max'].numpy(), num_voxels=16 ** 3, num_voxels_base=16 ** 3)
+    model = model_from_pcds(str(tmp_path), tv, stepsize=0.5, fast_color_thres=1e-4)
+    assert len(model.canonical_pcd) == len(can['pcd']) and len(model.joints) == 3

@@ -784,3 +784,21 @@ def test_graphed_step_with_regularisers_equals_fused_step(golden_tiny, use_graph
     for k in g0:
         tol = 1e-2 if k == "theta_weight" else 3 * RTOL
         assert rel_err(g1[k], g0[k]) < tol, k
+
+
+def test_reference_written_checkpoint_renders_like_the_reference():
+    """A `temporalpoints_last.tar` written by the reference (tests/golden/ref_mini_last.tar) loaded by render.load_checkpoint and
+    rendered on the B200 path: the reference's own output for the same rays within 1e-4."""
+    from articulated_point_nerf_b200.render import load_checkpoint
+    gd = os.path.join(ROOT, "tests", "golden")
+    model, _ = load_checkpoint(os.path.join(gd, "ref_mini_last.tar"), device="cuda")
+    model.forward_warp.fused_pose = False            # bit-compatible cloud (see conftest.model_from_golden)
+    ref = torch.load(os.path.join(gd, "ref_mini_render.pt"), weights_only=False)
+    rk = dict(ref["render_kwargs"], rays_o=ref["rays_o"].cuda(), rays_d=ref["rays_d"].cuda(), viewdirs=ref["viewdirs"].cuda())
+    for dec in ("tc", "fp32"):
+        model.decoder = dec
+        with torch.no_grad():
+            out = model(ref["t"].cuda(), render_depth=True, render_kwargs=rk)
+        assert rel_err(out["t_hat_pcd"], ref["t_hat_pcd"]) < 2e-6
+        assert rel_err(out["rgb_marched"], ref["rgb_marched"]) < RTOL, dec
+        assert rel_err(out["depth"], ref["depth"]) < RTOL, dec
