@@ -10,7 +10,7 @@
 // Row layout: MLP row 8*m + k is neighbour k of kept sample m.  x0 row = [PE(rel_c) 63 | feat 128 |
 // pose 0/64 | zero pad] with leading dimension ld0 = round_up(d_in, 4), i.e. the reference's own
 // column order so that torch-layout weights are consumed unchanged.
-#include "sgemm.cuh"
+#include "tgemm.cuh"
 
 #define AGG_C APN_C
 #define AGG_K APN_K
@@ -341,7 +341,7 @@ static int colsum(cudaStream_t st, const float* A, int lda, int rows, int N, flo
 // RGBNet backward (lib/tineuvox.py:77-88): d_rgb -> weight gradients of the three Linear layers and d_h (M,128) of
 // the rgb branch; shared by the fp32 and tensor-core backward paths
 int agg_rgbnet_bwd_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* sv,
-                          const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h, ApnSide* side) {
+                          const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h, ApnSide* side, bool tensor_cores) {
   const int M = in->M;
   const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 8);
   const int KV = AGG_C + APN_PE_VIEW;   // 155
@@ -356,16 +356,20 @@ int agg_rgbnet_bwd_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_m
     APN_CUDA(cudaEventRecord(side->fork[0], st));
     APN_CUDA(cudaStreamWaitEvent(s0, side->fork[0], 0));
   }
-  APN_CHECK_ARG(gemm_wgrad(s0, d_v0, AGG_V0, sv->fv, AGG_FV_LD, g->d_rgb_v0_w, KV, M, AGG_V0, KV, md) == 0, "wgrad v0");
+  // tensor_cores (the tensor-core training path): the same four products as 3xTF32 GEMMs (tgemm.cuh); the exact fp32 path
+  // keeps the CUDA-core SGEMMs
+  auto wgrad = tensor_cores ? tgemm_wgrad : gemm_wgrad;
+  auto dgrad = tensor_cores ? tgemm_dgrad : gemm_dgrad;
+  APN_CHECK_ARG(wgrad(s0, d_v0, AGG_V0, sv->fv, AGG_FV_LD, g->d_rgb_v0_w, KV, M, AGG_V0, KV, md) == 0, "wgrad v0");
   APN_CHECK_ARG(colsum(s0, d_v0, AGG_V0, M, AGG_V0, g->d_rgb_v0_b, md) == 0, "colsum v0");
-  APN_CHECK_ARG(gemm_dgrad(st, d_v0, AGG_V0, w->rgb_v0_w, KV, d_fv, AGG_FV_LD, M, KV, AGG_V0, nullptr, 0, 1.f, md) == 0, "dgrad v0");
+  APN_CHECK_ARG(dgrad(st, d_v0, AGG_V0, w->rgb_v0_w, KV, d_fv, AGG_FV_LD, M, KV, AGG_V0, nullptr, 0, 1.f, md) == 0, "dgrad v0");
   if (side) {
     APN_CUDA(cudaEventRecord(side->fork[1], st));
     APN_CUDA(cudaStreamWaitEvent(s1, side->fork[1], 0));
   }
-  APN_CHECK_ARG(gemm_wgrad(s1, d_fv, AGG_FV_LD, sv->h, AGG_C, g->d_rgb_feat_w, AGG_C, M, AGG_C, AGG_C, md) == 0, "wgrad rgb feat");
+  APN_CHECK_ARG(wgrad(s1, d_fv, AGG_FV_LD, sv->h, AGG_C, g->d_rgb_feat_w, AGG_C, M, AGG_C, AGG_C, md) == 0, "wgrad rgb feat");
   APN_CHECK_ARG(colsum(s1, d_fv, AGG_FV_LD, M, AGG_C, g->d_rgb_feat_b, md) == 0, "colsum rgb feat");
-  APN_CHECK_ARG(gemm_dgrad(st, d_fv, AGG_FV_LD, w->rgb_feat_w, AGG_C, d_h, AGG_C, M, AGG_C, AGG_C, nullptr, 0, 1.f, md) == 0, "dgrad rgb feat");
+  APN_CHECK_ARG(dgrad(st, d_fv, AGG_FV_LD, w->rgb_feat_w, AGG_C, d_h, AGG_C, M, AGG_C, AGG_C, nullptr, 0, 1.f, md) == 0, "dgrad rgb feat");
   return 0;
 }
 

@@ -28,7 +28,7 @@
 //              hi*hi + hi*lo + lo*hi are accumulated in fp32: fp32-class results (the parity mode).
 // PE chunk columns: [rel_c(3) sin(30) cos(30) 0] (the reference's own order).  A pose embedding (d_in = 255) is
 // constant over rows: W0[:,191:255] * pose is folded into the layer-0 bias by every CTA at start-up.
-#include "sgemm.cuh"
+#include "tgemm.cuh"
 #include "aggregate_tc.cuh"
 
 struct TcParams {
@@ -89,7 +89,7 @@ extern "C" int apn_aggregate_tc_point_table(const float* feat, const float* w0, 
   cudaStream_t st = (cudaStream_t)stream_;
   APN_CHECK_ARG(feat && w0 && ptable, "null pointer");
   APN_CHECK_ARG(d_in >= APN_PE_POS + APN_C && d_in <= 256 && N > 0, "bad sizes");
-  APN_CHECK_ARG(gemm_forward(st, feat, APN_C, w0 + APN_PE_POS, d_in, nullptr, ptable, APN_C, N, APN_C, APN_C, 1.f) == 0,
+  APN_CHECK_ARG(tgemm_forward(st, feat, APN_C, w0 + APN_PE_POS, d_in, nullptr, ptable, APN_C, N, APN_C, APN_C, 1.f) == 0,
                 "point table gemm");
   return 0;
 }

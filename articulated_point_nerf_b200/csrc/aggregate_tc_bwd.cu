@@ -11,7 +11,7 @@
 //                     layers stay in tensor memory (480 of 512 columns) until the CTA has consumed its tiles.
 // The feature columns of layer 0 go through the per-point table: dP (N x 128) is scattered here and turned
 // into d_feat = dP W0_feat and dW0_feat = dP^T feat by two exact fp32 GEMMs over the N points.
-#include "sgemm.cuh"
+#include "tgemm.cuh"
 #include "aggregate_tc.cuh"
 
 #define TCB_NCHUNKS 8          // W3^T (2), W2^T (2), W1^T (2), W0_pe^T (2): [n = in feature][k = out feature] tiles
@@ -684,7 +684,7 @@ static int aggregate_bwd_tc_impl(const apn_agg_inputs* in, const apn_mlp_weights
   const int n_tiles = apn_div_up(M, TC_SAMPLES);
   const int grid = n_tiles < APN_SM_COUNT ? n_tiles : APN_SM_COUNT;
   if (do1) {
-    if (agg_rgbnet_bwd_launch(st, in, w, sv, g, b.d_v0, b.d_fv, b.d_h, side)) return -1;
+    if (agg_rgbnet_bwd_launch(st, in, w, sv, g, b.d_v0, b.d_fv, b.d_h, side, true)) return -1;
     const int wblocks = min(apn_div_up(M, 8), APN_SM_COUNT * 8);
     APN_CUDA(cudaMemsetAsync(b.d_ptable, 0, (size_t)N * APN_C * sizeof(float) + 1024, st));   // table + hmax
     tc_density_bwd_kernel<<<wblocks, 256, 0, st>>>(M, in->m_dev, in->interval, sv->h, sv->exp_d, w->density_w, g->d_alpha, b.d_h,
@@ -715,7 +715,7 @@ static int aggregate_bwd_tc_impl(const apn_agg_inputs* in, const apn_mlp_weights
   }
   // feature columns of layer 0 through the per-point table: d_feat = dP W0_feat, dW0_feat += dP^T feat
   if (do1 && g->d_feat)                         // phase 1 keeps it on the caller's stream: it is what the caller waits for
-    APN_CHECK_ARG(gemm_dgrad_accum(sw, b.d_ptable, APN_C, w->w[0] + APN_PE_POS, in->d_in, g->d_feat, APN_C, N, APN_C, APN_C) == 0,
+    APN_CHECK_ARG(tgemm_dgrad_accum(sw, b.d_ptable, APN_C, w->w[0] + APN_PE_POS, in->d_in, g->d_feat, APN_C, N, APN_C, APN_C) == 0,
                   "dgrad point table");      // accumulates, like every other gradient of this entry point
   if (do2) {
     if (side && phase == 2) {
@@ -723,7 +723,7 @@ static int aggregate_bwd_tc_impl(const apn_agg_inputs* in, const apn_mlp_weights
       APN_CUDA(cudaStreamWaitEvent(side->s[0], side->fork[2], 0));
       sw = side->s[0];
     }
-    APN_CHECK_ARG(gemm_wgrad(sw, b.d_ptable, APN_C, in->feat, APN_C, g->d_w[0] + APN_PE_POS, in->d_in, N, APN_C, APN_C) == 0,
+    APN_CHECK_ARG(tgemm_wgrad(sw, b.d_ptable, APN_C, in->feat, APN_C, g->d_w[0] + APN_PE_POS, in->d_in, N, APN_C, APN_C) == 0,
                   "wgrad point table");
     TcWgradParams p;
     p.tape = (const uint8_t*)tape;

@@ -28,7 +28,7 @@ int apn_side_streams(ApnSide** out);
 // aggregate.cu: RGBNet backward: weight gradients + d_h (M,128) of the rgb branch.  With `side`, the weight-gradient
 // GEMMs run on the side streams (forked from `st`) and are NOT joined: the caller joins side->join[*] before it returns.
 int agg_rgbnet_bwd_launch(cudaStream_t st, const apn_agg_inputs* in, const apn_mlp_weights* w, const apn_agg_outputs* sv,
-                          const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h, ApnSide* side = nullptr);
+                          const apn_agg_grads* g, float* d_v0, float* d_fv, float* d_h, ApnSide* side = nullptr, bool tensor_cores = false);
 
 #define APN_CHECK_ARG(cond, msg)                                   \
   do {                                                             \
