@@ -320,6 +320,8 @@ def main():
         model.decoder = args.decoder
     model.decoder_train = args.decoder_train
     host = [pack_host(b, pin=True) for b in make_batches(scene, mode, n_steps, rank, repose=repose)]
+    n_views = len(scene.HW)
+    views = [(i + 3 * rank) % n_views for i in range(n_steps)]        # render: the view of step i (as make_batches picks it)
     rk = scene.render_kwargs()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     opt = bucket = None
@@ -355,10 +357,18 @@ def main():
                 b_d = b_h.to(dev)
                 gs.reserve((t_h.to(dev), b_d[:, 0:3].contiguous(), b_d[:, 3:6].contiguous()))
 
-    def run_step(t_dev, buf_dev, stepper=None):
+    def run_step(t_dev, buf_dev, stepper=None, view=None):
         if mode == "train" and (stepper or gs) is not None:
             return (stepper or gs).step_packed(t_dev, buf_dev, decay)       # counts arrive later (gs.history)
-        t, ro, rd, vd, tgt = unpack_dev(t_dev, buf_dev)
+        if view is not None:
+            # render, end to end: the frame's rays come from the CAMERA (K, c2w: ~100 bytes, kernel arguments) in one launch
+            # on the device (apn_rays_of_a_view) — what render.render_viewpoints does — instead of 36 bytes per pixel of H2D
+            from articulated_point_nerf_b200 import ops as _ops
+            t, tgt = t_dev, None
+            ro, rd, vd = _ops.rays_of_a_view(scene.cfg.H, scene.cfg.W, scene.Ks[view], scene.poses[view], dev,
+                                             inverse_y=scene.cfg.inverse_y)
+        else:
+            t, ro, rd, vd, tgt = unpack_dev(t_dev, buf_dev)
         kw = dict(rk, rays_o=ro, rays_d=rd, viewdirs=vd)
         if mode == "train":
             out = train_step(model, opt, bucket, t, kw, tgt, decay_factor=decay, regularisers=reg, extra_loss=extra)
@@ -390,11 +400,14 @@ def main():
             stepper = gs_stages
         on_host = e2e and (gs is not None)     # the graphed step takes the pinned host buffers directly (one H2D copy each)
         for i in range(args.warmup):
+            cam = views[i] if (e2e and mode == "render") else None
             if on_host:
                 t_d, b_d = host[i]
+            elif cam is not None:
+                t_d, b_d = host[i][0].to(dev, non_blocking=True), None
             else:
                 t_d, b_d = (host[i][0].to(dev, non_blocking=True), host[i][1].to(dev, non_blocking=True)) if e2e else dev_in[i]
-            o = run_step(t_d, b_d, stepper)
+            o = run_step(t_d, b_d, stepper, view=cam)
             if e2e:
                 (o.item() if mode == "train" else o.cpu())
         for st_ in (gs, gs_stages):
@@ -422,13 +435,16 @@ def main():
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
+            cam = views[i] if (e2e and mode == "render") else None
             if on_host:
                 t_d, b_d = host[i]
+            elif cam is not None:
+                t_d, b_d = host[i][0].to(dev, non_blocking=True), None     # the pose (time or rot_params); the camera goes by value
             elif e2e:
                 t_d, b_d = host[i][0].to(dev, non_blocking=True), host[i][1].to(dev, non_blocking=True)
             else:
                 t_d, b_d = dev_in[i]
-            o = run_step(t_d, b_d, stepper)
+            o = run_step(t_d, b_d, stepper, view=cam)
             if lagged:
                 if pending_read is not None:
                     pending_read()
@@ -478,7 +494,8 @@ def main():
     rays_per_step = len(host[0][1])
     value = rays_per_step * world * args.steps / (total_ms * 1e-3)
     e2e_val = rays_per_step * world * args.steps / (e2e_ms * 1e-3)
-    h2d = host[0][1].numel() * 4 + 4
+    # train: the packed (R, 12) batch + t.  render: the pose (t or rot_params) + the camera (K 3x3, c2w 3x4 as kernel arguments)
+    h2d = (host[0][1].numel() * 4 + 4) if mode == "train" else (host[0][0].numel() * 4 + (9 + 12) * 4)
     d2h = 4 if mode == "train" else rays_per_step * 3 * 4
 
     # roofline of the dominant kernel group: the decoder (feat_net + heads; fwd [+ bwd]) — the only dense contraction
