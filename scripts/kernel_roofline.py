@@ -74,6 +74,12 @@ def main():
         _lib.check(lib.apn_lbs_fwd(P(raw_w), P(theta), 1e-6, None, P(bone_T), P(xyz), P(gt), N, J, P(xyz_out), P(ginv), P(w_out),
                                    None, P(bbox), S()), "lbs_fwd")
     rec("lbs_fwd", N * (4 * J + 12 + 12 + 36 + 4 * J) + 64 * J, lbs_fwd, "raw weights in, xyz in/out, 3x3 inverse out, merged weights out")
+
+    def lbs_fwd_render():          # w_out = NULL: what a no-grad render launches (SURVEY.md §8(d)'s byte count)
+        _lib.check(lib.apn_lbs_fwd(P(raw_w), P(theta), 1e-6, None, P(bone_T), P(xyz), P(gt), N, J, P(xyz_out), P(ginv), None,
+                                   None, P(bbox), S()), "lbs_fwd")
+    rec("lbs_fwd_render", N * (4 * J + 12 + 12 + 36) + 64 * J, lbs_fwd_render,
+        "SURVEY 8(d): raw weights in, xyz in/out, 3x3 inverse out (merged weights not stored)")
     d_xyz = torch.randn(N, 3, device=dev, generator=g)
     d_ginv = torch.randn(N, 9, device=dev, generator=g)
     d_raw = torch.empty(N, J, device=dev)
