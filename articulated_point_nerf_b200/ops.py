@@ -872,6 +872,11 @@ def aggregate_tc_train(c: AggConst, xyz, ginv, feat, pose_emb, weights: Sequence
 # --------------------------------------------------------------------------------------
 # K4: compositing
 # --------------------------------------------------------------------------------------
+# measurement hook (bench.py): a list here makes every compositing forward also return, per ray, how many samples the walk
+# visited before the early stop (T < 1e-3) — the samples the kernel actually read; appended as (R,) int32 device tensors
+RECORD_VISITED = None
+
+
 class _Composite(torch.autograd.Function):
     """pre-mask + Alphas2Weights + post-mask + segment_coo (lib/temporalpoints.py:611-677)."""
 
@@ -889,7 +894,9 @@ class _Composite(torch.autograd.Function):
         extra_m = _empty((R, n_extra), dev) if n_extra else None
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         T_save = _empty((M,), dev) if need_grad else None
-        n_used = _empty((R,), dev, torch.int32) if need_grad else None
+        n_used = _empty((R,), dev, torch.int32) if (need_grad or RECORD_VISITED is not None) else None
+        if RECORD_VISITED is not None:
+            RECORD_VISITED.append(n_used)
         with stage("Alphas2Weights"):
             check(lib.apn_composite_fwd(ptr(alpha), ptr(rgb), ptr(step_id) if want_depth else None, ptr(extra), n_extra,
                                         ptr(ray_start), R, float(thres), float(bg), ptr(rgb_m), ptr(last), ptr(depth),

@@ -540,6 +540,21 @@ def main():
            "Alphas2Weights": 2 * (M_avg * 24 + R_st * 24),          # main + direct branch
            "Alphas2Weights_bwd": M_avg * 40 + R_st * 24,
            "adam": 28 * sum(p.numel() for p in model.parameters() if p.requires_grad)}
+    visited_note = None
+    if mode == "render":
+        # the compositing forward stops LOADING a ray's samples at the early stop (T < 1e-3): count the samples the walk
+        # actually visits (one extra, untimed frame with ops.RECORD_VISITED) and charge only those
+        from articulated_point_nerf_b200 import ops as _ops
+        _ops.RECORD_VISITED = []
+        t_d, b_d = host[n_steps - 1][0].to(dev), host[n_steps - 1][1].to(dev)
+        run_step(t_d, b_d)
+        torch.cuda.synchronize()
+        visited = sum(int(v.sum().item()) for v in _ops.RECORD_VISITED)            # main + direct branch
+        _ops.RECORD_VISITED = None
+        M_last = counts[-1].get("M", 0) if counts else 0
+        alg["Alphas2Weights"] = visited * 24 + 2 * R_st * 24
+        visited_note = (f"bytes of the samples the walk visits before the early stop: {visited} of {2 * M_last} (main + direct branch) "
+                        f"on the last frame")
     hbm_peak = peaks.get("hbm_gbs", 6500.0)
     hbm_stages = {}
     for name, (n, ms) in stage_tot.items():
@@ -547,10 +562,8 @@ def main():
             gbs = alg[name] * args.steps / (ms * 1e-3) / 1e9
             hbm_stages[name] = {"algorithmic_bytes_per_step": int(alg[name]), "achieved_gbs": round(gbs, 1),
                                 "frac": round(gbs / hbm_peak, 4)}
-            if name == "Alphas2Weights" and mode != "train":
-                # the forward walk stops loading a ray's samples at the early stop (T < 1e-3): the algorithmic figure counts
-                # every kept sample, the kernel never touches those behind the stop, so the fraction can exceed 1
-                hbm_stages[name]["note"] = "bytes counted for all kept samples; samples behind a ray's early stop are never read"
+            if name == "Alphas2Weights" and visited_note:
+                hbm_stages[name]["note"] = visited_note
     if args.stages and rank == 0:
         for name, (n, ms) in sorted(stage_tot.items(), key=lambda kv: -kv[1][1]):
             print(f"  stage {name:22s} calls {n:4d}  total {ms:9.3f} ms  avg {ms / n:8.4f} ms", file=sys.stderr)
