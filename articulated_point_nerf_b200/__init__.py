@@ -12,5 +12,6 @@ from .temporalpoints import NoPointsException, TemporalPoints          # noqa: F
 from .render import (PoseCache, load_checkpoint, model_from_pcds,      # noqa: F401
                      render_repose, render_viewpoints, save_checkpoint,
                      save_pcds)
+from .export import export_point_cloud                                 # noqa: F401
 
 __version__ = "0.1.0"
