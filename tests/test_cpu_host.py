@@ -401,3 +401,24 @@ def test_export_point_cloud_on_an_analytic_field(tmp_path):
     tv = heads.TiNeuVoxHeads(can['xyz_min'].numpy(), can['xyz_max'].numpy(), num_voxels=16 ** 3, num_voxels_base=16 ** 3)
     model = model_from_pcds(str(tmp_path), tv, stepsize=0.5, fast_color_thres=1e-4)
     assert len(model.canonical_pcd) == len(can['pcd']) and len(model.joints) == 3
+
+
+def test_nvtx_ranges_are_callable_without_a_tool():
+    """apn_range_push / apn_range_pop (nvtx3, header-only): without an attached profiler the calls are no-ops that must not
+    fail; `_lib.stage` emits them when APN_NVTX / _lib.nvtx(True) is on, named after the reference's profiler ranges."""
+    from articulated_point_nerf_b200 import _lib
+    lib = _lib.load()
+    assert isinstance(lib.apn_range_push(b"sample_ray+knn+knn-post"), int)
+    assert isinstance(lib.apn_range_pop(), int)
+    ref_names = {"transform_net", "calc_rec_abs_T", "weighted_G_tw", "sample_ray", "knn", "knn-post", "feat_net", "densitynet", "rgbnet",
+                 "poc_fre", "forward_warp", "pre-mask", "Alphas2Weights", "post-mask", "segment_coo"}   # lib/temporalpoints.py:421-653, pointwarper.py:217-241
+    used = set()
+    for v in _lib.NVTX_NAMES.values():
+        used |= set(v.decode().split("+"))
+    assert ref_names <= used | {"grid_build"}, ref_names - used
+    _lib.nvtx(True)
+    try:
+        with _lib.stage("forward_warp"):
+            pass
+    finally:
+        _lib.nvtx(False)
