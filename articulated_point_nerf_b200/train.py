@@ -289,11 +289,23 @@ class FusedTrainStep:
 
     # ---- stage A: pose -> LBS -> grid -> ray samples + exact 8-NN
     @torch.no_grad()
-    def forward_sampling(self, t, render_kwargs, sampler=None):
+    def refresh_decoder_state(self):
+        """Re-derives the decoder's packed state on the CURRENT stream: forward and backward weight tiles + the per-point
+        layer-0 table (ops.PackedDecoder).  None of it depends on the pose, so GraphedTrainStep runs it on a side stream
+        beside the pose -> LBS -> grid -> k-NN chain; the decoder's own `get` calls then find the caches fresh."""
+        from . import ops
+        m = self.model
+        ws = [ops._f32(w) for w in m._mlp_weights()]
+        d_in = ops.PE_POS + ops.FEAT_DIM + int(m.pose_embedding_dim)
+        m._packed_decoder.get(ws, d_in, ops._f32(m.canonical_feat))
+        m._packed_decoder.get_bwd(ws, d_in)
+
+    def forward_sampling(self, t, render_kwargs, sampler=None, zero_bucket: bool = True):
         from . import ops
         m, fw = self.model, self.model.forward_warp
         dev = m.joints.device
-        self.bucket.zero()
+        if zero_bucket:
+            self.bucket.zero()
         t_embed = ops.time_embed(t, m.time_poc)
         wb = fw._mlp_params()
         cp = _Ctx((False, False, m.joints.requires_grad, *[w.requires_grad for w in wb]))
@@ -469,6 +481,13 @@ class GraphedTrainStep:
         graph B   Adam
     Per step the host copies the inputs into the static buffers, writes ~30 step sizes, and launches two graphs.
 
+    Branches inside the graph (captured fork / join on a side stream; they also run, the same way, in the eager mode):
+      * the decoder's derived state (weight tiles, per-point table) and the bucket memset do not depend on the pose: they
+        run beside the pose -> LBS -> grid -> k-NN chain, whose kernels leave most SMs idle, and join before the decoder;
+      * with one rank the optimiser is split: every parameter whose gradient is final after the decoder backward
+        (canonical_feat, the MLPs: ~99 % of the bytes) is updated beside the LBS / pose backward (one 8-CTA cluster + a
+        small grid), the skinning weights / joints / pose network after it.
+
     Overflow: if a batch yields more samples than the workspace holds, the kernels truncate, raise a flag that travels with
     the bucket through the all-reduce (so every rank sees it) and Adam skips the update on the device.  The host notices
     on a later call (it polls, it never waits), enlarges the workspace, re-captures and raises WorkspaceOverflow; `flush()`
@@ -521,6 +540,9 @@ class GraphedTrainStep:
         self.status = bucket.status
         self.skip_word = self.status[:1]          # non-zero (on any rank, after the all-reduce) => Adam skips
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self._side = torch.cuda.Stream(device=dev)            # branch of the step (decoder state; early Adam part)
+        self.branches = True                                   # False: everything on one stream (A/B measurements, tests)
+        self._adam_early, self._adam_late, self._ss_perm = [], [], []
         self._pinned = [torch.zeros(9, dtype=torch.float32).pin_memory() for _ in range(self.RING)]   # status[0:8] | loss
         self._pinned_ss = None
         self.step_sizes = None
@@ -552,17 +574,49 @@ class GraphedTrainStep:
             self.cand_cap, self.m_cap = cand_cap, m_cap
             self.graphs, self.sampler = None, None
 
-    def _body_a(self, split: bool = False):
-        """forward + decoder backward [+ LBS / pose backward unless `split`: then only up to canonical_feat.grad]."""
+    def _body_a(self, split: bool = False, adam_skip=False):
+        """forward + decoder backward [+ LBS / pose backward unless `split`: then only up to canonical_feat.grad].
+        `adam_skip` (one rank only): None / a device word = also run the optimiser, its early part beside the LBS / pose
+        backward; False = no optimiser launch here."""
+        cur = torch.cuda.current_stream(self.dev)
         if self.packed is not None:
             for i, dst in enumerate((self.rays_o, self.rays_d, self.viewdirs, self.target)):
                 dst.copy_(self.packed[:, 3 * i:3 * i + 3])
-        st = self.fused.forward_sampling(self.t, self.rk, self.sampler)
-        loss = self.fused.decode_and_backward(st, self.rk, self.target, warp_backward=not split, stop_after_feat=split)
+        packed = self.model._packed_decoder
+        force = packed.force
+        if self.branches:
+            # branch 1: bucket memset + decoder state, beside the pose -> LBS -> grid -> k-NN chain
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self.bucket.zero()
+                self.fused.refresh_decoder_state()
+            packed.force = False               # the decoder's own look-ups hit the caches refreshed above
+        try:
+            st = self.fused.forward_sampling(self.t, self.rk, self.sampler, zero_bucket=not self.branches)
+            if self.branches:
+                cur.wait_stream(self._side)
+            self._body_status()               # flags are final after sampling; the bucket (and its status words) is zeroed
+            inline_adam = adam_skip is not False and not split
+            loss = self.fused.decode_and_backward(st, self.rk, self.target, warp_backward=not split and not inline_adam,
+                                                  stop_after_feat=split)
+        finally:
+            packed.force = force
         self._st = st
-        if not split:
-            self.loss.copy_(loss.reshape(1))
-            self._body_status()
+        if split:
+            return
+        self.loss.copy_(loss.reshape(1))
+        if inline_adam:
+            # branch 2: every gradient but those of the warp is final
+            if self.branches and self._adam_early:
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    self._launch_adam(self._adam_early, adam_skip)
+                self.fused.warp_backward(st)
+                self._launch_adam(self._adam_late, adam_skip)
+                cur.wait_stream(self._side)
+            else:
+                self.fused.warp_backward(st)
+                self._body_b(adam_skip)
 
     def _body_a2(self):
         """rest of the decoder backward (weight gradients) + regularisers"""
@@ -571,23 +625,49 @@ class GraphedTrainStep:
 
     def _body_a3(self):
         self.fused.warp_backward(self._st)
-        self._body_status()
 
     def _body_status(self):
         self.status[:1].copy_(self.sampler.counts[2:3])            # int flags -> float status word (0.0 = clean)
         self.status[1:6].copy_(self.sampler.counts[0:5])           # counts, for the host's bookkeeping
 
-    def _body_b(self, launches, skip=None):
-        off = 0
+    def _launch_adam(self, parts, skip=None):
+        for cls, ap, off in parts:
+            ap.launch_dev(self.step_sizes[off:off + ap.n], self.skip_word if skip is None else skip, *cls)
+
+    def _body_b(self, skip=None):
+        self._launch_adam(self._adam_early, skip)
+        self._launch_adam(self._adam_late, skip)
+
+    def _plan_adam(self, launches):
+        """Splits every (betas, eps) class of the optimiser's launch plan into the parameters the warp backward writes
+        (skinning weights, theta_weight, joints, pose network: `late`) and the rest (`early`), as two descriptor tables;
+        `_ss_perm[k]` = index into the plan-ordered step sizes of the k-th slot of the device step-size vector
+        ([class 0 early | class 0 late | class 1 early | ...]).  With more than one rank Adam follows the all-reduce in
+        one piece: everything is `late`."""
+        from . import ops
+        m = self.model
+        late_ptrs = {p.data_ptr() for p in [m.weights, m.theta_weight, m.joints, *m.forward_warp.parameters()]}
+        self._adam_early, self._adam_late, self._ss_perm = [], [], []
+        base = 0
         for cls, ap, sizes in launches:
-            ap.launch_dev(self.step_sizes[off:off + len(sizes)], self.skip_word if skip is None else skip, *cls)
-            off += len(sizes)
+            idx_e = [i for i, e in enumerate(ap.keep) if e[0].data_ptr() not in late_ptrs] if self.world == 1 else []
+            if not idx_e or len(idx_e) == ap.n:
+                self._adam_late.append((cls, ap, len(self._ss_perm)))
+                self._ss_perm += [base + i for i in range(ap.n)]
+            else:
+                idx_l = [i for i in range(ap.n) if i not in set(idx_e)]
+                self._adam_early.append((cls, ops.AdamPlan([ap.keep[i] for i in idx_e]), len(self._ss_perm)))
+                self._ss_perm += [base + i for i in idx_e]
+                self._adam_late.append((cls, ops.AdamPlan([ap.keep[i] for i in idx_l]), len(self._ss_perm)))
+                self._ss_perm += [base + i for i in idx_l]
+            base += len(sizes)
 
     def _capture(self, launches):
         from . import ops
         dev = self.dev
         self.sampler = ops.StaticSampler(self.R, self.cand_cap, self.m_cap, dev)
-        n = sum(len(sz) for _, _, sz in launches)
+        self._plan_adam(launches)
+        n = len(self._ss_perm)
         self.step_sizes = torch.zeros(max(n, 1), device=dev)
         self._pinned_ss = [torch.zeros(max(n, 1), dtype=torch.float32).pin_memory() for _ in range(self.RING)]
         self._ss_events = [None] * self.RING
@@ -595,6 +675,7 @@ class GraphedTrainStep:
         self.graphs = None
         if not self.use_graph:
             return
+        one = self.world == 1
         # warm-up on a side stream (allocator + lazy module state), then capture
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -604,17 +685,19 @@ class GraphedTrainStep:
             from . import _lib
             for _ in range(2):
                 n0 = _lib.launch_count()
-                self._body_a()
-                self._body_b(launches, skip=warm_skip)
+                if one:
+                    self._body_a(adam_skip=warm_skip)
+                else:
+                    self._body_a()
+                    self._body_b(warm_skip)
                 self.launches_per_step = _lib.launch_count() - n0     # our kernels in one replayed step
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         ga, ga2, ga3, gb = torch.cuda.CUDAGraph(), None, None, None
         with self.bucket.direct_accum():
-            if self.world == 1:                      # no collective between the backward and Adam: ONE graph per step
+            if one:                                  # no collective between the backward and Adam: ONE graph per step
                 with torch.cuda.graph(ga):
-                    self._body_a()
-                    self._body_b(launches)
+                    self._body_a(adam_skip=None)
             else:
                 # four graphs around the three all-reduces: [forward + decoder backward up to canonical_feat.grad] | that
                 # gradient (~90 % of the bytes) reduces on the communication stream while [decoder weight gradients +
@@ -631,7 +714,7 @@ class GraphedTrainStep:
                     with torch.cuda.graph(ga3, pool=ga.pool()):
                         self._body_a3()
                 with torch.cuda.graph(gb, pool=ga.pool()):
-                    self._body_b(launches)
+                    self._body_b()
         packed.force = False
         self.graphs = (ga, ga2, ga3, gb)
 
@@ -707,11 +790,9 @@ class GraphedTrainStep:
         if self._ss_events[slot] is not None:
             self._ss_events[slot].synchronize()                 # the copy that last used this pinned slot has run
         ss = self._pinned_ss[slot]
-        off = 0
-        for _, _, sizes in launches:
-            for v in sizes:
-                ss[off] = v
-                off += 1
+        flat_sizes = [v for _, _, sizes in launches for v in sizes]
+        for k, src in enumerate(self._ss_perm):
+            ss[k] = flat_sizes[src]
         self.step_sizes.copy_(ss, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -721,7 +802,7 @@ class GraphedTrainStep:
             if self.graphs is not None:
                 self.graphs[0].replay()
             else:
-                self._body_a(split=split)
+                self._body_a(split=split, adam_skip=None if self.world == 1 else False)
             if self.world > 1:
                 cur = torch.cuda.current_stream(self.dev)
                 if split:
@@ -748,7 +829,8 @@ class GraphedTrainStep:
                     with _lib_stage("allreduce"):
                         self.bucket.all_reduce_avg()
             if self.graphs is None:
-                self._body_b(launches)
+                if self.world > 1:
+                    self._body_b()
             elif self.graphs[3] is not None:
                 self.graphs[3].replay()
         pin = self._pinned[slot]

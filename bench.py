@@ -246,6 +246,8 @@ def main():
                          "sparsity + transformation regulariser + joint chamfer (configs/nerf/default.py:96-103) + the 2-D chamfer "
                          "term against synthetic mask pixels (5 views x 3000 pixels, 3000 random projected points)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: one all-reduce of the whole bucket after the backward (A/B)")
+    ap.add_argument("--no-branches", action="store_true",
+                    help="graphed step on ONE stream: no side-stream branch for the decoder state / the early Adam part (A/B)")
     ap.add_argument("--train-path", default="graph", choices=["graph", "static", "dynamic"],
                     help="training step: CUDA graphs over the sync-free step (default), the same step launched eagerly, "
                          "or the dynamic step with its two host read-backs")
@@ -349,6 +351,8 @@ def main():
         cal = (t0, b0[:, 0:3].contiguous(), b0[:, 3:6].contiguous())
         gs = GraphedTrainStep(model, opt, bucket, len(b0), rk, calibrate=cal, use_graph=args.train_path == "graph",
                               packed_inputs=True, regularisers=reg, extra_loss=extra)
+        gs.branches = not args.no_branches
+        base_cfg["graph_branches"] = gs.branches
         seen = set()
         for t_h, b_h in host:                       # one sampling pass per distinct view: the workspace fits the densest one
             key = float(t_h.reshape(-1)[0])
@@ -397,6 +401,7 @@ def main():
             if gs_stages is None:
                 gs_stages = GraphedTrainStep(model, opt, bucket, gs.R, rk, cand_cap=gs.cand_cap, m_cap=gs.m_cap, use_graph=False,
                                              packed_inputs=True, regularisers=reg, extra_loss=extra)
+                gs_stages.branches = False       # stage brackets time a serial chain
             stepper = gs_stages
         on_host = e2e and (gs is not None)     # the graphed step takes the pinned host buffers directly (one H2D copy each)
         for i in range(args.warmup):

@@ -508,8 +508,8 @@ def test_static_sampler_equals_dynamic_sampler(golden_tiny):
         assert c3[2] & 2 and c3[0] == dyn.n_candidates // 2 and c3[3] == dyn.n_candidates
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_graphed_train_step_equals_fused_step(golden_any, use_graph):
+@pytest.mark.parametrize("use_graph,branches", [(False, True), (True, True), (True, False)])
+def test_graphed_train_step_equals_fused_step(golden_any, use_graph, branches):
     """train.GraphedTrainStep (no host read-back; CUDA graphs) against the dynamic fused step.
 
     Training is chaotic at the level of float-atomics noise (two runs of the SAME dynamic path differ by ~1e-3 in some
@@ -557,6 +557,7 @@ def test_graphed_train_step_equals_fused_step(golden_any, use_graph):
     t, ro, rd, vd, tgt = batches[0]
     l_dyn = float(train_step(m_dyn, o_dyn, b_dyn, t, dict(rk0, rays_o=ro, rays_d=rd, viewdirs=vd), tgt, decay_factor=decay))
     gs = GraphedTrainStep(m_gr, o_gr, b_gr, R, rk0, calibrate=batches[0], use_graph=use_graph)
+    gs.branches = branches      # side-stream branches (decoder state beside the sampling chain, early Adam part beside the warp backward)
     l_gr = float(gs.step(t, ro, rd, vd, tgt, decay_factor=decay))
     gs.flush()
     assert gs.last_counts["M"] == m_dyn.last_counts["M"] > 0
