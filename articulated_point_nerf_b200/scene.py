@@ -328,7 +328,8 @@ def make_scene(cfg: SceneConfig | str) -> Scene:
 # model construction on top of a scene (tests, bench.py, smoke())
 # --------------------------------------------------------------------------------------
 def build_model(scene: Scene, seed: int = 0, density_bias: float = 7.0, theta_std: float = 0.2,
-                density_gain: float = 300.0, rgb_gain: float = 8.0, device=None, density_std: float = 2.5):
+                density_gain: float = 300.0, rgb_gain: float = 8.0, device=None, density_std: float = 2.5,
+                no_view_dir: bool = False, frozen_view_dir=None):
     """TemporalPoints on random-init weights of the reference's architecture, with the output heads rescaled so
     that kept-sample alpha spreads over (0,1) and early ray termination triggers."""
     from .heads import TiNeuVoxHeads, poc_fre
@@ -336,13 +337,14 @@ def build_model(scene: Scene, seed: int = 0, density_bias: float = 7.0, theta_st
     torch.manual_seed(seed)
     cfg = scene.cfg
     heads = TiNeuVoxHeads(scene.xyz_min.numpy(), scene.xyz_max.numpy(), num_voxels=cfg.num_voxels,
-                          num_voxels_base=cfg.num_voxels, alpha_init=1e-3, net_width=128, no_view_dir=False)
+                          num_voxels_base=cfg.num_voxels, alpha_init=1e-3, net_width=128, no_view_dir=no_view_dir)
     model = TemporalPoints(
         canonical_pcd=scene.canonical_pcd.clone(), canonical_alpha=scene.canonical_alpha.clone(),
         canonical_feat=scene.canonical_feat.clone(), canonical_rgbs=scene.canonical_rgbs.clone(),
         skeleton_pcd=scene.skeleton_pcd.clone(), joints=scene.joints.clone(), bones=scene.bones,
         xyz_min=scene.xyz_min.numpy(), xyz_max=scene.xyz_max.numpy(), tineuvox=heads, stepsize=cfg.stepsize,
-        voxel_size=scene.voxel_size, fast_color_thres=cfg.fast_color_thres, pose_embedding_dim=cfg.pose_embedding_dim)
+        voxel_size=scene.voxel_size, fast_color_thres=cfg.fast_color_thres, pose_embedding_dim=cfg.pose_embedding_dim,
+        frozen_view_dir=frozen_view_dir)
     with torch.no_grad():
         # density head calibrated on a CPU sample of decoder features (random points, offsets of the size the k-NN
         # produces): pre-activation density + act_shift ~ N(0, density_std) => median kept-sample alpha ~ 0.3, a spread over

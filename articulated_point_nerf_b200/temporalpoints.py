@@ -137,13 +137,20 @@ class TemporalPoints(torch.nn.Module):
                         m.reset_parameters()
         self.view_poc = tineuvox.view_poc
         self.pos_poc = tineuvox.pos_poc
+        # no_view_dir (lib/tineuvox.py:112-113, lib/temporalpoints.py:504-505): the RGB head has no view columns.  The
+        # kernels always form [f | PE(view)]: the head's first view layer is handed over with 27 zero columns appended
+        # (_mlp_weights), which contributes exact zeros — the product of finite PE values with 0.
         self.no_view_dir = tineuvox.no_view_dir
-        assert not self.no_view_dir, "configs keep no_view_dir=False (configs/nerf/default.py:67); the fused heads expect view PE"
-        assert frozen_view_dir is None, "frozen_view_dir is not used by the shipped configs"
         self.tineuvox = tineuvox
         self.register_buffer('xyz_max_canonical', canonical_pcd.max(dim=0)[0])
         self.register_buffer('xyz_min_canonical', canonical_pcd.min(dim=0)[0])
-        self.frozen_view_dir = frozen_view_dir
+        # frozen_view_dir (run.py:480-481 `use_global_view_dir`; lib/temporalpoints.py:155-159,507-508): one view direction
+        # for every ray.  `viewdirs_emb` is the reference's (frozen) parameter — state-dict surface; the kernels embed the
+        # direction themselves, so every ray simply carries `frozen_view_dir` (_view_dirs).
+        self.frozen_view_dir = None if frozen_view_dir is None else torch.as_tensor(frozen_view_dir).float().reshape(3)
+        if self.frozen_view_dir is not None:
+            self.viewdirs_emb = torch.nn.Parameter(poc_fre(self.frozen_view_dir, self.view_poc)[None], requires_grad=False)
+        object.__setattr__(self, '_frozen_dirs', None)
         self.pose_embedding_dim = pose_embedding_dim
         if pose_embedding_dim > 0:
             d = len(joints) * (3 * len(self.pos_poc) * 2 + 3)
@@ -367,9 +374,24 @@ class TemporalPoints(torch.nn.Module):
         ws = []
         for l in lin:
             ws += [l.weight, l.bias]
+        v0_w = rn.views_linears[0].weight
+        if self.no_view_dir:       # (64, 128) -> (64, 155): zero view columns; differentiable, so autograd slices the gradient back
+            v0_w = torch.cat([v0_w, v0_w.new_zeros(v0_w.shape[0], ops.FEAT_DIM + ops.PE_VIEW - v0_w.shape[1])], dim=1)
         ws += [self.densitynet.weight, self.densitynet.bias, rn.feature_linears.weight, rn.feature_linears.bias,
-               rn.views_linears[0].weight, rn.views_linears[0].bias, rn.views_linears[2].weight, rn.views_linears[2].bias]
+               v0_w, rn.views_linears[0].bias, rn.views_linears[2].weight, rn.views_linears[2].bias]
         return ws
+
+    def _view_dirs(self, viewdirs, n_rays: int):
+        """The (R,3) view directions the heads see: the caller's, or `frozen_view_dir` for every ray
+        (lib/temporalpoints.py:507-512)."""
+        if self.frozen_view_dir is None:
+            return ops._f32(viewdirs)
+        dev = self.joints.device
+        fd = self._frozen_dirs
+        if fd is None or fd.shape[0] < n_rays or fd.device != dev:
+            fd = self.frozen_view_dir.to(dev).reshape(1, 3).expand(max(int(n_rays), 1), 3).contiguous()
+            object.__setattr__(self, '_frozen_dirs', fd)
+        return fd[:n_rays]
 
     def _merge_rules_i32(self):
         """int32 copy of flat_merging_rules for the kernel, None while the rules are the identity
@@ -478,7 +500,7 @@ class TemporalPoints(torch.nn.Module):
                 'alphainv_last': None, 'grid': None, 'joints': joints, 'bones': bones,
             }
         interval = float(render_kwargs['stepsize']) * float(self.tineuvox.voxel_size_ratio)
-        c = ops.AggConst(pts=smp.pts, nn_idx=smp.nn_idx, ray_id=smp.ray_id, viewdirs=ops._f32(viewdirs),
+        c = ops.AggConst(pts=smp.pts, nn_idx=smp.nn_idx, ray_id=smp.ray_id, viewdirs=self._view_dirs(viewdirs, R),
                          canonical_alpha=self.canonical_alpha.detach(), canonical_rgbs=self.canonical_rgbs.detach(),
                          direct_eps=self.direct_eps.detach(), mean_min_distance=self._mmd_float, eps=float(self.eps),
                          act_shift=float(self.tineuvox.act_shift), interval=interval, direct=True)

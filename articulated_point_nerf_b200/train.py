@@ -272,7 +272,9 @@ class FusedTrainStep:
     @staticmethod
     def eligible(model) -> bool:
         fw = model.forward_warp
-        return (model.decoder_train == "tc" and model.joints.is_cuda and fw.fused_pose
+        # no_view_dir models hand the kernels a zero-padded COPY of the first view layer (TemporalPoints._mlp_weights): its
+        # gradient has to flow back through that padding, which only the autograd path does
+        return (model.decoder_train == "tc" and model.joints.is_cuda and fw.fused_pose and not model.no_view_dir
                 and fw._fused_tables(model.joints.device) is not None)
 
     @torch.no_grad()
@@ -342,8 +344,7 @@ class FusedTrainStep:
         m = self.model
         dev = m.joints.device
         cp, cl, wb, xyz, ginv, bone_Ts, smp, R = (st[k] for k in ("cp", "cl", "wb", "xyz", "ginv", "bone_Ts", "smp", "R"))
-        viewdirs = render_kwargs['viewdirs']
-        c = ops.AggConst(pts=smp.pts, nn_idx=smp.nn_idx, ray_id=smp.ray_id, viewdirs=ops._f32(viewdirs),
+        c = ops.AggConst(pts=smp.pts, nn_idx=smp.nn_idx, ray_id=smp.ray_id, viewdirs=m._view_dirs(render_kwargs['viewdirs'], R),
                          canonical_alpha=m.canonical_alpha, canonical_rgbs=m.canonical_rgbs, direct_eps=m.direct_eps,
                          mean_min_distance=m._mmd_float, eps=float(m.eps), act_shift=float(m.tineuvox.act_shift),
                          interval=float(render_kwargs['stepsize']) * float(m.tineuvox.voxel_size_ratio), direct=False,

@@ -176,7 +176,11 @@ class OraclePath:
 
     def __init__(self, state: Dict[str, torch.Tensor], canonical_pcd, bones, *, stepsize, voxel_size,
                  fast_color_thres, act_shift, voxel_size_ratio, mean_min_distance=None, eps=1e-6,
-                 neighbours=8, pose_embedding_dim=0, feat_depth=4, posbase_pe=10, viewbase_pe=4, timebase_pe=8):
+                 neighbours=8, pose_embedding_dim=0, feat_depth=4, posbase_pe=10, viewbase_pe=4, timebase_pe=8,
+                 no_view_dir=False, frozen_view_dir=False):
+        """no_view_dir: the RGB head takes no view columns (lib/tineuvox.py:112-113, lib/temporalpoints.py:504-505);
+        frozen_view_dir: every ray uses state['viewdirs_emb'] (lib/temporalpoints.py:157-159,507-508)."""
+        self.no_view_dir, self.frozen_view_dir = no_view_dir, frozen_view_dir
         self.s = state
         self.pcd = canonical_pcd.to(F32)
         self.bones = bones
@@ -273,7 +277,7 @@ class OraclePath:
     def rgbnet(self, h, views):
         s = self.s
         f = Fnn.linear(h, s['rgbnet.feature_linears.weight'], s['rgbnet.feature_linears.bias'])
-        x = torch.cat([f, views], -1)
+        x = f if views is None else torch.cat([f, views], -1)           # lib/tineuvox.py:80-88
         x = torch.relu(Fnn.linear(x, s['rgbnet.views_linears.0.weight'], s['rgbnet.views_linears.0.bias']))
         return Fnn.linear(x, s['rgbnet.views_linears.2.weight'], s['rgbnet.views_linears.2.bias'])
 
@@ -356,7 +360,12 @@ class OraclePath:
         density = Fnn.linear(h, s['densitynet.weight'], s['densitynet.bias']).squeeze(-1)
         interval = stepsize * self.vsr
         alpha = Raw2Alpha.apply(density.flatten(), self.act_shift, interval)
-        vemb = poc_fre(viewdirs, self.view_poc)[ray_id]
+        if self.no_view_dir:                                             # lib/temporalpoints.py:504-512
+            vemb = None
+        elif self.frozen_view_dir:
+            vemb = s['viewdirs_emb'].expand(len(ray_id), -1)
+        else:
+            vemb = poc_fre(viewdirs, self.view_poc)[ray_id]
         rgb = torch.sigmoid(self.rgbnet(h, vemb))
         lbs_w = None
         if merged_weights is not None:

@@ -160,7 +160,8 @@ def import_reference():
     return _REF
 
 
-def build_reference_model(scene, seed=0, density_bias=7.0, theta_std=0.2, density_gain=300.0, rgb_gain=8.0):
+def build_reference_model(scene, seed=0, density_bias=7.0, theta_std=0.2, density_gain=300.0, rgb_gain=8.0,
+                          no_view_dir=False, frozen_view_dir=None):
     """Instantiate the reference TiNeuVox (tiny grid; only its heads are used) and TemporalPoints."""
     tineuvox, temporalpoints, _, _ = import_reference()
     torch.manual_seed(seed)
@@ -168,14 +169,14 @@ def build_reference_model(scene, seed=0, density_bias=7.0, theta_std=0.2, densit
     cfg = scene.cfg
     tv = tineuvox.TiNeuVox(scene.xyz_min.numpy(), scene.xyz_max.numpy(), num_voxels=16 ** 3, num_voxels_base=16 ** 3,
                            alpha_init=1e-3, fast_color_thres=cfg.fast_color_thres, voxel_dim=4, defor_depth=3,
-                           net_width=128, no_view_dir=False)
+                           net_width=128, no_view_dir=no_view_dir)
     model = temporalpoints.TemporalPoints(
         canonical_pcd=scene.canonical_pcd.clone(), canonical_alpha=scene.canonical_alpha.clone(),
         canonical_feat=scene.canonical_feat.clone(), canonical_rgbs=scene.canonical_rgbs.clone(),
         skeleton_pcd=scene.skeleton_pcd.clone(), joints=scene.joints.clone(), bones=scene.bones,
         xyz_min=scene.xyz_min.numpy(), xyz_max=scene.xyz_max.numpy(), tineuvox=tv,
         stepsize=cfg.stepsize, voxel_size=scene.voxel_size, fast_color_thres=cfg.fast_color_thres,
-        pose_embedding_dim=cfg.pose_embedding_dim)
+        pose_embedding_dim=cfg.pose_embedding_dim, frozen_view_dir=frozen_view_dir)
     with torch.no_grad():
         model.densitynet.bias.fill_(density_bias)
         model.densitynet.weight.mul_(density_gain)      # spread alpha over (0, 1)

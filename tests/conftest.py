@@ -61,7 +61,7 @@ def golden_any(request):
     return load_golden(request.param)
 
 
-def oracle_from_golden(g):
+def oracle_from_golden(g, **oracle_kw):
     from oracle.path_oracle import OraclePath
     from articulated_point_nerf_b200.scene import CONFIGS
     cfg = CONFIGS[g["config"]]
@@ -69,7 +69,17 @@ def oracle_from_golden(g):
     return OraclePath(state, g["canonical_pcd"], g["bones"], stepsize=cfg.stepsize, voxel_size=g["voxel_size"],
                       fast_color_thres=cfg.fast_color_thres, act_shift=g["act_shift"],
                       voxel_size_ratio=g["voxel_size_ratio"], mean_min_distance=g["mean_min_distance"],
-                      pose_embedding_dim=cfg.pose_embedding_dim), cfg
+                      pose_embedding_dim=cfg.pose_embedding_dim, **oracle_kw), cfg
+
+
+@pytest.fixture(scope="session")
+def golden_frozen_view(golden_tiny):
+    """The reference run with `frozen_view_dir` (oracle/make_golden_viewdir.py): ref_tiny.pt's scene, rays and parameters
+    plus the frozen `viewdirs_emb`; -> (golden dict in ref_tiny's layout with the extra state, the variant's record)."""
+    v = load_golden("tiny_viewdir")
+    g = dict(golden_tiny)
+    g["state_dict"] = dict(golden_tiny["state_dict"], **v["frozen"]["state_dict_extra"])
+    return g, dict(v["frozen"], t=v["t"], target=v["target"])
 
 
 @pytest.fixture(scope="session")
@@ -82,7 +92,7 @@ def oracle_any(golden_any):
     return oracle_from_golden(golden_any)
 
 
-def model_from_golden(g, device="cuda", fused_pose=False):
+def model_from_golden(g, device="cuda", fused_pose=False, **model_kw):
     """The product's TemporalPoints carrying the reference's parameters from the golden file.
 
     fused_pose=False: the pose chain runs through the PyTorch ops, whose bone transforms are bit-compatible with the
@@ -93,7 +103,7 @@ def model_from_golden(g, device="cuda", fused_pose=False):
     pose kernel (fused_pose=True) results are therefore compared with the oracle evaluated on the kernel's own cloud."""
     from articulated_point_nerf_b200.scene import make_scene, build_model
     scene = make_scene(g["config"])
-    model = build_model(scene)
+    model = build_model(scene, **model_kw)
     missing, unexpected = model.load_state_dict(g["state_dict"], strict=False)
     assert not unexpected, unexpected
     assert all(k.startswith("tineuvox.") for k in missing), missing

@@ -853,3 +853,91 @@ def test_c2_sized_step_matches_the_reference(decoder_train):
             assert rel_err(got.double().sum(0), ref["colsum"]) < 10 * tol, k
         else:
             assert rel_err(got, ref) < tol, k
+
+
+@pytest.mark.parametrize("decoder_train", ["fp32", "tc"])
+def test_frozen_view_dir_matches_the_reference(golden_frozen_view, decoder_train):
+    """`frozen_view_dir` (run.py:480-481 use_global_view_dir; lib/temporalpoints.py:157-159,507-508) against the reference's own
+    run (oracle/make_golden_viewdir.py): render outputs, the training loss, the gradients behind the RGB head; the graphed
+    step serves the variant too (the frozen direction replaces the batch's view directions)."""
+    g, v = golden_frozen_view
+    model, scene = model_from_golden(g, frozen_view_dir=v["frozen_view_dir"])
+    assert torch.equal(model.viewdirs_emb.cpu(), v["state_dict_extra"]["viewdirs_emb"])
+    model.decoder_train = decoder_train
+    rk = _rk(scene, g)
+    rk["viewdirs"] = torch.randn_like(rk["viewdirs"])              # must be ignored
+    with torch.no_grad():
+        out = model(v["t"].cuda(), render_depth=True, render_kwargs=rk)
+    assert model.last_counts["M"] == len(g["render"]["agg"]["ray_id"])
+    for k in ["t_hat_pcd", "rgb_marched", "alphainv_last", "depth", "rgb_marched_direct"]:
+        assert rel_err(out[k], v["render"][k]) < RTOL, k
+    assert rel_err(out["rgb_marched"], g["render"]["out"]["rgb_marched"]) > 1e-3     # the variant does change the image
+    model.zero_grad(set_to_none=True)
+    res = model(v["t"].cuda(), False, rk, render_pcd_direct=False)
+    loss = F.mse_loss(res["rgb_marched"], v["target"].cuda()) * 200.0
+    loss.backward()
+    assert abs(float(loss) - float(v["train"]["loss"])) < 1e-4 * float(v["train"]["loss"])
+    named = dict(model.named_parameters())
+    tol = RTOL if decoder_train == "fp32" else TC_TOL
+    for k, ref in v["train"]["grads"].items():
+        assert rel_err(named[k].grad, ref) < tol, k
+    if decoder_train == "tc":
+        from articulated_point_nerf_b200.train import GradBucket, GraphedTrainStep, create_optimizer
+        m2, _ = model_from_golden(g, fused_pose=True, frozen_view_dir=v["frozen_view_dir"])
+        m2.decoder_train = "tc"
+        opt = create_optimizer(m2)
+        gs = GraphedTrainStep(m2, opt, GradBucket(opt), len(g["rays_o"]), scene.render_kwargs(),
+                              calibrate=(v["t"].cuda(), rk["rays_o"], rk["rays_d"]))
+        l2 = float(gs.step(v["t"].cuda(), rk["rays_o"], rk["rays_d"], rk["viewdirs"], v["target"].cuda()))
+        gs.flush()
+        assert abs(l2 - float(v["train"]["loss"])) < 2e-3 * float(v["train"]["loss"])    # fused pose kernel: its own cloud (bbox-face samples)
+
+
+def test_no_view_dir_head(golden_tiny):
+    """`no_view_dir=True`: the RGB head without view columns, served by the same kernels through zero view columns; render
+    and gradients (autograd path: the fused step is not eligible) against the CPU oracle carrying the same parameters."""
+    from articulated_point_nerf_b200.train import FusedTrainStep
+    g = golden_tiny
+    sd = dict(g["state_dict"])
+    sd["rgbnet.views_linears.0.weight"] = sd["rgbnet.views_linears.0.weight"][:, :128].clone()
+    g2 = dict(g, state_dict=sd)
+    model, scene = model_from_golden(g2, no_view_dir=True)
+    assert tuple(model.rgbnet.views_linears[0].weight.shape) == (64, 128)
+    assert not FusedTrainStep.eligible(model)
+    from conftest import oracle_from_golden
+    orc, cfg = oracle_from_golden(g2, no_view_dir=True)
+    rk = _rk(scene, g)
+    for dec in ("tc", "fp32"):
+        model.decoder = dec
+        with torch.no_grad():
+            warped = model.warp(g["render"]["t"].cuda())
+            out = model(g["render"]["t"].cuda(), render_depth=True, render_kwargs=rk, warped=warped)
+            ref = orc.forward(g["render"]["t"], None, rays_o=g["rays_o"], rays_d=g["rays_d"], viewdirs=g["viewdirs"], near=cfg.near,
+                              far=cfg.far, stepsize=cfg.stepsize, bg=cfg.bg, cloud=warped["xyz"].cpu(),
+                              ginv3=warped["ginv"].cpu().view(-1, 3, 3))
+        for k in ["rgb_marched", "alphainv_last", "depth"]:
+            assert rel_err(out[k], ref[k]) < RTOL, (dec, k)
+    for p in orc.s.values():
+        if p.is_floating_point():
+            p.requires_grad_(True)
+    target = g["train"]["target"]
+    for dec in ("fp32", "tc"):
+        model.decoder_train = dec
+        model.zero_grad(set_to_none=True)
+        warped = model.warp(g["train"]["t"].cuda())
+        res = model(g["train"]["t"].cuda(), False, rk, render_pcd_direct=False, warped=warped)
+        loss = F.mse_loss(res["rgb_marched"], target.cuda()) * 200.0
+        loss.backward()
+        for p in orc.s.values():
+            p.grad = None
+        o = orc.forward(g["train"]["t"], None, rays_o=g["rays_o"], rays_d=g["rays_d"], viewdirs=g["viewdirs"], near=cfg.near,
+                        far=cfg.far, stepsize=cfg.stepsize, bg=cfg.bg, cloud=warped["xyz"].detach().cpu(),
+                        ginv3=warped["ginv"].detach().cpu().view(-1, 3, 3))
+        lo = F.mse_loss(o["rgb_marched"], target) * 200.0
+        lo.backward()
+        assert abs(float(loss) - float(lo)) < 1e-4 * float(lo)
+        named = dict(model.named_parameters())
+        for k in ("rgbnet.views_linears.0.weight", "rgbnet.views_linears.0.bias", "rgbnet.feature_linears.weight",
+                  "rgbnet.views_linears.2.weight", "densitynet.weight", "feat_net.4.weight"):
+            assert named[k].grad.shape == orc.s[k].grad.shape, k
+            assert rel_err(named[k].grad, orc.s[k].grad) < (RTOL if dec == "fp32" else TC_TOL), (dec, k)

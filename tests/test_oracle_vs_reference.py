@@ -122,3 +122,45 @@ def test_batch_chamfer_loss_matches_reference():
         loss.backward()
         assert _rel(loss.detach(), c["loss"]) < 1e-6
         assert _rel(p1.grad, c["grad1"]) < 1e-6
+
+
+def test_frozen_view_dir_matches_reference(golden_frozen_view):
+    """`frozen_view_dir` (run.py:480-481, lib/temporalpoints.py:157-159,507-508): the reference's own run with one global
+    view direction; render outputs, loss and the gradients behind the RGB head."""
+    from conftest import oracle_from_golden
+    g, v = golden_frozen_view
+    orc, cfg = oracle_from_golden(g, frozen_view_dir=True)
+    with torch.no_grad():
+        out = _call(orc, cfg, g, t=v["t"])
+    for k in ["rgb_marched", "alphainv_last", "depth", "rgb_marched_direct", "t_hat_pcd"]:
+        assert _rel(out[k], v["render"][k]) < RTOL, k
+    assert _rel(out["rgb_marched"], g["render"]["out"]["rgb_marched"]) > 1e-3      # the variant does change the image
+    for k, p in orc.s.items():
+        if p.is_floating_point() and k != "viewdirs_emb":
+            p.requires_grad_(True)
+    out = _call(orc, cfg, g, t=v["t"])
+    loss = F.mse_loss(out["rgb_marched"], v["target"]) * 200.0
+    loss.backward()
+    assert abs(loss.item() - v["train"]["loss"].item()) < 1e-4 * v["train"]["loss"].item()
+    for k, ref in v["train"]["grads"].items():
+        assert _rel(orc.s[k].grad, ref) < RTOL, k
+
+
+def test_no_view_dir_head_is_the_view_head_with_zero_view_columns(golden_tiny):
+    """`no_view_dir=True` has no reference behaviour on this path (lib/temporalpoints.py:504-514 raises UnboundLocalError,
+    oracle/make_golden_viewdir.py); the evident intent — rgbnet(h) without view columns — equals the view head with its
+    view columns zeroed, which is how the kernels serve it."""
+    from conftest import oracle_from_golden
+    g = dict(golden_tiny)
+    w = g["state_dict"]["rgbnet.views_linears.0.weight"]
+    g["state_dict"] = dict(g["state_dict"], **{"rgbnet.views_linears.0.weight": w[:, :128].clone()})
+    o_nv, cfg = oracle_from_golden(g, no_view_dir=True)
+    wz = w.clone()
+    wz[:, 128:] = 0
+    g["state_dict"] = dict(g["state_dict"], **{"rgbnet.views_linears.0.weight": wz})
+    o_z, _ = oracle_from_golden(g)
+    with torch.no_grad():
+        a = _call(o_nv, cfg, g, t=g["render"]["t"])
+        b = _call(o_z, cfg, g, t=g["render"]["t"])
+    assert _rel(a["rgb_marched"], b["rgb_marched"]) < 1e-6
+    assert _rel(a["rgb_marched"], g["render"]["out"]["rgb_marched"]) > 1e-3
