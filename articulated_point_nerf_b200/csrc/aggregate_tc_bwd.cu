@@ -661,8 +661,13 @@ static int aggregate_bwd_tc_impl(const apn_agg_inputs* in, const apn_mlp_weights
                                  const apn_agg_outputs* sv, const void* tape, const apn_agg_grads* g, void* scratch,
                                  size_t scratch_bytes, int phase, apn_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  APN_CHECK_ARG(phase >= 0 && phase <= 2, "phase must be 0, 1 or 2");
-  const bool do1 = phase != 2, do2 = phase != 1;
+  // phase 0: everything.  1 | 2: through canonical_feat.grad | the rest (data-parallel step: the point-feature gradient is
+  // exchanged while the weight gradients are computed).  3 | 4: through tc_dgrad (d_xyz, d_ginv final: the LBS / pose
+  // backward can start) | every parameter gradient (point table, feat_net) — the branches of the one-GPU graph; 4 = 5 (d_feat
+  // only, on the caller's stream) + 6 (the weight gradients), which are independent of each other.
+  APN_CHECK_ARG(phase >= 0 && phase <= 6, "phase must be 0..6");
+  const bool do1 = phase == 0 || phase == 1 || phase == 3, do2 = phase == 0 || phase == 2 || phase == 4 || phase == 6;
+  const bool do_feat = phase == 0 || phase == 1 || phase == 4 || phase == 5;
   APN_CHECK_ARG(in && w && packed_bwd && sv && tape && g, "null pointer");
   APN_CHECK_ARG(in->d_in == APN_PE_POS + APN_C || (in->d_in > APN_PE_POS + APN_C && in->d_in <= 256 && in->pose_emb),
                 "d_in must be 191, or 192..256 with a pose embedding");
@@ -708,21 +713,16 @@ static int aggregate_bwd_tc_impl(const apn_agg_inputs* in, const apn_mlp_weights
     APN_LAUNCH_CHECK();
   }
   cudaStream_t sw = st;
-  if (side && phase == 0) {                     // the point-table GEMMs only need tc_dgrad's d_ptable
+  if (side && do2) {                            // the point-table GEMMs only need tc_dgrad's d_ptable
     APN_CUDA(cudaEventRecord(side->fork[2], st));
     APN_CUDA(cudaStreamWaitEvent(side->s[0], side->fork[2], 0));
     sw = side->s[0];
   }
   // feature columns of layer 0 through the per-point table: d_feat = dP W0_feat, dW0_feat += dP^T feat
-  if (do1 && g->d_feat)                         // phase 1 keeps it on the caller's stream: it is what the caller waits for
+  if (do_feat && g->d_feat)                     // phase 1 keeps it on the caller's stream: it is what the caller waits for
     APN_CHECK_ARG(tgemm_dgrad_accum(sw, b.d_ptable, APN_C, w->w[0] + APN_PE_POS, in->d_in, g->d_feat, APN_C, N, APN_C, APN_C) == 0,
                   "dgrad point table");      // accumulates, like every other gradient of this entry point
   if (do2) {
-    if (side && phase == 2) {
-      APN_CUDA(cudaEventRecord(side->fork[2], st));
-      APN_CUDA(cudaStreamWaitEvent(side->s[0], side->fork[2], 0));
-      sw = side->s[0];
-    }
     APN_CHECK_ARG(tgemm_wgrad(sw, b.d_ptable, APN_C, in->feat, APN_C, g->d_w[0] + APN_PE_POS, in->d_in, N, APN_C, APN_C) == 0,
                   "wgrad point table");
     TcWgradParams p;
@@ -748,7 +748,7 @@ static int aggregate_bwd_tc_impl(const apn_agg_inputs* in, const apn_mlp_weights
   if (side) {                                   // join: everything this call launched is ordered before what follows on st
     // only the side streams THIS call forked (under stream capture a wait on an event of a stream that is not part of the
     // capture is an error): phase 1 / 0 fork both in the heads backward, phase 2 only the point-table stream
-    for (int i = 0; i < (do1 ? 2 : 1); ++i) {
+    for (int i = 0; i < (do1 ? 2 : (do2 ? 1 : 0)); ++i) {
       APN_CUDA(cudaEventRecord(side->join[i], side->s[i]));
       APN_CUDA(cudaStreamWaitEvent(st, side->join[i], 0));
     }

@@ -786,7 +786,8 @@ class _AggregateTC(torch.autograd.Function):
     def backward_prepare(ctx, d_alpha, d_rgb):
         """Allocates / binds every gradient buffer and builds the argument structs; `backward_launch(state, phase)` runs the
         kernels: phase 0 = all, or 1 (through canonical_feat.grad) then 2 (the rest) for a data-parallel step that starts
-        exchanging the point-feature gradient while the weight gradients are still being computed (apn_aggregate_bwd_tc_phase)."""
+        exchanging the point-feature gradient while the weight gradients are still being computed (apn_aggregate_bwd_tc_phase);
+        or 3 (through tc_dgrad: d_xyz / d_ginv final) then 4 (every parameter gradient) — the two branches of the one-GPU graph."""
         lib = _lib.load()
         c = ctx.c
         sv = ctx.saved_tensors

@@ -334,11 +334,15 @@ class FusedTrainStep:
 
     # ---- stage B: decoder -> compositing -> loss -> backward of everything (gradients land in the bucket)
     @torch.no_grad()
-    def decode_and_backward(self, st, render_kwargs, target, warp_backward: bool = True, stop_after_feat: bool = False):
+    def decode_and_backward(self, st, render_kwargs, target, warp_backward: bool = True, stop_after_feat: bool = False,
+                            stop_after_dgrad: bool = False):
         """warp_backward=False stops after the decoder backward (every decoder gradient is then final in the bucket: a
         data-parallel caller can start reducing them) and leaves the rest to `warp_backward(st)`.
         stop_after_feat=True stops even earlier, as soon as canonical_feat.grad is final (phase 1 of the decoder backward,
-        apn_aggregate_bwd_tc_phase); `decoder_backward_rest(st)` continues.  -> loss (the render loss in that case)."""
+        apn_aggregate_bwd_tc_phase); `decoder_backward_rest(st)` continues.  -> loss (the render loss in that case).
+        stop_after_dgrad=True stops as soon as d_xyz / d_ginv are final (phase 3): the two halves that remain are independent
+        — `decoder_backward_params(st)` (phase 4: every parameter gradient of the decoder) and
+        `regularise_and_warp_backward(st)` (regularisers, LBS + pose backward; -> total loss) — and may run on two streams."""
         from . import ops
         from .heads import poc_fre
         m = self.model
@@ -371,9 +375,9 @@ class FusedTrainStep:
         # ---- backward, in autograd's order
         d_alpha, d_rgb = ops._Composite.backward(cc, d_rgb_m, None, None, None)[:2]
         state = ops._AggregateTC.backward_prepare(ca, d_alpha, d_rgb)
-        st.update(agg_state=state, ws=ws, pose_emb=pose_emb, pose_graph=pose_graph, render_loss=loss)
-        if stop_after_feat:
-            ops._AggregateTC.backward_launch(state, 1)
+        st.update(agg_state=state, ws=ws, pose_emb=pose_emb, pose_graph=pose_graph, render_loss=loss, ga=state["result"])
+        if stop_after_feat or stop_after_dgrad:
+            ops._AggregateTC.backward_launch(state, 1 if stop_after_feat else 3)
             return loss
         ops._AggregateTC.backward_launch(state, 0)
         return self._after_decoder(st, warp_backward)
@@ -385,17 +389,53 @@ class FusedTrainStep:
         ops._AggregateTC.backward_launch(st["agg_state"], 2)
         return self._after_decoder(st, warp_backward)
 
-    def _after_decoder(self, st, warp_backward):
+    @torch.no_grad()
+    def decoder_backward_params(self, st):
+        """After stop_after_dgrad=True: every parameter gradient of the decoder (point features, feat_net, pose embedding)."""
+        from . import ops
+        ops._AggregateTC.backward_launch(st["agg_state"], 4)
+        self._decoder_param_grads(st)
+
+    @torch.no_grad()
+    def decoder_backward_feat(self, st):
+        """After stop_after_dgrad=True: canonical_feat.grad only (phase 5); independent of decoder_backward_weights."""
+        from . import ops
+        ops._AggregateTC.backward_launch(st["agg_state"], 5)
+        self._accumulate([self.model.canonical_feat], st["ga"][4:5])
+
+    @torch.no_grad()
+    def decoder_backward_weights(self, st):
+        """After stop_after_dgrad=True: the decoder's weight / pose-embedding gradients (phase 6)."""
+        from . import ops
+        ops._AggregateTC.backward_launch(st["agg_state"], 6)
+        self._accumulate(list(st["ws"]), st["ga"][6:])
+        if st["pose_graph"]:
+            with torch.enable_grad():
+                st["pose_emb"].backward(st["ga"][5])
+
+    @torch.no_grad()
+    def regularise_and_warp_backward(self, st):
+        """After stop_after_dgrad=True: regularisers (+ extra loss) on d_xyz, then the LBS and pose backward.  -> total loss."""
+        loss = st["render_loss"]
+        if self.has_extra_terms():
+            loss = self._regularise(st, st["ga"][2], loss)
+        self.warp_backward(st)
+        return loss
+
+    def _decoder_param_grads(self, st):
         m = self.model
-        ga, ws, loss = st["agg_state"]["result"], st["ws"], st["render_loss"]
+        ga, ws = st["ga"], st["ws"]
         self._accumulate([m.canonical_feat], ga[4:5])                      # None where the kernels wrote into .grad directly
         self._accumulate(list(ws), ga[6:])
         if st["pose_graph"]:
             with torch.enable_grad():
                 st["pose_emb"].backward(ga[5])                              # accumulates into the bucket slices
-        st["ga"] = ga
+
+    def _after_decoder(self, st, warp_backward):
+        loss = st["render_loss"]
+        self._decoder_param_grads(st)
         if self.has_extra_terms():
-            loss = self._regularise(st, ga[2], loss)
+            loss = self._regularise(st, st["ga"][2], loss)
         if warp_backward:
             self.warp_backward(st)
         return loss
@@ -485,9 +525,10 @@ class GraphedTrainStep:
     Branches inside the graph (captured fork / join on a side stream; they also run, the same way, in the eager mode):
       * the decoder's derived state (weight tiles, per-point table) and the bucket memset do not depend on the pose: they
         run beside the pose -> LBS -> grid -> k-NN chain, whose kernels leave most SMs idle, and join before the decoder;
-      * with one rank the optimiser is split: every parameter whose gradient is final after the decoder backward
-        (canonical_feat, the MLPs: ~99 % of the bytes) is updated beside the LBS / pose backward (one 8-CTA cluster + a
-        small grid), the skinning weights / joints / pose network after it.
+      * with one rank the backward forks three ways as soon as tc_dgrad has produced d_xyz / d_ginv
+        (apn_aggregate_bwd_tc_phase 3 | 5 | 6): [d_feat GEMM, Adam of canonical_feat (~90 % of the optimiser's bytes)] beside
+        [point-table wgrad GEMM || tc_wgrad, Adam of the decoder's MLPs] beside [regularisers, LBS backward, pose backward
+        (one 8-CTA cluster), Adam of the skinning weights / joints / pose network].
 
     Overflow: if a batch yields more samples than the workspace holds, the kernels truncate, raise a flag that travels with
     the bucket through the all-reduce (so every rank sees it) and Adam skips the update on the device.  The host notices
@@ -541,9 +582,10 @@ class GraphedTrainStep:
         self.status = bucket.status
         self.skip_word = self.status[:1]          # non-zero (on any rank, after the all-reduce) => Adam skips
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
-        self._side = torch.cuda.Stream(device=dev)            # branch of the step (decoder state; early Adam part)
+        self._side = torch.cuda.Stream(device=dev)            # branches of the step (decoder state; parameter gradients + Adam)
+        self._side2 = torch.cuda.Stream(device=dev)
         self.branches = True                                   # False: everything on one stream (A/B measurements, tests)
-        self._adam_early, self._adam_late, self._ss_perm = [], [], []
+        self._adam_feat, self._adam_early, self._adam_late, self._ss_perm = [], [], [], []
         self._pinned = [torch.zeros(9, dtype=torch.float32).pin_memory() for _ in range(self.RING)]   # status[0:8] | loss
         self._pinned_ss = None
         self.step_sizes = None
@@ -598,26 +640,33 @@ class GraphedTrainStep:
                 cur.wait_stream(self._side)
             self._body_status()               # flags are final after sampling; the bucket (and its status words) is zeroed
             inline_adam = adam_skip is not False and not split
+            fork = inline_adam and self.branches
             loss = self.fused.decode_and_backward(st, self.rk, self.target, warp_backward=not split and not inline_adam,
-                                                  stop_after_feat=split)
+                                                  stop_after_feat=split, stop_after_dgrad=fork)
         finally:
             packed.force = force
         self._st = st
         if split:
             return
+        if fork:
+            # branch 2, as soon as tc_dgrad has produced d_xyz / d_ginv: the decoder's parameter gradients (point-table GEMMs,
+            # tc_wgrad) and the Adam update of those parameters beside [regularisers, LBS + pose backward, Adam of the rest]
+            self._side.wait_stream(cur)
+            self._side2.wait_stream(cur)
+            with torch.cuda.stream(self._side):          # point features: d_feat GEMM, then their Adam update (~90 % of its bytes)
+                self.fused.decoder_backward_feat(st)
+                self._launch_adam(self._adam_feat, adam_skip)
+            with torch.cuda.stream(self._side2):         # decoder weights: point-table wgrad GEMM || tc_wgrad, then their Adam
+                self.fused.decoder_backward_weights(st)
+                self._launch_adam(self._adam_early, adam_skip)
+            loss = self.fused.regularise_and_warp_backward(st)
+            self._launch_adam(self._adam_late, adam_skip)
+            cur.wait_stream(self._side)
+            cur.wait_stream(self._side2)
+        elif inline_adam:
+            self.fused.warp_backward(st)
+            self._body_b(adam_skip)
         self.loss.copy_(loss.reshape(1))
-        if inline_adam:
-            # branch 2: every gradient but those of the warp is final
-            if self.branches and self._adam_early:
-                self._side.wait_stream(cur)
-                with torch.cuda.stream(self._side):
-                    self._launch_adam(self._adam_early, adam_skip)
-                self.fused.warp_backward(st)
-                self._launch_adam(self._adam_late, adam_skip)
-                cur.wait_stream(self._side)
-            else:
-                self.fused.warp_backward(st)
-                self._body_b(adam_skip)
 
     def _body_a2(self):
         """rest of the decoder backward (weight gradients) + regularisers"""
@@ -636,31 +685,34 @@ class GraphedTrainStep:
             ap.launch_dev(self.step_sizes[off:off + ap.n], self.skip_word if skip is None else skip, *cls)
 
     def _body_b(self, skip=None):
+        self._launch_adam(self._adam_feat, skip)
         self._launch_adam(self._adam_early, skip)
         self._launch_adam(self._adam_late, skip)
 
     def _plan_adam(self, launches):
-        """Splits every (betas, eps) class of the optimiser's launch plan into the parameters the warp backward writes
-        (skinning weights, theta_weight, joints, pose network: `late`) and the rest (`early`), as two descriptor tables;
-        `_ss_perm[k]` = index into the plan-ordered step sizes of the k-th slot of the device step-size vector
-        ([class 0 early | class 0 late | class 1 early | ...]).  With more than one rank Adam follows the all-reduce in
-        one piece: everything is `late`."""
+        """Splits every (betas, eps) class of the optimiser's launch plan by the branch of the backward that completes a
+        parameter's gradient: `feat` (canonical_feat), `late` (what the warp backward writes: skinning weights, theta_weight,
+        joints, pose network), `early` (the rest: the decoder's MLPs, ...), as separate descriptor tables; `_ss_perm[k]` =
+        index into the plan-ordered step sizes of the k-th slot of the device step-size vector.  With more than one rank
+        Adam follows the all-reduce in one piece: everything is `late`."""
         from . import ops
         m = self.model
         late_ptrs = {p.data_ptr() for p in [m.weights, m.theta_weight, m.joints, *m.forward_warp.parameters()]}
-        self._adam_early, self._adam_late, self._ss_perm = [], [], []
+        feat_ptr = m.canonical_feat.data_ptr()
+        self._adam_feat, self._adam_early, self._adam_late, self._ss_perm = [], [], [], []
         base = 0
         for cls, ap, sizes in launches:
-            idx_e = [i for i, e in enumerate(ap.keep) if e[0].data_ptr() not in late_ptrs] if self.world == 1 else []
-            if not idx_e or len(idx_e) == ap.n:
-                self._adam_late.append((cls, ap, len(self._ss_perm)))
+            label = [2 if (self.world > 1 or e[0].data_ptr() in late_ptrs) else (0 if e[0].data_ptr() == feat_ptr else 1)
+                     for e in ap.keep]
+            if len(set(label)) == 1:
+                (self._adam_feat, self._adam_early, self._adam_late)[label[0]].append((cls, ap, len(self._ss_perm)))
                 self._ss_perm += [base + i for i in range(ap.n)]
             else:
-                idx_l = [i for i in range(ap.n) if i not in set(idx_e)]
-                self._adam_early.append((cls, ops.AdamPlan([ap.keep[i] for i in idx_e]), len(self._ss_perm)))
-                self._ss_perm += [base + i for i in idx_e]
-                self._adam_late.append((cls, ops.AdamPlan([ap.keep[i] for i in idx_l]), len(self._ss_perm)))
-                self._ss_perm += [base + i for i in idx_l]
+                for part, dst in enumerate((self._adam_feat, self._adam_early, self._adam_late)):
+                    idx = [i for i, l in enumerate(label) if l == part]
+                    if idx:
+                        dst.append((cls, ops.AdamPlan([ap.keep[i] for i in idx]), len(self._ss_perm)))
+                        self._ss_perm += [base + i for i in idx]
             base += len(sizes)
 
     def _capture(self, launches):

@@ -322,7 +322,12 @@ int apn_aggregate_bwd_tc(const apn_agg_inputs* in, const apn_mlp_weights* w, con
  * everything up to g->d_feat (heads, density, dgrad chain, d_xyz / d_ginv, d_feat = dP W0_feat) — the gradient of the point
  * features, ~90 % of the bytes a rank exchanges, is final when it returns and its all-reduce can start; phase 2 adds the
  * feat_net weight gradients, the point-table weight gradient and the pose-embedding gradient from the SAME scratch buffer
- * (untouched in between).  phase 0 == apn_aggregate_bwd_tc.  Phase 1 followed by phase 2 gives the same results. */
+ * (untouched in between).  phase 0 == apn_aggregate_bwd_tc.  Phase 1 followed by phase 2 gives the same results.
+ * A second split for the one-GPU step: phase 3 stops as soon as d_xyz / d_ginv are final (heads, density, dgrad chain) — the
+ * LBS / pose backward can start —, phase 4 adds EVERY parameter gradient (d_feat and the weight gradients); the caller may run
+ * phase 4 on another stream beside the LBS / pose backward.  Phase 3 followed by phase 4 gives the same results as phase 0.
+ * Phase 4 = phase 5 (d_feat = dP W0_feat only, entirely on the caller's stream) + phase 6 (the weight gradients), in any order
+ * or on two streams: they write disjoint buffers and only read what phase 3 left in the scratch. */
 int apn_aggregate_bwd_tc_phase(const apn_agg_inputs* in, const apn_mlp_weights* w, const void* packed_bwd,
                                const apn_agg_outputs* saved, const void* tape, const apn_agg_grads* g, void* scratch,
                                size_t scratch_bytes, int phase, apn_stream_t stream);

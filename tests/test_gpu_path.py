@@ -941,3 +941,47 @@ def test_no_view_dir_head(golden_tiny):
                   "rgbnet.views_linears.2.weight", "densitynet.weight", "feat_net.4.weight"):
             assert named[k].grad.shape == orc.s[k].grad.shape, k
             assert rel_err(named[k].grad, orc.s[k].grad) < (RTOL if dec == "fp32" else TC_TOL), (dec, k)
+
+
+def test_decoder_backward_split_in_phases_equals_the_single_pass(golden_any):
+    """apn_aggregate_bwd_tc_phase: 3 then 4, or 3 then 6 and 5 (the branches of the graphed one-GPU step; the LBS / pose backward
+    runs BEFORE the parameter-gradient phases here: it must only need what phase 3 produced) and 1 then 2 (data-parallel step)
+    against the single pass."""
+    from articulated_point_nerf_b200.train import FusedTrainStep, GradBucket, create_optimizer
+    g = golden_any
+    target = g["train"]["target"].cuda()
+    got = {}
+    for mode in ("single", "dgrad_split", "three_way", "feat_split"):
+        model, scene = model_from_golden(g, fused_pose=True)
+        model.decoder_train = "tc"
+        opt = create_optimizer(model)
+        bucket = GradBucket(opt)
+        fs = FusedTrainStep(model, opt, bucket)
+        rk = _rk(scene, g)
+        with bucket.direct_accum():
+            st = fs.forward_sampling(g["train"]["t"].cuda(), rk)
+            if mode == "single":
+                loss = fs.decode_and_backward(st, rk, target)
+            elif mode == "dgrad_split":
+                fs.decode_and_backward(st, rk, target, stop_after_dgrad=True)
+                loss = fs.regularise_and_warp_backward(st)
+                fs.decoder_backward_params(st)
+            elif mode == "three_way":                      # phases 3, then 6 and 5 in the "wrong" order
+                fs.decode_and_backward(st, rk, target, stop_after_dgrad=True)
+                fs.decoder_backward_weights(st)
+                loss = fs.regularise_and_warp_backward(st)
+                fs.decoder_backward_feat(st)
+            else:
+                fs.decode_and_backward(st, rk, target, stop_after_feat=True)
+                loss = fs.decoder_backward_rest(st)
+        torch.cuda.synchronize()
+        got[mode] = (float(loss), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None})
+    l0, g0 = got["single"]
+    assert any(float(v.abs().max()) > 0 for v in g0.values())
+    for mode in ("dgrad_split", "three_way", "feat_split"):
+        l1, g1 = got[mode]
+        assert l1 == l0, mode
+        assert g1.keys() == g0.keys()
+        for k in g0:
+            tol = 1e-2 if k == "theta_weight" else 3 * RTOL      # float atomics: run-to-run noise
+            assert rel_err(g1[k], g0[k]) < tol, (mode, k)
