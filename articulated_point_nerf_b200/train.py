@@ -525,10 +525,11 @@ class GraphedTrainStep:
     Branches inside the graph (captured fork / join on a side stream; they also run, the same way, in the eager mode):
       * the decoder's derived state (weight tiles, per-point table) and the bucket memset do not depend on the pose: they
         run beside the pose -> LBS -> grid -> k-NN chain, whose kernels leave most SMs idle, and join before the decoder;
-      * with one rank the backward forks three ways as soon as tc_dgrad has produced d_xyz / d_ginv
+      * (unless the gradient exchange is split) the backward forks three ways as soon as tc_dgrad has produced d_xyz / d_ginv
         (apn_aggregate_bwd_tc_phase 3 | 5 | 6): [d_feat GEMM, Adam of canonical_feat (~90 % of the optimiser's bytes)] beside
         [point-table wgrad GEMM || tc_wgrad, Adam of the decoder's MLPs] beside [regularisers, LBS backward, pose backward
-        (one 8-CTA cluster), Adam of the skinning weights / joints / pose network].
+        (one 8-CTA cluster), Adam of the skinning weights / joints / pose network]; the Adam parts only with one rank (with
+        more, Adam follows the all-reduce).
 
     Overflow: if a batch yields more samples than the workspace holds, the kernels truncate, raise a flag that travels with
     the bucket through the all-reduce (so every rank sees it) and Adam skips the update on the device.  The host notices
@@ -640,7 +641,7 @@ class GraphedTrainStep:
                 cur.wait_stream(self._side)
             self._body_status()               # flags are final after sampling; the bucket (and its status words) is zeroed
             inline_adam = adam_skip is not False and not split
-            fork = inline_adam and self.branches
+            fork = self.branches and not split       # (the split mode's graphs end where the all-reduces start)
             loss = self.fused.decode_and_backward(st, self.rk, self.target, warp_backward=not split and not inline_adam,
                                                   stop_after_feat=split, stop_after_dgrad=fork)
         finally:
@@ -655,12 +656,15 @@ class GraphedTrainStep:
             self._side2.wait_stream(cur)
             with torch.cuda.stream(self._side):          # point features: d_feat GEMM, then their Adam update (~90 % of its bytes)
                 self.fused.decoder_backward_feat(st)
-                self._launch_adam(self._adam_feat, adam_skip)
+                if inline_adam:
+                    self._launch_adam(self._adam_feat, adam_skip)
             with torch.cuda.stream(self._side2):         # decoder weights: point-table wgrad GEMM || tc_wgrad, then their Adam
                 self.fused.decoder_backward_weights(st)
-                self._launch_adam(self._adam_early, adam_skip)
+                if inline_adam:
+                    self._launch_adam(self._adam_early, adam_skip)
             loss = self.fused.regularise_and_warp_backward(st)
-            self._launch_adam(self._adam_late, adam_skip)
+            if inline_adam:                              # (more than one rank: Adam follows the all-reduce, _body_b)
+                self._launch_adam(self._adam_late, adam_skip)
             cur.wait_stream(self._side)
             cur.wait_stream(self._side2)
         elif inline_adam:

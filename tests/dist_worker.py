@@ -20,7 +20,7 @@ def run(rank, world, port, mode, out_dir):
     model, scene = model_from_golden(g, fused_pose=True)
     model.decoder_train = "tc"
     opt = create_optimizer(model)
-    bucket = make_bucket(model, opt, overlap=True)
+    bucket = make_bucket(model, opt, overlap=(mode != "graph1"))          # graph1: ONE all-reduce of the whole bucket per step
     R = len(g["rays_o"])
     a, b = shard_rays(R, rank, world)
     t = g["train"]["t"].cuda()
@@ -35,11 +35,13 @@ def run(rank, world, port, mode, out_dir):
         out = {"flat": bucket.flat[:bucket.total].cpu(), "loss": float(loss), "M": model.last_counts["M"]}
     else:
         # the graph-captured step with its split all-reduce (early slice on the communication stream), two iterations
-        gs = GraphedTrainStep(model, opt, bucket, b - a, scene.render_kwargs(), calibrate=(t, ro, rd), use_graph=(mode == "graph"))
+        before = {k: p.detach().clone() for k, p in model.named_parameters()}
+        gs = GraphedTrainStep(model, opt, bucket, b - a, scene.render_kwargs(), calibrate=(t, ro, rd), use_graph=(mode != "static"))
         losses = [float(gs.step(t, ro, rd, vd, tgt)) for _ in range(2)]
         gs.flush()
         out = {"params": {k: p.detach().cpu() for k, p in model.named_parameters()}, "losses": losses, "M": gs.last_counts["M"],
-               "split": bucket.split, "total": bucket.total}
+               "split": bucket.split, "total": bucket.total,
+               "moved": sorted(k for k, p in model.named_parameters() if not torch.equal(p.detach(), before[k]))}
     torch.save(out, os.path.join(out_dir, f"rank{rank}_{mode}.pt"))
     dist.barrier()
     dist.destroy_process_group()

@@ -48,12 +48,20 @@ def test_two_rank_gradient_equals_single_process_full_batch(golden_tiny, tmp_pat
         assert rel_err(a, b) < tol, (o, p.shape)
 
 
-@pytest.mark.parametrize("mode", ["static", "graph"])
+@pytest.mark.parametrize("mode", ["static", "graph", "graph1"])
 def test_two_rank_graphed_step_keeps_ranks_identical(golden_tiny, tmp_path, mode):
-    """The sync-free step at world size 2 (early slice reduced beside the LBS / pose backward, late slice + status, Adam):
-    both ranks end with bit-identical parameters after two iterations, and the decoder slice really is the bulk."""
-    r0, r1 = _launch(mode, tmp_path, 29633 if mode == "static" else 29635)
-    assert 0 < r0["split"] < r0["total"]          # two slices: the decoder's (90 % of the bytes at c2 size) and the rest
+    """The sync-free step at world size 2 (early slice reduced beside the LBS / pose backward, late slice + status, Adam;
+    `graph1`: one all-reduce of the whole bucket between a forward + backward graph with side-stream branches and the Adam
+    graph — what make_bucket picks for small buckets): both ranks end with bit-identical parameters after two iterations, and
+    the decoder slice really is the bulk."""
+    r0, r1 = _launch(mode, tmp_path, {"static": 29633, "graph": 29635, "graph1": 29637}[mode])
+    if mode == "graph1":
+        assert r0["split"] == 0
+    else:
+        assert 0 < r0["split"] < r0["total"]      # two slices: the decoder's (90 % of the bytes at c2 size) and the rest
     for k in r0["params"]:
         assert torch.equal(r0["params"][k], r1["params"][k]), k
     assert all(map(lambda x: x == x, r0["losses"] + r1["losses"]))       # finite
+    for k in ("canonical_feat", "feat_net.0.weight", "rgbnet.feature_linears.weight", "weights", "joints"):   # Adam ran on every slice
+        assert k in r0["moved"], k
+    assert r0["losses"][1] != r0["losses"][0]
