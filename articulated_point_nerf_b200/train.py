@@ -203,16 +203,29 @@ def decoder_parameters(model):
     return ps
 
 
+def warp_parameters(model):
+    """The parameters whose gradients only the LBS / pose backward completes — and the only ones the sampling stage of the
+    NEXT step reads (pose network, joints, skinning weights): the `late` slice of a pipelined bucket."""
+    return [model.weights, model.theta_weight, model.joints, *model.forward_warp.parameters()]
+
+
 OVERLAP_MIN_FLOATS = 8 << 20       # 32 MiB of gradients
 
 
-def make_bucket(model, optimizer, overlap="auto") -> "GradBucket":
-    """The flat gradient bucket of a data-parallel run.  With `overlap` the decoder's parameters form the early slice with
-    canonical_feat at the front (see GradBucket): GraphedTrainStep then reduces them in three parts beside the backward.
-    "auto": only when the bucket is large (>= 32 MiB).  Measured on 8 x B200 (gpurun_out/r2l_*, r2m_*): at c4 (61 MB) the
-    overlapped exchange wins (2.30 vs 2.33 ms / step), at c2 (17.6 MB) one all-reduce after the backward does (1.01 vs 1.03 ms):
-    the persistent decoder kernels occupy every SM, so NCCL's blocks mostly wait for them anyway, and each extra graph
-    boundary costs ~10 us."""
+def make_bucket(model, optimizer, overlap="pipeline") -> "GradBucket":
+    """The flat gradient bucket of a data-parallel run.
+    "pipeline" (default): [canonical_feat | every other parameter the warp does not own | warp parameters | status] —
+        GraphedTrainStep then reduces the first two parts (~99 % of the bytes) on the communication stream BESIDE THE NEXT
+        STEP's pose -> LBS -> grid -> k-NN chain, which only reads the warp parameters; only the small warp slice is exchanged
+        inside the step.
+    True: [canonical_feat | decoder MLPs | rest | status], reduced in three parts beside the backward of the same step
+        (measured on 8 x B200, gpurun_out/r2l_*, r2m_*: wins at c4 = 61 MB, 2.30 vs 2.33 ms, loses at c2 = 17.6 MB, 1.03 vs
+        1.01 ms: the persistent decoder kernels occupy every SM, and each extra graph boundary costs ~10 us).
+    "auto": True from 32 MiB of gradients, else False.   False: one all-reduce of the whole bucket after the backward."""
+    if overlap == "pipeline":
+        warp = {id(p) for p in warp_parameters(model)}
+        early = [p for g in optimizer.param_groups for p in g['params'] if p.requires_grad and id(p) not in warp]
+        return GradBucket(optimizer, early=early, first=[model.canonical_feat])
     if overlap == "auto":
         n = sum(p.numel() for g in optimizer.param_groups for p in g['params'] if p.requires_grad)
         overlap = n >= OVERLAP_MIN_FLOATS
@@ -522,6 +535,15 @@ class GraphedTrainStep:
         graph B   Adam
     Per step the host copies the inputs into the static buffers, writes ~30 step sizes, and launches two graphs.
 
+    More than one rank, bucket from make_bucket(..., "pipeline"): the exchange is software-pipelined ACROSS steps —
+        main stream    graph P1 [zero warp slice, pose, LBS, grid, samples + 8-NN]   (reads only the warp parameters)
+                       wait for the communication stream
+                       graph P2 [decoder, compositing, loss, backward with its three branches]
+                       all-reduce of the warp slice + status (small), Adam of the warp parameters
+        comm stream    all-reduce of the decoder slice (~99 % of the bytes), Adam of those parameters, graph PP [zero the
+                       decoder slice, weight tiles, per-point table] — all of it beside the NEXT step's graph P1.
+    Same arithmetic as the unpipelined step: every parameter is updated before its next reader runs.
+
     Branches inside the graph (captured fork / join on a side stream; they also run, the same way, in the eager mode):
       * the decoder's derived state (weight tiles, per-point table) and the bucket memset do not depend on the pose: they
         run beside the pose -> LBS -> grid -> k-NN chain, whose kernels leave most SMs idle, and join before the decoder;
@@ -587,6 +609,13 @@ class GraphedTrainStep:
         self._side2 = torch.cuda.Stream(device=dev)
         self.branches = True                                   # False: everything on one stream (A/B measurements, tests)
         self._adam_feat, self._adam_early, self._adam_late, self._ss_perm = [], [], [], []
+        # pipelined exchange: needs the bucket split exactly at the warp parameters (make_bucket(..., "pipeline"))
+        self.pipelined = False
+        if self.world > 1 and bucket.split > 0:
+            warp = {p.data_ptr() for p in warp_parameters(model)}
+            self.pipelined = all((p.data_ptr() in warp) == (o >= bucket.split) for p, o in zip(bucket.params, bucket.offsets))
+        self.skip_copy = torch.zeros(1, device=dev)          # the reduced skip word, for the Adam part on the comm stream
+        self._pg, self._need_pp = None, True
         self._pinned = [torch.zeros(9, dtype=torch.float32).pin_memory() for _ in range(self.RING)]   # status[0:8] | loss
         self._pinned_ss = None
         self.step_sizes = None
@@ -650,26 +679,60 @@ class GraphedTrainStep:
         if split:
             return
         if fork:
-            # branch 2, as soon as tc_dgrad has produced d_xyz / d_ginv: the decoder's parameter gradients (point-table GEMMs,
-            # tc_wgrad) and the Adam update of those parameters beside [regularisers, LBS + pose backward, Adam of the rest]
-            self._side.wait_stream(cur)
-            self._side2.wait_stream(cur)
-            with torch.cuda.stream(self._side):          # point features: d_feat GEMM, then their Adam update (~90 % of its bytes)
-                self.fused.decoder_backward_feat(st)
-                if inline_adam:
-                    self._launch_adam(self._adam_feat, adam_skip)
-            with torch.cuda.stream(self._side2):         # decoder weights: point-table wgrad GEMM || tc_wgrad, then their Adam
-                self.fused.decoder_backward_weights(st)
-                if inline_adam:
-                    self._launch_adam(self._adam_early, adam_skip)
-            loss = self.fused.regularise_and_warp_backward(st)
-            if inline_adam:                              # (more than one rank: Adam follows the all-reduce, _body_b)
-                self._launch_adam(self._adam_late, adam_skip)
-            cur.wait_stream(self._side)
-            cur.wait_stream(self._side2)
+            loss = self._backward_branches(st, cur, inline_adam, adam_skip)
         elif inline_adam:
             self.fused.warp_backward(st)
             self._body_b(adam_skip)
+        self.loss.copy_(loss.reshape(1))
+
+    def _backward_branches(self, st, cur, inline_adam, adam_skip):
+        """After decode_and_backward(stop_after_dgrad=True), i.e. as soon as tc_dgrad has produced d_xyz / d_ginv: the decoder's
+        parameter gradients (+ the Adam update of those parameters) beside [regularisers, LBS + pose backward (+ Adam of the
+        rest)].  -> total loss."""
+        self._side.wait_stream(cur)
+        self._side2.wait_stream(cur)
+        with torch.cuda.stream(self._side):          # point features: d_feat GEMM, then their Adam update (~90 % of its bytes)
+            self.fused.decoder_backward_feat(st)
+            if inline_adam:
+                self._launch_adam(self._adam_feat, adam_skip)
+        with torch.cuda.stream(self._side2):         # decoder weights: point-table wgrad GEMM || tc_wgrad, then their Adam
+            self.fused.decoder_backward_weights(st)
+            if inline_adam:
+                self._launch_adam(self._adam_early, adam_skip)
+        loss = self.fused.regularise_and_warp_backward(st)
+        if inline_adam:                              # (more than one rank: Adam follows the all-reduce)
+            self._launch_adam(self._adam_late, adam_skip)
+        cur.wait_stream(self._side)
+        cur.wait_stream(self._side2)
+        return loss
+
+    # ---- pipelined exchange (more than one rank): P1 | PP | P2, see the class docstring
+    def _body_p1(self):
+        if self.packed is not None:
+            for i, dst in enumerate((self.rays_o, self.rays_d, self.viewdirs, self.target)):
+                dst.copy_(self.packed[:, 3 * i:3 * i + 3])
+        if not self.bucket.attached():
+            self.bucket.attach()
+        self.bucket.flat[self.bucket.split:].zero_()                   # warp slice + status words
+        self._st = self.fused.forward_sampling(self.t, self.rk, self.sampler, zero_bucket=False)
+        self._body_status()
+
+    def _body_pp(self):
+        self.bucket.flat[:self.bucket.split].zero_()                   # decoder slice
+        self.fused.refresh_decoder_state()
+
+    def _body_p2(self):
+        cur = torch.cuda.current_stream(self.dev)
+        packed = self.model._packed_decoder
+        force, packed.force = packed.force, False                       # PP has refreshed the decoder state
+        try:
+            if self.branches:
+                self.fused.decode_and_backward(self._st, self.rk, self.target, stop_after_dgrad=True)
+                loss = self._backward_branches(self._st, cur, False, None)
+            else:
+                loss = self.fused.decode_and_backward(self._st, self.rk, self.target)
+        finally:
+            packed.force = force
         self.loss.copy_(loss.reshape(1))
 
     def _body_a2(self):
@@ -698,15 +761,17 @@ class GraphedTrainStep:
         parameter's gradient: `feat` (canonical_feat), `late` (what the warp backward writes: skinning weights, theta_weight,
         joints, pose network), `early` (the rest: the decoder's MLPs, ...), as separate descriptor tables; `_ss_perm[k]` =
         index into the plan-ordered step sizes of the k-th slot of the device step-size vector.  With more than one rank
-        Adam follows the all-reduce in one piece: everything is `late`."""
+        Adam follows the all-reduce in one piece (everything is `late`) unless the exchange is pipelined: then `late` follows
+        the all-reduce of the warp slice on the main stream, `feat` + `early` that of the decoder slice on the other."""
         from . import ops
         m = self.model
-        late_ptrs = {p.data_ptr() for p in [m.weights, m.theta_weight, m.joints, *m.forward_warp.parameters()]}
+        late_ptrs = {p.data_ptr() for p in warp_parameters(m)}
         feat_ptr = m.canonical_feat.data_ptr()
         self._adam_feat, self._adam_early, self._adam_late, self._ss_perm = [], [], [], []
         base = 0
         for cls, ap, sizes in launches:
-            label = [2 if (self.world > 1 or e[0].data_ptr() in late_ptrs) else (0 if e[0].data_ptr() == feat_ptr else 1)
+            one_piece = self.world > 1 and not self.pipelined
+            label = [2 if (one_piece or e[0].data_ptr() in late_ptrs) else (0 if e[0].data_ptr() == feat_ptr else 1)
                      for e in ap.keep]
             if len(set(label)) == 1:
                 (self._adam_feat, self._adam_early, self._adam_late)[label[0]].append((cls, ap, len(self._ss_perm)))
@@ -729,9 +794,11 @@ class GraphedTrainStep:
         self._pinned_ss = [torch.zeros(max(n, 1), dtype=torch.float32).pin_memory() for _ in range(self.RING)]
         self._ss_events = [None] * self.RING
         packed = self.model._packed_decoder
-        self.graphs = None
+        self.graphs, self._pg, self._need_pp = None, None, True
         if not self.use_graph:
             return
+        if self.pipelined:
+            return self._capture_pipelined()
         one = self.world == 1
         # warm-up on a side stream (allocator + lazy module state), then capture
         s = torch.cuda.Stream(device=dev)
@@ -774,6 +841,68 @@ class GraphedTrainStep:
                     self._body_b()
         packed.force = False
         self.graphs = (ga, ga2, ga3, gb)
+
+    def _capture_pipelined(self):
+        from . import _lib
+        dev, packed = self.dev, self.model._packed_decoder
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s), self.bucket.direct_accum():
+            packed.force = True
+            warm_skip = torch.ones(1, device=dev)     # Adam skips during warm-up: parameters and moments stay untouched
+            for _ in range(2):
+                n0 = _lib.launch_count()
+                self._body_p1()
+                self._body_pp()
+                self._body_p2()
+                self._body_b(warm_skip)
+                self.launches_per_step = _lib.launch_count() - n0
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        g1, gp, g2, gbl, gbe = (torch.cuda.CUDAGraph() for _ in range(5))
+        with self.bucket.direct_accum():
+            with torch.cuda.graph(g1):
+                self._body_p1()
+            with torch.cuda.graph(gp):                # (allocates nothing: its own pool is fine beside P1 on another stream)
+                self._body_pp()
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self._body_p2()
+            with torch.cuda.graph(gbl):
+                self._launch_adam(self._adam_late)
+            with torch.cuda.graph(gbe):
+                self._launch_adam(self._adam_feat, self.skip_copy)
+                self._launch_adam(self._adam_early, self.skip_copy)
+        packed.force = False
+        self._pg = (g1, gp, g2, gbl, gbe)
+
+    def _step_pipelined(self, ss, params):
+        cur, comm, pg = torch.cuda.current_stream(self.dev), self.comm_stream, self._pg
+        pg[0].replay() if pg else self._body_p1()
+        if self._need_pp:                             # first step after a (re-)capture: nothing has prepared the decoder state yet
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                pg[1].replay() if pg else self._body_pp()
+            self._need_pp = False
+        cur.wait_stream(comm)                         # Adam of the decoder slice (previous step) + PP have run
+        self.step_sizes.copy_(ss, non_blocking=True)  # (only now: that Adam read the previous step's sizes)
+        pg[2].replay() if pg else self._body_p2()
+        with _lib_stage("allreduce_late"):
+            self.bucket.all_reduce_avg(part=1)        # warp slice + status: issued FIRST, the only exchange inside the step
+        self.skip_copy.copy_(self.status[:1])
+        comm.wait_stream(cur)
+        if params:                                    # (host-side bookkeeping; before PP keys its caches on the versions)
+            torch.autograd.graph.increment_version(params)
+        with torch.cuda.stream(comm):
+            with _lib_stage("allreduce_early"):
+                self.bucket.all_reduce_avg(part=0)    # decoder slice: beside the next step's P1
+            if pg:
+                pg[4].replay()
+                pg[1].replay()
+            else:
+                self._launch_adam(self._adam_feat, self.skip_copy)
+                self._launch_adam(self._adam_early, self.skip_copy)
+                self._body_pp()
+        pg[3].replay() if pg else self._launch_adam(self._adam_late)
 
     # ------------------------------------------------------------------------------------------
     def _poll(self, wait: bool = False):
@@ -820,8 +949,18 @@ class GraphedTrainStep:
         torch.cuda.synchronize(self.dev)
         self._pending = []
 
+    def sync_parameters(self):
+        """Pipelined exchange only: the decoder's parameters of the last step are updated on the communication stream, beside
+        whatever the main stream does next.  Anything OTHER than the next step() that reads them on the current stream (a
+        validation render, a checkpoint) calls this first: the current stream then waits for that update (no host wait)."""
+        if self.pipelined:
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
+
     def flush(self):
-        """Waits for the steps in flight and raises WorkspaceOverflow if one of them was skipped."""
+        """Waits for the steps in flight (on every stream) and raises WorkspaceOverflow if one of them was skipped."""
+        self.sync_parameters()
+        if self.pipelined:
+            self.comm_stream.synchronize()
         self._poll(wait=True)
 
     @torch.no_grad()
@@ -850,17 +989,18 @@ class GraphedTrainStep:
         flat_sizes = [v for _, _, sizes in launches for v in sizes]
         for k, src in enumerate(self._ss_perm):
             ss[k] = flat_sizes[src]
-        self.step_sizes.copy_(ss, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        self._ss_events[slot] = ev
+        if not self.pipelined:
+            self.step_sizes.copy_(ss, non_blocking=True)
         with self.bucket.direct_accum():
             split = self.world > 1 and self.bucket.split > 0
-            if self.graphs is not None:
+            if self.pipelined:
+                self._step_pipelined(ss, params)
+                params = None
+            elif self.graphs is not None:
                 self.graphs[0].replay()
             else:
                 self._body_a(split=split, adam_skip=None if self.world == 1 else False)
-            if self.world > 1:
+            if self.world > 1 and not self.pipelined:
                 cur = torch.cuda.current_stream(self.dev)
                 if split:
                     # canonical_feat.grad (90 % of the bucket) is final: reduce it on the communication stream while the
@@ -885,11 +1025,16 @@ class GraphedTrainStep:
                 else:
                     with _lib_stage("allreduce"):
                         self.bucket.all_reduce_avg()
-            if self.graphs is None:
+            if self.pipelined:
+                pass
+            elif self.graphs is None:
                 if self.world > 1:
                     self._body_b()
             elif self.graphs[3] is not None:
                 self.graphs[3].replay()
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ss_events[slot] = ev                     # the copy out of this pinned step-size slot has run
         pin = self._pinned[slot]
         pin[:8].copy_(self.status[:8], non_blocking=True)
         pin[8:9].copy_(self.loss, non_blocking=True)

@@ -329,7 +329,8 @@ def main():
     opt = bucket = None
     if mode == "train":
         opt = create_optimizer(model)
-        bucket = GradBucket(opt) if args.no_overlap else make_bucket(model, opt)          # large buckets: three slices reduced beside the backward
+        # default: the pipelined layout (decoder slice reduced beside the next step's sampling stage); --no-overlap: one all-reduce
+        bucket = GradBucket(opt) if args.no_overlap else make_bucket(model, opt)
     decay = 0.1 ** (1.0 / (160 * 1000))
     counts = []
     gs = gs_stages = None
@@ -353,6 +354,9 @@ def main():
                               packed_inputs=True, regularisers=reg, extra_loss=extra)
         gs.branches = not args.no_branches
         base_cfg["graph_branches"] = gs.branches
+        if world > 1:
+            base_cfg["grad_exchange"] = ("pipelined across steps (decoder slice beside the next step's sampling stage)" if gs.pipelined
+                                         else "three parts beside the backward" if bucket.split > 0 else "one all-reduce after the backward")
         seen = set()
         for t_h, b_h in host:                       # one sampling pass per distinct view: the workspace fits the densest one
             key = float(t_h.reshape(-1)[0])

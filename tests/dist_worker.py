@@ -20,7 +20,9 @@ def run(rank, world, port, mode, out_dir):
     model, scene = model_from_golden(g, fused_pose=True)
     model.decoder_train = "tc"
     opt = create_optimizer(model)
-    bucket = make_bucket(model, opt, overlap=(mode != "graph1"))          # graph1: ONE all-reduce of the whole bucket per step
+    # graph1: ONE all-reduce of the whole bucket per step; pipe*: the exchange pipelined across steps (the default bucket);
+    # static / graph: three parts beside the backward of the same step
+    bucket = make_bucket(model, opt, overlap={"graph1": False, "pipe": "pipeline", "pipe_static": "pipeline"}.get(mode, True))
     R = len(g["rays_o"])
     a, b = shard_rays(R, rank, world)
     t = g["train"]["t"].cuda()
@@ -36,8 +38,9 @@ def run(rank, world, port, mode, out_dir):
     else:
         # the graph-captured step with its split all-reduce (early slice on the communication stream), two iterations
         before = {k: p.detach().clone() for k, p in model.named_parameters()}
-        gs = GraphedTrainStep(model, opt, bucket, b - a, scene.render_kwargs(), calibrate=(t, ro, rd), use_graph=(mode != "static"))
-        losses = [float(gs.step(t, ro, rd, vd, tgt)) for _ in range(2)]
+        gs = GraphedTrainStep(model, opt, bucket, b - a, scene.render_kwargs(), calibrate=(t, ro, rd), use_graph=not mode.endswith("static"))
+        assert gs.pipelined == mode.startswith("pipe")
+        losses = [float(gs.step(t, ro, rd, vd, tgt)) for _ in range(3)]
         gs.flush()
         out = {"params": {k: p.detach().cpu() for k, p in model.named_parameters()}, "losses": losses, "M": gs.last_counts["M"],
                "split": bucket.split, "total": bucket.total,

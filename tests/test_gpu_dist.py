@@ -48,13 +48,17 @@ def test_two_rank_gradient_equals_single_process_full_batch(golden_tiny, tmp_pat
         assert rel_err(a, b) < tol, (o, p.shape)
 
 
-@pytest.mark.parametrize("mode", ["static", "graph", "graph1"])
+_RUNS = {}
+
+
+@pytest.mark.parametrize("mode", ["static", "graph", "graph1", "pipe", "pipe_static"])
 def test_two_rank_graphed_step_keeps_ranks_identical(golden_tiny, tmp_path, mode):
     """The sync-free step at world size 2 (early slice reduced beside the LBS / pose backward, late slice + status, Adam;
     `graph1`: one all-reduce of the whole bucket between a forward + backward graph with side-stream branches and the Adam
-    graph — what make_bucket picks for small buckets): both ranks end with bit-identical parameters after two iterations, and
-    the decoder slice really is the bulk."""
-    r0, r1 = _launch(mode, tmp_path, {"static": 29633, "graph": 29635, "graph1": 29637}[mode])
+    graph — what make_bucket picks for small buckets): `pipe` / `pipe_static`: the exchange pipelined across steps, graphs / eager):
+    both ranks end with bit-identical parameters after three iterations, and the decoder slice really is the bulk."""
+    r0, r1 = _launch(mode, tmp_path, {"static": 29633, "graph": 29635, "graph1": 29637, "pipe": 29639, "pipe_static": 29641}[mode])
+    _RUNS[mode] = r0
     if mode == "graph1":
         assert r0["split"] == 0
     else:
@@ -65,3 +69,19 @@ def test_two_rank_graphed_step_keeps_ranks_identical(golden_tiny, tmp_path, mode
     for k in ("canonical_feat", "feat_net.0.weight", "rgbnet.feature_linears.weight", "weights", "joints"):   # Adam ran on every slice
         assert k in r0["moved"], k
     assert r0["losses"][1] != r0["losses"][0]
+
+
+def test_pipelined_exchange_trains_like_the_unpipelined_step(golden_tiny, tmp_path):
+    """Same arithmetic, other schedule: the losses of three iterations of the pipelined exchange (decoder slice reduced and
+    applied beside the NEXT step's sampling stage) equal those of the step that reduces the whole bucket before Adam.  A
+    decoder that ran on stale weights / a stale point table, or a sampling stage that ran before the warp parameters were
+    updated, shows up in iterations 2 and 3."""
+    for i, mode in enumerate(("graph1", "pipe", "pipe_static")):
+        if mode not in _RUNS:
+            _RUNS[mode] = _launch(mode, tmp_path, 29651 + 2 * i)[0]
+    ref = _RUNS["graph1"]["losses"]
+    assert abs(ref[1] - ref[0]) > 1e-3 * abs(ref[0]) and abs(ref[2] - ref[1]) > 1e-3 * abs(ref[0])   # the steps do move the loss
+    for mode in ("pipe", "pipe_static"):
+        got = _RUNS[mode]["losses"]
+        for a, b in zip(got, ref):
+            assert abs(a - b) < 1e-4 * abs(b), (mode, got, ref)
