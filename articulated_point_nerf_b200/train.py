@@ -770,7 +770,7 @@ class GraphedTrainStep:
         self._adam_feat, self._adam_early, self._adam_late, self._ss_perm = [], [], [], []
         base = 0
         for cls, ap, sizes in launches:
-            one_piece = self.world > 1 and not self.pipelined
+            one_piece = (self.world > 1 and not self.pipelined) or (self.world == 1 and not self.branches)
             label = [2 if (one_piece or e[0].data_ptr() in late_ptrs) else (0 if e[0].data_ptr() == feat_ptr else 1)
                      for e in ap.keep]
             if len(set(label)) == 1:
