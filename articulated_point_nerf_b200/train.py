@@ -104,7 +104,7 @@ class GradBucket:
     data-parallel exchange is an all-reduce over it.
 
     Layout: [early | late | status].  `early` holds the parameters named by `early` (GraphedTrainStep passes the
-    decoder's: canonical_feat, feat_net, rgbnet, densitynet — 90 % of the bytes — whose gradients are complete as soon as
+    decoder's: canonical_feat, feat_net, rgbnet, densitynet — ~80 % of the bytes — whose gradients are complete as soon as
     the decoder backward has run), `late` the rest (skinning weights, joints, pose network: complete after the LBS and
     pose backward).  The two parts can be reduced separately, the first one overlapping the LBS / pose backward.
     `status` (64 floats) is a side channel that travels with the `late` all-reduce (a device-side flag every rank has to
@@ -115,7 +115,7 @@ class GradBucket:
     def __init__(self, optimizer: torch.optim.Optimizer, early=(), first=()):
         """`first` (a subset of `early`) goes to the very front: [first | rest of early | late | status]; `first_split` /
         `split` are the two boundaries.  GraphedTrainStep puts canonical_feat there: its gradient is final before the
-        decoder's weight gradients are (apn_aggregate_bwd_tc_phase) and is ~90 % of the bytes."""
+        decoder's weight gradients are (apn_aggregate_bwd_tc_phase) and is ~80 % of the bytes."""
         params = [p for g in optimizer.param_groups for p in g['params'] if p.requires_grad]
         assert params, "no trainable parameters"
         early_ids = {id(p) for p in early}
@@ -215,7 +215,7 @@ OVERLAP_MIN_FLOATS = 8 << 20       # 32 MiB of gradients
 def make_bucket(model, optimizer, overlap="pipeline") -> "GradBucket":
     """The flat gradient bucket of a data-parallel run.
     "pipeline" (default): [canonical_feat | every other parameter the warp does not own | warp parameters | status] —
-        GraphedTrainStep then reduces the first two parts (~99 % of the bytes) on the communication stream BESIDE THE NEXT
+        GraphedTrainStep then reduces the first two parts (82 % of the bytes at c2 / c4 sizes) on the communication stream BESIDE THE NEXT
         STEP's pose -> LBS -> grid -> k-NN chain, which only reads the warp parameters; only the small warp slice is exchanged
         inside the step.
     True: [canonical_feat | decoder MLPs | rest | status], reduced in three parts beside the backward of the same step
@@ -540,7 +540,7 @@ class GraphedTrainStep:
                        wait for the communication stream
                        graph P2 [decoder, compositing, loss, backward with its three branches]
                        all-reduce of the warp slice + status (small), Adam of the warp parameters
-        comm stream    all-reduce of the decoder slice (~99 % of the bytes), Adam of those parameters, graph PP [zero the
+        comm stream    all-reduce of the decoder slice (82 % of the bytes at c2 / c4 sizes), Adam of those parameters, graph PP [zero the
                        decoder slice, weight tiles, per-point table] — all of it beside the NEXT step's graph P1.
     Same arithmetic as the unpipelined step: every parameter is updated before its next reader runs.
 
@@ -548,7 +548,7 @@ class GraphedTrainStep:
       * the decoder's derived state (weight tiles, per-point table) and the bucket memset do not depend on the pose: they
         run beside the pose -> LBS -> grid -> k-NN chain, whose kernels leave most SMs idle, and join before the decoder;
       * (unless the gradient exchange is split) the backward forks three ways as soon as tc_dgrad has produced d_xyz / d_ginv
-        (apn_aggregate_bwd_tc_phase 3 | 5 | 6): [d_feat GEMM, Adam of canonical_feat (~90 % of the optimiser's bytes)] beside
+        (apn_aggregate_bwd_tc_phase 3 | 5 | 6): [d_feat GEMM, Adam of canonical_feat (~80 % of the optimiser's bytes)] beside
         [point-table wgrad GEMM || tc_wgrad, Adam of the decoder's MLPs] beside [regularisers, LBS backward, pose backward
         (one 8-CTA cluster), Adam of the skinning weights / joints / pose network]; the Adam parts only with one rank (with
         more, Adam follows the all-reduce).
@@ -691,7 +691,7 @@ class GraphedTrainStep:
         rest)].  -> total loss."""
         self._side.wait_stream(cur)
         self._side2.wait_stream(cur)
-        with torch.cuda.stream(self._side):          # point features: d_feat GEMM, then their Adam update (~90 % of its bytes)
+        with torch.cuda.stream(self._side):          # point features: d_feat GEMM, then their Adam update (~80 % of its bytes)
             self.fused.decoder_backward_feat(st)
             if inline_adam:
                 self._launch_adam(self._adam_feat, adam_skip)
@@ -824,7 +824,7 @@ class GraphedTrainStep:
                     self._body_a(adam_skip=None)
             else:
                 # four graphs around the three all-reduces: [forward + decoder backward up to canonical_feat.grad] | that
-                # gradient (~90 % of the bytes) reduces on the communication stream while [decoder weight gradients +
+                # gradient (~80 % of the bytes) reduces on the communication stream while [decoder weight gradients +
                 # regularisers] run | the decoder's weight gradients reduce while [LBS + pose backward] runs | late slice +
                 # status reduce | [Adam]
                 split = self.bucket.split > 0
@@ -1003,7 +1003,7 @@ class GraphedTrainStep:
             if self.world > 1 and not self.pipelined:
                 cur = torch.cuda.current_stream(self.dev)
                 if split:
-                    # canonical_feat.grad (90 % of the bucket) is final: reduce it on the communication stream while the
+                    # canonical_feat.grad (~80 % of the bucket) is final: reduce it on the communication stream while the
                     # decoder's weight gradients are computed here; then those, beside the LBS / pose backward
                     self.comm_stream.wait_stream(cur)
                     with torch.cuda.stream(self.comm_stream), _lib_stage("allreduce_feat"):

@@ -68,3 +68,74 @@ def test_flat_bucket_allreduce_reproduces_single_process_gradient():
         vals.append(flat[o:o + p.numel()])
         o += (p.numel() + 63) // 64 * 64
     assert torch.allclose(torch.cat(vals), ref, rtol=1e-5, atol=1e-6)
+
+
+def _worker_parts(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from articulated_point_nerf_b200.scene import build_model, make_scene
+    from articulated_point_nerf_b200.train import create_optimizer, make_bucket
+    model = build_model(make_scene("tiny"))
+    opt = create_optimizer(model)
+    bucket = make_bucket(model, opt)                              # the pipelined layout
+    gen = torch.Generator().manual_seed(100 + rank)
+    bucket.flat[:bucket.total].copy_(torch.randn(bucket.total, generator=gen))
+    bucket.status[:1].fill_(float(rank))                          # a flag raised on rank 1 only
+    before = bucket.flat.clone()
+    bucket.all_reduce_avg(part=1)                                 # warp slice + status: the exchange inside the step
+    mid = bucket.flat.clone()
+    bucket.all_reduce_avg(part=0)                                 # decoder slice: the exchange beside the next step
+    q.put((rank, bucket.split, bucket.total, before.tolist(), mid.tolist(), bucket.flat.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_bucket_layout_and_slice_exchange():
+    """make_bucket(model, opt) = "pipeline": [canonical_feat | other non-warp parameters | warp parameters | status]; the two
+    slices are exchanged separately (part=1 inside the step, part=0 beside the next one) and together cover the bucket; the
+    status words travel with the warp slice, so a flag raised on one rank is non-zero on every rank after it."""
+    from articulated_point_nerf_b200.scene import build_model, make_scene
+    from articulated_point_nerf_b200.train import GradBucket, create_optimizer, decoder_parameters, make_bucket, warp_parameters
+    model = build_model(make_scene("tiny"))
+    opt = create_optimizer(model)
+    b = make_bucket(model, opt)
+    warp = {id(p) for p in warp_parameters(model)}
+    assert b.params[0] is model.canonical_feat and b.offsets[0] == 0
+    assert 0 < b.first_split < b.split < b.total
+    for p, o in zip(b.params, b.offsets):
+        assert (id(p) in warp) == (o >= b.split)
+        assert o % 64 == 0 and p.grad.data_ptr() == b.flat.data_ptr() + 4 * o
+    assert {id(p) for p in decoder_parameters(model)} <= {id(p) for p, o in zip(b.params, b.offsets) if o < b.split}
+    assert b.split > 0.5 * b.total                                  # (82 % at c2 / c4 sizes: canonical_feat grows with the cloud)
+    assert sum(p.numel() for p in b.params) == b.numel == sum(p.numel() for g in opt.param_groups for p in g["params"])
+    # the other layouts
+    b3 = make_bucket(model, opt, True)
+    assert b3.params[0] is model.canonical_feat and 0 < b3.first_split < b3.split
+    assert {id(p) for p, o in zip(b3.params, b3.offsets) if o < b3.split} == {id(p) for p in decoder_parameters(model)}
+    b1 = make_bucket(model, opt, False)
+    assert b1.split == 0 and isinstance(b1, GradBucket)
+    assert make_bucket(model, opt, "auto").split == 0               # tiny scene: far below 32 MiB of gradients
+    # two ranks
+    world, port = 2, 29100 + (os.getpid() % 400)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_parts, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, split, total, before, mid, after = q.get(timeout=300)
+        got[r] = (split, total, torch.tensor(before), torch.tensor(mid), torch.tensor(after))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    split, total = got[0][0], got[0][1]
+    assert (split, total) == (b.split, b.total)
+    avg = 0.5 * (got[0][2] + got[1][2])
+    for r in range(world):
+        _, _, before, mid, after = got[r]
+        assert torch.equal(mid[:split], before[:split])             # part=1 leaves the decoder slice alone
+        assert torch.allclose(mid[split:], avg[split:], rtol=0, atol=1e-6)
+        assert torch.equal(after[split:], mid[split:])              # part=0 leaves the warp slice alone
+        assert torch.allclose(after[:split], avg[:split], rtol=0, atol=1e-6)
+        assert float(after[total]) == 0.5                           # the flag of rank 1, averaged: non-zero everywhere

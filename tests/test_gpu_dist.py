@@ -62,7 +62,7 @@ def test_two_rank_graphed_step_keeps_ranks_identical(golden_tiny, tmp_path, mode
     if mode == "graph1":
         assert r0["split"] == 0
     else:
-        assert 0 < r0["split"] < r0["total"]      # two slices: the decoder's (90 % of the bytes at c2 size) and the rest
+        assert 0 < r0["split"] < r0["total"]      # two slices: the decoder's (~80 % of the bytes at c2 size) and the rest
     for k in r0["params"]:
         assert torch.equal(r0["params"][k], r1["params"][k]), k
     assert all(map(lambda x: x == x, r0["losses"] + r1["losses"]))       # finite
