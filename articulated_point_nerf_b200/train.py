@@ -905,14 +905,20 @@ class GraphedTrainStep:
         pg[3].replay() if pg else self._launch_adam(self._adam_late)
 
     # ------------------------------------------------------------------------------------------
+    POLL_LAG = 2
+
     def _poll(self, wait: bool = False):
-        """Looks at the status of finished steps (never waits unless `wait`)."""
+        """Looks at the status of finished steps (never waits unless `wait`).  With more than one rank the ranks must notice
+        an overflowed step in the SAME call (one that raises issues no collective while the others would): a step is looked
+        at exactly POLL_LAG calls later — its status words are all-reduced, so every rank reads the same flag, and a step
+        that old has long finished, so the wait is free."""
         overflow = None
         keep = []
         for ev, pin, idx in self._pending:
-            if wait:
+            due = wait or (self.world > 1 and idx <= self._steps - self.POLL_LAG)
+            if due:
                 ev.synchronize()
-            if wait or ev.query():
+            if due or (self.world == 1 and ev.query()):
                 flags = pin[0].item()
                 self.last_counts = dict(R=self.R, candidates=int(pin[1].item()), M=int(pin[2].item()),     # mean over ranks
                                         N=len(self.model.canonical_pcd))
