@@ -533,8 +533,8 @@ def test_aggregate_tensor_core_backward_matches_fp32_kernels_on_ragged_sizes(M):
     """Tile tails and multi-tile accumulation (CTAs that walk several tiles; slab reduction of the wgrad) of the
     tensor-core backward against the fp32 CUDA-core backward on random weights: every entry within 5e-4 of the tensor's
     scale (split-fp16 carries 22 mantissa bits; the PE backward multiplies its rounding by up to 2^9).
-    The weights are seeded so that no LeakyReLU kink flip separates the two forwards (scripts/debug_tc_bwd2.py measures
-    what a flip in a dominant row does: ~1e-2 on that step's layer-0 gradients, in either implementation)."""
+    The weights are seeded so that no LeakyReLU kink flip separates the two forwards (measured while
+    the kernel was brought up: a flip in a dominant row moves that step's layer-0 gradients by ~1e-2, in either implementation)."""
     ops = _ops()
     torch.manual_seed(1)
     g = torch.Generator().manual_seed(100 + M)
