@@ -139,3 +139,23 @@ def test_pipelined_bucket_layout_and_slice_exchange():
         assert torch.equal(after[split:], mid[split:])              # part=0 leaves the warp slice alone
         assert torch.allclose(after[:split], avg[:split], rtol=0, atol=1e-6)
         assert float(after[total]) == 0.5                           # the flag of rank 1, averaged: non-zero everywhere
+
+
+def test_tile_shares_of_a_frame_partition_its_pixels():
+    """render.tile_pixels (16x16 tiles dealt round-robin): the shares of all ranks are disjoint, sorted,
+    cover the frame — also when the frame is not a multiple of the tile — and are balanced to within one tile row."""
+    from articulated_point_nerf_b200.render import tile_pixels
+    for H, W, world, tile in [(400, 400, 8, 16), (37, 53, 3, 16), (16, 16, 4, 16), (2048, 2048, 8, 16), (5, 7, 2, 4)]:
+        shares = [tile_pixels(H, W, r, world, tile) for r in range(world)]
+        allpix = torch.cat(shares).long()
+        assert len(allpix) == H * W and torch.equal(allpix.sort()[0], torch.arange(H * W))
+        for s in shares:
+            assert s.dtype == torch.int32 and bool((s[1:] > s[:-1]).all())
+        n_tiles = ((H + tile - 1) // tile) * ((W + tile - 1) // tile)
+        if n_tiles >= world:
+            sizes = [len(s) for s in shares]
+            assert max(sizes) - min(sizes) <= tile * tile * (1 + (n_tiles % world != 0)) + tile * max(H, W)
+        # a pixel's owner is its tile's raster index modulo the world size
+        y, x = 3 % H, 5 % W
+        owner = ((y // tile) * ((W + tile - 1) // tile) + x // tile) % world
+        assert (y * W + x) in set(shares[owner].tolist())
